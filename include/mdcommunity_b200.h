@@ -1,0 +1,179 @@
+/*
+ * mdcommunity_b200.h -- C ABI of the B200-native MultiDismantler rollout path (libmdb200.so, sm_100a only).
+ *
+ * The reference (KelvinRyman/MDCommunity) is pure Python and has no FFI of its own; the entry points below
+ * are what a binding for its hot path would call.  Each one names the reference code it replaces
+ * (paths relative to /root/reference/code; U/ = MultiDismantler_unit_cost/, D/ = MultiDismantler_degree_cost/).
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes only; every pointer inside the structs is a DEVICE pointer unless
+ *     the field comment says "host".
+ *   - return 0 on success, a negative MD_E* code for bad arguments, a positive cudaError_t for CUDA failures.
+ *   - nothing is allocated, nothing synchronises: the caller owns all buffers (sized with the helpers at the end)
+ *     and orders work with the cudaStream_t it passes.
+ *   - one host thread per GPU process.  There is no CPU fallback.
+ *
+ * Node addressing: a batch holds B graphs; graph g owns the global node slots [g*S, (g+1)*S) where the stride
+ * S is a multiple of MD_TILE_M.  Slots >= n_nodes[g] are padding (label -1 for ever).
+ */
+#ifndef MDCOMMUNITY_B200_H
+#define MDCOMMUNITY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MD_MAX_LAYERS 4
+#define MD_EMBED 64     /* EMBEDDING_SIZE, U/MultiDismantler_torch.py:35 */
+#define MD_HIDDEN 32    /* REG_HIDDEN, :53 */
+#define MD_AUX 4        /* aux_dim, :58 */
+#define MD_GATE 128     /* w_layer1 width, U/MultiDismantler_net_graphsage.py:83 */
+#define MD_BP_ITERS 3   /* max_bp_iter, U/MultiDismantler_torch.py:62 */
+#define MD_TILE_M 128   /* node rows per CTA tile in the embedding / Q kernels */
+
+#define MD_EINVAL (-1)
+#define MD_ETOOBIG (-2)
+#define MD_ELAYERS (-3)
+
+typedef void* md_stream_t; /* cudaStream_t */
+
+/* Static topology of a batch (replaces graph.Graph / Graph_test adjacency lists, U/graph.py:8-30,70-84,
+ * and the per-step PrepareBatchGraph COO rebuild, U/PrepareBatchGraph.py:76-177: the CSR is built once). */
+typedef struct md_graphs {
+  int32_t n_graphs;                      /* B */
+  int32_t n_layers;                      /* L: 2 for the reference network; 3 allowed for the LMCC / aggregation kernels */
+  int32_t stride;                        /* S, multiple of MD_TILE_M */
+  int32_t n_total;                       /* B * S */
+  const int32_t* rowptr[MD_MAX_LAYERS];  /* [n_total + 1] per layer */
+  const int32_t* col[MD_MAX_LAYERS];     /* [nnz_l] neighbour = global node id; row order = edge_list order */
+  const int32_t* n_nodes;                /* [B] */
+  const int32_t* n_edges;                /* [L][B] undirected edge counts (graph.num_edges) */
+  const int32_t* max_rank;               /* [B] LMCC of the intact graph (graph.max_rank) */
+  const float* node_w[MD_MAX_LAYERS];    /* degree cost: [n_total] w_l(v) = deg/maxdeg as f32 (D/graph.py:39-51); NULL for unit cost */
+  const double* node_cost;               /* degree cost: [n_total] f64 w0[v]/W0 + w1[v]/W1 (D/mvc_env.py:127-133); NULL for unit cost */
+} md_graphs_t;
+
+/* Mutable environment state of the batch (replaces MvcEnv fields covered_set / remove_edge / numCoveredEdges /
+ * score / MaxCCList, U/mvc_env.py:8-52, and PrepareBatchGraph.get_status_info's counters, U/PrepareBatchGraph.py:35-74). */
+typedef struct md_state {
+  int32_t* label;        /* [n_total] mutual-component id = global id of its smallest node; -1 = removed or padding */
+  int32_t* deg[MD_MAX_LAYERS]; /* [n_total] alive degree per layer */
+  int32_t* act_list;     /* [n_total] graph g's active nodes, ascending, at [g*S, g*S + n_act[g]) */
+  int32_t* n_act;        /* [B] */
+  int32_t* n_removed;    /* [B] |covered_set| */
+  int32_t* cov_edges;    /* [L][B] numCoveredEdges */
+  int32_t* alive_edges;  /* [L][B] */
+  int32_t* max_deg;      /* [L][B] */
+  int64_t* twohop;       /* [L][B] sum_v C(deg_alive(v), 2) */
+  int32_t* rank;         /* [B] current LMCC size */
+  int32_t* done;         /* [B] isTerminal */
+  int32_t* n_steps;      /* [B] removals so far */
+  double* score;         /* [B] AUDC accumulator (f64, reference op order) */
+  float* aux;            /* [B][L][4] aux features for the next forward */
+  unsigned long long* best; /* [B] packed (orderable q << 32 | ~local id) arg-max key, written by md_qhead */
+  int32_t* trace_action; /* [B][max_steps] local node ids removed */
+  int32_t* trace_rank;   /* [B][max_steps] LMCC after each removal */
+  double* trace_maxcc;   /* [B][max_steps] MaxCCList entries */
+  int32_t* n_done;       /* [1] number of terminal graphs */
+  int32_t max_steps;
+  int32_t cost_mode;     /* 0 = unit cost reward, 1 = degree cost reward */
+  /* scratch for the large-graph (multi-CTA) LMCC path, may be NULL when stride <= md_env_small_max_stride() */
+  int32_t* parent;       /* [n_total] */
+  int32_t* comp_size;    /* [n_total] */
+  int32_t* flags;        /* [8] */
+} md_state_t;
+
+/* The 14-tensor checkpoint (U/MultiDismantler_net_graphsage.py:42-89, U/MRGNN/mutil_layer_weight.py:252-264),
+ * row-major f32 exactly as stored, plus two host-precomputed products used by the fused iteration kernel. */
+typedef struct md_weights {
+  const float* w_n2l;     /* [2][64] */
+  const float* conv1;     /* [64][64]  p_node_conv */
+  const float* conv2;     /* [64][64]  p_node_conv2 */
+  const float* conv3;     /* [128][64] p_node_conv3 */
+  const float* w13;       /* [64][64]  p_node_conv  @ p_node_conv3[:64]  (formed in f64, rounded once) */
+  const float* w23;       /* [64][64]  p_node_conv2 @ p_node_conv3[64:] */
+  const float* trans;     /* [64][64]  layerNodeAttention_weight.trans */
+  const float* bias;      /* [64] */
+  const float* logis_w;   /* [64] */
+  const float* logis_b;   /* [1] */
+  const float* cross;     /* [64]  cross_product */
+  const float* h1;        /* [64][32] */
+  const float* h2;        /* [36] (= last_w) */
+  const float* wl1;       /* [64][128] w_layer1 */
+  const float* wl2;       /* [128] w_layer2 */
+} md_weights_t;
+
+/* Per-step activations. */
+typedef struct md_work {
+  float* h[2][MD_MAX_LAYERS];   /* ping-pong node embeddings, [n_total][64] each */
+  float* psum;                  /* [MD_BP_ITERS][L][n_total / MD_TILE_M][64] per-tile partial sums of H (subgsum) */
+  float* gconst;                /* [B][MD_GCONST] per-graph constants for the Q head */
+  float* q;                     /* [n_total] Q value per node slot (valid for active nodes) */
+} md_work_t;
+#define MD_GCONST 16 /* s[L], gate_softmax[L], aux_dot[L] padded */
+
+/* ---- environment ------------------------------------------------------------------------------------- */
+
+/* MvcEnv.s0 (U/mvc_env.py:31-52) for every graph of the batch: clears the state and runs the initial
+ * mutual-component prune (Mcc.MCC, U/Mcc.py:30-38). */
+int md_env_reset(const md_graphs_t* g, const md_state_t* s, md_stream_t stream);
+
+/* MvcEnv.stepWithoutReward (U/mvc_env.py:74-87) + getReward / getMaxConnectedNodesNum (:133-162) + Mcc.MCC for
+ * every non-terminal graph, followed by PrepareBatchGraph.get_status_info (U/PrepareBatchGraph.py:35-100).
+ * action source: actions != NULL -> actions[g * action_stride + (action_index >= 0 ? action_index : n_steps[g])]
+ * (local node id, < 0 = skip this graph); actions == NULL -> the arg-max key md_qhead left in s->best. */
+int md_env_step(const md_graphs_t* g, const md_state_t* s, const int32_t* actions, int32_t action_stride,
+                int32_t action_index, md_stream_t stream);
+
+/* largest graph stride the single-CTA (shared-memory) env kernel handles; larger strides use the multi-CTA path */
+int32_t md_env_small_max_stride(void);
+
+/* ---- Q network ---------------------------------------------------------------------------------------- */
+
+/* Node input features + first embedding (U/MultiDismantler_net_graphsage.py:248-287; D/MultiDismantler_net.py:222-240). */
+int md_embed_init(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
+                  md_stream_t stream);
+
+/* One message-passing iteration for all layers: neighbour sum over alive edges (torch_sparse.spmm n2n, :290-291),
+ * dense transforms (:294-309), relu + L2 normalise (:309-310), and the per-graph sum of the OLD embeddings
+ * (spmm subgsum, :297-298) as per-tile partials.  iter = 0..2; reads h[iter&1], writes h[(iter+1)&1]. */
+int md_embed_iter(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
+                  int32_t iter, md_stream_t stream);
+
+/* Virtual (graph) node chain y0..y3 (:272-287,301-321), its inter-layer fusion rows
+ * (BitwiseMultipyLogis, U/MRGNN/mutil_layer_weight.py:266-313) and the per-graph Q-head constants. */
+int md_graph_embed(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
+                   md_stream_t stream);
+
+/* Inter-layer fusion of node rows + Q head + masked arg-max (net_graphsage.py:323-393, Predict's -inf mask
+ * U/MultiDismantler_torch.py:286-300 and argMax :799-807).  Reads h[MD_BP_ITERS & 1]. */
+int md_qhead(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
+             md_stream_t stream);
+
+/* n_steps lock-step greedy iterations (GetSol loop body, U/MultiDismantler_torch.py:759-784): forward + env step. */
+int md_rollout_steps(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
+                     int32_t n_steps, md_stream_t stream);
+
+/* Top-k selection for GetSolution's stepRatio mode (np.argsort(-pred)[:step], U/MultiDismantler_torch.py:725):
+ * out_local_ids[g][0..topk) = graph g's active nodes ranked by (q descending, id ascending), -1 padded.
+ * Feed it to md_env_step(actions = out_local_ids, action_stride = topk, action_index = j) for j = 0..topk-1. */
+int md_select_topk(const md_graphs_t* g, const md_state_t* s, const md_work_t* k, int32_t* out_local_ids,
+                   int32_t topk, md_stream_t stream);
+
+/* ---- operator boundary -------------------------------------------------------------------------------- */
+
+/* torch_sparse.spmm replacement (call sites net_graphsage.py:290,297,350,377): Y[r] = sum_e val[e] * X[col[e]]
+ * over CSR row r.  val == NULL means all ones.  D must be a multiple of 4, X and Y 16-byte aligned. */
+int md_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* val, const float* X, float* Y,
+                    int32_t n_rows, int32_t D, md_stream_t stream);
+
+/* ---- sizing helpers (host) ------------------------------------------------------------------------------ */
+int64_t md_psum_floats(int32_t n_layers, int32_t n_total);
+const char* md_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDCOMMUNITY_B200_H */

@@ -1,0 +1,101 @@
+"""ctypes binding of libmdb200.so (the C ABI declared in include/mdcommunity_b200.h).
+
+There is no CPU fallback: if the library cannot be built/loaded the import of the compute path fails loudly.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+MAX_LAYERS = 4
+EMBED = 64
+HIDDEN = 32
+AUX = 4
+GATE = 128
+BP_ITERS = 3
+TILE_M = 128
+GCONST = 16
+
+_i32p = C.POINTER(C.c_int32)
+_f32p = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+
+class MdGraphs(C.Structure):
+    _fields_ = [
+        ("n_graphs", C.c_int32), ("n_layers", C.c_int32), ("stride", C.c_int32), ("n_total", C.c_int32),
+        ("rowptr", _vp * MAX_LAYERS), ("col", _vp * MAX_LAYERS),
+        ("n_nodes", _vp), ("n_edges", _vp), ("max_rank", _vp),
+        ("node_w", _vp * MAX_LAYERS), ("node_cost", _vp),
+    ]
+
+
+class MdState(C.Structure):
+    _fields_ = [
+        ("label", _vp), ("deg", _vp * MAX_LAYERS), ("act_list", _vp), ("n_act", _vp), ("n_removed", _vp),
+        ("cov_edges", _vp), ("alive_edges", _vp), ("max_deg", _vp), ("twohop", _vp), ("rank", _vp),
+        ("done", _vp), ("n_steps", _vp), ("score", _vp), ("aux", _vp), ("best", _vp),
+        ("trace_action", _vp), ("trace_rank", _vp), ("trace_maxcc", _vp), ("n_done", _vp),
+        ("max_steps", C.c_int32), ("cost_mode", C.c_int32),
+        ("parent", _vp), ("comp_size", _vp), ("flags", _vp),
+    ]
+
+
+class MdWeights(C.Structure):
+    _fields_ = [(n, _vp) for n in (
+        "w_n2l", "conv1", "conv2", "conv3", "w13", "w23", "trans", "bias", "logis_w", "logis_b", "cross", "h1", "h2",
+        "wl1", "wl2")]
+
+
+class MdWork(C.Structure):
+    _fields_ = [("h", (_vp * MAX_LAYERS) * 2), ("psum", _vp), ("gconst", _vp), ("q", _vp)]
+
+
+_LIB = None
+
+_SIGS = {
+    "md_env_reset": ([C.POINTER(MdGraphs), C.POINTER(MdState), _vp], C.c_int),
+    "md_env_step": ([C.POINTER(MdGraphs), C.POINTER(MdState), _vp, C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_env_small_max_stride": ([], C.c_int32),
+    "md_embed_init": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
+    "md_embed_iter": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),
+    "md_graph_embed": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
+    "md_qhead": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
+    "md_rollout_steps": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),
+    "md_select_topk": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWork), _vp, C.c_int32, _vp], C.c_int),
+    "md_spmm_csr_f32": ([_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_psum_floats": ([C.c_int32, C.c_int32], C.c_int64),
+    "md_version": ([], C.c_char_p),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def lib():
+    """Load (building first if the sources changed) the shared library; raises if unavailable."""
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB
+        if not os.path.exists(path) or os.environ.get("MDB200_REBUILD"):
+            path = _build.build()
+        else:
+            try:
+                path = _build.build()  # no-op when the stamp matches
+            except Exception:
+                pass  # a box without nvcc still uses the prebuilt .so that travelled with the snapshot
+        h = C.CDLL(path)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(h, name)  # AttributeError if the symbol is missing: fail loudly
+            fn.argtypes = args
+            fn.restype = res
+        _LIB = h
+    return _LIB
+
+
+def check(rc, what):
+    if rc != 0:
+        if rc > 0:
+            raise RuntimeError("%s: CUDA error %d" % (what, rc))
+        raise RuntimeError("%s: %s" % (what, {-1: "invalid argument", -2: "size not supported", -3: "unsupported layer count"}.get(rc, rc)))

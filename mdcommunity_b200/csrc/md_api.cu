@@ -1,0 +1,24 @@
+// Lock-step greedy rollout driver: the body of GetSol's `while not isTerminal()` loop
+// (reference MultiDismantler_torch.py:759-784) for a whole batch, enqueued n_steps times on one stream.
+#include "md_common.cuh"
+
+extern "C" int md_rollout_steps(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
+                                int32_t n_steps, md_stream_t stream) {
+  for (int i = 0; i < n_steps; ++i) {
+    int rc = md_embed_init(g, s, w, k, stream);
+    if (rc) return rc;
+    for (int it = 0; it < MD_BP_ITERS; ++it) {
+      rc = md_embed_iter(g, s, w, k, it, stream);
+      if (rc) return rc;
+    }
+    rc = md_graph_embed(g, s, w, k, stream);
+    if (rc) return rc;
+    rc = md_qhead(g, s, w, k, stream);
+    if (rc) return rc;
+    rc = md_env_step(g, s, nullptr, 0, -1, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" const char* md_version(void) { return "mdcommunity_b200 0.1 (sm_100a)"; }

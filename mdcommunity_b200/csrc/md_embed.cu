@@ -1,0 +1,479 @@
+// Node-embedding kernels of the Q network.
+//
+// Replaces (reference, /root/reference/code/MultiDismantler_unit_cost/MultiDismantler_net_graphsage.py):
+//   md_embed_init  : :248-287   node features (alive degree / max alive degree, or the degree-cost weights of
+//                               D/PrepareBatchGraph.py:133-136), relu(x @ w_n2l), L2 normalise
+//   md_embed_iter  : :288-310   torch_sparse.spmm(n2nsum) + three dense transforms + relu + normalise, and the
+//                               torch_sparse.spmm(subgsum) of :297-298 as per-tile partial sums
+//   md_graph_embed : :272-287, :301-321 (virtual node chain), U/MRGNN/mutil_layer_weight.py:266-313 (fusion of the
+//                               graph rows), net_graphsage.py:350-351,377-390 (per-graph parts of the Q head)
+//
+// Layout: embeddings H[l] are [n_total][64] f32 rows addressed by global node id, so neighbour gathers need no
+// re-indexing; only the rows listed in act_list (active nodes, compacted per graph by the env kernel) are touched.
+#include "md_common.cuh"
+
+namespace md {
+
+// =================================================================================================
+// md_embed_init
+// =================================================================================================
+__global__ void __launch_bounds__(256) embed_init_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K) {
+  const int l = blockIdx.y;
+  const int tpg = G.stride / TILE_M;
+  const int g = blockIdx.x / tpg;
+  const int t = blockIdx.x % tpg;
+  const int nact = S.n_act[g];
+  if (t * TILE_M >= nact) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float w0a = W.w_n2l[2 * lane], w0b = W.w_n2l[2 * lane + 1];
+  const float w1a = W.w_n2l[D + 2 * lane], w1b = W.w_n2l[D + 2 * lane + 1];
+  const bool degree_cost = G.node_w[0] != nullptr;
+  const float dmax = (float)S.max_deg[l * G.n_graphs + g];
+  float* __restrict__ H = K.h[0][l];
+  for (int r = t * TILE_M + warp; r < min(nact, (t + 1) * TILE_M); r += 8) {
+    const int v = S.act_list[g * G.stride + r];
+    float x0, x1;
+    if (degree_cost) {
+      x0 = G.node_w[l][v];
+      x1 = 1.0f;
+    } else {
+      x0 = (float)S.deg[l][v] / dmax;  // degree / degree_max, both exact small integers in f32 (:255-258)
+      x1 = x0;
+    }
+    float a = fmaxf(fmaf(x1, w1a, x0 * w0a), 0.f);
+    float b = fmaxf(fmaf(x1, w1b, x0 * w0b), 0.f);
+    const float nrm = sqrtf(warp_sum(a * a + b * b));
+    const float den = fmaxf(nrm, 1e-12f);  // F.normalize eps
+    *reinterpret_cast<float2*>(H + (size_t)v * D + 2 * lane) = make_float2(a / den, b / den);
+  }
+}
+
+// =================================================================================================
+// md_embed_iter : persistent CTAs, one 128-row tile at a time
+// =================================================================================================
+constexpr int IT_T = 256;
+constexpr int EMAX = 2048;  // staged alive-neighbour slots per tile
+struct IterSmem {
+  float A[TILE_M * A_LD];   // [row][0:64] = neighbour sum P, [row][64:128] = own embedding H
+  float Wm[2 * D * D];      // merged weight [128][64]: rows 0..63 = w13, 64..127 = w23
+  int eu[EMAX];             // staged neighbour ids (-1 = dead edge)
+  int v[TILE_M];            // global node id of the row, -1 = padding row
+  int lv[TILE_M];           // its label
+  int beg[TILE_M];          // first CSR entry
+  int off[TILE_M + 1];      // exclusive scan of the row degrees inside the tile
+  unsigned char er[EMAX];   // tile row of the staged entry
+};
+
+__device__ __forceinline__ void tile_gemm_128(const float* __restrict__ A, const float* __restrict__ Wm, int ty, int tx,
+                                              float (&acc)[8][4]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+#pragma unroll 2
+  for (int k0 = 0; k0 < 2 * D; k0 += 4) {
+    float4 a[8], w[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(A + (ty + 16 * i) * A_LD + k0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(Wm + (k0 + kk) * D + 4 * tx);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i][0] = fmaf(a[i].x, w[0].x, acc[i][0]);
+      acc[i][1] = fmaf(a[i].x, w[0].y, acc[i][1]);
+      acc[i][2] = fmaf(a[i].x, w[0].z, acc[i][2]);
+      acc[i][3] = fmaf(a[i].x, w[0].w, acc[i][3]);
+      acc[i][0] = fmaf(a[i].y, w[1].x, acc[i][0]);
+      acc[i][1] = fmaf(a[i].y, w[1].y, acc[i][1]);
+      acc[i][2] = fmaf(a[i].y, w[1].z, acc[i][2]);
+      acc[i][3] = fmaf(a[i].y, w[1].w, acc[i][3]);
+      acc[i][0] = fmaf(a[i].z, w[2].x, acc[i][0]);
+      acc[i][1] = fmaf(a[i].z, w[2].y, acc[i][1]);
+      acc[i][2] = fmaf(a[i].z, w[2].z, acc[i][2]);
+      acc[i][3] = fmaf(a[i].z, w[2].w, acc[i][3]);
+      acc[i][0] = fmaf(a[i].w, w[3].x, acc[i][0]);
+      acc[i][1] = fmaf(a[i].w, w[3].y, acc[i][1]);
+      acc[i][2] = fmaf(a[i].w, w[3].z, acc[i][2]);
+      acc[i][3] = fmaf(a[i].w, w[3].w, acc[i][3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(IT_T, 2) embed_iter_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K,
+                                                            int iter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  IterSmem& sm = *reinterpret_cast<IterSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int tpg = G.stride / TILE_M;
+  const int tiles_per_layer = G.n_graphs * tpg;
+  const int n_tiles = tiles_per_layer * G.n_layers;
+  const int32_t* __restrict__ label = S.label;
+
+  // merged weight, resident for the lifetime of the CTA
+  for (int i = tid; i < D * D / 4; i += IT_T) {
+    reinterpret_cast<float4*>(sm.Wm)[i] = reinterpret_cast<const float4*>(W.w13)[i];
+    reinterpret_cast<float4*>(sm.Wm + D * D)[i] = reinterpret_cast<const float4*>(W.w23)[i];
+  }
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int l = tile / tiles_per_layer;
+    const int gt = tile - l * tiles_per_layer;
+    const int g = gt / tpg, t = gt - g * tpg;
+    const int nact = S.n_act[g];
+    if (t * TILE_M >= nact) continue;  // uniform
+    const int rows = min(TILE_M, nact - t * TILE_M);
+    const int32_t* __restrict__ rp = G.rowptr[l];
+    const int32_t* __restrict__ cl = G.col[l];
+    const float* __restrict__ Hin = K.h[iter & 1][l];
+    float* __restrict__ Hout = K.h[(iter + 1) & 1][l];
+    __syncthreads();  // previous tile's readers of A / staging are done
+
+    // ---- stage A: row descriptors ------------------------------------------------------------------
+    if (tid < TILE_M) {
+      int v = -1, lv = -1, b = 0, d = 0;
+      if (tid < rows) {
+        v = S.act_list[g * G.stride + t * TILE_M + tid];
+        lv = label[v];
+        b = rp[v];
+        d = rp[v + 1] - b;
+      }
+      sm.v[tid] = v;
+      sm.lv[tid] = lv;
+      sm.beg[tid] = b;
+      sm.off[tid] = d;
+    }
+    __syncthreads();
+    // exclusive scan of the 128 row degrees by warp 0 (4 per lane)
+    if (warp == 0) {
+      int d0 = sm.off[4 * lane], d1 = sm.off[4 * lane + 1], d2 = sm.off[4 * lane + 2], d3 = sm.off[4 * lane + 3];
+      int s = d0 + d1 + d2 + d3, incl = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      int ex = incl - s;
+      sm.off[4 * lane] = ex;
+      sm.off[4 * lane + 1] = ex + d0;
+      sm.off[4 * lane + 2] = ex + d0 + d1;
+      sm.off[4 * lane + 3] = ex + d0 + d1 + d2;
+      if (lane == 31) sm.off[TILE_M] = incl;
+    }
+    __syncthreads();
+    const int etot = sm.off[TILE_M];
+    const bool staged = etot <= EMAX;
+
+    // ---- stage B: alive-neighbour list of the tile (edge-parallel) -------------------------------------
+    if (staged) {
+      for (int e = tid; e < etot; e += IT_T) {
+        int lo = 0, hi = TILE_M - 1;  // largest row with off[row] <= e
+        while (lo < hi) {
+          int mid = (lo + hi + 1) >> 1;
+          if (sm.off[mid] <= e) lo = mid; else hi = mid - 1;
+        }
+        const int u = cl[sm.beg[lo] + (e - sm.off[lo])];
+        sm.eu[e] = (label[u] == sm.lv[lo]) ? u : -1;
+        sm.er[e] = (unsigned char)lo;
+      }
+    }
+    __syncthreads();
+
+    // ---- stage C: gather.  warp w owns tile rows [16w, 16w+16); lane holds columns 2*lane, 2*lane+1 ------
+    {
+      const int r0 = warp * 16;
+      // own rows -> A[:, 64:128]
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int v = sm.v[r0 + i];
+        float2 h = make_float2(0.f, 0.f);
+        if (v >= 0) h = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)v * D) + lane);
+        *reinterpret_cast<float2*>(sm.A + (r0 + i) * A_LD + D + 2 * lane) = h;
+      }
+      if (staged) {
+        const int e0 = sm.off[r0], e1 = sm.off[r0 + 16];
+        int cur = r0;
+        float2 acc = make_float2(0.f, 0.f);
+        for (int e = e0; e < e1; e += 8) {
+          float2 val[8];
+          int rr[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            val[j] = make_float2(0.f, 0.f);
+            rr[j] = -1;
+            if (e + j < e1) {
+              const int u = sm.eu[e + j];
+              rr[j] = sm.er[e + j];
+              if (u >= 0) val[j] = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)u * D) + lane);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (rr[j] >= 0) {
+              if (rr[j] != cur) {  // warp-uniform: finish the rows up to rr[j]
+                *reinterpret_cast<float2*>(sm.A + cur * A_LD + 2 * lane) = acc;
+                for (int z = cur + 1; z < rr[j]; ++z)
+                  *reinterpret_cast<float2*>(sm.A + z * A_LD + 2 * lane) = make_float2(0.f, 0.f);
+                cur = rr[j];
+                acc = make_float2(0.f, 0.f);
+              }
+              acc.x += val[j].x;
+              acc.y += val[j].y;
+            }
+          }
+        }
+        *reinterpret_cast<float2*>(sm.A + cur * A_LD + 2 * lane) = acc;
+        for (int z = cur + 1; z < r0 + 16; ++z)
+          *reinterpret_cast<float2*>(sm.A + z * A_LD + 2 * lane) = make_float2(0.f, 0.f);
+      } else {
+        // hub tile: read the CSR directly, 32 edges at a time
+        for (int i = 0; i < 16; ++i) {
+          const int r = r0 + i;
+          float2 acc = make_float2(0.f, 0.f);
+          if (sm.v[r] >= 0) {
+            const int b = sm.beg[r], d = sm.off[r + 1] - sm.off[r], lv = sm.lv[r];
+            for (int c0 = 0; c0 < d; c0 += 32) {
+              int u = -1;
+              if (c0 + lane < d) {
+                u = cl[b + c0 + lane];
+                if (label[u] != lv) u = -1;
+              }
+              unsigned m = __ballot_sync(0xffffffffu, u >= 0);
+              while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const int uu = __shfl_sync(0xffffffffu, u, j);
+                const float2 hv = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)uu * D) + lane);
+                acc.x += hv.x;
+                acc.y += hv.y;
+              }
+            }
+          }
+          *reinterpret_cast<float2*>(sm.A + r * A_LD + 2 * lane) = acc;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- per-tile partial of the subgraph sum (old embeddings), fixed order => deterministic --------------
+    {
+      const int c = tid & 63, part = tid >> 6;  // 4 row quarters x 64 columns
+      float s = 0.f;
+      for (int r = part * 32; r < part * 32 + 32; ++r) s += sm.A[r * A_LD + D + c];
+      // reuse the staging area for the 4 partials
+      float* red = reinterpret_cast<float*>(sm.eu);
+      red[part * 64 + c] = s;
+    }
+    __syncthreads();
+    if (tid < 64) {
+      const float* red = reinterpret_cast<const float*>(sm.eu);
+      const float s = ((red[tid] + red[64 + tid]) + red[128 + tid]) + red[192 + tid];
+      K.psum[(((size_t)iter * G.n_layers + l) * tiles_per_layer + gt) * D + tid] = s;
+    }
+
+    // ---- dense transform: out = [P, H] @ [w13; w23], relu, L2 normalise ------------------------------------
+    float acc[8][4];
+    tile_gemm_128(sm.A, sm.Wm, ty, tx, acc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[i][c] = fmaxf(acc[i][c], 0.f);
+        ss = fmaf(acc[i][c], acc[i][c], ss);
+      }
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+      const float den = fmaxf(sqrtf(ss), 1e-12f);
+      const int v = sm.v[ty + 16 * i];
+      if (v >= 0)
+        *reinterpret_cast<float4*>(Hout + (size_t)v * D + 4 * tx) =
+            make_float4(acc[i][0] / den, acc[i][1] / den, acc[i][2] / den, acc[i][3] / den);
+    }
+  }
+}
+
+// =================================================================================================
+// md_graph_embed : one CTA per graph, L*64 threads
+// =================================================================================================
+__device__ __forceinline__ float group_sum64(float v, float* scratch, int l, int c) {
+  // sum over the 64 threads (2 warps) of layer l
+  v = warp_sum(v);
+  __syncthreads();
+  if ((c & 31) == 0) scratch[l * 2 + (c >> 5)] = v;
+  __syncthreads();
+  return scratch[l * 2] + scratch[l * 2 + 1];
+}
+
+__global__ void __launch_bounds__(MD_MAX_LAYERS* D) graph_embed_kernel(md_graphs_t G, md_state_t S, md_weights_t W,
+                                                                      md_work_t K) {
+  const int g = blockIdx.x;
+  const int L = G.n_layers;
+  const int l = threadIdx.x >> 6, c = threadIdx.x & 63;
+  __shared__ float y[MD_MAX_LAYERS][D], sbuf[MD_MAX_LAYERS][D], T[MD_MAX_LAYERS][D], hid[MD_MAX_LAYERS][MD_GATE];
+  __shared__ float scratch[2 * MD_MAX_LAYERS];
+  __shared__ float dots[MD_MAX_LAYERS][MD_MAX_LAYERS], sval[MD_MAX_LAYERS], gate[MD_MAX_LAYERS];
+  const int nact = S.n_act[g];
+  const int tpg = G.stride / TILE_M;
+  const int ntile = (nact + TILE_M - 1) / TILE_M;
+  const int tiles_per_layer = G.n_graphs * tpg;
+
+  // y0 = normalize(relu([1,1] @ w_n2l))   (:272-287)
+  float yv = fmaxf(W.w_n2l[c] + W.w_n2l[D + c], 0.f);
+  {
+    const float nrm = sqrtf(group_sum64(yv * yv, scratch, l, c));
+    yv = yv / fmaxf(nrm, 1e-12f);
+  }
+  y[l][c] = yv;
+  for (int it = 0; it < MD_BP_ITERS; ++it) {
+    float s = 0.f;
+    const float* ps = K.psum + (((size_t)it * L + l) * tiles_per_layer + (size_t)g * tpg) * D + c;
+    for (int t = 0; t < ntile; ++t) s += ps[(size_t)t * D];
+    sbuf[l][c] = s;
+    __syncthreads();
+    float o = 0.f;
+    for (int k = 0; k < D; ++k) o = fmaf(sbuf[l][k], W.w13[k * D + c], o);
+    for (int k = 0; k < D; ++k) o = fmaf(y[l][k], W.w23[k * D + c], o);
+    o = fmaxf(o, 0.f);
+    const float nrm = sqrtf(group_sum64(o * o, scratch, l, c));  // contains __syncthreads: y reads are done
+    y[l][c] = o / fmaxf(nrm, 1e-12f);
+    __syncthreads();
+  }
+
+  // ---- fusion of the graph rows (BitwiseMultipyLogis) ------------------------------------------------
+  {
+    float o = 0.f;
+    for (int k = 0; k < D; ++k) o = fmaf(y[l][k], W.trans[k * D + c], o);
+    T[l][c] = tanhf(o + W.bias[c]);
+  }
+  __syncthreads();
+  const float lw = W.logis_w[c], lb = W.logis_b[0];
+  for (int k = 0; k < L; ++k) {  // dots[p=l][k] = (T_k . T_l . lw)
+    const float d = group_sum64(T[k][c] * T[l][c] * lw, scratch, l, c);
+    if (c == 0) dots[l][k] = d;
+  }
+  __syncthreads();
+  float x = T[l][c];
+  {
+    float a[MD_MAX_LAYERS], mx = -1e30f, den = 0.f;
+    for (int k = 0; k < L; ++k) {
+      a[k] = 1.f / (1.f + expf(-(dots[l][k] + lb)));
+      mx = fmaxf(mx, a[k]);
+    }
+    for (int k = 0; k < L; ++k) {
+      a[k] = expf(a[k] - mx);
+      den += a[k];
+    }
+    for (int k = 0; k < L; ++k)
+      if (k != l) x = fmaf(a[k] / den, T[k][c], x);
+  }
+  {
+    const float nrm = sqrtf(group_sum64(x * x, scratch, l, c));
+    x = x / fmaxf(nrm, 1e-12f);
+  }
+  __syncthreads();
+  y[l][c] = x;  // yf_l
+  __syncthreads();
+  // s_l = yf_l . cross_product ; gate_l = relu(yf_l @ w_layer1) @ w_layer2
+  {
+    const float s = group_sum64(x * W.cross[c], scratch, l, c);
+    if (c == 0) sval[l] = s;
+  }
+  for (int j = c; j < MD_GATE; j += D) {
+    float o = 0.f;
+    for (int k = 0; k < D; ++k) o = fmaf(y[l][k], W.wl1[k * MD_GATE + j], o);
+    hid[l][j] = fmaxf(o, 0.f) * W.wl2[j];
+  }
+  __syncthreads();
+  {
+    const float gsum = group_sum64(hid[l][c] + hid[l][c + D], scratch, l, c);
+    if (c == 0) gate[l] = gsum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float* gc = K.gconst + (size_t)g * MD_GCONST;
+    float mx = gate[0];
+    for (int k = 1; k < L; ++k) mx = fmaxf(mx, gate[k]);
+    float e[MD_MAX_LAYERS], den = 0.f;
+    for (int k = 0; k < L; ++k) {
+      e[k] = expf(gate[k] - mx);
+      den += e[k];
+    }
+    for (int k = 0; k < L; ++k) {
+      const float* ax = S.aux + ((size_t)g * L + k) * MD_AUX;
+      float aq = 0.f;
+      for (int i = 0; i < MD_AUX; ++i) aq = fmaf(ax[i], W.h2[MD_HIDDEN + i], aq);
+      gc[k] = sval[k];
+      gc[4 + k] = e[k] / den;
+      gc[8 + k] = aq;
+    }
+  }
+}
+
+}  // namespace md
+
+// =================================================================================================
+// host entry points
+// =================================================================================================
+static int check_common(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k) {
+  if (!g || !s || !w || !k) return MD_EINVAL;
+  if (g->n_layers < 1 || g->n_layers > MD_MAX_LAYERS) return MD_ELAYERS;
+  if (g->stride % MD_TILE_M != 0 || g->n_total != g->n_graphs * g->stride) return MD_EINVAL;
+  return 0;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+extern "C" int md_embed_init(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
+                             md_stream_t stream) {
+  int rc = check_common(g, s, w, k);
+  if (rc) return rc;
+  dim3 grid(g->n_graphs * (g->stride / MD_TILE_M), g->n_layers);
+  md::embed_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*g, *s, *w, *k);
+  MD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int md_embed_iter(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
+                             int32_t iter, md_stream_t stream) {
+  int rc = check_common(g, s, w, k);
+  if (rc) return rc;
+  if (iter < 0 || iter >= MD_BP_ITERS) return MD_EINVAL;
+  static bool configured = false;
+  const int smem = (int)sizeof(md::IterSmem);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(md::embed_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int n_tiles = g->n_graphs * (g->stride / MD_TILE_M) * g->n_layers;
+  int grid = 2 * sm_count();
+  if (grid > n_tiles) grid = n_tiles;
+  md::embed_iter_kernel<<<grid, md::IT_T, smem, (cudaStream_t)stream>>>(*g, *s, *w, *k, iter);
+  MD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int md_graph_embed(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
+                              md_stream_t stream) {
+  int rc = check_common(g, s, w, k);
+  if (rc) return rc;
+  md::graph_embed_kernel<<<g->n_graphs, g->n_layers * md::D, 0, (cudaStream_t)stream>>>(*g, *s, *w, *k);
+  MD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int64_t md_psum_floats(int32_t n_layers, int32_t n_total) {
+  return (int64_t)MD_BP_ITERS * n_layers * (n_total / MD_TILE_M) * MD_EMBED;
+}

@@ -1,0 +1,307 @@
+// Environment step for the batch: node removal, LMCC recompute (iterative mutual-component pruning with a
+// shared-memory union-find), AUDC accumulation and the per-graph status counters the next forward needs.
+//
+// Replaces (reference, /root/reference/code/MultiDismantler_unit_cost): mvc_env.py:31-52 (s0), :74-87
+// (stepWithoutReward), :133-162 (getReward, getMaxConnectedNodesNum), Mcc.py:3-38 (MCC / deledge),
+// PrepareBatchGraph.py:35-100 (get_status_info + aux features); degree-cost reward: D/mvc_env.py:127-133.
+//
+// State equivalence: the reference keeps (covered_set, remove_edge[l]).  Here a node's label is the id of its
+// mutual component (smallest member); an edge is alive iff both end labels are equal and >= 0.  remove_edge is
+// the set of edges between differently-labelled live nodes, so it never needs to be stored.
+#include "md_common.cuh"
+
+namespace md {
+
+constexpr int ENV_T = 512;
+constexpr int ENV_W = ENV_T / 32;
+constexpr int ENV_SMALL_MAX = 16384;  // 3 int arrays of S entries in shared memory (192 KB)
+
+__device__ __forceinline__ int uf_find(volatile int* par, int x) {
+  int p = par[x];
+  while (p != x) {  // path halving; parents only ever move towards smaller ids, racy writes stay valid
+    int gp = par[p];
+    par[x] = gp;
+    x = gp;
+    p = par[x];
+  }
+  return x;
+}
+
+__device__ __forceinline__ void uf_unite(int* par, int a, int b) {
+  int ra = uf_find(par, a), rb = uf_find(par, b);
+  while (ra != rb) {
+    int hi = max(ra, rb), lo = min(ra, rb);
+    int old = atomicCAS(&par[hi], hi, lo);  // hook the larger root under the smaller: roots are minima
+    if (old == hi) break;
+    ra = uf_find(par, old);
+    rb = uf_find(par, lo);
+  }
+}
+
+struct BlockRed {
+  int i[ENV_W];
+  long long ll[ENV_W];
+};
+
+__device__ __forceinline__ int block_sum_i(int v, BlockRed& r) {
+  v = warp_sum_i(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) r.i[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int k = 0; k < ENV_W; ++k) t += r.i[k];
+  return t;
+}
+__device__ __forceinline__ int block_max_i(int v, BlockRed& r) {
+  v = warp_max_i(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) r.i[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = r.i[0];
+#pragma unroll
+  for (int k = 1; k < ENV_W; ++k) t = max(t, r.i[k]);
+  return t;
+}
+__device__ __forceinline__ long long block_sum_ll(long long v, BlockRed& r) {
+  v = warp_sum_ll(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) r.ll[threadIdx.x >> 5] = v;
+  __syncthreads();
+  long long t = 0;
+#pragma unroll
+  for (int k = 0; k < ENV_W; ++k) t += r.ll[k];
+  return t;
+}
+
+// One CTA per graph.  init != 0: MvcEnv.s0; otherwise one stepWithoutReward.
+__global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_t S, const int32_t* forced,
+                                                       int forced_stride, int forced_index, int init) {
+  extern __shared__ int smem[];
+  const int g = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int St = G.stride;
+  const int base = g * St;
+  const int N = G.n_nodes[g];
+  const int L = G.n_layers;
+  int* lab = smem;
+  int* par = smem + St;
+  int* tmp = smem + 2 * St;
+  __shared__ BlockRed red;
+  __shared__ int s_action;
+  __shared__ int s_scan[ENV_W];
+
+  if (!init && S.done[g]) return;
+
+  // ---- pick the action -----------------------------------------------------------------------------
+  if (tid == 0) {
+    int a = -1;
+    if (!init) {
+      if (forced != nullptr) {
+        const int idx = forced_index >= 0 ? forced_index : S.n_steps[g];
+        if (idx < forced_stride) a = forced[(size_t)g * forced_stride + idx];
+      } else {
+        unsigned long long key = S.best[g];
+        if (key != 0ull) a = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+      }
+      if (a >= N) a = -1;
+    }
+    s_action = a;
+    S.best[g] = 0ull;
+  }
+  for (int v = tid; v < St; v += ENV_T) lab[v] = init ? (v < N ? 0 : -1) : (S.label[base + v] < 0 ? -1 : S.label[base + v] - base);
+  __syncthreads();
+  const int a = s_action;
+  if (!init && (a < 0 || lab[a] < 0)) return;  // nothing to remove (uniform exit)
+
+  if (!init) {
+    // numCoveredEdges[l] += #neighbours still alive and not cut from a  (mvc_env.py:81-84) == deg_alive_l(a)
+    if (tid < L) S.cov_edges[tid * G.n_graphs + g] += S.deg[tid][base + a];
+    __syncthreads();
+    if (tid == 0) lab[a] = -1;
+    __syncthreads();
+  }
+
+  // ---- Mcc.MCC: refine the partition layer by layer until every layer is stable ----------------------
+  int stable = 0, l = 0;
+  while (stable < L) {
+    const int32_t* __restrict__ rp = G.rowptr[l];
+    const int32_t* __restrict__ cl = G.col[l];
+    for (int v = tid; v < N; v += ENV_T) par[v] = v;
+    __syncthreads();
+    for (int v = tid; v < N; v += ENV_T) {
+      const int lv = lab[v];
+      if (lv < 0) continue;
+      const int e1 = rp[base + v + 1];
+      for (int e = rp[base + v]; e < e1; ++e) {
+        const int u = cl[e] - base;
+        if (u < v && lab[u] == lv) uf_unite(par, u, v);
+      }
+    }
+    __syncthreads();
+    int changed = 0;
+    for (int v = tid; v < N; v += ENV_T) {
+      int r = -1;
+      if (lab[v] >= 0) {
+        r = uf_find(par, v);
+        changed |= (r != lab[v]);
+      }
+      tmp[v] = r;
+    }
+    changed = __syncthreads_or(changed);
+    for (int v = tid; v < N; v += ENV_T) lab[v] = tmp[v];
+    __syncthreads();
+    stable = changed ? 1 : stable + 1;
+    l = (l + 1 == L) ? 0 : l + 1;
+  }
+
+  // ---- component sizes -> LMCC rank (Mcc.find_max_set_length) ------------------------------------------
+  for (int v = tid; v < N; v += ENV_T) tmp[v] = 0;
+  __syncthreads();
+  for (int v = tid; v < N; v += ENV_T)
+    if (lab[v] >= 0) atomicAdd(&tmp[lab[v]], 1);
+  __syncthreads();
+  int mx = 0;
+  for (int v = tid; v < N; v += ENV_T) mx = max(mx, tmp[v]);
+  const int rank = block_max_i(mx, red);
+
+  // ---- alive degree per layer + status counters (get_status_info) ----------------------------------------
+  bool terminal = false;
+  for (int ll = 0; ll < L; ++ll) {
+    const int32_t* __restrict__ rp = G.rowptr[ll];
+    const int32_t* __restrict__ cl = G.col[ll];
+    int dsum = 0, dmax = 0;
+    long long th = 0;
+    for (int v = tid; v < St; v += ENV_T) {
+      int d = 0;
+      if (v < N && lab[v] >= 0) {
+        const int lv = lab[v];
+        const int e1 = rp[base + v + 1];
+        for (int e = rp[base + v]; e < e1; ++e) d += (lab[cl[e] - base] == lv);
+      }
+      S.deg[ll][base + v] = d;
+      if (ll == 0 && v < N) par[v] = d;  // keep layer-0 degree for the compaction below
+      dsum += d;
+      dmax = max(dmax, d);
+      th += (long long)d * (d - 1) / 2;
+    }
+    const int tot = block_sum_i(dsum, red);
+    const int dm = block_max_i(dmax, red);
+    const long long t2 = block_sum_ll(th, red);
+    if (tid == 0) {
+      S.alive_edges[ll * G.n_graphs + g] = tot / 2;
+      S.max_deg[ll * G.n_graphs + g] = dm;
+      S.twohop[ll * G.n_graphs + g] = t2;
+    }
+    terminal |= (tot == 0);
+  }
+  __syncthreads();
+
+  // ---- write labels back, compact the active nodes (ascending id, PrepareBatchGraph.py:128-138) -----------
+  int running = 0;
+  for (int v0 = 0; v0 < St; v0 += ENV_T) {
+    const int v = v0 + tid;
+    int flag = 0;
+    if (v < St) {
+      S.label[base + v] = (v < N && lab[v] >= 0) ? lab[v] + base : -1;
+      flag = (v < N && par[v] > 0) ? 1 : 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int lane = tid & 31, wid = tid >> 5;
+    if (lane == 0) s_scan[wid] = __popc(bal);
+    __syncthreads();
+    int woff = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < ENV_W; ++k) {
+      const int c = s_scan[k];
+      if (k < wid) woff += c;
+      total += c;
+    }
+    if (flag) S.act_list[base + running + woff + __popc(bal & ((1u << lane) - 1u))] = base + v;
+    running += total;
+    __syncthreads();
+  }
+
+  // ---- bookkeeping: reward / AUDC in f64 with the reference's operation order ---------------------------
+  if (tid == 0) {
+    const int B = G.n_graphs;
+    S.n_act[g] = running;
+    S.rank[g] = rank;
+    int nrem = init ? 0 : S.n_removed[g] + 1;
+    S.n_removed[g] = nrem;
+    if (init) {
+      S.score[g] = 0.0;
+      S.n_steps[g] = 0;
+      for (int ll = 0; ll < L; ++ll) S.cov_edges[ll * B + g] = 0;
+    } else {
+      const double rk = (double)rank;
+      const double mr = (double)G.max_rank[g];
+      double r, mcc;
+      if (S.cost_mode == 0) {
+        // U/mvc_env.py:133-137: r_t = -rank / (max_rank * N); score += -r_t; MaxCCList.append(-r_t * N)
+        r = __ddiv_rn(rk, __dmul_rn(mr, (double)N));
+        mcc = __dmul_rn(r, (double)N);
+      } else {
+        // D/mvc_env.py:127-133: r_t = -rank / max_rank * (w0[a]/W0 + w1[a]/W1) / 2; MaxCCList.append(rank / max_rank)
+        mcc = __ddiv_rn(rk, mr);
+        r = __ddiv_rn(__dmul_rn(mcc, G.node_cost[base + a]), 2.0);
+      }
+      S.score[g] = __dadd_rn(S.score[g], r);
+      const int t = S.n_steps[g];
+      if (t < S.max_steps) {
+        S.trace_action[(size_t)g * S.max_steps + t] = a;
+        S.trace_rank[(size_t)g * S.max_steps + t] = rank;
+        S.trace_maxcc[(size_t)g * S.max_steps + t] = mcc;
+      }
+      S.n_steps[g] = t + 1;
+    }
+    // aux features for the next forward (PrepareBatchGraph.py:92-100): quotients in f64, then cast to f32
+    for (int ll = 0; ll < L; ++ll) {
+      float* ax = S.aux + ((size_t)g * L + ll) * MD_AUX;
+      const int E = G.n_edges[ll * B + g];
+      ax[0] = (float)__ddiv_rn((double)nrem, (double)N);
+      ax[1] = E > 0 ? (float)__ddiv_rn((double)S.cov_edges[ll * B + g], (double)E) : 0.f;
+      ax[2] = (float)__ddiv_rn((double)S.twohop[ll * B + g], (double)((long long)N * (long long)N));
+      ax[3] = 1.0f;
+    }
+    const int was_done = init ? 0 : S.done[g];
+    S.done[g] = terminal ? 1 : 0;
+    if (terminal && !was_done) atomicAdd(S.n_done, 1);
+  }
+}
+
+}  // namespace md
+
+extern "C" int32_t md_env_small_max_stride(void) { return md::ENV_SMALL_MAX; }
+
+static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
+                      int32_t forced_index, int init, md_stream_t stream) {
+  if (!g || !s) return MD_EINVAL;
+  if (g->n_layers < 1 || g->n_layers > MD_MAX_LAYERS) return MD_ELAYERS;
+  if (g->stride % MD_TILE_M != 0 || g->n_total != g->n_graphs * g->stride) return MD_EINVAL;
+  if (g->stride > md::ENV_SMALL_MAX) return MD_ETOOBIG;
+  const size_t smem = (size_t)3 * g->stride * sizeof(int);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(md::env_step_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (init) {
+    cudaError_t e = cudaMemsetAsync(s->n_done, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  md::env_step_small<<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init);
+  MD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int md_env_reset(const md_graphs_t* g, const md_state_t* s, md_stream_t stream) {
+  return env_launch(g, s, nullptr, 0, -1, 1, stream);
+}
+
+extern "C" int md_env_step(const md_graphs_t* g, const md_state_t* s, const int32_t* actions, int32_t action_stride,
+                           int32_t action_index, md_stream_t stream) {
+  return env_launch(g, s, actions, action_stride, action_index, 0, stream);
+}

@@ -1,0 +1,171 @@
+"""Graph containers: host-side multiplex graph (mirror of the reference's graph.Graph_test fields) and the
+device-resident batch (multi-layer CSR, built once, never rebuilt during a rollout).
+
+Reference: /root/reference/code/MultiDismantler_unit_cost/graph.py:8-30 (Graph), :70-84 (Graph_test), :53-68 (GSet);
+degree-cost node weights /root/reference/code/MultiDismantler_degree_cost/graph.py:39-51.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+TILE_M = _lib.TILE_M
+
+
+class Graph_test:
+    """Static multiplex graph given as per-layer undirected edge lists (the reference passes two nx.Graph objects;
+    any object with .nodes/.edges works, as do plain arrays).
+
+    Fields mirror the reference: num_nodes, edge_list, num_edges, weights, max_rank.  max_rank (LMCC of the intact
+    graph, reference ori_rank) is filled in by the GPU when the graph is placed in a GraphBatch.
+    """
+
+    def __init__(self, G1, G2=None, *more_layers, num_nodes=None, cost="unit"):
+        layers = [G1] + ([G2] if G2 is not None else []) + list(more_layers)
+        self.edge_list = []
+        for G in layers:
+            if hasattr(G, "edges") and hasattr(G, "nodes"):
+                if num_nodes is None:
+                    num_nodes = len(G.nodes)
+                e = np.array(list(G.edges()), dtype=np.int64).reshape(-1, 2)
+            else:
+                e = np.asarray(G, dtype=np.int64).reshape(-1, 2)
+            self.edge_list.append(e)
+        if num_nodes is None:
+            num_nodes = int(max((int(e.max()) + 1 if e.size else 0) for e in self.edge_list))
+        self.num_nodes = int(num_nodes)
+        for e in self.edge_list:
+            if e.size and (e.min() < 0 or e.max() >= self.num_nodes):
+                raise ValueError("edge endpoint out of range")
+            if e.size and np.any(e[:, 0] == e[:, 1]):
+                raise ValueError("self loops are not allowed (the reference's read_multiplex drops them)")
+        self.num_layers = len(self.edge_list)
+        self.num_edges = [int(len(e)) for e in self.edge_list]
+        self.max_rank = 0
+        self.cost = cost
+        self.weights = None
+        if cost == "degree":
+            self.cal_degree()
+
+    def cal_degree(self):
+        """D/graph.py:39-51: weights[l][v] = deg_l(v) / max_v deg_l(v) in float64."""
+        self.weights = []
+        for e in self.edge_list:
+            deg = np.bincount(e.ravel(), minlength=self.num_nodes).astype(np.int64)
+            self.weights.append(deg / max(int(deg.max()), 1))
+
+
+class GSet:
+    """graph.GSet (U/graph.py:53-68)."""
+
+    def __init__(self):
+        self.graph_pool = {}
+
+    def InsertGraph(self, gid, graph):
+        assert gid not in self.graph_pool
+        self.graph_pool[gid] = graph
+
+    def Get(self, gid):
+        assert gid in self.graph_pool
+        return self.graph_pool[gid]
+
+    def Sample(self):
+        assert self.graph_pool
+        gid = np.random.choice(list(self.graph_pool.keys()))
+        return self.graph_pool[gid]
+
+    def Clear(self):
+        self.graph_pool.clear()
+
+
+def build_csr(num_nodes, edges):
+    """Symmetric CSR whose row order is the reference's in_edges insertion order
+    (graph_struct.add_edge(x, y) then (y, x), U/PrepareBatchGraph.py:155-161): neighbours sorted by edge index."""
+    e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    dst = np.stack([e[:, 1], e[:, 0]], 1).ravel()
+    src = np.stack([e[:, 0], e[:, 1]], 1).ravel()
+    order = np.argsort(dst, kind="stable")
+    rowptr = np.zeros(num_nodes + 1, np.int64)
+    np.cumsum(np.bincount(dst, minlength=num_nodes), out=rowptr[1:])
+    return rowptr, src[order]
+
+
+class GraphBatch:
+    """B graphs resident in HBM as one block-diagonal multi-layer CSR (md_graphs_t).
+
+    Global node id = g * stride + v with stride a multiple of 128, so embedding rows, labels and degrees are
+    plain arrays indexed by global id and per-graph kernels never straddle graphs.
+    """
+
+    def __init__(self, graphs, device=None, cost=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mdcommunity_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.lib()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.graphs = list(graphs)
+        B = len(self.graphs)
+        assert B > 0
+        L = self.graphs[0].num_layers
+        assert all(g.num_layers == L for g in self.graphs)
+        if L > _lib.MAX_LAYERS:
+            raise ValueError("at most %d layers" % _lib.MAX_LAYERS)
+        self.cost = cost if cost is not None else self.graphs[0].cost
+        nmax = max(g.num_nodes for g in self.graphs)
+        S = max(TILE_M, (nmax + TILE_M - 1) // TILE_M * TILE_M)
+        if B * S >= 2 ** 31:
+            raise ValueError("batch too large for int32 node ids")
+        self.B, self.L, self.S, self.n_total = B, L, S, B * S
+        dev = self.device
+        self.rowptr, self.col, self.nnz = [], [], []
+        for l in range(L):
+            rp = np.zeros(B * S + 1, np.int64)
+            cols = []
+            pos = 0
+            for gi, g in enumerate(self.graphs):
+                r, c = build_csr(g.num_nodes, g.edge_list[l])
+                rp[gi * S:gi * S + g.num_nodes + 1] = r + pos
+                rp[gi * S + g.num_nodes + 1:(gi + 1) * S + 1] = r[-1] + pos
+                cols.append(c + gi * S)
+                pos += int(r[-1])
+            if pos >= 2 ** 31:
+                raise ValueError("too many edges for int32 CSR offsets")
+            self.nnz.append(pos)
+            self.rowptr.append(torch.from_numpy(rp.astype(np.int32)).to(dev))
+            c = np.concatenate(cols) if cols else np.zeros(0, np.int64)
+            self.col.append(torch.from_numpy(c.astype(np.int32)).to(dev) if c.size else torch.zeros(1, dtype=torch.int32, device=dev))
+        self.n_nodes = torch.tensor([g.num_nodes for g in self.graphs], dtype=torch.int32, device=dev)
+        self.n_edges = torch.tensor([[g.num_edges[l] for g in self.graphs] for l in range(L)], dtype=torch.int32, device=dev)
+        self.max_rank = torch.ones(B, dtype=torch.int32, device=dev)
+        self.node_w, self.node_cost = [], None
+        if self.cost == "degree":
+            if L != 2:
+                raise ValueError("degree-cost reward is defined for two layers (D/mvc_env.py:127-133)")
+            cost_arr = np.zeros(B * S, np.float64)
+            ws = [np.zeros(B * S, np.float32) for _ in range(L)]
+            for gi, g in enumerate(self.graphs):
+                if g.weights is None:
+                    g.cal_degree()
+                # D/mvc_env.py:129-130: Python sum over the weight dict (sequential f64 adds in node order)
+                tot = [float(sum(g.weights[l].tolist())) for l in range(L)]
+                cost_arr[gi * S:gi * S + g.num_nodes] = g.weights[0] / tot[0] + g.weights[1] / tot[1]
+                for l in range(L):
+                    ws[l][gi * S:gi * S + g.num_nodes] = g.weights[l].astype(np.float32)
+            self.node_w = [torch.from_numpy(w).to(dev) for w in ws]
+            self.node_cost = torch.from_numpy(cost_arr).to(dev)
+        st = _lib.MdGraphs()
+        st.n_graphs, st.n_layers, st.stride, st.n_total = B, L, S, B * S
+        for l in range(L):
+            st.rowptr[l] = self.rowptr[l].data_ptr()
+            st.col[l] = self.col[l].data_ptr()
+            if self.node_w:
+                st.node_w[l] = self.node_w[l].data_ptr()
+        st.n_nodes = self.n_nodes.data_ptr()
+        st.n_edges = self.n_edges.data_ptr()
+        st.max_rank = self.max_rank.data_ptr()
+        st.node_cost = self.node_cost.data_ptr() if self.node_cost is not None else None
+        self.c = st
+
+    def ptr(self):
+        return C.byref(self.c)

@@ -1,0 +1,199 @@
+"""Device-resident lock-step greedy rollout over a batch of graphs.
+
+This is the B200 replacement for the reference's hot loop (GetSol / GetSolution / Test,
+/root/reference/code/MultiDismantler_unit_cost/MultiDismantler_torch.py:711-784): every graph of the batch advances
+one removal per iteration; graphs never interact (segment sums, max degree, arg-max and LMCC are all per graph),
+so batching B independent rollouts is exactly B reference rollouts.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graph import GraphBatch
+
+
+class QWeights:
+    """The reference's 14-tensor state_dict on the device, plus the two merged products the fused kernel uses."""
+
+    KEYS = ["w_n2l", "p_node_conv", "p_node_conv2", "p_node_conv3", "h1_weight", "h2_weight", "cross_product",
+            "w_layer1", "w_layer2", "layerNodeAttention_weight.trans", "layerNodeAttention_weight.bias",
+            "layerNodeAttention_weight.logis.parameter.weight", "layerNodeAttention_weight.logis.parameter.bias"]
+
+    def __init__(self, state_dict, device):
+        sd = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in state_dict.items()}
+        for k in self.KEYS:
+            if k not in sd:
+                raise KeyError("checkpoint lacks %s (older 10-key checkpoints without fusion/gate weights are not usable)" % k)
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        c1, c2, c3 = sd["p_node_conv"].astype(np.float64), sd["p_node_conv2"].astype(np.float64), sd["p_node_conv3"].astype(np.float64)
+        host = {
+            "w_n2l": f(sd["w_n2l"]), "conv1": f(sd["p_node_conv"]), "conv2": f(sd["p_node_conv2"]), "conv3": f(sd["p_node_conv3"]),
+            # [P@c1, H@c2] @ c3 == P @ (c1 @ c3[:64]) + H @ (c2 @ c3[64:]); products formed in f64, rounded once
+            "w13": f(c1 @ c3[:64]), "w23": f(c2 @ c3[64:]),
+            "trans": f(sd["layerNodeAttention_weight.trans"]), "bias": f(sd["layerNodeAttention_weight.bias"]),
+            "logis_w": f(sd["layerNodeAttention_weight.logis.parameter.weight"]).reshape(-1),
+            "logis_b": f(sd["layerNodeAttention_weight.logis.parameter.bias"]).reshape(-1),
+            "cross": f(sd["cross_product"]).reshape(-1), "h1": f(sd["h1_weight"]), "h2": f(sd["h2_weight"]).reshape(-1),
+            "wl1": f(sd["w_layer1"]), "wl2": f(sd["w_layer2"]).reshape(-1),
+        }
+        # one flat 16-byte aligned buffer
+        offs, total = {}, 0
+        for k, a in host.items():
+            offs[k] = total
+            total += (a.size + 3) // 4 * 4
+        flat = np.zeros(total, np.float32)
+        for k, a in host.items():
+            flat[offs[k]:offs[k] + a.size] = a.ravel()
+        self.flat = torch.from_numpy(flat).to(device)
+        self.c = _lib.MdWeights()
+        for k in host:
+            setattr(self.c, k, self.flat.data_ptr() + 4 * offs[k])
+
+    def ptr(self):
+        return C.byref(self.c)
+
+
+class BatchRollout:
+    """Owns the mutable env state + activations for one GraphBatch and drives the kernels.
+
+    results after run(): score [B] f64 (AUDC), n_steps [B], actions [B, T] (-1 padded), ranks [B, T], maxcc [B, T].
+    """
+
+    def __init__(self, batch: GraphBatch, weights: QWeights = None, max_steps=None):
+        self.batch = batch
+        self.lib = batch.lib
+        self.w = weights
+        dev = batch.device
+        B, L, S, nt = batch.B, batch.L, batch.S, batch.n_total
+        self.max_steps = int(max_steps if max_steps is not None else max(g.num_nodes for g in batch.graphs))
+        i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+        self.label = i32(nt)
+        self.deg = [i32(nt) for _ in range(L)]
+        self.act_list = i32(nt)
+        self.n_act, self.n_removed, self.rank, self.done, self.n_steps = i32(B), i32(B), i32(B), i32(B), i32(B)
+        self.cov_edges, self.alive_edges, self.max_deg = i32(L, B), i32(L, B), i32(L, B)
+        self.twohop = torch.zeros(L, B, dtype=torch.int64, device=dev)
+        self.score = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.aux = torch.zeros(B, L, 4, dtype=torch.float32, device=dev)
+        self.best = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.trace_action = torch.full((B, self.max_steps), -1, dtype=torch.int32, device=dev)
+        self.trace_rank = i32(B, self.max_steps)
+        self.trace_maxcc = torch.zeros(B, self.max_steps, dtype=torch.float64, device=dev)
+        self.n_done = i32(1)
+        self.large = S > self.lib.md_env_small_max_stride()
+        self.parent = i32(nt) if self.large else None
+        self.comp_size = i32(nt) if self.large else None
+        self.flags = i32(8)
+        s = _lib.MdState()
+        s.label = self.label.data_ptr()
+        for l in range(L):
+            s.deg[l] = self.deg[l].data_ptr()
+        for name in ("act_list", "n_act", "n_removed", "cov_edges", "alive_edges", "max_deg", "twohop", "rank", "done",
+                     "n_steps", "score", "aux", "best", "trace_action", "trace_rank", "trace_maxcc", "n_done", "flags"):
+            setattr(s, name, getattr(self, name).data_ptr())
+        s.parent = self.parent.data_ptr() if self.large else None
+        s.comp_size = self.comp_size.data_ptr() if self.large else None
+        s.max_steps = self.max_steps
+        s.cost_mode = 1 if batch.cost == "degree" else 0
+        self.s = s
+        # activations
+        self.h = [[torch.zeros(nt, _lib.EMBED, dtype=torch.float32, device=dev) for _ in range(L)] for _ in range(2)]
+        self.psum = torch.zeros(int(self.lib.md_psum_floats(L, nt)), dtype=torch.float32, device=dev)
+        self.gconst = torch.zeros(B, _lib.GCONST, dtype=torch.float32, device=dev)
+        self.q = torch.zeros(nt, dtype=torch.float32, device=dev)
+        k = _lib.MdWork()
+        for i in range(2):
+            for l in range(L):
+                k.h[i][l] = self.h[i][l].data_ptr()
+        k.psum, k.gconst, k.q = self.psum.data_ptr(), self.gconst.data_ptr(), self.q.data_ptr()
+        self.k = k
+        self._pinned_done = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.kernel_launches = 0
+        self.reset()
+
+    # -- helpers ----------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.batch.device).cuda_stream)
+
+    def _g(self):
+        return self.batch.ptr()
+
+    def reset(self):
+        """MvcEnv.s0 for every graph; also fills graph.max_rank (Graph_test.ori_rank) on first use."""
+        self.trace_action.fill_(-1)
+        _lib.check(self.lib.md_env_reset(self._g(), C.byref(self.s), self._stream()), "md_env_reset")
+        self.kernel_launches += 1
+        if not getattr(self.batch, "_max_rank_set", False):
+            self.batch.max_rank.copy_(self.rank)
+            mr = self.rank.cpu().numpy()
+            for g, r in zip(self.batch.graphs, mr):
+                g.max_rank = int(r)
+            self.batch._max_rank_set = True
+
+    def forward(self):
+        """One Q-network evaluation for all non-terminal graphs (test_forward + the Predict mask + arg-max key)."""
+        lib, g, s, w, k, st = self.lib, self._g(), C.byref(self.s), self.w.ptr(), C.byref(self.k), self._stream()
+        _lib.check(lib.md_embed_init(g, s, w, k, st), "md_embed_init")
+        for it in range(_lib.BP_ITERS):
+            _lib.check(lib.md_embed_iter(g, s, w, k, it, st), "md_embed_iter")
+        _lib.check(lib.md_graph_embed(g, s, w, k, st), "md_graph_embed")
+        _lib.check(lib.md_qhead(g, s, w, k, st), "md_qhead")
+        self.kernel_launches += 3 + _lib.BP_ITERS
+
+    def step(self, actions=None, index=-1):
+        """stepWithoutReward for every non-terminal graph.  actions: None -> arg-max of the last forward();
+        int32 device tensor [B, stride] of local node ids -> column `index` (or column n_steps[g] when index < 0)."""
+        if actions is None:
+            rc = self.lib.md_env_step(self._g(), C.byref(self.s), None, 0, -1, self._stream())
+        else:
+            assert actions.dtype == torch.int32 and actions.is_cuda and actions.is_contiguous()
+            rc = self.lib.md_env_step(self._g(), C.byref(self.s), C.c_void_p(actions.data_ptr()), actions.shape[1],
+                                      index, self._stream())
+        _lib.check(rc, "md_env_step")
+        self.kernel_launches += 1
+
+    def num_done(self):
+        self._pinned_done.copy_(self.n_done, non_blocking=True)
+        torch.cuda.current_stream(self.batch.device).synchronize()
+        return int(self._pinned_done[0])
+
+    def run(self, chunk=8, step=1):
+        """Greedy rollout to termination (GetSol when step == 1, GetSolution's top-`step` batches otherwise)."""
+        B = self.batch.B
+        it = 0
+        topk = None
+        if step > 1:
+            topk = torch.empty(B, step, dtype=torch.int32, device=self.batch.device)
+        while True:
+            if step == 1:
+                _lib.check(self.lib.md_rollout_steps(self._g(), C.byref(self.s), self.w.ptr(), C.byref(self.k), chunk,
+                                                     self._stream()), "md_rollout_steps")
+                self.kernel_launches += chunk * (4 + _lib.BP_ITERS)
+            else:
+                for _ in range(chunk):
+                    self.forward()
+                    _lib.check(self.lib.md_select_topk(self._g(), C.byref(self.s), C.byref(self.k),
+                                                       C.c_void_p(topk.data_ptr()), step, self._stream()), "md_select_topk")
+                    self.kernel_launches += 1
+                    for j in range(step):
+                        self.step(topk, j)
+            it += chunk
+            if self.num_done() >= B or it > self.max_steps + chunk:
+                break
+        return self.results()
+
+    def results(self):
+        torch.cuda.current_stream(self.batch.device).synchronize()
+        return dict(score=self.score.cpu().numpy(), n_steps=self.n_steps.cpu().numpy(),
+                    actions=self.trace_action.cpu().numpy(), ranks=self.trace_rank.cpu().numpy(),
+                    maxcc=self.trace_maxcc.cpu().numpy())
+
+    # -- inspection (tests / Predict mirror) ----------------------------------------------------------
+    def q_values(self, gi):
+        """(active local ids ascending, q f32) of graph gi after forward()."""
+        n = int(self.n_act[gi])
+        S = self.batch.S
+        ids = self.act_list[gi * S:gi * S + n].long()
+        return (ids - gi * S).cpu().numpy(), self.q[ids].cpu().numpy()

@@ -1,0 +1,162 @@
+"""CUDA path vs the oracle / the committed golden vectors.  All tests call through the C ABI (ctypes)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_cases, load_golden_graph
+
+pytestmark = pytest.mark.gpu
+
+Q_RTOL, Q_ATOL = 1e-4, 1e-6  # north_star: Q within 1e-4 relative; 1e-6 absolute floor (|q| ~ 1e-3)
+
+
+def _mdb():
+    import mdcommunity_b200 as mdb
+    return mdb
+
+
+def _load_batch(variant, max_n=None):
+    mdb = _mdb()
+    zs, graphs = [], []
+    for p in golden_cases(variant, max_n):
+        z = np.load(p)
+        zs.append(z)
+        graphs.append(mdb.Graph_test(z["edges0"], z["edges1"], num_nodes=int(z["num_nodes"]), cost=variant))
+    batch = mdb.GraphBatch(graphs, cost=variant)
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_%s.npz" % variant))), batch.device)
+    return zs, graphs, batch, w
+
+
+def _forced(zs, key, device):
+    T = max(len(z[key]) for z in zs)
+    a = np.full((len(zs), T + 1), -1, np.int32)
+    for i, z in enumerate(zs):
+        a[i, :len(z[key])] = z[key]
+    return torch.from_numpy(a).to(device), T
+
+
+@pytest.mark.parametrize("variant", ["unit", "degree"])
+def test_env_random_actions_bit_exact(variant):
+    """Ragged batch of every golden graph, reference random-action traces: LMCC / AUDC / counters bit-exact."""
+    mdb = _mdb()
+    zs, graphs, batch, w = _load_batch(variant)
+    ro = mdb.BatchRollout(batch, w)
+    for z, g in zip(zs, graphs):
+        assert g.max_rank == int(z["max_rank"])
+    acts, T = _forced(zs, "random_actions", batch.device)
+    for t in range(T):
+        ro.step(acts)
+        cov = ro.cov_edges.cpu().numpy()
+        done = ro.done.cpu().numpy()
+        for i, z in enumerate(zs):
+            n = len(z["random_actions"])
+            if t < n:
+                assert list(cov[:, i]) == list(z["random_cov_edges"][t]), (variant, i, t)
+                assert bool(done[i]) == (t == n - 1), (variant, i, t)
+    r = ro.results()
+    for i, z in enumerate(zs):
+        n = len(z["random_actions"])
+        assert r["n_steps"][i] == n
+        assert np.array_equal(r["actions"][i, :n], z["random_actions"])
+        assert r["score"][i] == z["random_score"][-1]
+        assert np.array_equal(r["maxcc"][i, :n], z["random_maxcc"])
+        # pruned edges: len(remove_edge)/2 = E - covered - alive; terminal => alive == 0
+    assert ro.num_done() == len(zs)
+
+
+@pytest.mark.parametrize("variant", ["unit", "degree"])
+def test_q_teacher_forced(variant):
+    """Feed the reference's greedy actions; per step compare active set + aux (exact) and Q (1e-4 rel + 1e-6)."""
+    mdb = _mdb()
+    zs, graphs, batch, w = _load_batch(variant)
+    ro = mdb.BatchRollout(batch, w)
+    acts, T = _forced(zs, "greedy_actions", batch.device)
+    worst = 0.0
+    agree = total = 0
+    for t in range(T):
+        ro.forward()
+        aux = ro.aux.cpu().numpy()
+        best = ro.best.cpu().numpy().astype(np.uint64)
+        for i, z in enumerate(zs):
+            if t >= len(z["greedy_actions"]):
+                continue
+            off = z["greedy_off"]
+            ids, q = ro.q_values(i)
+            assert np.array_equal(ids, z["greedy_active"][off[t]:off[t + 1]]), (variant, i, t)
+            assert np.array_equal(aux[i], z["greedy_aux"][t]), (variant, i, t)
+            qg = z["greedy_q"][off[t]:off[t + 1]]
+            err = np.abs(q - qg) - (Q_RTOL * np.abs(qg) + Q_ATOL)
+            worst = max(worst, float(np.max(np.abs(q - qg) / (np.abs(qg) + 1e-2))))
+            assert np.all(err <= 0), (variant, i, t, float(np.max(np.abs(q - qg))))
+            # arg-max key decodes to the first max of our own q
+            pick = int(0xFFFFFFFF - (int(best[i]) & 0xFFFFFFFF))
+            assert pick == int(ids[np.argmax(q)]), (variant, i, t)
+            total += 1
+            a = int(z["greedy_actions"][t])
+            if pick == a:
+                agree += 1
+            else:  # the reference picked another node: only legal on a rounding-level tie
+                qa = q[list(ids).index(a)]
+                assert abs(q.max() - qa) <= Q_RTOL * abs(q.max()) + Q_ATOL, (variant, i, t)
+        ro.step(acts)
+    r = ro.results()
+    for i, z in enumerate(zs):
+        n = len(z["greedy_actions"])
+        assert r["n_steps"][i] == n
+        assert r["score"][i] == float(z["greedy_final_score"])  # bit-exact AUDC on the same removal sequence
+        assert np.array_equal(r["maxcc"][i, :n], z["greedy_maxcc"])
+    assert agree >= 0.6 * total
+    print("worst scaled Q error %.3e, arg-max agreement %d/%d" % (worst, agree, total))
+
+
+@pytest.mark.parametrize("variant", ["unit", "degree"])
+def test_free_running_rollout(variant):
+    """GetSol end to end on the device.  The removal sequence must equal the reference's up to the first step
+    whose top-two Q gap is below tolerance; AUDC must match the oracle replay of OUR sequence bit-exactly."""
+    from oracle import md_oracle as orc
+    mdb = _mdb()
+    zs, graphs, batch, w = _load_batch(variant)
+    ro = mdb.BatchRollout(batch, w)
+    r = ro.run()
+    for i, z in enumerate(zs):
+        n = int(r["n_steps"][i])
+        sol = r["actions"][i, :n]
+        _, _, og = load_golden_graph(golden_cases(variant)[i])
+        env = orc.OracleEnv(variant)
+        env.s0(og)
+        for a in sol:
+            assert not env.isTerminal()
+            env.stepWithoutReward(int(a))
+        assert env.isTerminal()
+        assert env.score == r["score"][i]
+        assert env.rank_list == list(r["ranks"][i, :n])
+        ref = z["greedy_actions"]
+        same = 0
+        while same < min(n, len(ref)) and sol[same] == ref[same]:
+            same += 1
+        if same == len(ref) == n:
+            assert r["score"][i] == float(z["greedy_final_score"])
+        else:  # first divergence must be a near-tie in the reference's own Q vector
+            off = z["greedy_off"]
+            qg = z["greedy_q"][off[same]:off[same + 1]]
+            ids = list(z["greedy_active"][off[same]:off[same + 1]])
+            gap = abs(qg[ids.index(int(ref[same]))] - qg[ids.index(int(sol[same]))])
+            assert gap <= Q_RTOL * abs(qg.max()) + Q_ATOL, (variant, i, same, gap)
+
+
+def test_spmm_operator():
+    from mdcommunity_b200.ops import spmm
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    for (m, n, nnz, D) in [(1, 1, 1, 64), (50, 70, 400, 64), (1000, 1000, 6000, 64), (300, 200, 5000, 4), (64, 64, 0, 64),
+                           (257, 129, 3000, 128)]:
+        row = torch.randint(0, m, (nnz,), device=dev)
+        col = torch.randint(0, n, (nnz,), device=dev)
+        val = torch.randn(nnz, device=dev)
+        x = torch.randn(n, D, device=dev)
+        ref = torch.zeros(m, D, device=dev, dtype=torch.float64).index_add_(0, row, x.double()[col] * val.double()[:, None])
+        out = spmm(torch.stack([row, col]), val, m, n, x)
+        assert out.shape == (m, D)
+        torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
