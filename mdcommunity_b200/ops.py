@@ -28,6 +28,9 @@ def spmm_csr(rowptr, col, val, matrix, m):
     if D % 4:
         raise ValueError("feature width must be a multiple of 4")
     y = torch.empty(m, D, dtype=torch.float32, device=x.device)
+    if col.numel() == 0:  # all rows empty: the kernel still needs a non-null column pointer
+        col = torch.zeros(1, dtype=torch.int32, device=x.device)
+        val = None
     stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
     rc = _lib.lib().md_spmm_csr_f32(C.c_void_p(rowptr.data_ptr()), C.c_void_p(col.data_ptr()),
                                     C.c_void_p(val.data_ptr()) if val is not None else None,

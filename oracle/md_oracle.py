@@ -224,7 +224,7 @@ def _fuse(w, e0, e1, p):
     return t[p] + alpha[:, k].unsqueeze(1) * t[k]
 
 
-def forward_q(w, envs, variant):
+def forward_q(w, envs, variant, trace=None):
     """test_forward over a batch of env states; returns (q [n_total] f32, active id list per graph).
 
     Unit cost builds node features from the alive degree (net_graphsage.py:248-261); degree cost
@@ -267,6 +267,9 @@ def forward_q(w, envs, variant):
         node_input = torch.cat(x, 0) if x else torch.zeros((0, 2))
         h = F.normalize(torch.relu(torch.matmul(node_input, w["w_n2l"])), p=2, dim=1)
         y = F.normalize(torch.relu(torch.matmul(torch.ones((B, 2)), w["w_n2l"])), p=2, dim=1)
+        if trace is not None:
+            trace.setdefault("h", {})[(l, 0)] = h.numpy().copy()
+            trace.setdefault("y", {})[(l, 0)] = y.numpy().copy()
         for _ in range(MAX_BP_ITER):
             pool = spmm_coo(row, col, n, h)
             node_linear = torch.matmul(pool, w["p_node_conv"])
@@ -276,11 +279,18 @@ def forward_q(w, envs, variant):
             h = F.normalize(torch.relu(torch.matmul(merged, w["p_node_conv3"])), p=2, dim=1)
             y_merged = torch.cat([y_linear, torch.matmul(y, w["p_node_conv2"])], 1)
             y = F.normalize(torch.relu(torch.matmul(y_merged, w["p_node_conv3"])), p=2, dim=1)
+            if trace is not None:
+                trace["h"][(l, _ + 1)] = h.numpy().copy()
+                trace["y"][(l, _ + 1)] = y.numpy().copy()
+                trace.setdefault("ypool", {})[(l, _)] = y_pool.numpy().copy()
         node_emb.append(h)
         y_emb.append(y)
     e0 = torch.cat([node_emb[0], y_emb[0]], 0)
     e1 = torch.cat([node_emb[1], y_emb[1]], 0)
     fused = [F.normalize(_fuse(w, e0, e1, p), p=2, dim=1) for p in range(L)]
+    if trace is not None:
+        trace["fused"] = [f.numpy().copy() for f in fused]
+        trace["n"] = n
     qs, gates = [], []
     for l in range(L):
         hf, yf = fused[l][:n], fused[l][n:]
@@ -296,6 +306,9 @@ def forward_q(w, envs, variant):
         gates.append(torch.matmul(torch.relu(torch.matmul(rep_y, w["w_layer1"])), w["w_layer2"]))
     sm = F.softmax(torch.cat(gates, 1), dim=1)
     q = sm[:, 0:1] * qs[0] + sm[:, 1:2] * qs[1]
+    if trace is not None:
+        trace["gate_softmax"] = sm.numpy().copy()
+        trace["q_layers"] = [x.numpy().copy() for x in qs]
     return q[:, 0].numpy(), act_ids, off
 
 
