@@ -14,6 +14,10 @@ from . import _lib
 TILE_M = _lib.TILE_M
 
 
+def _pin(t):
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
 class Graph_test:
     """Static multiplex graph given as per-layer undirected edge lists (the reference passes two nx.Graph objects;
     any object with .nodes/.edges works, as do plain arrays).
@@ -99,7 +103,56 @@ class GraphBatch:
     plain arrays indexed by global id and per-graph kernels never straddle graphs.
     """
 
-    def __init__(self, graphs, device=None, cost=None):
+    @staticmethod
+    def prepare_host(graphs, cost=None):
+        """Host side of the upload: block-diagonal CSR per layer (+ degree-cost node weights) as pinned tensors --
+        the input data format of the device path."""
+        graphs = list(graphs)
+        cost = cost if cost is not None else graphs[0].cost
+        B = len(graphs)
+        L = graphs[0].num_layers
+        nmax = max(g.num_nodes for g in graphs)
+        S = max(TILE_M, (nmax + TILE_M - 1) // TILE_M * TILE_M)
+        if B * S >= 2 ** 31:
+            raise ValueError("batch too large for int32 node ids")
+        rowptr, col, nnz = [], [], []
+        for l in range(L):
+            rp = np.zeros(B * S + 1, np.int64)
+            cols = []
+            pos = 0
+            for gi, g in enumerate(graphs):
+                r, c = build_csr(g.num_nodes, g.edge_list[l])
+                rp[gi * S:gi * S + g.num_nodes + 1] = r + pos
+                rp[gi * S + g.num_nodes + 1:(gi + 1) * S + 1] = r[-1] + pos
+                cols.append(c + gi * S)
+                pos += int(r[-1])
+            if pos >= 2 ** 31:
+                raise ValueError("too many edges for int32 CSR offsets")
+            nnz.append(pos)
+            c = np.concatenate(cols) if pos else np.zeros(1, np.int64)
+            rowptr.append(_pin(torch.from_numpy(rp.astype(np.int32))))
+            col.append(_pin(torch.from_numpy(c.astype(np.int32))))
+        out = dict(B=B, L=L, S=S, rowptr=rowptr, col=col, nnz=nnz, cost=cost,
+                   n_nodes=_pin(torch.tensor([g.num_nodes for g in graphs], dtype=torch.int32)),
+                   n_edges=_pin(torch.tensor([[g.num_edges[l] for g in graphs] for l in range(L)], dtype=torch.int32)))
+        if cost == "degree":
+            if L != 2:
+                raise ValueError("degree-cost reward is defined for two layers (D/mvc_env.py:127-133)")
+            cost_arr = np.zeros(B * S, np.float64)
+            ws = [np.zeros(B * S, np.float32) for _ in range(L)]
+            for gi, g in enumerate(graphs):
+                if g.weights is None:
+                    g.cal_degree()
+                # D/mvc_env.py:129-130: Python sum over the weight dict (sequential f64 adds in node order)
+                tot = [float(sum(g.weights[l].tolist())) for l in range(L)]
+                cost_arr[gi * S:gi * S + g.num_nodes] = g.weights[0] / tot[0] + g.weights[1] / tot[1]
+                for l in range(L):
+                    ws[l][gi * S:gi * S + g.num_nodes] = g.weights[l].astype(np.float32)
+            out["node_w"] = [_pin(torch.from_numpy(w)) for w in ws]
+            out["node_cost"] = _pin(torch.from_numpy(cost_arr))
+        return out
+
+    def __init__(self, graphs, device=None, cost=None, host=None):
         if not torch.cuda.is_available():
             raise RuntimeError("mdcommunity_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.lib()
@@ -112,48 +165,25 @@ class GraphBatch:
         if L > _lib.MAX_LAYERS:
             raise ValueError("at most %d layers" % _lib.MAX_LAYERS)
         self.cost = cost if cost is not None else self.graphs[0].cost
-        nmax = max(g.num_nodes for g in self.graphs)
-        S = max(TILE_M, (nmax + TILE_M - 1) // TILE_M * TILE_M)
-        if B * S >= 2 ** 31:
-            raise ValueError("batch too large for int32 node ids")
+        if host is None:
+            host = self.prepare_host(self.graphs, self.cost)
+        S = host["S"]
+        assert host["B"] == B and host["L"] == L and host["cost"] == self.cost
         self.B, self.L, self.S, self.n_total = B, L, S, B * S
         dev = self.device
-        self.rowptr, self.col, self.nnz = [], [], []
-        for l in range(L):
-            rp = np.zeros(B * S + 1, np.int64)
-            cols = []
-            pos = 0
-            for gi, g in enumerate(self.graphs):
-                r, c = build_csr(g.num_nodes, g.edge_list[l])
-                rp[gi * S:gi * S + g.num_nodes + 1] = r + pos
-                rp[gi * S + g.num_nodes + 1:(gi + 1) * S + 1] = r[-1] + pos
-                cols.append(c + gi * S)
-                pos += int(r[-1])
-            if pos >= 2 ** 31:
-                raise ValueError("too many edges for int32 CSR offsets")
-            self.nnz.append(pos)
-            self.rowptr.append(torch.from_numpy(rp.astype(np.int32)).to(dev))
-            c = np.concatenate(cols) if cols else np.zeros(0, np.int64)
-            self.col.append(torch.from_numpy(c.astype(np.int32)).to(dev) if c.size else torch.zeros(1, dtype=torch.int32, device=dev))
-        self.n_nodes = torch.tensor([g.num_nodes for g in self.graphs], dtype=torch.int32, device=dev)
-        self.n_edges = torch.tensor([[g.num_edges[l] for g in self.graphs] for l in range(L)], dtype=torch.int32, device=dev)
+        self.nnz = list(host["nnz"])
+        up = lambda t: t.to(dev, non_blocking=True)
+        self.rowptr = [up(t) for t in host["rowptr"]]
+        self.col = [up(t) for t in host["col"]]
+        self.n_nodes, self.n_edges = up(host["n_nodes"]), up(host["n_edges"])
         self.max_rank = torch.ones(B, dtype=torch.int32, device=dev)
         self.node_w, self.node_cost = [], None
         if self.cost == "degree":
-            if L != 2:
-                raise ValueError("degree-cost reward is defined for two layers (D/mvc_env.py:127-133)")
-            cost_arr = np.zeros(B * S, np.float64)
-            ws = [np.zeros(B * S, np.float32) for _ in range(L)]
-            for gi, g in enumerate(self.graphs):
-                if g.weights is None:
-                    g.cal_degree()
-                # D/mvc_env.py:129-130: Python sum over the weight dict (sequential f64 adds in node order)
-                tot = [float(sum(g.weights[l].tolist())) for l in range(L)]
-                cost_arr[gi * S:gi * S + g.num_nodes] = g.weights[0] / tot[0] + g.weights[1] / tot[1]
-                for l in range(L):
-                    ws[l][gi * S:gi * S + g.num_nodes] = g.weights[l].astype(np.float32)
-            self.node_w = [torch.from_numpy(w).to(dev) for w in ws]
-            self.node_cost = torch.from_numpy(cost_arr).to(dev)
+            self.node_w = [up(t) for t in host["node_w"]]
+            self.node_cost = up(host["node_cost"])
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in
+                             host["rowptr"] + host["col"] + [host["n_nodes"], host["n_edges"]] +
+                             (host["node_w"] + [host["node_cost"]] if self.cost == "degree" else []))
         st = _lib.MdGraphs()
         st.n_graphs, st.n_layers, st.stride, st.n_total = B, L, S, B * S
         for l in range(L):

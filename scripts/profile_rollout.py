@@ -1,0 +1,42 @@
+"""Short profiling target: a warm-up rollout, then `--steps` lock-step iterations from the intact state bracketed by
+cudaProfilerStart/Stop (use ncu --profile-from-start off).  Prints CUDA-event time of the bracketed region."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mdcommunity_b200 as mdb  # noqa: E402
+from mdcommunity_b200 import _lib, gmm  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--cost", default="degree")
+ap.add_argument("--n", type=int, default=1000)
+ap.add_argument("--graphs", type=int, default=256)
+ap.add_argument("--steps", type=int, default=4)
+ap.add_argument("--skip", type=int, default=0, help="un-profiled steps after the reset")
+args = ap.parse_args()
+
+graphs = [gmm.gmm_graph(args.n, i, cost=args.cost) for i in range(args.graphs)]
+batch = mdb.GraphBatch(graphs, "cuda:0", args.cost)
+w = mdb.QWeights(dict(np.load(os.path.join(ROOT, "tests", "golden", "weights_%s.npz" % args.cost))), batch.device)
+ro = mdb.BatchRollout(batch, w)
+ro.run()
+ro.reset()
+lib = ro.lib
+if args.skip:
+    _lib.check(lib.md_rollout_steps(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), args.skip, ro._stream()), "steps")
+torch.cuda.synchronize()
+print("active nodes", int(ro.n_act.sum()), "alive directed edges", (2 * ro.alive_edges.sum(1)).tolist())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.profiler.start()
+e0.record()
+_lib.check(lib.md_rollout_steps(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), args.steps, ro._stream()), "steps")
+e1.record()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("%d steps: %.3f ms (%.3f ms/step)" % (args.steps, e0.elapsed_time(e1), e0.elapsed_time(e1) / args.steps))
