@@ -46,6 +46,8 @@ typedef struct md_graphs {
   int32_t n_layers;                      /* L: 2 for the reference network; 3 allowed for the LMCC / aggregation kernels */
   int32_t stride;                        /* S, multiple of MD_TILE_M */
   int32_t n_total;                       /* B * S */
+  int32_t max_graph_nnz;                 /* max over graphs of the CSR entries of one graph summed over layers (host) */
+  int32_t reserved0;
   const int32_t* rowptr[MD_MAX_LAYERS];  /* [n_total + 1] per layer */
   const int32_t* col[MD_MAX_LAYERS];     /* [nnz_l] neighbour = global node id; row order = edge_list order */
   const int32_t* n_nodes;                /* [B] */
@@ -83,6 +85,7 @@ typedef struct md_state {
   int32_t* parent;       /* [n_total] */
   int32_t* comp_size;    /* [n_total] */
   int32_t* flags;        /* [8] */
+  int32_t* cur_action;   /* [B] action applied in the running step (-1 = graph untouched) */
 } md_state_t;
 
 /* The 14-tensor checkpoint (U/MultiDismantler_net_graphsage.py:42-89, U/MRGNN/mutil_layer_weight.py:252-264),
@@ -129,6 +132,8 @@ int md_env_step(const md_graphs_t* g, const md_state_t* s, const int32_t* action
 
 /* largest graph stride the single-CTA (shared-memory) env kernel handles; larger strides use the multi-CTA path */
 int32_t md_env_small_max_stride(void);
+/* test hook: route every batch through the multi-CTA (global-memory, cooperative) env kernel */
+void md_debug_force_large_env(int32_t on);
 
 /* ---- Q network ---------------------------------------------------------------------------------------- */
 

@@ -24,6 +24,7 @@ _vp = C.c_void_p
 class MdGraphs(C.Structure):
     _fields_ = [
         ("n_graphs", C.c_int32), ("n_layers", C.c_int32), ("stride", C.c_int32), ("n_total", C.c_int32),
+        ("max_graph_nnz", C.c_int32), ("reserved0", C.c_int32),
         ("rowptr", _vp * MAX_LAYERS), ("col", _vp * MAX_LAYERS),
         ("n_nodes", _vp), ("n_edges", _vp), ("max_rank", _vp),
         ("node_w", _vp * MAX_LAYERS), ("node_cost", _vp),
@@ -37,7 +38,7 @@ class MdState(C.Structure):
         ("done", _vp), ("n_steps", _vp), ("score", _vp), ("aux", _vp), ("best", _vp),
         ("trace_action", _vp), ("trace_rank", _vp), ("trace_maxcc", _vp), ("n_done", _vp),
         ("max_steps", C.c_int32), ("cost_mode", C.c_int32),
-        ("parent", _vp), ("comp_size", _vp), ("flags", _vp),
+        ("parent", _vp), ("comp_size", _vp), ("flags", _vp), ("cur_action", _vp),
     ]
 
 
@@ -57,6 +58,7 @@ _SIGS = {
     "md_env_reset": ([C.POINTER(MdGraphs), C.POINTER(MdState), _vp], C.c_int),
     "md_env_step": ([C.POINTER(MdGraphs), C.POINTER(MdState), _vp, C.c_int32, C.c_int32, _vp], C.c_int),
     "md_env_small_max_stride": ([], C.c_int32),
+    "md_debug_force_large_env": ([C.c_int32], None),
     "md_embed_init": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_embed_iter": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),
     "md_graph_embed": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),

@@ -49,20 +49,31 @@ __global__ void __launch_bounds__(256) embed_init_kernel(md_graphs_t G, md_state
 }
 
 // =================================================================================================
-// md_embed_iter : persistent CTAs, one 128-row tile at a time
+// md_embed_iter : persistent, warp-specialised CTAs (one per SM)
+//   8 producer warps gather tile t+1 (alive-neighbour sums + own rows) into one half of a double-buffered
+//   shared-memory A tile while 8 consumer warps run the dense transform + normalise epilogue on tile t.
+//   Hand-off through named barriers (full[2] / empty[2]); the merged 128x64 weight stays resident in smem.
 // =================================================================================================
-constexpr int IT_T = 256;
+constexpr int IT_PROD = 256;
+constexpr int IT_CONS = 256;
+constexpr int IT_T = IT_PROD + IT_CONS;
 constexpr int EMAX = 2048;  // staged alive-neighbour slots per tile
+constexpr int GCH = 16;     // neighbour rows in flight per producer warp
 struct IterSmem {
-  float A[TILE_M * A_LD];   // [row][0:64] = neighbour sum P, [row][64:128] = own embedding H
-  float Wm[2 * D * D];      // merged weight [128][64]: rows 0..63 = w13, 64..127 = w23
-  int eu[EMAX];             // staged neighbour ids (-1 = dead edge)
-  int v[TILE_M];            // global node id of the row, -1 = padding row
-  int lv[TILE_M];           // its label
-  int beg[TILE_M];          // first CSR entry
-  int off[TILE_M + 1];      // exclusive scan of the row degrees inside the tile
-  unsigned char er[EMAX];   // tile row of the staged entry
+  float A[2][TILE_M * A_LD];  // [buf][row][0:64] = neighbour sum P, [row][64:128] = own embedding H
+  float Wm[2 * D * D];        // merged weight [128][64]: rows 0..63 = w13, 64..127 = w23
+  float red[4 * D];           // partial column sums
+  int eu[EMAX];               // staged neighbour ids (-1 = dead edge)
+  int v[2][TILE_M];           // global node id of the row, -1 = padding row
+  int lv[TILE_M];             // its label
+  int beg[TILE_M];            // first CSR entry
+  int off[TILE_M + 1];        // exclusive scan of the row degrees inside the tile
+  unsigned char er[EMAX];     // tile row of the staged entry
 };
+
+enum { BAR_FULL0 = 1, BAR_EMPTY0 = 3, BAR_PROD = 5 };
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ void tile_gemm_128(const float* __restrict__ A, const float* __restrict__ Wm, int ty, int tx,
                                               float (&acc)[8][4]) {
@@ -99,198 +110,235 @@ __device__ __forceinline__ void tile_gemm_128(const float* __restrict__ A, const
   }
 }
 
-__global__ void __launch_bounds__(IT_T, 2) embed_iter_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K,
+struct TileIter {  // the tile sequence both roles walk in lock step
+  int tile, n_tiles, tiles_per_layer, tpg;
+  int l, gt, g, t, nact;
+  __device__ __forceinline__ bool next(const md_state_t& S) {
+    for (; tile < n_tiles; tile += gridDim.x) {
+      l = tile / tiles_per_layer;
+      gt = tile - l * tiles_per_layer;
+      g = gt / tpg;
+      t = gt - g * tpg;
+      nact = S.n_act[g];
+      if (t * TILE_M < nact) return true;
+    }
+    return false;
+  }
+};
+
+__global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K,
                                                             int iter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   IterSmem& sm = *reinterpret_cast<IterSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = tid & 15, ty = tid >> 4;
-  const int tpg = G.stride / TILE_M;
-  const int tiles_per_layer = G.n_graphs * tpg;
-  const int n_tiles = tiles_per_layer * G.n_layers;
+  const int tid = threadIdx.x;
   const int32_t* __restrict__ label = S.label;
+  TileIter ti;
+  ti.tpg = G.stride / TILE_M;
+  ti.tiles_per_layer = G.n_graphs * ti.tpg;
+  ti.n_tiles = ti.tiles_per_layer * G.n_layers;
+  ti.tile = blockIdx.x;
 
-  // merged weight, resident for the lifetime of the CTA
-  for (int i = tid; i < D * D / 4; i += IT_T) {
-    reinterpret_cast<float4*>(sm.Wm)[i] = reinterpret_cast<const float4*>(W.w13)[i];
-    reinterpret_cast<float4*>(sm.Wm + D * D)[i] = reinterpret_cast<const float4*>(W.w23)[i];
-  }
+  if (tid < IT_PROD) {
+    // ===================================== PRODUCER =====================================
+    const int lane = tid & 31, warp = tid >> 5;
+    int it = 0;
+    for (; ti.next(S); ti.tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int l = ti.l, g = ti.g, t = ti.t;
+      const int rows = min(TILE_M, ti.nact - t * TILE_M);
+      const int32_t* __restrict__ rp = G.rowptr[l];
+      const int32_t* __restrict__ cl = G.col[l];
+      const float* __restrict__ Hin = K.h[iter & 1][l];
+      float* A = sm.A[buf];
+      if (it >= 2) bar_sync(BAR_EMPTY0 + buf, IT_T);  // consumers are done with this buffer
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int l = tile / tiles_per_layer;
-    const int gt = tile - l * tiles_per_layer;
-    const int g = gt / tpg, t = gt - g * tpg;
-    const int nact = S.n_act[g];
-    if (t * TILE_M >= nact) continue;  // uniform
-    const int rows = min(TILE_M, nact - t * TILE_M);
-    const int32_t* __restrict__ rp = G.rowptr[l];
-    const int32_t* __restrict__ cl = G.col[l];
-    const float* __restrict__ Hin = K.h[iter & 1][l];
-    float* __restrict__ Hout = K.h[(iter + 1) & 1][l];
-    __syncthreads();  // previous tile's readers of A / staging are done
-
-    // ---- stage A: row descriptors ------------------------------------------------------------------
-    if (tid < TILE_M) {
-      int v = -1, lv = -1, b = 0, d = 0;
-      if (tid < rows) {
-        v = S.act_list[g * G.stride + t * TILE_M + tid];
-        lv = label[v];
-        b = rp[v];
-        d = rp[v + 1] - b;
-      }
-      sm.v[tid] = v;
-      sm.lv[tid] = lv;
-      sm.beg[tid] = b;
-      sm.off[tid] = d;
-    }
-    __syncthreads();
-    // exclusive scan of the 128 row degrees by warp 0 (4 per lane)
-    if (warp == 0) {
-      int d0 = sm.off[4 * lane], d1 = sm.off[4 * lane + 1], d2 = sm.off[4 * lane + 2], d3 = sm.off[4 * lane + 3];
-      int s = d0 + d1 + d2 + d3, incl = s;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += n;
-      }
-      int ex = incl - s;
-      sm.off[4 * lane] = ex;
-      sm.off[4 * lane + 1] = ex + d0;
-      sm.off[4 * lane + 2] = ex + d0 + d1;
-      sm.off[4 * lane + 3] = ex + d0 + d1 + d2;
-      if (lane == 31) sm.off[TILE_M] = incl;
-    }
-    __syncthreads();
-    const int etot = sm.off[TILE_M];
-    const bool staged = etot <= EMAX;
-
-    // ---- stage B: alive-neighbour list of the tile (edge-parallel) -------------------------------------
-    if (staged) {
-      for (int e = tid; e < etot; e += IT_T) {
-        int lo = 0, hi = TILE_M - 1;  // largest row with off[row] <= e
-        while (lo < hi) {
-          int mid = (lo + hi + 1) >> 1;
-          if (sm.off[mid] <= e) lo = mid; else hi = mid - 1;
+      // ---- stage A: row descriptors -------------------------------------------------------------------
+      if (tid < TILE_M) {
+        int v = -1, lv = -1, b = 0, d = 0;
+        if (tid < rows) {
+          v = S.act_list[g * G.stride + t * TILE_M + tid];
+          lv = label[v];
+          b = rp[v];
+          d = rp[v + 1] - b;
         }
-        const int u = cl[sm.beg[lo] + (e - sm.off[lo])];
-        sm.eu[e] = (label[u] == sm.lv[lo]) ? u : -1;
-        sm.er[e] = (unsigned char)lo;
+        sm.v[buf][tid] = v;
+        sm.lv[tid] = lv;
+        sm.beg[tid] = b;
+        sm.off[tid] = d;
       }
-    }
-    __syncthreads();
+      bar_sync(BAR_PROD, IT_PROD);
+      if (warp == 0) {  // exclusive scan of the 128 row degrees (4 per lane)
+        int d0 = sm.off[4 * lane], d1 = sm.off[4 * lane + 1], d2 = sm.off[4 * lane + 2], d3 = sm.off[4 * lane + 3];
+        int s = d0 + d1 + d2 + d3, incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int n = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += n;
+        }
+        int ex = incl - s;
+        sm.off[4 * lane] = ex;
+        sm.off[4 * lane + 1] = ex + d0;
+        sm.off[4 * lane + 2] = ex + d0 + d1;
+        sm.off[4 * lane + 3] = ex + d0 + d1 + d2;
+        if (lane == 31) sm.off[TILE_M] = incl;
+      }
+      bar_sync(BAR_PROD, IT_PROD);
+      const int etot = sm.off[TILE_M];
+      const bool staged = etot <= EMAX;
 
-    // ---- stage C: gather.  warp w owns tile rows [16w, 16w+16); lane holds columns 2*lane, 2*lane+1 ------
-    {
-      const int r0 = warp * 16;
-      // own rows -> A[:, 64:128]
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int v = sm.v[r0 + i];
-        float2 h = make_float2(0.f, 0.f);
-        if (v >= 0) h = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)v * D) + lane);
-        *reinterpret_cast<float2*>(sm.A + (r0 + i) * A_LD + D + 2 * lane) = h;
-      }
+      // ---- stage B: alive-neighbour list of the tile (edge-parallel) --------------------------------------
       if (staged) {
-        const int e0 = sm.off[r0], e1 = sm.off[r0 + 16];
-        int cur = r0;
-        float2 acc = make_float2(0.f, 0.f);
-        for (int e = e0; e < e1; e += 8) {
-          float2 val[8];
-          int rr[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            val[j] = make_float2(0.f, 0.f);
-            rr[j] = -1;
-            if (e + j < e1) {
-              const int u = sm.eu[e + j];
-              rr[j] = sm.er[e + j];
-              if (u >= 0) val[j] = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)u * D) + lane);
-            }
+        for (int e = tid; e < etot; e += IT_PROD) {
+          int lo = 0, hi = TILE_M - 1;  // largest row with off[row] <= e
+          while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (sm.off[mid] <= e) lo = mid; else hi = mid - 1;
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (rr[j] >= 0) {
-              if (rr[j] != cur) {  // warp-uniform: finish the rows up to rr[j]
-                *reinterpret_cast<float2*>(sm.A + cur * A_LD + 2 * lane) = acc;
-                for (int z = cur + 1; z < rr[j]; ++z)
-                  *reinterpret_cast<float2*>(sm.A + z * A_LD + 2 * lane) = make_float2(0.f, 0.f);
-                cur = rr[j];
-                acc = make_float2(0.f, 0.f);
-              }
-              acc.x += val[j].x;
-              acc.y += val[j].y;
-            }
-          }
+          const int u = cl[sm.beg[lo] + (e - sm.off[lo])];
+          sm.eu[e] = (label[u] == sm.lv[lo]) ? u : -1;
+          sm.er[e] = (unsigned char)lo;
         }
-        *reinterpret_cast<float2*>(sm.A + cur * A_LD + 2 * lane) = acc;
-        for (int z = cur + 1; z < r0 + 16; ++z)
-          *reinterpret_cast<float2*>(sm.A + z * A_LD + 2 * lane) = make_float2(0.f, 0.f);
-      } else {
-        // hub tile: read the CSR directly, 32 edges at a time
-        for (int i = 0; i < 16; ++i) {
-          const int r = r0 + i;
+      }
+      bar_sync(BAR_PROD, IT_PROD);
+
+      // ---- stage C: gather.  warp w owns tile rows [16w, 16w+16); lane holds columns 2*lane, 2*lane+1 ------
+      {
+        const int r0 = warp * 16;
+        {
+          float2 h[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int v = sm.v[buf][r0 + i];
+            h[i] = make_float2(0.f, 0.f);
+            if (v >= 0) h[i] = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)v * D) + lane);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(A + (r0 + i) * A_LD + D + 2 * lane) = h[i];
+        }
+        if (staged) {
+          const int e0 = sm.off[r0], e1 = sm.off[r0 + 16];
+          int cur = r0;
           float2 acc = make_float2(0.f, 0.f);
-          if (sm.v[r] >= 0) {
-            const int b = sm.beg[r], d = sm.off[r + 1] - sm.off[r], lv = sm.lv[r];
-            for (int c0 = 0; c0 < d; c0 += 32) {
-              int u = -1;
-              if (c0 + lane < d) {
-                u = cl[b + c0 + lane];
-                if (label[u] != lv) u = -1;
+          for (int e = e0; e < e1; e += GCH) {
+            float2 val[GCH];
+            int rr[GCH];
+#pragma unroll
+            for (int j = 0; j < GCH; ++j) {
+              val[j] = make_float2(0.f, 0.f);
+              rr[j] = -1;
+              if (e + j < e1) {
+                const int u = sm.eu[e + j];
+                if (u >= 0) {
+                  rr[j] = sm.er[e + j];
+                  val[j] = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)u * D) + lane);
+                }
               }
-              unsigned m = __ballot_sync(0xffffffffu, u >= 0);
-              while (m) {
-                const int j = __ffs(m) - 1;
-                m &= m - 1;
-                const int uu = __shfl_sync(0xffffffffu, u, j);
-                const float2 hv = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)uu * D) + lane);
-                acc.x += hv.x;
-                acc.y += hv.y;
+            }
+#pragma unroll
+            for (int j = 0; j < GCH; ++j) {
+              if (rr[j] >= 0) {
+                if (rr[j] != cur) {  // warp-uniform: finish the rows up to rr[j]
+                  *reinterpret_cast<float2*>(A + cur * A_LD + 2 * lane) = acc;
+                  for (int z = cur + 1; z < rr[j]; ++z)
+                    *reinterpret_cast<float2*>(A + z * A_LD + 2 * lane) = make_float2(0.f, 0.f);
+                  cur = rr[j];
+                  acc = make_float2(0.f, 0.f);
+                }
+                acc.x += val[j].x;
+                acc.y += val[j].y;
               }
             }
           }
-          *reinterpret_cast<float2*>(sm.A + r * A_LD + 2 * lane) = acc;
+          *reinterpret_cast<float2*>(A + cur * A_LD + 2 * lane) = acc;
+          for (int z = cur + 1; z < r0 + 16; ++z)
+            *reinterpret_cast<float2*>(A + z * A_LD + 2 * lane) = make_float2(0.f, 0.f);
+        } else {
+          // hub tile: read the CSR directly, 32 edges at a time
+          for (int i = 0; i < 16; ++i) {
+            const int r = r0 + i;
+            float2 acc = make_float2(0.f, 0.f);
+            if (sm.v[buf][r] >= 0) {
+              const int b = sm.beg[r], d = sm.off[r + 1] - sm.off[r], lv = sm.lv[r];
+              for (int c0 = 0; c0 < d; c0 += 32) {
+                int u = -1;
+                if (c0 + lane < d) {
+                  u = cl[b + c0 + lane];
+                  if (label[u] != lv) u = -1;
+                }
+                unsigned m = __ballot_sync(0xffffffffu, u >= 0);
+                while (m) {
+                  const int j = __ffs(m) - 1;
+                  m &= m - 1;
+                  const int uu = __shfl_sync(0xffffffffu, u, j);
+                  const float2 hv = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)uu * D) + lane);
+                  acc.x += hv.x;
+                  acc.y += hv.y;
+                }
+              }
+            }
+            *reinterpret_cast<float2*>(A + r * A_LD + 2 * lane) = acc;
+          }
         }
       }
-    }
-    __syncthreads();
+      __threadfence_block();
+      bar_arrive(BAR_FULL0 + buf, IT_T);  // hand the tile to the consumers
+      bar_sync(BAR_PROD, IT_PROD);        // all producer warps finished writing A (needed for the column sums)
 
-    // ---- per-tile partial of the subgraph sum (old embeddings), fixed order => deterministic --------------
-    {
-      const int c = tid & 63, part = tid >> 6;  // 4 row quarters x 64 columns
-      float s = 0.f;
-      for (int r = part * 32; r < part * 32 + 32; ++r) s += sm.A[r * A_LD + D + c];
-      // reuse the staging area for the 4 partials
-      float* red = reinterpret_cast<float*>(sm.eu);
-      red[part * 64 + c] = s;
-    }
-    __syncthreads();
-    if (tid < 64) {
-      const float* red = reinterpret_cast<const float*>(sm.eu);
-      const float s = ((red[tid] + red[64 + tid]) + red[128 + tid]) + red[192 + tid];
-      K.psum[(((size_t)iter * G.n_layers + l) * tiles_per_layer + gt) * D + tid] = s;
-    }
-
-    // ---- dense transform: out = [P, H] @ [w13; w23], relu, L2 normalise ------------------------------------
-    float acc[8][4];
-    tile_gemm_128(sm.A, sm.Wm, ty, tx, acc);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float ss = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        acc[i][c] = fmaxf(acc[i][c], 0.f);
-        ss = fmaf(acc[i][c], acc[i][c], ss);
+      // ---- per-tile partial of the subgraph sum (old embeddings), fixed order => deterministic --------------
+      {
+        const int c = tid & 63, part = tid >> 6;  // 4 row quarters x 64 columns
+        float s = 0.f;
+        for (int r = part * 32; r < part * 32 + 32; ++r) s += A[r * A_LD + D + c];
+        sm.red[part * D + c] = s;
       }
-      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-      const float den = fmaxf(sqrtf(ss), 1e-12f);
-      const int v = sm.v[ty + 16 * i];
-      if (v >= 0)
-        *reinterpret_cast<float4*>(Hout + (size_t)v * D + 4 * tx) =
-            make_float4(acc[i][0] / den, acc[i][1] / den, acc[i][2] / den, acc[i][3] / den);
+      bar_sync(BAR_PROD, IT_PROD);
+      if (tid < D) {
+        const float s = ((sm.red[tid] + sm.red[D + tid]) + sm.red[2 * D + tid]) + sm.red[3 * D + tid];
+        K.psum[(((size_t)iter * G.n_layers + l) * ti.tiles_per_layer + ti.gt) * D + tid] = s;
+      }
+      // (the next iteration's first write to sm.red / staging happens after further BAR_PROD syncs)
+    }
+    // drain: match the consumers' last empty-arrivals so no barrier is left half-arrived
+    for (int j = max(0, it - 2); j < it; ++j) bar_sync(BAR_EMPTY0 + (j & 1), IT_T);
+  } else {
+    // ===================================== CONSUMER =====================================
+    const int ct = tid - IT_PROD;
+    const int tx = ct & 15, ty = ct >> 4;
+    // merged weight, resident for the lifetime of the CTA (consumers only touch Wm)
+    for (int i = ct; i < D * D / 4; i += IT_CONS) {
+      reinterpret_cast<float4*>(sm.Wm)[i] = reinterpret_cast<const float4*>(W.w13)[i];
+      reinterpret_cast<float4*>(sm.Wm + D * D)[i] = reinterpret_cast<const float4*>(W.w23)[i];
+    }
+    bar_sync(BAR_PROD + 1, IT_CONS);
+    int it = 0;
+    for (; ti.next(S); ti.tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      float* __restrict__ Hout = K.h[(iter + 1) & 1][ti.l];
+      bar_sync(BAR_FULL0 + buf, IT_T);
+      float acc[8][4];
+      tile_gemm_128(sm.A[buf], sm.Wm, ty, tx, acc);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[i][c] = fmaxf(acc[i][c], 0.f);
+          ss = fmaf(acc[i][c], acc[i][c], ss);
+        }
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+        // x / max(|x|, eps) as x * rcp_rn(.): one correctly rounded reciprocal per row instead of 4 IEEE divisions
+        // per thread (the division subroutine was 30% of the first version's instructions); differs by <= 1 ulp
+        const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
+        const int v = sm.v[buf][ty + 16 * i];
+        if (v >= 0)
+          *reinterpret_cast<float4*>(Hout + (size_t)v * D + 4 * tx) =
+              make_float4(acc[i][0] * inv, acc[i][1] * inv, acc[i][2] * inv, acc[i][3] * inv);
+      }
+      __threadfence_block();
+      bar_arrive(BAR_EMPTY0 + buf, IT_T);
     }
   }
 }
@@ -458,7 +506,7 @@ extern "C" int md_embed_iter(const md_graphs_t* g, const md_state_t* s, const md
     configured = true;
   }
   const int n_tiles = g->n_graphs * (g->stride / MD_TILE_M) * g->n_layers;
-  int grid = 2 * sm_count();
+  int grid = sm_count();
   if (grid > n_tiles) grid = n_tiles;
   md::embed_iter_kernel<<<grid, md::IT_T, smem, (cudaStream_t)stream>>>(*g, *s, *w, *k, iter);
   MD_CHECK_LAUNCH();

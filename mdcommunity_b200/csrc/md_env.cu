@@ -75,8 +75,11 @@ __device__ __forceinline__ long long block_sum_ll(long long v, BlockRed& r) {
 }
 
 // One CTA per graph.  init != 0: MvcEnv.s0; otherwise one stepWithoutReward.
+// CACHED: the graph's CSR (all layers) is copied into shared memory once, with node ids and row offsets made
+// graph-local, so the ~10 edge sweeps of a step (prune rounds + degree recount) never leave the SM.
+template <bool CACHED>
 __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_t S, const int32_t* forced,
-                                                       int forced_stride, int forced_index, int init) {
+                                                       int forced_stride, int forced_index, int init, int max_nnz) {
   extern __shared__ int smem[];
   const int g = blockIdx.x;
   const int tid = threadIdx.x;
@@ -87,6 +90,12 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int* lab = smem;
   int* par = smem + St;
   int* tmp = smem + 2 * St;
+  // cached CSR: rows [L][St + 1] then columns [max_nnz]
+  int* c_rp = smem + 3 * St;
+  int* c_cl = c_rp + L * (St + 1);
+  const int32_t* rp_l[MD_MAX_LAYERS];
+  const int32_t* cl_l[MD_MAX_LAYERS];
+  int voff = 0;  // id offset to subtract from a neighbour id, row-pointer base
   __shared__ BlockRed red;
   __shared__ int s_action;
   __shared__ int s_scan[ENV_W];
@@ -114,6 +123,27 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   const int a = s_action;
   if (!init && (a < 0 || lab[a] < 0)) return;  // nothing to remove (uniform exit)
 
+  if (CACHED) {
+    int pos = 0;
+    for (int ll = 0; ll < L; ++ll) {
+      const int32_t* __restrict__ rp = G.rowptr[ll] + base;
+      const int32_t* __restrict__ cl = G.col[ll];
+      const int e0 = rp[0], cnt = rp[St] - e0;
+      for (int v = tid; v <= St; v += ENV_T) c_rp[ll * (St + 1) + v] = rp[v] - e0 + pos;
+      for (int e = tid; e < cnt; e += ENV_T) c_cl[pos + e] = cl[e0 + e] - base;
+      rp_l[ll] = c_rp + ll * (St + 1);
+      cl_l[ll] = c_cl;
+      pos += cnt;
+    }
+    __syncthreads();
+  } else {
+    for (int ll = 0; ll < L; ++ll) {
+      rp_l[ll] = G.rowptr[ll] + base;
+      cl_l[ll] = G.col[ll];
+    }
+    voff = base;
+  }
+
   if (!init) {
     // numCoveredEdges[l] += #neighbours still alive and not cut from a  (mvc_env.py:81-84) == deg_alive_l(a)
     if (tid < L) S.cov_edges[tid * G.n_graphs + g] += S.deg[tid][base + a];
@@ -125,16 +155,16 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   // ---- Mcc.MCC: refine the partition layer by layer until every layer is stable ----------------------
   int stable = 0, l = 0;
   while (stable < L) {
-    const int32_t* __restrict__ rp = G.rowptr[l];
-    const int32_t* __restrict__ cl = G.col[l];
+    const int32_t* rp = rp_l[l];
+    const int32_t* cl = cl_l[l];
     for (int v = tid; v < N; v += ENV_T) par[v] = v;
     __syncthreads();
     for (int v = tid; v < N; v += ENV_T) {
       const int lv = lab[v];
       if (lv < 0) continue;
-      const int e1 = rp[base + v + 1];
-      for (int e = rp[base + v]; e < e1; ++e) {
-        const int u = cl[e] - base;
+      const int e1 = rp[v + 1];
+      for (int e = rp[v]; e < e1; ++e) {
+        const int u = cl[e] - voff;
         if (u < v && lab[u] == lv) uf_unite(par, u, v);
       }
     }
@@ -168,16 +198,16 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   // ---- alive degree per layer + status counters (get_status_info) ----------------------------------------
   bool terminal = false;
   for (int ll = 0; ll < L; ++ll) {
-    const int32_t* __restrict__ rp = G.rowptr[ll];
-    const int32_t* __restrict__ cl = G.col[ll];
+    const int32_t* rp = rp_l[ll];
+    const int32_t* cl = cl_l[ll];
     int dsum = 0, dmax = 0;
     long long th = 0;
     for (int v = tid; v < St; v += ENV_T) {
       int d = 0;
       if (v < N && lab[v] >= 0) {
         const int lv = lab[v];
-        const int e1 = rp[base + v + 1];
-        for (int e = rp[base + v]; e < e1; ++e) d += (lab[cl[e] - base] == lv);
+        const int e1 = rp[v + 1];
+        for (int e = rp[v]; e < e1; ++e) d += (lab[cl[e] - voff] == lv);
       }
       S.deg[ll][base + v] = d;
       if (ll == 0 && v < N) par[v] = d;  // keep layer-0 degree for the compaction below
@@ -272,27 +302,39 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
 
 }  // namespace md
 
-extern "C" int32_t md_env_small_max_stride(void) { return md::ENV_SMALL_MAX; }
+int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
+                      int32_t forced_index, int init, md_stream_t stream);
+
+static int g_force_large = 0;
+extern "C" int32_t md_env_small_max_stride(void) { return g_force_large ? 0 : md::ENV_SMALL_MAX; }
+extern "C" void md_debug_force_large_env(int32_t on) { g_force_large = on; }
 
 static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
                       int32_t forced_index, int init, md_stream_t stream) {
   if (!g || !s) return MD_EINVAL;
   if (g->n_layers < 1 || g->n_layers > MD_MAX_LAYERS) return MD_ELAYERS;
   if (g->stride % MD_TILE_M != 0 || g->n_total != g->n_graphs * g->stride) return MD_EINVAL;
-  if (g->stride > md::ENV_SMALL_MAX) return MD_ETOOBIG;
-  const size_t smem = (size_t)3 * g->stride * sizeof(int);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(md::env_step_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (g_force_large || g->stride > md::ENV_SMALL_MAX) return md_env_step_large(g, s, forced, forced_stride, forced_index, init, stream);
+  const size_t base_smem = (size_t)3 * g->stride * sizeof(int);
+  const size_t cached_smem = base_smem + ((size_t)g->n_layers * (g->stride + 1) + (size_t)g->max_graph_nnz) * sizeof(int);
+  const bool cached = g->max_graph_nnz > 0 && cached_smem <= 200 * 1024;
+  const size_t smem = cached ? cached_smem : base_smem;
+  static size_t configured[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > configured[cached]) {
+    cudaError_t e = cached ? cudaFuncSetAttribute(md::env_step_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(md::env_step_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
+    configured[cached] = smem;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (init) {
     cudaError_t e = cudaMemsetAsync(s->n_done, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return (int)e;
   }
-  md::env_step_small<<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init);
+  if (cached)
+    md::env_step_small<true><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz);
+  else
+    md::env_step_small<false><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, 0);
   MD_CHECK_LAUNCH();
   return 0;
 }

@@ -1,0 +1,338 @@
+// Environment step for graphs too large for one CTA's shared memory (e.g. config C4: N = 1M, 3 layers):
+// one persistent cooperative kernel, all state in global memory (labels / parents stay L2-resident: 4 MB at N=1M),
+// grid-wide barriers between the phases, no host round trip inside a step.
+//
+// Same semantics and reference citations as md_env.cu (mvc_env.py:31-52,74-87,133-162; Mcc.py:3-38;
+// PrepareBatchGraph.py:35-100).  LMCC = iterative mutual-component pruning: per layer an ECL-CC style union-find
+// (hook the larger root under the smaller with atomicCAS, path halving) restricted to edges whose end points
+// carry the same label, repeated round-robin over the layers until L consecutive layers leave the labels unchanged.
+#include "md_common.cuh"
+
+namespace md {
+
+constexpr int LG_T = 256;
+
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+__device__ __forceinline__ int guf_find(int* par, int x) {
+  int p = ld_volatile(par + x);
+  while (p != x) {
+    int gp = ld_volatile(par + p);
+    if (gp != p) par[x] = gp;  // path halving (benign race: parents only move towards smaller ids)
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+
+__device__ __forceinline__ void guf_unite(int* par, int a, int b) {
+  int ra = guf_find(par, a), rb = guf_find(par, b);
+  while (ra != rb) {
+    const int hi = max(ra, rb), lo = min(ra, rb);
+    const int old = atomicCAS(par + hi, hi, lo);
+    if (old == hi) break;
+    ra = guf_find(par, old);
+    rb = guf_find(par, lo);
+  }
+}
+
+// sense-free monotone grid barrier; all CTAs are co-resident (cooperative launch)
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += 1;
+    const unsigned target = epoch * gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t S, const int32_t* forced,
+                                                      int forced_stride, int forced_index, int init, int cpg,
+                                                      int chunk) {
+  const int tid = threadIdx.x;
+  const int gtid = blockIdx.x * LG_T + tid;
+  const int gsz = gridDim.x * LG_T;
+  const int St = G.stride, B = G.n_graphs, L = G.n_layers, NT = G.n_total;
+  unsigned* bar = reinterpret_cast<unsigned*>(S.flags);  // flags[0] barrier counter, [1..3] changed flags
+  int* flags = S.flags;
+  unsigned epoch = 0;
+  int* par = S.parent;
+  int* label = S.label;
+  __shared__ int s_red[LG_T / 32];
+  __shared__ int s_off;
+
+  // ---- P0: pick / validate the action, apply it --------------------------------------------------------
+  if (init) {
+    for (int v = gtid; v < NT; v += gsz) {
+      const int g = v / St;
+      label[v] = (v - g * St) < G.n_nodes[g] ? g * St : -1;
+    }
+  }
+  for (int g = gtid; g < B; g += gsz) {
+    int a = -1;
+    if (!init && !S.done[g]) {
+      if (forced != nullptr) {
+        const int idx = forced_index >= 0 ? forced_index : S.n_steps[g];
+        if (idx < forced_stride) a = forced[(size_t)g * forced_stride + idx];
+      } else {
+        const unsigned long long key = S.best[g];
+        if (key != 0ull) a = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+      }
+      if (a >= G.n_nodes[g]) a = -1;
+      if (a >= 0 && label[g * St + a] < 0) a = -1;
+      if (a >= 0) {
+        for (int l = 0; l < L; ++l) S.cov_edges[l * B + g] += S.deg[l][g * St + a];
+        label[g * St + a] = -1;
+      }
+    }
+    S.cur_action[g] = a;
+    S.best[g] = 0ull;
+    S.rank[g] = (init || a >= 0) ? 0 : S.rank[g];
+    if (init || a >= 0)
+      for (int l = 0; l < L; ++l) {
+        S.alive_edges[l * B + g] = 0;
+        S.max_deg[l * B + g] = 0;
+        S.twohop[l * B + g] = 0;
+      }
+  }
+  // flags[1..3]: "labels changed" flag of round r lives in slot r % 3 (memset to 0 by the host before the launch);
+  // a slot is re-cleared two rounds after its use, when every CTA has certainly read it.
+  grid_barrier(bar, epoch);
+
+  // ---- Mcc.MCC --------------------------------------------------------------------------------------------
+  int stable = 0, l = 0, round = 0;
+  while (stable < L) {
+    const int32_t* __restrict__ rp = G.rowptr[l];
+    const int32_t* __restrict__ cl = G.col[l];
+    int* chg = flags + 1 + (round % 3);
+    for (int v = gtid; v < NT; v += gsz) par[v] = v;
+    if (gtid == 0) flags[1 + ((round + 1) % 3)] = 0;  // slot of the next round (last used in round - 2)
+    grid_barrier(bar, epoch);
+    for (int v = gtid; v < NT; v += gsz) {
+      const int lv = label[v];
+      if (lv < 0) continue;
+      const int e1 = rp[v + 1];
+      for (int e = rp[v]; e < e1; ++e) {
+        const int u = cl[e];
+        if (u < v && label[u] == lv) guf_unite(par, u, v);
+      }
+    }
+    grid_barrier(bar, epoch);
+    int changed = 0;
+    for (int v = gtid; v < NT; v += gsz) {
+      const int lv = label[v];
+      if (lv < 0) continue;
+      const int r = guf_find(par, v);
+      if (r != lv) {
+        label[v] = r;  // only this thread reads/writes label[v] in this phase
+        changed = 1;
+      }
+    }
+    if (__syncthreads_or(changed) && tid == 0) atomicOr(chg, 1);
+    grid_barrier(bar, epoch);
+    const int any = ld_volatile(chg);
+    stable = any ? 1 : stable + 1;
+    l = (l + 1 == L) ? 0 : l + 1;
+    ++round;
+  }
+
+  // ---- component sizes, alive degrees, per-graph counters -------------------------------------------------
+  int* csz = S.comp_size;
+  for (int v = gtid; v < NT; v += gsz) csz[v] = 0;
+  grid_barrier(bar, epoch);
+  for (int v = gtid; v < NT; v += gsz) {
+    const int lv = label[v];
+    if (lv >= 0) atomicAdd(csz + lv, 1);
+    const int g = v / St;
+    if (!init && S.cur_action[g] < 0) continue;  // untouched graph: keep its counters
+    for (int ll = 0; ll < L; ++ll) {
+      int d = 0;
+      if (lv >= 0) {
+        const int32_t* __restrict__ rp = G.rowptr[ll];
+        const int32_t* __restrict__ cl = G.col[ll];
+        const int e1 = rp[v + 1];
+        for (int e = rp[v]; e < e1; ++e) d += (label[cl[e]] == lv);
+      }
+      S.deg[ll][v] = d;
+      // warp-aggregated when the whole warp sits in one graph (always true for large graphs)
+      const int g0 = __shfl_sync(0xffffffffu, g, 0);
+      if (__all_sync(0xffffffffu, g == g0)) {
+        const int ds = warp_sum_i(d), dm = warp_max_i(d);
+        const long long th = warp_sum_ll((long long)d * (d - 1) / 2);
+        if ((tid & 31) == 0 && ds) {
+          atomicAdd(&S.alive_edges[ll * B + g], ds);  // holds 2x the edge count until the epilogue halves it
+          atomicMax(&S.max_deg[ll * B + g], dm);
+          atomicAdd(reinterpret_cast<unsigned long long*>(&S.twohop[ll * B + g]), (unsigned long long)th);
+        }
+      } else if (d) {
+        atomicAdd(&S.alive_edges[ll * B + g], d);
+        atomicMax(&S.max_deg[ll * B + g], d);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&S.twohop[ll * B + g]), (unsigned long long)((long long)d * (d - 1) / 2));
+      }
+    }
+  }
+  grid_barrier(bar, epoch);
+  for (int v = gtid; v < NT; v += gsz) {
+    const int g = v / St;
+    if (!init && S.cur_action[g] < 0) continue;
+    int c = csz[v];
+    const int g0 = __shfl_sync(0xffffffffu, g, 0);
+    if (__all_sync(0xffffffffu, g == g0)) {
+      c = warp_max_i(c);
+      if ((tid & 31) == 0 && c) atomicMax(&S.rank[g], c);
+    } else if (c) {
+      atomicMax(&S.rank[g], c);
+    }
+  }
+
+  // ---- compaction of the active nodes: per-chunk counts, then ordered write ----------------------------------
+  // chunk c covers nodes [g*St + k*chunk, g*St + min((k+1)*chunk, St)) with g = c / cpg, k = c % cpg
+  int* ccount = par;  // parents are dead now; B * cpg entries
+  const int nchunks = B * cpg;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int g = c / cpg, k = c - g * cpg;
+    const int v0 = g * St + k * chunk, v1 = g * St + min((k + 1) * chunk, St);
+    int cnt = 0;
+    for (int v = v0 + tid; v < v1; v += LG_T) cnt += (S.deg[0][v] > 0);
+    cnt = warp_sum_i(cnt);
+    if ((tid & 31) == 0) s_red[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < LG_T / 32; ++w) t += s_red[w];
+      ccount[c] = t;
+    }
+    __syncthreads();
+  }
+  grid_barrier(bar, epoch);
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int g = c / cpg, k = c - g * cpg;
+    if (!init && S.cur_action[g] < 0) continue;  // uniform per block
+    int part = 0;
+    for (int j = tid; j < k; j += LG_T) part += ld_volatile(ccount + g * cpg + j);
+    part = warp_sum_i(part);
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < LG_T / 32; ++w) t += s_red[w];
+      s_off = t;
+      if (k == cpg - 1) S.n_act[g] = t + ld_volatile(ccount + c);
+    }
+    __syncthreads();
+    int running = s_off;
+    const int v0 = g * St + k * chunk, v1 = g * St + min((k + 1) * chunk, St);
+    for (int vb = v0; vb < v1; vb += LG_T) {
+      const int v = vb + tid;
+      const int flag = (v < v1 && S.deg[0][v] > 0) ? 1 : 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, flag);
+      const int lane = tid & 31, wid = tid >> 5;
+      __syncthreads();
+      if (lane == 0) s_red[wid] = __popc(bal);
+      __syncthreads();
+      int woff = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < LG_T / 32; ++w) {
+        const int cc = s_red[w];
+        if (w < wid) woff += cc;
+        total += cc;
+      }
+      if (flag) S.act_list[g * St + running + woff + __popc(bal & ((1u << lane) - 1u))] = v;
+      running += total;
+    }
+    __syncthreads();
+  }
+  grid_barrier(bar, epoch);
+
+  // ---- per-graph bookkeeping (identical arithmetic to md_env.cu) ----------------------------------------------
+  for (int g = gtid; g < B; g += gsz) {
+    const int a = S.cur_action[g];
+    if (!init && a < 0) continue;
+    const int N = G.n_nodes[g];
+    const int rank = S.rank[g];
+    bool terminal = false;
+    for (int ll = 0; ll < L; ++ll) {
+      const int e2 = S.alive_edges[ll * B + g];
+      S.alive_edges[ll * B + g] = e2 / 2;
+      terminal |= (e2 == 0);
+    }
+    const int nrem = init ? 0 : S.n_removed[g] + 1;
+    S.n_removed[g] = nrem;
+    if (init) {
+      S.score[g] = 0.0;
+      S.n_steps[g] = 0;
+      for (int ll = 0; ll < L; ++ll) S.cov_edges[ll * B + g] = 0;
+    } else {
+      const double rk = (double)rank, mr = (double)G.max_rank[g];
+      double r, mcc;
+      if (S.cost_mode == 0) {
+        r = __ddiv_rn(rk, __dmul_rn(mr, (double)N));
+        mcc = __dmul_rn(r, (double)N);
+      } else {
+        mcc = __ddiv_rn(rk, mr);
+        r = __ddiv_rn(__dmul_rn(mcc, G.node_cost[g * St + a]), 2.0);
+      }
+      S.score[g] = __dadd_rn(S.score[g], r);
+      const int t = S.n_steps[g];
+      if (t < S.max_steps) {
+        S.trace_action[(size_t)g * S.max_steps + t] = a;
+        S.trace_rank[(size_t)g * S.max_steps + t] = rank;
+        S.trace_maxcc[(size_t)g * S.max_steps + t] = mcc;
+      }
+      S.n_steps[g] = t + 1;
+    }
+    for (int ll = 0; ll < L; ++ll) {
+      float* ax = S.aux + ((size_t)g * L + ll) * MD_AUX;
+      const int E = G.n_edges[ll * B + g];
+      ax[0] = (float)__ddiv_rn((double)nrem, (double)N);
+      ax[1] = E > 0 ? (float)__ddiv_rn((double)S.cov_edges[ll * B + g], (double)E) : 0.f;
+      ax[2] = (float)__ddiv_rn((double)S.twohop[ll * B + g], (double)((long long)N * (long long)N));
+      ax[3] = 1.0f;
+    }
+    S.done[g] = terminal ? 1 : 0;
+    if (terminal) atomicAdd(S.n_done, 1);
+  }
+}
+
+}  // namespace md
+
+int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
+                      int32_t forced_index, int init, md_stream_t stream) {
+  if (!s->parent || !s->comp_size || !s->flags || !s->cur_action) return MD_EINVAL;
+  static int grid = 0;
+  if (grid == 0) {
+    int dev = 0, nsm = 0, occ = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop) return MD_EINVAL;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, md::env_step_large, md::LG_T, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (occ > 4) occ = 4;
+    grid = nsm * occ;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(s->flags, 0, 8 * sizeof(int32_t), st);
+  if (e != cudaSuccess) return (int)e;
+  if (init) {
+    e = cudaMemsetAsync(s->n_done, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  int cpg = grid / g->n_graphs;
+  if (cpg < 1) cpg = 1;
+  int chunk = (g->stride + cpg - 1) / cpg;
+  chunk = (chunk + 31) / 32 * 32;
+  cpg = (g->stride + chunk - 1) / chunk;
+  md_graphs_t gg = *g;
+  md_state_t ss = *s;
+  void* args[] = {&gg, &ss, (void*)&forced, &forced_stride, &forced_index, &init, &cpg, &chunk};
+  e = cudaLaunchCooperativeKernel((const void*)md::env_step_large, dim3(grid), dim3(md::LG_T), args, 0, st);
+  if (e != cudaSuccess) return (int)e;
+  return 0;
+}

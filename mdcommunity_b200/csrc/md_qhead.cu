@@ -176,10 +176,10 @@ __global__ void __launch_bounds__(QH_T, (L == 2 ? 2 : 1)) qhead_kernel(md_graphs
         ss += __shfl_xor_sync(0xffffffffu, ss, 2);
         ss += __shfl_xor_sync(0xffffffffu, ss, 4);
         ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-        const float dn = fmaxf(sqrtf(ss), 1e-12f);
+        const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
         const float s = sg[p];
         *reinterpret_cast<float4*>(rowp + p * D) =
-            make_float4(x.x / dn * s, x.y / dn * s, x.z / dn * s, x.w / dn * s);
+            make_float4(x.x * inv * s, x.y * inv * s, x.z * inv * s, x.w * inv * s);
       }
     }
     __syncwarp();

@@ -132,7 +132,10 @@ class GraphBatch:
             c = np.concatenate(cols) if pos else np.zeros(1, np.int64)
             rowptr.append(_pin(torch.from_numpy(rp.astype(np.int32))))
             col.append(_pin(torch.from_numpy(c.astype(np.int32))))
-        out = dict(B=B, L=L, S=S, rowptr=rowptr, col=col, nnz=nnz, cost=cost,
+        gnnz = np.zeros(B, np.int64)
+        for l in range(L):
+            gnnz += 2 * np.array([g.num_edges[l] for g in graphs], np.int64)
+        out = dict(B=B, L=L, S=S, rowptr=rowptr, col=col, nnz=nnz, cost=cost, max_graph_nnz=int(gnnz.max()),
                    n_nodes=_pin(torch.tensor([g.num_nodes for g in graphs], dtype=torch.int32)),
                    n_edges=_pin(torch.tensor([[g.num_edges[l] for g in graphs] for l in range(L)], dtype=torch.int32)))
         if cost == "degree":
@@ -186,6 +189,7 @@ class GraphBatch:
                              (host["node_w"] + [host["node_cost"]] if self.cost == "degree" else []))
         st = _lib.MdGraphs()
         st.n_graphs, st.n_layers, st.stride, st.n_total = B, L, S, B * S
+        st.max_graph_nnz = min(int(host["max_graph_nnz"]), 2 ** 31 - 1)
         for l in range(L):
             st.rowptr[l] = self.rowptr[l].data_ptr()
             st.col[l] = self.col[l].data_ptr()

@@ -86,12 +86,14 @@ class BatchRollout:
         self.parent = i32(nt) if self.large else None
         self.comp_size = i32(nt) if self.large else None
         self.flags = i32(8)
+        self.cur_action = i32(B)
         s = _lib.MdState()
         s.label = self.label.data_ptr()
         for l in range(L):
             s.deg[l] = self.deg[l].data_ptr()
         for name in ("act_list", "n_act", "n_removed", "cov_edges", "alive_edges", "max_deg", "twohop", "rank", "done",
-                     "n_steps", "score", "aux", "best", "trace_action", "trace_rank", "trace_maxcc", "n_done", "flags"):
+                     "n_steps", "score", "aux", "best", "trace_action", "trace_rank", "trace_maxcc", "n_done", "flags",
+                     "cur_action"):
             setattr(s, name, getattr(self, name).data_ptr())
         s.parent = self.parent.data_ptr() if self.large else None
         s.comp_size = self.comp_size.data_ptr() if self.large else None

@@ -37,12 +37,22 @@ def _forced(zs, key, device):
     return torch.from_numpy(a).to(device), T
 
 
+@pytest.fixture(params=["small", "large"])
+def env_path(request):
+    """small = one CTA per graph (shared memory), large = cooperative multi-CTA kernel (global memory)."""
+    from mdcommunity_b200 import _lib
+    _lib.lib().md_debug_force_large_env(1 if request.param == "large" else 0)
+    yield request.param
+    _lib.lib().md_debug_force_large_env(0)
+
+
 @pytest.mark.parametrize("variant", ["unit", "degree"])
-def test_env_random_actions_bit_exact(variant):
+def test_env_random_actions_bit_exact(variant, env_path):
     """Ragged batch of every golden graph, reference random-action traces: LMCC / AUDC / counters bit-exact."""
     mdb = _mdb()
     zs, graphs, batch, w = _load_batch(variant)
     ro = mdb.BatchRollout(batch, w)
+    assert ro.large == (env_path == "large")
     for z, g in zip(zs, graphs):
         assert g.max_rank == int(z["max_rank"])
     acts, T = _forced(zs, "random_actions", batch.device)
@@ -112,7 +122,7 @@ def test_q_teacher_forced(variant):
 
 
 @pytest.mark.parametrize("variant", ["unit", "degree"])
-def test_free_running_rollout(variant):
+def test_free_running_rollout(variant, env_path):
     """GetSol end to end on the device.  The removal sequence must equal the reference's up to the first step
     whose top-two Q gap is below tolerance; AUDC must match the oracle replay of OUR sequence bit-exactly."""
     from oracle import md_oracle as orc
