@@ -64,6 +64,8 @@ typedef struct md_state {
   int32_t* deg[MD_MAX_LAYERS]; /* [n_total] alive degree per layer */
   int32_t* act_list;     /* [n_total] graph g's active nodes, ascending, at [g*S, g*S + n_act[g]) */
   int32_t* n_act;        /* [B] */
+  int32_t* aptr[MD_MAX_LAYERS]; /* [n_total + 1] CSR of the ALIVE edges in compact order: row g*S + p is active node p of graph g */
+  int32_t* acol[MD_MAX_LAYERS]; /* [nnz_l] alive neighbours (global ids); graph g uses its static CSR region */
   int32_t* n_removed;    /* [B] |covered_set| */
   int32_t* cov_edges;    /* [L][B] numCoveredEdges */
   int32_t* alive_edges;  /* [L][B] */
@@ -132,6 +134,7 @@ int md_env_step(const md_graphs_t* g, const md_state_t* s, const int32_t* action
 
 /* largest graph stride the single-CTA (shared-memory) env kernel handles; larger strides use the multi-CTA path */
 int32_t md_env_small_max_stride(void);
+int32_t md_env_uses_small_path(const md_graphs_t* g);
 /* test hook: route every batch through the multi-CTA (global-memory, cooperative) env kernel */
 void md_debug_force_large_env(int32_t on);
 

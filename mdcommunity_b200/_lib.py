@@ -33,7 +33,7 @@ class MdGraphs(C.Structure):
 
 class MdState(C.Structure):
     _fields_ = [
-        ("label", _vp), ("deg", _vp * MAX_LAYERS), ("act_list", _vp), ("n_act", _vp), ("n_removed", _vp),
+        ("label", _vp), ("deg", _vp * MAX_LAYERS), ("act_list", _vp), ("n_act", _vp), ("aptr", _vp * MAX_LAYERS), ("acol", _vp * MAX_LAYERS), ("n_removed", _vp),
         ("cov_edges", _vp), ("alive_edges", _vp), ("max_deg", _vp), ("twohop", _vp), ("rank", _vp),
         ("done", _vp), ("n_steps", _vp), ("score", _vp), ("aux", _vp), ("best", _vp),
         ("trace_action", _vp), ("trace_rank", _vp), ("trace_maxcc", _vp), ("n_done", _vp),
@@ -59,6 +59,7 @@ _SIGS = {
     "md_env_step": ([C.POINTER(MdGraphs), C.POINTER(MdState), _vp, C.c_int32, C.c_int32, _vp], C.c_int),
     "md_env_small_max_stride": ([], C.c_int32),
     "md_debug_force_large_env": ([C.c_int32], None),
+    "md_env_uses_small_path": ([C.POINTER(MdGraphs)], C.c_int32),
     "md_embed_init": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_embed_iter": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),
     "md_graph_embed": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),

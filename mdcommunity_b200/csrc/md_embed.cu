@@ -57,18 +57,15 @@ __global__ void __launch_bounds__(256) embed_init_kernel(md_graphs_t G, md_state
 constexpr int IT_PROD = 256;
 constexpr int IT_CONS = 256;
 constexpr int IT_T = IT_PROD + IT_CONS;
-constexpr int EMAX = 2048;  // staged alive-neighbour slots per tile
+constexpr int EMAX = 3072;  // staged alive-neighbour slots per tile
 constexpr int GCH = 16;     // neighbour rows in flight per producer warp
 struct IterSmem {
   float A[2][TILE_M * A_LD];  // [buf][row][0:64] = neighbour sum P, [row][64:128] = own embedding H
   float Wm[2 * D * D];        // merged weight [128][64]: rows 0..63 = w13, 64..127 = w23
   float red[4 * D];           // partial column sums
-  int eu[EMAX];               // staged neighbour ids (-1 = dead edge)
+  int eu[EMAX];               // staged alive-neighbour ids of the tile
   int v[2][TILE_M];           // global node id of the row, -1 = padding row
-  int lv[TILE_M];             // its label
-  int beg[TILE_M];            // first CSR entry
-  int off[TILE_M + 1];        // exclusive scan of the row degrees inside the tile
-  unsigned char er[EMAX];     // tile row of the staged entry
+  int off[TILE_M + 1];        // first staged entry of each tile row (from the alive CSR row pointers)
 };
 
 enum { BAR_FULL0 = 1, BAR_EMPTY0 = 3, BAR_PROD = 5 };
@@ -131,7 +128,6 @@ __global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_s
   extern __shared__ __align__(16) unsigned char smem_raw[];
   IterSmem& sm = *reinterpret_cast<IterSmem*>(smem_raw);
   const int tid = threadIdx.x;
-  const int32_t* __restrict__ label = S.label;
   TileIter ti;
   ti.tpg = G.stride / TILE_M;
   ti.tiles_per_layer = G.n_graphs * ti.tpg;
@@ -140,66 +136,35 @@ __global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_s
 
   if (tid < IT_PROD) {
     // ===================================== PRODUCER =====================================
+    // Streams the alive CSR the env kernel emitted in compact order: the rows of a tile are consecutive, so the
+    // tile's neighbour list is one contiguous, coalesced copy and row boundaries come from the row pointers.
     const int lane = tid & 31, warp = tid >> 5;
     int it = 0;
     for (; ti.next(S); ti.tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const int l = ti.l, g = ti.g, t = ti.t;
       const int rows = min(TILE_M, ti.nact - t * TILE_M);
-      const int32_t* __restrict__ rp = G.rowptr[l];
-      const int32_t* __restrict__ cl = G.col[l];
+      const int32_t* __restrict__ aptr = S.aptr[l] + g * G.stride + t * TILE_M;
+      const int32_t* __restrict__ acol = S.acol[l];
       const float* __restrict__ Hin = K.h[iter & 1][l];
       float* A = sm.A[buf];
       if (it >= 2) bar_sync(BAR_EMPTY0 + buf, IT_T);  // consumers are done with this buffer
 
-      // ---- stage A: row descriptors -------------------------------------------------------------------
-      if (tid < TILE_M) {
-        int v = -1, lv = -1, b = 0, d = 0;
-        if (tid < rows) {
-          v = S.act_list[g * G.stride + t * TILE_M + tid];
-          lv = label[v];
-          b = rp[v];
-          d = rp[v + 1] - b;
-        }
-        sm.v[buf][tid] = v;
-        sm.lv[tid] = lv;
-        sm.beg[tid] = b;
-        sm.off[tid] = d;
-      }
-      bar_sync(BAR_PROD, IT_PROD);
-      if (warp == 0) {  // exclusive scan of the 128 row degrees (4 per lane)
-        int d0 = sm.off[4 * lane], d1 = sm.off[4 * lane + 1], d2 = sm.off[4 * lane + 2], d3 = sm.off[4 * lane + 3];
-        int s = d0 + d1 + d2 + d3, incl = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int n = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += n;
-        }
-        int ex = incl - s;
-        sm.off[4 * lane] = ex;
-        sm.off[4 * lane + 1] = ex + d0;
-        sm.off[4 * lane + 2] = ex + d0 + d1;
-        sm.off[4 * lane + 3] = ex + d0 + d1 + d2;
-        if (lane == 31) sm.off[TILE_M] = incl;
+      // ---- stage A: row descriptors (one coalesced load each) ---------------------------------------------
+      const int b0 = aptr[0];
+      if (tid <= TILE_M) {
+        const int r = min(tid, rows);
+        sm.off[tid] = aptr[r] - b0;
+        if (tid < TILE_M) sm.v[buf][tid] = tid < rows ? S.act_list[g * G.stride + t * TILE_M + tid] : -1;
       }
       bar_sync(BAR_PROD, IT_PROD);
       const int etot = sm.off[TILE_M];
       const bool staged = etot <= EMAX;
-
-      // ---- stage B: alive-neighbour list of the tile (edge-parallel) --------------------------------------
+      // ---- stage B: the tile's alive-neighbour ids, contiguous in acol -----------------------------------
       if (staged) {
-        for (int e = tid; e < etot; e += IT_PROD) {
-          int lo = 0, hi = TILE_M - 1;  // largest row with off[row] <= e
-          while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (sm.off[mid] <= e) lo = mid; else hi = mid - 1;
-          }
-          const int u = cl[sm.beg[lo] + (e - sm.off[lo])];
-          sm.eu[e] = (label[u] == sm.lv[lo]) ? u : -1;
-          sm.er[e] = (unsigned char)lo;
-        }
+        for (int e = tid; e < etot; e += IT_PROD) sm.eu[e] = acol[b0 + e];
+        bar_sync(BAR_PROD, IT_PROD);
       }
-      bar_sync(BAR_PROD, IT_PROD);
 
       // ---- stage C: gather.  warp w owns tile rows [16w, 16w+16); lane holds columns 2*lane, 2*lane+1 ------
       {
@@ -215,69 +180,44 @@ __global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_s
 #pragma unroll
           for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(A + (r0 + i) * A_LD + D + 2 * lane) = h[i];
         }
-        if (staged) {
-          const int e0 = sm.off[r0], e1 = sm.off[r0 + 16];
-          int cur = r0;
-          float2 acc = make_float2(0.f, 0.f);
-          for (int e = e0; e < e1; e += GCH) {
-            float2 val[GCH];
-            int rr[GCH];
+        const int e0 = sm.off[r0], e1 = sm.off[r0 + 16];
+        int cur = r0, nb = sm.off[r0 + 1];
+        float2 acc = make_float2(0.f, 0.f);
+        for (int e = e0; e < e1; e += GCH) {
+          float2 val[GCH];
+          if (staged) {
 #pragma unroll
             for (int j = 0; j < GCH; ++j) {
               val[j] = make_float2(0.f, 0.f);
-              rr[j] = -1;
-              if (e + j < e1) {
-                const int u = sm.eu[e + j];
-                if (u >= 0) {
-                  rr[j] = sm.er[e + j];
-                  val[j] = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)u * D) + lane);
-                }
-              }
+              if (e + j < e1) val[j] = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)sm.eu[e + j] * D) + lane);
             }
+          } else {  // hub tile: neighbour ids straight from global memory
+            int u = 0;
+            if (lane < GCH && e + lane < e1) u = acol[b0 + e + lane];
 #pragma unroll
             for (int j = 0; j < GCH; ++j) {
-              if (rr[j] >= 0) {
-                if (rr[j] != cur) {  // warp-uniform: finish the rows up to rr[j]
-                  *reinterpret_cast<float2*>(A + cur * A_LD + 2 * lane) = acc;
-                  for (int z = cur + 1; z < rr[j]; ++z)
-                    *reinterpret_cast<float2*>(A + z * A_LD + 2 * lane) = make_float2(0.f, 0.f);
-                  cur = rr[j];
-                  acc = make_float2(0.f, 0.f);
-                }
-                acc.x += val[j].x;
-                acc.y += val[j].y;
-              }
+              const int uu = __shfl_sync(0xffffffffu, u, j);
+              val[j] = make_float2(0.f, 0.f);
+              if (e + j < e1) val[j] = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)uu * D) + lane);
             }
           }
+#pragma unroll
+          for (int j = 0; j < GCH; ++j) {
+            if (e + j < e1) {
+              while (e + j >= nb) {  // warp-uniform: row `cur` is complete (rows without alive edges get zeros)
+                *reinterpret_cast<float2*>(A + cur * A_LD + 2 * lane) = acc;
+                acc = make_float2(0.f, 0.f);
+                ++cur;
+                nb = sm.off[cur + 1];
+              }
+              acc.x += val[j].x;
+              acc.y += val[j].y;
+            }
+          }
+        }
+        for (; cur < r0 + 16; ++cur) {
           *reinterpret_cast<float2*>(A + cur * A_LD + 2 * lane) = acc;
-          for (int z = cur + 1; z < r0 + 16; ++z)
-            *reinterpret_cast<float2*>(A + z * A_LD + 2 * lane) = make_float2(0.f, 0.f);
-        } else {
-          // hub tile: read the CSR directly, 32 edges at a time
-          for (int i = 0; i < 16; ++i) {
-            const int r = r0 + i;
-            float2 acc = make_float2(0.f, 0.f);
-            if (sm.v[buf][r] >= 0) {
-              const int b = sm.beg[r], d = sm.off[r + 1] - sm.off[r], lv = sm.lv[r];
-              for (int c0 = 0; c0 < d; c0 += 32) {
-                int u = -1;
-                if (c0 + lane < d) {
-                  u = cl[b + c0 + lane];
-                  if (label[u] != lv) u = -1;
-                }
-                unsigned m = __ballot_sync(0xffffffffu, u >= 0);
-                while (m) {
-                  const int j = __ffs(m) - 1;
-                  m &= m - 1;
-                  const int uu = __shfl_sync(0xffffffffu, u, j);
-                  const float2 hv = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)uu * D) + lane);
-                  acc.x += hv.x;
-                  acc.y += hv.y;
-                }
-              }
-            }
-            *reinterpret_cast<float2*>(A + r * A_LD + 2 * lane) = acc;
-          }
+          acc = make_float2(0.f, 0.f);
         }
       }
       __threadfence_block();
@@ -296,7 +236,6 @@ __global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_s
         const float s = ((sm.red[tid] + sm.red[D + tid]) + sm.red[2 * D + tid]) + sm.red[3 * D + tid];
         K.psum[(((size_t)iter * G.n_layers + l) * ti.tiles_per_layer + ti.gt) * D + tid] = s;
       }
-      // (the next iteration's first write to sm.red / staging happens after further BAR_PROD syncs)
     }
     // drain: match the consumers' last empty-arrivals so no barrier is left half-arrived
     for (int j = max(0, it - 2); j < it; ++j) bar_sync(BAR_EMPTY0 + (j & 1), IT_T);

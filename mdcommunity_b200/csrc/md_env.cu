@@ -14,7 +14,8 @@ namespace md {
 
 constexpr int ENV_T = 512;
 constexpr int ENV_W = ENV_T / 32;
-constexpr int ENV_SMALL_MAX = 16384;  // 3 int arrays of S entries in shared memory (192 KB)
+constexpr int ENV_SMALL_MAX = 16384;           // largest stride the single-CTA kernel accepts
+constexpr size_t ENV_SMALL_SMEM = 200 * 1024;  // labels + union-find + staged CSR must fit in this much shared memory
 
 __device__ __forceinline__ int uf_find(volatile int* par, int x) {
   int p = par[x];
@@ -75,27 +76,28 @@ __device__ __forceinline__ long long block_sum_ll(long long v, BlockRed& r) {
 }
 
 // One CTA per graph.  init != 0: MvcEnv.s0; otherwise one stepWithoutReward.
-// CACHED: the graph's CSR (all layers) is copied into shared memory once, with node ids and row offsets made
-// graph-local, so the ~10 edge sweeps of a step (prune rounds + degree recount) never leave the SM.
-template <bool CACHED>
+// The graph's CSR (all layers) is copied into shared memory once, with graph-local node ids, together with the
+// source row of every entry, so that (a) the ~10 edge sweeps of a step never leave the SM and (b) the union-find
+// hooking runs edge-parallel (one thread per CSR entry) and hubs cannot serialise a warp.
+// Besides the labels / degrees / counters the kernel emits, per layer, the CSR of the *alive* edges of the active
+// nodes in compact (act_list) order: aptr[l][g*S + p] .. aptr[l][g*S + p + 1] indexes acol[l].  The three
+// message-passing iterations of the next forward stream it without re-checking labels.
 __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_t S, const int32_t* forced,
                                                        int forced_stride, int forced_index, int init, int max_nnz) {
   extern __shared__ int smem[];
   const int g = blockIdx.x;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
   const int St = G.stride;
   const int base = g * St;
   const int N = G.n_nodes[g];
   const int L = G.n_layers;
-  int* lab = smem;
-  int* par = smem + St;
-  int* tmp = smem + 2 * St;
-  // cached CSR: rows [L][St + 1] then columns [max_nnz]
-  int* c_rp = smem + 3 * St;
-  int* c_cl = c_rp + L * (St + 1);
-  const int32_t* rp_l[MD_MAX_LAYERS];
-  const int32_t* cl_l[MD_MAX_LAYERS];
-  int voff = 0;  // id offset to subtract from a neighbour id, row-pointer base
+  int* lab = smem;                  // [St] graph-local label, -1 = removed / padding
+  int* par = smem + St;             // [St] union-find parent; later the alive degree of the current layer
+  int* tmp = smem + 2 * St;         // [St] scratch; later the compact list of active nodes
+  int* c_rp = smem + 3 * St;        // [L][St + 1] row offsets into c_cl / c_src
+  int* c_cl = c_rp + L * (St + 1);  // [max_nnz] neighbour (graph-local id)
+  int* c_src = c_cl + max_nnz;      // [max_nnz] row of the entry
   __shared__ BlockRed red;
   __shared__ int s_action;
   __shared__ int s_scan[ENV_W];
@@ -123,7 +125,9 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   const int a = s_action;
   if (!init && (a < 0 || lab[a] < 0)) return;  // nothing to remove (uniform exit)
 
-  if (CACHED) {
+  // ---- stage the graph's CSR in shared memory ---------------------------------------------------------
+  int lay_pos[MD_MAX_LAYERS + 1];
+  {
     int pos = 0;
     for (int ll = 0; ll < L; ++ll) {
       const int32_t* __restrict__ rp = G.rowptr[ll] + base;
@@ -131,41 +135,35 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       const int e0 = rp[0], cnt = rp[St] - e0;
       for (int v = tid; v <= St; v += ENV_T) c_rp[ll * (St + 1) + v] = rp[v] - e0 + pos;
       for (int e = tid; e < cnt; e += ENV_T) c_cl[pos + e] = cl[e0 + e] - base;
-      rp_l[ll] = c_rp + ll * (St + 1);
-      cl_l[ll] = c_cl;
+      lay_pos[ll] = pos;
       pos += cnt;
     }
+    lay_pos[L] = pos;
     __syncthreads();
-  } else {
     for (int ll = 0; ll < L; ++ll) {
-      rp_l[ll] = G.rowptr[ll] + base;
-      cl_l[ll] = G.col[ll];
+      const int* rp = c_rp + ll * (St + 1);
+      for (int v = tid; v < N; v += ENV_T)
+        for (int e = rp[v]; e < rp[v + 1]; ++e) c_src[e] = v;
     }
-    voff = base;
   }
 
   if (!init) {
     // numCoveredEdges[l] += #neighbours still alive and not cut from a  (mvc_env.py:81-84) == deg_alive_l(a)
     if (tid < L) S.cov_edges[tid * G.n_graphs + g] += S.deg[tid][base + a];
-    __syncthreads();
     if (tid == 0) lab[a] = -1;
-    __syncthreads();
   }
+  __syncthreads();
 
   // ---- Mcc.MCC: refine the partition layer by layer until every layer is stable ----------------------
   int stable = 0, l = 0;
   while (stable < L) {
-    const int32_t* rp = rp_l[l];
-    const int32_t* cl = cl_l[l];
     for (int v = tid; v < N; v += ENV_T) par[v] = v;
     __syncthreads();
-    for (int v = tid; v < N; v += ENV_T) {
-      const int lv = lab[v];
-      if (lv < 0) continue;
-      const int e1 = rp[v + 1];
-      for (int e = rp[v]; e < e1; ++e) {
-        const int u = cl[e] - voff;
-        if (u < v && lab[u] == lv) uf_unite(par, u, v);
+    for (int e = lay_pos[l] + tid; e < lay_pos[l + 1]; e += ENV_T) {  // edge-parallel hooking
+      const int v = c_src[e], u = c_cl[e];
+      if (u < v) {
+        const int lv = lab[v];
+        if (lv >= 0 && lab[u] == lv) uf_unite(par, u, v);
       }
     }
     __syncthreads();
@@ -195,11 +193,11 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   for (int v = tid; v < N; v += ENV_T) mx = max(mx, tmp[v]);
   const int rank = block_max_i(mx, red);
 
-  // ---- alive degree per layer + status counters (get_status_info) ----------------------------------------
+  // ---- per layer: alive degree, status counters (get_status_info), alive CSR ------------------------------
   bool terminal = false;
+  int n_act = 0;
   for (int ll = 0; ll < L; ++ll) {
-    const int32_t* rp = rp_l[ll];
-    const int32_t* cl = cl_l[ll];
+    const int* rp = c_rp + ll * (St + 1);
     int dsum = 0, dmax = 0;
     long long th = 0;
     for (int v = tid; v < St; v += ENV_T) {
@@ -207,10 +205,10 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       if (v < N && lab[v] >= 0) {
         const int lv = lab[v];
         const int e1 = rp[v + 1];
-        for (int e = rp[v]; e < e1; ++e) d += (lab[cl[e] - voff] == lv);
+        for (int e = rp[v]; e < e1; ++e) d += (lab[c_cl[e]] == lv);
       }
       S.deg[ll][base + v] = d;
-      if (ll == 0 && v < N) par[v] = d;  // keep layer-0 degree for the compaction below
+      par[v] = d;
       dsum += d;
       dmax = max(dmax, d);
       th += (long long)d * (d - 1) / 2;
@@ -224,38 +222,85 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       S.twohop[ll * G.n_graphs + g] = t2;
     }
     terminal |= (tot == 0);
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- write labels back, compact the active nodes (ascending id, PrepareBatchGraph.py:128-138) -----------
-  int running = 0;
-  for (int v0 = 0; v0 < St; v0 += ENV_T) {
-    const int v = v0 + tid;
-    int flag = 0;
-    if (v < St) {
-      S.label[base + v] = (v < N && lab[v] >= 0) ? lab[v] + base : -1;
-      flag = (v < N && par[v] > 0) ? 1 : 0;
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, flag);
-    const int lane = tid & 31, wid = tid >> 5;
-    if (lane == 0) s_scan[wid] = __popc(bal);
-    __syncthreads();
-    int woff = 0, total = 0;
+    if (ll == 0) {
+      // write labels back, compact the active nodes (ascending id, PrepareBatchGraph.py:128-138) into tmp[]
+      int running = 0;
+      for (int v0 = 0; v0 < St; v0 += ENV_T) {
+        const int v = v0 + tid;
+        int flag = 0;
+        if (v < St) {
+          S.label[base + v] = (v < N && lab[v] >= 0) ? lab[v] + base : -1;
+          flag = (v < N && par[v] > 0) ? 1 : 0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) s_scan[wid] = __popc(bal);
+        __syncthreads();
+        int woff = 0, total = 0;
 #pragma unroll
-    for (int k = 0; k < ENV_W; ++k) {
-      const int c = s_scan[k];
-      if (k < wid) woff += c;
-      total += c;
+        for (int k = 0; k < ENV_W; ++k) {
+          const int c = s_scan[k];
+          if (k < wid) woff += c;
+          total += c;
+        }
+        if (flag) {
+          const int p = running + woff + __popc(bal & ((1u << lane) - 1u));
+          S.act_list[base + p] = base + v;
+          tmp[p] = v;
+        }
+        running += total;
+        __syncthreads();
+      }
+      n_act = running;
     }
-    if (flag) S.act_list[base + running + woff + __popc(bal & ((1u << lane) - 1u))] = base + v;
-    running += total;
-    __syncthreads();
+
+    // alive CSR of layer ll in compact order: exclusive scan of the alive degrees, then ordered fill
+    {
+      const int e0 = G.rowptr[ll][base];  // the graph's region of acol[ll] is its static CSR region
+      int32_t* __restrict__ aptr = S.aptr[ll] + base;
+      int32_t* __restrict__ acol = S.acol[ll];
+      int running = 0;
+      for (int p0 = 0; p0 < n_act; p0 += ENV_T) {
+        const int p = p0 + tid;
+        const int v = p < n_act ? tmp[p] : -1;
+        const int d = v >= 0 ? par[v] : 0;
+        int incl = d;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int n = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += n;
+        }
+        if (lane == 31) s_scan[wid] = incl;
+        __syncthreads();
+        int woff = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < ENV_W; ++k) {
+          const int c = s_scan[k];
+          if (k < wid) woff += c;
+          total += c;
+        }
+        if (v >= 0) {
+          int o = e0 + running + woff + incl - d;
+          aptr[p] = o;
+          const int lv = lab[v];
+          const int e1 = rp[v + 1];
+          for (int e = rp[v]; e < e1; ++e) {
+            const int u = c_cl[e];
+            if (lab[u] == lv) acol[o++] = u + base;
+          }
+        }
+        running += total;
+        __syncthreads();
+      }
+      if (tid == 0) aptr[n_act] = e0 + running;
+    }
   }
 
   // ---- bookkeeping: reward / AUDC in f64 with the reference's operation order ---------------------------
   if (tid == 0) {
     const int B = G.n_graphs;
-    S.n_act[g] = running;
+    S.n_act[g] = n_act;
     S.rank[g] = rank;
     int nrem = init ? 0 : S.n_removed[g] + 1;
     S.n_removed[g] = nrem;
@@ -294,9 +339,8 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       ax[2] = (float)__ddiv_rn((double)S.twohop[ll * B + g], (double)((long long)N * (long long)N));
       ax[3] = 1.0f;
     }
-    const int was_done = init ? 0 : S.done[g];
     S.done[g] = terminal ? 1 : 0;
-    if (terminal && !was_done) atomicAdd(S.n_done, 1);
+    if (terminal) atomicAdd(S.n_done, 1);
   }
 }
 
@@ -307,6 +351,11 @@ int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* 
 
 static int g_force_large = 0;
 extern "C" int32_t md_env_small_max_stride(void) { return g_force_large ? 0 : md::ENV_SMALL_MAX; }
+// 1 if this batch takes the single-CTA (shared-memory) env kernel, 0 for the cooperative global-memory kernel
+extern "C" int32_t md_env_uses_small_path(const md_graphs_t* g) {
+  const size_t smem = ((size_t)3 * g->stride + (size_t)g->n_layers * (g->stride + 1) + 2 * (size_t)g->max_graph_nnz) * sizeof(int);
+  return !(g_force_large || g->stride > md::ENV_SMALL_MAX || g->max_graph_nnz <= 0 || smem > md::ENV_SMALL_SMEM);
+}
 extern "C" void md_debug_force_large_env(int32_t on) { g_force_large = on; }
 
 static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
@@ -314,27 +363,21 @@ static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* 
   if (!g || !s) return MD_EINVAL;
   if (g->n_layers < 1 || g->n_layers > MD_MAX_LAYERS) return MD_ELAYERS;
   if (g->stride % MD_TILE_M != 0 || g->n_total != g->n_graphs * g->stride) return MD_EINVAL;
-  if (g_force_large || g->stride > md::ENV_SMALL_MAX) return md_env_step_large(g, s, forced, forced_stride, forced_index, init, stream);
-  const size_t base_smem = (size_t)3 * g->stride * sizeof(int);
-  const size_t cached_smem = base_smem + ((size_t)g->n_layers * (g->stride + 1) + (size_t)g->max_graph_nnz) * sizeof(int);
-  const bool cached = g->max_graph_nnz > 0 && cached_smem <= 200 * 1024;
-  const size_t smem = cached ? cached_smem : base_smem;
-  static size_t configured[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > configured[cached]) {
-    cudaError_t e = cached ? cudaFuncSetAttribute(md::env_step_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(md::env_step_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = ((size_t)3 * g->stride + (size_t)g->n_layers * (g->stride + 1) + 2 * (size_t)g->max_graph_nnz) * sizeof(int);
+  if (g_force_large || g->stride > md::ENV_SMALL_MAX || g->max_graph_nnz <= 0 || smem > md::ENV_SMALL_SMEM)
+    return md_env_step_large(g, s, forced, forced_stride, forced_index, init, stream);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(md::env_step_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured[cached] = smem;
+    configured = smem;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (init) {
     cudaError_t e = cudaMemsetAsync(s->n_done, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return (int)e;
   }
-  if (cached)
-    md::env_step_small<true><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz);
-  else
-    md::env_step_small<false><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, 0);
+  md::env_step_small<<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz);
   MD_CHECK_LAUNCH();
   return 0;
 }

@@ -190,22 +190,29 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
     }
   }
 
-  // ---- compaction of the active nodes: per-chunk counts, then ordered write ----------------------------------
+  // ---- compaction of the active nodes + alive CSR: per-chunk counts / degree sums, then ordered write ---------
   // chunk c covers nodes [g*St + k*chunk, g*St + min((k+1)*chunk, St)) with g = c / cpg, k = c % cpg
-  int* ccount = par;  // parents are dead now; B * cpg entries
+  int* ccount = par;  // parents are dead now; (1 + L) * B * cpg entries: [0] active count, [1 + l] alive-degree sum
   const int nchunks = B * cpg;
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const int g = c / cpg, k = c - g * cpg;
     const int v0 = g * St + k * chunk, v1 = g * St + min((k + 1) * chunk, St);
-    int cnt = 0;
-    for (int v = v0 + tid; v < v1; v += LG_T) cnt += (S.deg[0][v] > 0);
-    cnt = warp_sum_i(cnt);
-    if ((tid & 31) == 0) s_red[tid >> 5] = cnt;
-    __syncthreads();
-    if (tid == 0) {
-      int t = 0;
-      for (int w = 0; w < LG_T / 32; ++w) t += s_red[w];
-      ccount[c] = t;
+    for (int q = 0; q <= L; ++q) {
+      int cnt = 0;
+      if (q == 0) {
+        for (int v = v0 + tid; v < v1; v += LG_T) cnt += (S.deg[0][v] > 0);
+      } else {
+        for (int v = v0 + tid; v < v1; v += LG_T) cnt += S.deg[q - 1][v];
+      }
+      cnt = warp_sum_i(cnt);
+      __syncthreads();
+      if ((tid & 31) == 0) s_red[tid >> 5] = cnt;
+      __syncthreads();
+      if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < LG_T / 32; ++w) t += s_red[w];
+        ccount[q * nchunks + c] = t;
+      }
     }
     __syncthreads();
   }
@@ -213,40 +220,94 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const int g = c / cpg, k = c - g * cpg;
     if (!init && S.cur_action[g] < 0) continue;  // uniform per block
-    int part = 0;
-    for (int j = tid; j < k; j += LG_T) part += ld_volatile(ccount + g * cpg + j);
-    part = warp_sum_i(part);
-    __syncthreads();
-    if ((tid & 31) == 0) s_red[tid >> 5] = part;
-    __syncthreads();
-    if (tid == 0) {
-      int t = 0;
-      for (int w = 0; w < LG_T / 32; ++w) t += s_red[w];
-      s_off = t;
-      if (k == cpg - 1) S.n_act[g] = t + ld_volatile(ccount + c);
-    }
-    __syncthreads();
-    int running = s_off;
     const int v0 = g * St + k * chunk, v1 = g * St + min((k + 1) * chunk, St);
-    for (int vb = v0; vb < v1; vb += LG_T) {
-      const int v = vb + tid;
-      const int flag = (v < v1 && S.deg[0][v] > 0) ? 1 : 0;
-      const unsigned bal = __ballot_sync(0xffffffffu, flag);
-      const int lane = tid & 31, wid = tid >> 5;
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int q = 0; q <= L; ++q) {
+      // offset of this chunk inside its graph for quantity q
+      int part = 0;
+      for (int j = tid; j < k; j += LG_T) part += ld_volatile(ccount + q * nchunks + g * cpg + j);
+      part = warp_sum_i(part);
       __syncthreads();
-      if (lane == 0) s_red[wid] = __popc(bal);
+      if (lane == 0) s_red[wid] = part;
       __syncthreads();
-      int woff = 0, total = 0;
-#pragma unroll
-      for (int w = 0; w < LG_T / 32; ++w) {
-        const int cc = s_red[w];
-        if (w < wid) woff += cc;
-        total += cc;
+      if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < LG_T / 32; ++w) t += s_red[w];
+        s_off = t;
       }
-      if (flag) S.act_list[g * St + running + woff + __popc(bal & ((1u << lane) - 1u))] = v;
-      running += total;
+      __syncthreads();
+      int running = s_off;
+      __syncthreads();
+      if (q == 0) {
+        if (tid == 0 && k == cpg - 1) S.n_act[g] = running + ld_volatile(ccount + c);
+        for (int vb = v0; vb < v1; vb += LG_T) {
+          const int v = vb + tid;
+          const int flag = (v < v1 && S.deg[0][v] > 0) ? 1 : 0;
+          const unsigned bal = __ballot_sync(0xffffffffu, flag);
+          __syncthreads();
+          if (lane == 0) s_red[wid] = __popc(bal);
+          __syncthreads();
+          int woff = 0, total = 0;
+#pragma unroll
+          for (int w = 0; w < LG_T / 32; ++w) {
+            const int cc = s_red[w];
+            if (w < wid) woff += cc;
+            total += cc;
+          }
+          const int p = running + woff + __popc(bal & ((1u << lane) - 1u));
+          if (flag) {
+            S.act_list[g * St + p] = v;
+            csz[v] = p;  // component sizes are consumed; remember the compact position for the alive CSR
+          }
+          running += total;
+        }
+      } else {
+        const int ll = q - 1;
+        const int32_t* __restrict__ rp = G.rowptr[ll];
+        const int32_t* __restrict__ cl = G.col[ll];
+        const int e0 = rp[g * St];
+        int32_t* __restrict__ aptr = S.aptr[ll] + g * St;
+        int32_t* __restrict__ acol = S.acol[ll];
+        if (tid == 0 && k == cpg - 1) {
+          // n_act of this graph = offset of the last chunk + its count (recomputed: q == 0 pass already stored it)
+          int nact = 0;
+          for (int j = 0; j < cpg; ++j) nact += ld_volatile(ccount + g * cpg + j);
+          aptr[nact] = e0 + running + ld_volatile(ccount + q * nchunks + c);
+        }
+        for (int vb = v0; vb < v1; vb += LG_T) {
+          const int v = vb + tid;
+          const int d = v < v1 ? S.deg[ll][v] : 0;
+          int incl = d;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+          }
+          __syncthreads();
+          if (lane == 31) s_red[wid] = incl;
+          __syncthreads();
+          int woff = 0, total = 0;
+#pragma unroll
+          for (int w = 0; w < LG_T / 32; ++w) {
+            const int cc = s_red[w];
+            if (w < wid) woff += cc;
+            total += cc;
+          }
+          if (d > 0) {
+            int o = e0 + running + woff + incl - d;
+            aptr[csz[v]] = o;
+            const int lv = label[v];
+            const int e1 = rp[v + 1];
+            for (int e = rp[v]; e < e1; ++e) {
+              const int u = cl[e];
+              if (label[u] == lv) acol[o++] = u;
+            }
+          }
+          running += total;
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   grid_barrier(bar, epoch);
 

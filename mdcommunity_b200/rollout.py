@@ -72,6 +72,8 @@ class BatchRollout:
         self.label = i32(nt)
         self.deg = [i32(nt) for _ in range(L)]
         self.act_list = i32(nt)
+        self.aptr = [i32(nt + 1) for _ in range(L)]
+        self.acol = [i32(max(1, batch.nnz[l])) for l in range(L)]
         self.n_act, self.n_removed, self.rank, self.done, self.n_steps = i32(B), i32(B), i32(B), i32(B), i32(B)
         self.cov_edges, self.alive_edges, self.max_deg = i32(L, B), i32(L, B), i32(L, B)
         self.twohop = torch.zeros(L, B, dtype=torch.int64, device=dev)
@@ -82,7 +84,7 @@ class BatchRollout:
         self.trace_rank = i32(B, self.max_steps)
         self.trace_maxcc = torch.zeros(B, self.max_steps, dtype=torch.float64, device=dev)
         self.n_done = i32(1)
-        self.large = S > self.lib.md_env_small_max_stride()
+        self.large = not self.lib.md_env_uses_small_path(batch.ptr())
         self.parent = i32(nt) if self.large else None
         self.comp_size = i32(nt) if self.large else None
         self.flags = i32(8)
@@ -91,6 +93,8 @@ class BatchRollout:
         s.label = self.label.data_ptr()
         for l in range(L):
             s.deg[l] = self.deg[l].data_ptr()
+            s.aptr[l] = self.aptr[l].data_ptr()
+            s.acol[l] = self.acol[l].data_ptr()
         for name in ("act_list", "n_act", "n_removed", "cov_edges", "alive_edges", "max_deg", "twohop", "rank", "done",
                      "n_steps", "score", "aux", "best", "trace_action", "trace_rank", "trace_maxcc", "n_done", "flags",
                      "cur_action"):
