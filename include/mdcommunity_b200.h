@@ -137,6 +137,8 @@ int32_t md_env_small_max_stride(void);
 int32_t md_env_uses_small_path(const md_graphs_t* g);
 /* test hook: route every batch through the multi-CTA (global-memory, cooperative) env kernel */
 void md_debug_force_large_env(int32_t on);
+/* profiling hook (results become wrong): bit 0 skips the neighbour gather, bit 1 the dense transform of md_embed_iter */
+void md_debug_set_flags(int32_t flags);
 
 /* ---- Q network ---------------------------------------------------------------------------------------- */
 

@@ -59,6 +59,7 @@ _SIGS = {
     "md_env_step": ([C.POINTER(MdGraphs), C.POINTER(MdState), _vp, C.c_int32, C.c_int32, _vp], C.c_int),
     "md_env_small_max_stride": ([], C.c_int32),
     "md_debug_force_large_env": ([C.c_int32], None),
+    "md_debug_set_flags": ([C.c_int32], None),
     "md_env_uses_small_path": ([C.POINTER(MdGraphs)], C.c_int32),
     "md_embed_init": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_embed_iter": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),

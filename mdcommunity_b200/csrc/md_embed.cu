@@ -54,18 +54,29 @@ __global__ void __launch_bounds__(256) embed_init_kernel(md_graphs_t G, md_state
 //   shared-memory A tile while 8 consumer warps run the dense transform + normalise epilogue on tile t.
 //   Hand-off through named barriers (full[2] / empty[2]); the merged 128x64 weight stays resident in smem.
 // =================================================================================================
-constexpr int IT_PROD = 256;
+constexpr int IT_PROD = 512;  // 16 gather warps
 constexpr int IT_CONS = 256;
 constexpr int IT_T = IT_PROD + IT_CONS;
-constexpr int EMAX = 3072;  // staged alive-neighbour slots per tile
-constexpr int GCH = 16;     // neighbour rows in flight per producer warp
+constexpr int EMAX = 2048;  // staged alive-neighbour slots per tile
+constexpr int SEG = 32;     // entries per gather segment
+constexpr int MAXX = EMAX / SEG;  // most extra segments a staged tile can have
+constexpr int GCH = 8;      // neighbour rows in flight per half-warp
 struct IterSmem {
   float A[2][TILE_M * A_LD];  // [buf][row][0:64] = neighbour sum P, [row][64:128] = own embedding H
   float Wm[2 * D * D];        // merged weight [128][64]: rows 0..63 = w13, 64..127 = w23
-  float red[4 * D];           // partial column sums
+  float red[8 * D];           // partial column sums
+  float extra[MAXX * D];      // partial sums of the 2nd.. segments of long (hub) rows
   int eu[EMAX];               // staged alive-neighbour ids of the tile
   int v[2][TILE_M];           // global node id of the row, -1 = padding row
   int off[TILE_M + 1];        // first staged entry of each tile row (from the alive CSR row pointers)
+  int seg_beg[TILE_M + MAXX]; // work list: first entry / length / destination of every segment
+  int seg_len[TILE_M + MAXX];
+  int xbase[TILE_M];          // first `extra` slot of the row
+  int mcount, nsegs;
+  short seg_dst[TILE_M + MAXX];
+  unsigned char seg_row[TILE_M + MAXX];
+  unsigned char nseg[TILE_M];
+  unsigned char mrow[TILE_M];  // rows with more than one segment
 };
 
 enum { BAR_FULL0 = 1, BAR_EMPTY0 = 3, BAR_PROD = 5 };
@@ -124,7 +135,7 @@ struct TileIter {  // the tile sequence both roles walk in lock step
 };
 
 __global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K,
-                                                            int iter) {
+                                                            int iter, int dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   IterSmem& sm = *reinterpret_cast<IterSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -157,67 +168,118 @@ __global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_s
         sm.off[tid] = aptr[r] - b0;
         if (tid < TILE_M) sm.v[buf][tid] = tid < rows ? S.act_list[g * G.stride + t * TILE_M + tid] : -1;
       }
+      if (tid == 0) sm.mcount = 0;
       bar_sync(BAR_PROD, IT_PROD);
       const int etot = sm.off[TILE_M];
       const bool staged = etot <= EMAX;
-      // ---- stage B: the tile's alive-neighbour ids, contiguous in acol -----------------------------------
-      if (staged) {
+      // ---- stage B: the tile's alive-neighbour ids (contiguous in acol) + the balanced work list ---------------
+      // A row's neighbour list is cut into segments of <= SEG entries; segments are dealt round-robin to the 32
+      // half-warps, so a hub row (degree in the hundreds on the power-law GMM graphs) is summed by many half-warps
+      // in parallel instead of serialising one.  Segment 0 of a row lands in the A tile, the others in `extra`
+      // and are folded in segment order afterwards: the f32 result stays deterministic.
+      if (staged)
         for (int e = tid; e < etot; e += IT_PROD) sm.eu[e] = acol[b0 + e];
-        bar_sync(BAR_PROD, IT_PROD);
+      if (warp == 0) {
+        int nx[4], tot = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = sm.off[4 * lane + q + 1] - sm.off[4 * lane + q];
+          nx[q] = staged ? max(0, (n - 1) / SEG) : 0;  // extra segments of the row
+          tot += nx[q];
+        }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int n = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += n;
+        }
+        int xb = incl - tot;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = 4 * lane + q;
+          const int b = sm.off[r], n = sm.off[r + 1] - b;
+          sm.xbase[r] = xb;
+          sm.nseg[r] = (unsigned char)(1 + nx[q]);
+          if (nx[q] > 0) sm.mrow[atomicAdd(&sm.mcount, 1)] = (unsigned char)r;
+          for (int k = 0; k <= nx[q]; ++k) {
+            const int sidx = r + xb + k;
+            sm.seg_row[sidx] = (unsigned char)r;
+            sm.seg_beg[sidx] = b + k * SEG;
+            sm.seg_len[sidx] = staged ? min(SEG, n - k * SEG) : n;
+            sm.seg_dst[sidx] = (short)(k == 0 ? -1 : xb + k - 1);
+          }
+          xb += nx[q];
+        }
+        if (lane == 31) sm.nsegs = TILE_M + incl;
       }
+      bar_sync(BAR_PROD, IT_PROD);
 
-      // ---- stage C: gather.  warp w owns tile rows [16w, 16w+16); lane holds columns 2*lane, 2*lane+1 ------
-      {
-        const int r0 = warp * 16;
-        {
-          float2 h[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int v = sm.v[buf][r0 + i];
-            h[i] = make_float2(0.f, 0.f);
-            if (v >= 0) h[i] = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)v * D) + lane);
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(A + (r0 + i) * A_LD + D + 2 * lane) = h[i];
-        }
-        const int e0 = sm.off[r0], e1 = sm.off[r0 + 16];
-        int cur = r0, nb = sm.off[r0 + 1];
-        float2 acc = make_float2(0.f, 0.f);
-        for (int e = e0; e < e1; e += GCH) {
-          float2 val[GCH];
-          if (staged) {
+      // ---- stage C: gather.  A half-warp sums one segment; a lane holds 4 consecutive columns, so one LDG.128
+      //      per half-warp fetches a whole 256-byte neighbour row -----------------------------------------------
+      if (!(dbg & 1)) {
+        const int half = lane >> 4, l16 = lane & 15;
+        const float4* __restrict__ H4 = reinterpret_cast<const float4*>(Hin);
+        const int nsegs = sm.nsegs;
+        for (int s0 = warp * 2; s0 < nsegs; s0 += IT_PROD / 16) {
+          const int sidx = s0 + half;
+          const bool valid = sidx < nsegs;
+          const int b = valid ? sm.seg_beg[sidx] : 0, n = valid ? sm.seg_len[sidx] : 0;
+          const int nmax = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k0 = 0; k0 < nmax; k0 += GCH) {
+            float4 val[GCH];
 #pragma unroll
             for (int j = 0; j < GCH; ++j) {
-              val[j] = make_float2(0.f, 0.f);
-              if (e + j < e1) val[j] = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)sm.eu[e + j] * D) + lane);
-            }
-          } else {  // hub tile: neighbour ids straight from global memory
-            int u = 0;
-            if (lane < GCH && e + lane < e1) u = acol[b0 + e + lane];
-#pragma unroll
-            for (int j = 0; j < GCH; ++j) {
-              const int uu = __shfl_sync(0xffffffffu, u, j);
-              val[j] = make_float2(0.f, 0.f);
-              if (e + j < e1) val[j] = __ldg(reinterpret_cast<const float2*>(Hin + (size_t)uu * D) + lane);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < GCH; ++j) {
-            if (e + j < e1) {
-              while (e + j >= nb) {  // warp-uniform: row `cur` is complete (rows without alive edges get zeros)
-                *reinterpret_cast<float2*>(A + cur * A_LD + 2 * lane) = acc;
-                acc = make_float2(0.f, 0.f);
-                ++cur;
-                nb = sm.off[cur + 1];
+              val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (k0 + j < n) {
+                const int u = staged ? sm.eu[b + k0 + j] : acol[b0 + b + k0 + j];
+                val[j] = __ldg(H4 + (size_t)u * (D / 4) + l16);
               }
-              acc.x += val[j].x;
-              acc.y += val[j].y;
+            }
+#pragma unroll
+            for (int j = 0; j < GCH; ++j) {  // in CSR order
+              if (k0 + j < n) {
+                acc.x += val[j].x;
+                acc.y += val[j].y;
+                acc.z += val[j].z;
+                acc.w += val[j].w;
+              }
             }
           }
+          if (valid) {
+            const int dst = sm.seg_dst[sidx];
+            float* out = dst < 0 ? A + sm.seg_row[sidx] * A_LD : sm.extra + dst * D;
+            *reinterpret_cast<float4*>(out + 4 * l16) = acc;
+          }
         }
-        for (; cur < r0 + 16; ++cur) {
-          *reinterpret_cast<float2*>(A + cur * A_LD + 2 * lane) = acc;
-          acc = make_float2(0.f, 0.f);
+        // own rows -> A[:, 64:128]
+        float4 own[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int v = sm.v[buf][warp * 8 + 2 * i + half];
+          own[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (v >= 0) own[i] = __ldg(H4 + (size_t)v * (D / 4) + l16);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(A + (warp * 8 + 2 * i + half) * A_LD + D + 4 * l16) = own[i];
+        // fold the extra segments of hub rows, in segment order
+        const int mcount = sm.mcount;
+        if (mcount > 0) {
+          bar_sync(BAR_PROD, IT_PROD);
+          for (int m = warp * 2 + half; m < mcount; m += IT_PROD / 16) {
+            const int r = sm.mrow[m];
+            float4 acc = *reinterpret_cast<const float4*>(A + r * A_LD + 4 * l16);
+            const int xb = sm.xbase[r], nx = sm.nseg[r] - 1;
+            for (int k = 0; k < nx; ++k) {
+              const float4 x = *reinterpret_cast<const float4*>(sm.extra + (xb + k) * D + 4 * l16);
+              acc.x += x.x;
+              acc.y += x.y;
+              acc.z += x.z;
+              acc.w += x.w;
+            }
+            *reinterpret_cast<float4*>(A + r * A_LD + 4 * l16) = acc;
+          }
         }
       }
       __threadfence_block();
@@ -226,14 +288,16 @@ __global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_s
 
       // ---- per-tile partial of the subgraph sum (old embeddings), fixed order => deterministic --------------
       {
-        const int c = tid & 63, part = tid >> 6;  // 4 row quarters x 64 columns
+        const int c = tid & 63, part = tid >> 6;  // 8 row eighths x 64 columns
         float s = 0.f;
-        for (int r = part * 32; r < part * 32 + 32; ++r) s += A[r * A_LD + D + c];
+        for (int r = part * 16; r < part * 16 + 16; ++r) s += A[r * A_LD + D + c];
         sm.red[part * D + c] = s;
       }
       bar_sync(BAR_PROD, IT_PROD);
       if (tid < D) {
-        const float s = ((sm.red[tid] + sm.red[D + tid]) + sm.red[2 * D + tid]) + sm.red[3 * D + tid];
+        float s = sm.red[tid];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) s += sm.red[q * D + tid];
         K.psum[(((size_t)iter * G.n_layers + l) * ti.tiles_per_layer + ti.gt) * D + tid] = s;
       }
     }
@@ -255,6 +319,11 @@ __global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_s
       float* __restrict__ Hout = K.h[(iter + 1) & 1][ti.l];
       bar_sync(BAR_FULL0 + buf, IT_T);
       float acc[8][4];
+      if (dbg & 2) {
+        __threadfence_block();
+        bar_arrive(BAR_EMPTY0 + buf, IT_T);
+        continue;
+      }
       tile_gemm_128(sm.A[buf], sm.Wm, ty, tx, acc);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -404,6 +473,9 @@ __global__ void __launch_bounds__(MD_MAX_LAYERS* D) graph_embed_kernel(md_graphs
 // =================================================================================================
 // host entry points
 // =================================================================================================
+int g_md_debug_flags = 0;
+extern "C" void md_debug_set_flags(int32_t f) { g_md_debug_flags = f; }
+
 static int check_common(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k) {
   if (!g || !s || !w || !k) return MD_EINVAL;
   if (g->n_layers < 1 || g->n_layers > MD_MAX_LAYERS) return MD_ELAYERS;
@@ -447,7 +519,7 @@ extern "C" int md_embed_iter(const md_graphs_t* g, const md_state_t* s, const md
   const int n_tiles = g->n_graphs * (g->stride / MD_TILE_M) * g->n_layers;
   int grid = sm_count();
   if (grid > n_tiles) grid = n_tiles;
-  md::embed_iter_kernel<<<grid, md::IT_T, smem, (cudaStream_t)stream>>>(*g, *s, *w, *k, iter);
+  md::embed_iter_kernel<<<grid, md::IT_T, smem, (cudaStream_t)stream>>>(*g, *s, *w, *k, iter, g_md_debug_flags);
   MD_CHECK_LAUNCH();
   return 0;
 }

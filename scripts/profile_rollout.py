@@ -19,6 +19,8 @@ ap.add_argument("--n", type=int, default=1000)
 ap.add_argument("--graphs", type=int, default=256)
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--skip", type=int, default=0, help="un-profiled steps after the reset")
+ap.add_argument("--dbg", type=int, default=0, help="md_debug_set_flags value for the measured region")
+ap.add_argument("--iters", type=int, default=0, help="time N md_embed_iter launches alone instead of full steps")
 args = ap.parse_args()
 
 graphs = [gmm.gmm_graph(args.n, i, cost=args.cost) for i in range(args.graphs)]
@@ -33,6 +35,25 @@ if args.skip:
 torch.cuda.synchronize()
 print("active nodes", int(ro.n_act.sum()), "alive directed edges", (2 * ro.alive_edges.sum(1)).tolist())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if args.iters:
+    _lib.check(lib.md_embed_init(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()), "init")
+    for dbg in ((args.dbg,) if args.dbg else (0, 1, 2, 3)):
+        lib.md_debug_set_flags(dbg)
+        for rep in range(2):
+            torch.cuda.synchronize()
+            if rep == 1:
+                torch.cuda.profiler.start()
+            e0.record()
+            for i in range(args.iters):
+                _lib.check(lib.md_embed_iter(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), i % 3, ro._stream()), "iter")
+            e1.record()
+            torch.cuda.synchronize()
+            if rep == 1:
+                torch.cuda.profiler.stop()
+        print("dbg=%d: %.1f us per md_embed_iter launch" % (dbg, 1e3 * e0.elapsed_time(e1) / args.iters))
+    lib.md_debug_set_flags(0)
+    sys.exit(0)
+lib.md_debug_set_flags(args.dbg)
 torch.cuda.profiler.start()
 e0.record()
 _lib.check(lib.md_rollout_steps(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), args.steps, ro._stream()), "steps")
