@@ -125,6 +125,12 @@ typedef struct md_work {
  * mutual-component prune (Mcc.MCC, U/Mcc.py:30-38). */
 int md_env_reset(const md_graphs_t* g, const md_state_t* s, md_stream_t stream);
 
+/* Arbitrary environment state for Predict on replay states (U/MultiDismantler_torch.py:263-302 called from Fit :315-344):
+ * removed_mask[n_total] (1 = node in covered_set); the caller writes numCoveredEdges into s->cov_edges first
+ * (the reference recounts it from remove_edge in get_status_info, U/PrepareBatchGraph.py:45-52).  Labels, degrees,
+ * the alive CSR and the aux features are recomputed; score / traces are cleared. */
+int md_env_set_state(const md_graphs_t* g, const md_state_t* s, const uint8_t* removed_mask, md_stream_t stream);
+
 /* MvcEnv.stepWithoutReward (U/mvc_env.py:74-87) + getReward / getMaxConnectedNodesNum (:133-162) + Mcc.MCC for
  * every non-terminal graph, followed by PrepareBatchGraph.get_status_info (U/PrepareBatchGraph.py:35-100).
  * action source: actions != NULL -> actions[g * action_stride + (action_index >= 0 ? action_index : n_steps[g])]

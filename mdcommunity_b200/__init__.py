@@ -6,5 +6,7 @@ PyTorch supplies device memory and streams only.  No CPU fallback.
 """
 from .graph import Graph_test, GSet, GraphBatch  # noqa: F401
 from .rollout import BatchRollout, QWeights  # noqa: F401
+from .env import MvcEnv  # noqa: F401
+from .dismantler import MultiDismantler  # noqa: F401
 
 __version__ = "0.1.0"

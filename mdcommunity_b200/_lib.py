@@ -56,6 +56,7 @@ _LIB = None
 
 _SIGS = {
     "md_env_reset": ([C.POINTER(MdGraphs), C.POINTER(MdState), _vp], C.c_int),
+    "md_env_set_state": ([C.POINTER(MdGraphs), C.POINTER(MdState), _vp, _vp], C.c_int),
     "md_env_step": ([C.POINTER(MdGraphs), C.POINTER(MdState), _vp, C.c_int32, C.c_int32, _vp], C.c_int),
     "md_env_small_max_stride": ([], C.c_int32),
     "md_debug_force_large_env": ([C.c_int32], None),

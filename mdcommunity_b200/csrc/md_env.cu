@@ -120,7 +120,21 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
     s_action = a;
     S.best[g] = 0ull;
   }
-  for (int v = tid; v < St; v += ENV_T) lab[v] = init ? (v < N ? 0 : -1) : (S.label[base + v] < 0 ? -1 : S.label[base + v] - base);
+  // init == 1: MvcEnv.s0;  init == 2: arbitrary state given as a removed-node mask (passed through `forced`) with the
+  // caller's numCoveredEdges already in S.cov_edges (Predict on replay states, MultiDismantler_torch.py:263-302)
+  const unsigned char* mask = reinterpret_cast<const unsigned char*>(forced);
+  int n_masked = 0;
+  for (int v = tid; v < St; v += ENV_T) {
+    int lv;
+    if (init == 1) lv = v < N ? 0 : -1;
+    else if (init == 2) {
+      const bool rm = v < N && mask[base + v];
+      n_masked += rm;
+      lv = (v < N && !rm) ? 0 : -1;
+    } else lv = S.label[base + v] < 0 ? -1 : S.label[base + v] - base;
+    lab[v] = lv;
+  }
+  if (init == 2) n_masked = block_sum_i(n_masked, red);
   __syncthreads();
   const int a = s_action;
   if (!init && (a < 0 || lab[a] < 0)) return;  // nothing to remove (uniform exit)
@@ -302,12 +316,13 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
     const int B = G.n_graphs;
     S.n_act[g] = n_act;
     S.rank[g] = rank;
-    int nrem = init ? 0 : S.n_removed[g] + 1;
+    int nrem = init == 1 ? 0 : (init == 2 ? n_masked : S.n_removed[g] + 1);
     S.n_removed[g] = nrem;
     if (init) {
       S.score[g] = 0.0;
       S.n_steps[g] = 0;
-      for (int ll = 0; ll < L; ++ll) S.cov_edges[ll * B + g] = 0;
+      if (init == 1)
+        for (int ll = 0; ll < L; ++ll) S.cov_edges[ll * B + g] = 0;
     } else {
       const double rk = (double)rank;
       const double mr = (double)G.max_rank[g];
@@ -384,6 +399,12 @@ static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* 
 
 extern "C" int md_env_reset(const md_graphs_t* g, const md_state_t* s, md_stream_t stream) {
   return env_launch(g, s, nullptr, 0, -1, 1, stream);
+}
+
+extern "C" int md_env_set_state(const md_graphs_t* g, const md_state_t* s, const uint8_t* removed_mask,
+                                md_stream_t stream) {
+  if (!removed_mask) return MD_EINVAL;
+  return env_launch(g, s, reinterpret_cast<const int32_t*>(removed_mask), 0, -1, 2, stream);
 }
 
 extern "C" int md_env_step(const md_graphs_t* g, const md_state_t* s, const int32_t* actions, int32_t action_stride,

@@ -67,10 +67,18 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
   __shared__ int s_off;
 
   // ---- P0: pick / validate the action, apply it --------------------------------------------------------
+  const unsigned char* mask = reinterpret_cast<const unsigned char*>(forced);  // init == 2: removed-node mask
+  if (init) {
+    for (int g = gtid; g < B; g += gsz) S.n_removed[g] = 0;
+  }
+  if (init == 2) grid_barrier(bar, epoch);
   if (init) {
     for (int v = gtid; v < NT; v += gsz) {
       const int g = v / St;
-      label[v] = (v - g * St) < G.n_nodes[g] ? g * St : -1;
+      const bool inside = (v - g * St) < G.n_nodes[g];
+      const bool rm = init == 2 && inside && mask[v];
+      label[v] = (inside && !rm) ? g * St : -1;
+      if (rm) atomicAdd(&S.n_removed[g], 1);
     }
   }
   for (int g = gtid; g < B; g += gsz) {
@@ -323,12 +331,13 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
       S.alive_edges[ll * B + g] = e2 / 2;
       terminal |= (e2 == 0);
     }
-    const int nrem = init ? 0 : S.n_removed[g] + 1;
+    const int nrem = init ? S.n_removed[g] : S.n_removed[g] + 1;  // init: 0 (s0) or the mask population
     S.n_removed[g] = nrem;
     if (init) {
       S.score[g] = 0.0;
       S.n_steps[g] = 0;
-      for (int ll = 0; ll < L; ++ll) S.cov_edges[ll * B + g] = 0;
+      if (init == 1)
+        for (int ll = 0; ll < L; ++ll) S.cov_edges[ll * B + g] = 0;
     } else {
       const double rk = (double)rank, mr = (double)G.max_rank[g];
       double r, mcc;

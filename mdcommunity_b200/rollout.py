@@ -138,6 +138,13 @@ class BatchRollout:
                 g.max_rank = int(r)
             self.batch._max_rank_set = True
 
+    def set_state(self, removed_mask):
+        """Arbitrary state: removed_mask uint8 [n_total] on the device; self.cov_edges must hold numCoveredEdges."""
+        assert removed_mask.dtype == torch.uint8 and removed_mask.is_cuda and removed_mask.numel() == self.batch.n_total
+        _lib.check(self.lib.md_env_set_state(self._g(), C.byref(self.s), C.c_void_p(removed_mask.data_ptr()),
+                                             self._stream()), "md_env_set_state")
+        self.kernel_launches += 1
+
     def forward(self):
         """One Q-network evaluation for all non-terminal graphs (test_forward + the Predict mask + arg-max key)."""
         lib, g, s, w, k, st = self.lib, self._g(), C.byref(self.s), self.w.ptr(), C.byref(self.k), self._stream()

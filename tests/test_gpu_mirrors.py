@@ -1,0 +1,130 @@
+"""The reference-shaped host API (MvcEnv / MultiDismantler mirrors) on the device path, against golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(mdb, z, variant):
+    return mdb.Graph_test(z["edges0"], z["edges1"], num_nodes=int(z["num_nodes"]), cost=variant)
+
+
+@pytest.mark.parametrize("variant", ["unit", "degree"])
+def test_mvcenv_mirror_random_trace(variant):
+    """MvcEnv.s0 / stepWithoutReward / isTerminal / remove_edge bookkeeping reproduce the reference trace."""
+    import mdcommunity_b200 as mdb
+    for p in golden_cases(variant, max_n=200):
+        z = np.load(p)
+        g = _graph(mdb, z, variant)
+        env = mdb.MvcEnv(50)
+        env.s0(g)
+        assert g.max_rank == int(z["max_rank"])
+        for t, a in enumerate(z["random_actions"]):
+            assert not env.isTerminal()
+            env.stepWithoutReward(int(a))
+            assert env.score == z["random_score"][t]
+            assert env.MaxCCList[-1] == z["random_maxcc"][t]
+            assert list(env.numCoveredEdges) == list(z["random_cov_edges"][t])
+            assert [len(s) for s in env.remove_edge] == list(z["random_rm_edges"][t])
+        assert env.isTerminal()
+        assert env.action_list == [int(a) for a in z["random_actions"]]
+        with pytest.raises(AssertionError):
+            env.stepWithoutReward(int(z["random_actions"][0]))  # already covered (mvc_env.py:76-77)
+
+
+def test_mvcenv_step_rewards_and_random_action():
+    import random
+    import mdcommunity_b200 as mdb
+    from oracle import md_oracle as orc
+    z = np.load(os.path.join(GOLDEN, "unit_n100_s0.npz"))
+    g = _graph(mdb, z, "unit")
+    og = orc.MultiplexGraph(int(z["num_nodes"]), [z["edges0"], z["edges1"]])
+    env, oenv = mdb.MvcEnv(50), orc.OracleEnv("unit")
+    env.s0(g)
+    oenv.s0(og)
+    random.seed(3)
+    while not env.isTerminal():
+        a = env.randomAction()
+        active, _, _ = oenv.status()
+        assert env.avail_list == list(np.nonzero(active)[0])
+        r = env.step(a)
+        assert r == oenv.stepWithoutReward(a)
+        assert env.state_seq[-1] == env.action_list[:-1]
+    assert oenv.isTerminal()
+    assert len(env.reward_seq) == len(env.act_seq) == len(env.state_seq_edges)
+
+
+@pytest.mark.parametrize("variant", ["unit", "degree"])
+def test_driver_getsol_and_predict(variant):
+    import mdcommunity_b200 as mdb
+    from oracle import md_oracle as orc
+    dqn = mdb.MultiDismantler(cost=variant)
+    dqn.LoadModel(os.path.join(GOLDEN, "weights_%s.npz" % variant))
+    for gid, p in enumerate(golden_cases(variant, max_n=200)):
+        z = np.load(p)
+        g = _graph(mdb, z, variant)
+        dqn.InsertGraph(g, is_test=True)
+        score, sol, cost = dqn.GetSol(gid)
+        ref = [int(a) for a in z["greedy_actions"]]
+        if sol == ref:
+            assert score == float(z["greedy_final_score"])
+        # Predict on the reference's states (covered list + remove_edge sets rebuilt by the MvcEnv mirror)
+        env = mdb.MvcEnv(50)
+        env.s0(g)
+        off = z["greedy_off"]
+        for t in range(min(3, len(ref))):
+            pred = dqn.Predict([g], [env.action_list], [env.remove_edge])[0]
+            ids = z["greedy_active"][off[t]:off[t + 1]]
+            qg = z["greedy_q"][off[t]:off[t + 1]]
+            assert np.all(pred[np.setdiff1d(np.arange(g.num_nodes), ids)] == -(2147483647 / 2))
+            assert np.all(np.abs(pred[ids] - qg) <= 1e-4 * np.abs(qg) + 1e-6)
+            env.stepWithoutReward(ref[t])
+    dqn.ClearTestGraphs()
+
+
+def test_getsolution_topk_matches_oracle():
+    """GetSolution with step > 1 (testReal's stepRatio mode): same removal batches as the oracle's top-k rule."""
+    import mdcommunity_b200 as mdb
+    from oracle import md_oracle as orc
+    z = np.load(os.path.join(GOLDEN, "unit_n200_s0.npz"))
+    g = _graph(mdb, z, "unit")
+    dqn = mdb.MultiDismantler(cost="unit")
+    dqn.LoadModel(os.path.join(GOLDEN, "weights_unit.npz"))
+    dqn.InsertGraph(g, is_test=True)
+    sol, score, maxcc = dqn.GetSolution(0, step=4)
+    ow = orc.load_weights(os.path.join(GOLDEN, "weights_unit.npz"))
+    og = orc.MultiplexGraph(int(z["num_nodes"]), [z["edges0"], z["edges1"]])
+    r = orc.rollout(ow, og, "unit", forced_actions=sol)  # LMCC / AUDC of OUR sequence: bit-exact
+    assert r["score"] == score and r["maxcc"] == maxcc
+    free = orc.rollout(ow, og, "unit", step=4, record=True)
+    same = 0
+    while same < min(len(sol), len(free["sol"])) and sol[same] == free["sol"][same]:
+        same += 1
+    assert same >= 4  # at least the first batch is identical; later ones may differ on rounding-level ties
+
+
+def test_real_file_formats(tmp_path):
+    import mdcommunity_b200 as mdb
+    z = np.load(os.path.join(GOLDEN, "unit_n60_s3.npz"))
+    path = tmp_path / "toy_multiplex.edges"
+    with open(path, "w") as f:
+        for l, key in ((1, "edges0"), (2, "edges1")):
+            for u, v in z[key]:
+                f.write("%d %d %d\n" % (l, u + 1, v + 1))
+            f.write("%d 3 3\n" % l)  # self loop: dropped like the reference's read_multiplex
+    dqn = mdb.MultiDismantler(cost="unit")
+    dqn.LoadModel(os.path.join(GOLDEN, "weights_unit.npz"))
+    sol, secs, score = dqn.EvaluateRealData(str(path), str(tmp_path), 0.0, int(z["num_nodes"]), (1, 2))
+    ref = [int(a) for a in z["greedy_actions"]]
+    if sol == ref:
+        assert score == float(z["greedy_final_score"])
+    out = tmp_path / "StepRatio_0.0000"
+    lines = open(out / "Soluion_toy_multiplex_12.txt").read().split()
+    assert [int(x) for x in lines] == sol
+    lm = open(out / "NormalizedLMCC_toy_multiplex_12.txt").read().split()
+    assert len(lm) == int(z["num_nodes"]) + 2 and float(lm[0]) == 1.0
