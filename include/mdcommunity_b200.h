@@ -187,6 +187,9 @@ int md_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* val,
 
 /* ---- sizing helpers (host) ------------------------------------------------------------------------------ */
 int64_t md_psum_floats(int32_t n_layers, int32_t n_total);
+/* sizeof(md_graphs_t), sizeof(md_state_t), sizeof(md_weights_t), sizeof(md_work_t) as compiled: lets a binding check
+ * its own struct mirrors */
+void md_abi_sizes(int32_t* out4);
 const char* md_version(void);
 
 #ifdef __cplusplus

@@ -70,6 +70,7 @@ _SIGS = {
     "md_select_topk": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWork), _vp, C.c_int32, _vp], C.c_int),
     "md_spmm_csr_f32": ([_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
     "md_psum_floats": ([C.c_int32, C.c_int32], C.c_int64),
+    "md_abi_sizes": ([_vp], None),
     "md_version": ([], C.c_char_p),
 }
 
@@ -95,6 +96,11 @@ def lib():
             fn = getattr(h, name)  # AttributeError if the symbol is missing: fail loudly
             fn.argtypes = args
             fn.restype = res
+        sizes = (C.c_int32 * 4)()
+        h.md_abi_sizes(sizes)
+        mine = [C.sizeof(MdGraphs), C.sizeof(MdState), C.sizeof(MdWeights), C.sizeof(MdWork)]
+        if list(sizes) != mine:
+            raise RuntimeError("ctypes struct mirrors %s do not match the compiled ABI %s" % (mine, list(sizes)))
         _LIB = h
     return _LIB
 

@@ -21,4 +21,11 @@ extern "C" int md_rollout_steps(const md_graphs_t* g, const md_state_t* s, const
   return 0;
 }
 
+extern "C" void md_abi_sizes(int32_t* out4) {
+  out4[0] = (int32_t)sizeof(md_graphs_t);
+  out4[1] = (int32_t)sizeof(md_state_t);
+  out4[2] = (int32_t)sizeof(md_weights_t);
+  out4[3] = (int32_t)sizeof(md_work_t);
+}
+
 extern "C" const char* md_version(void) { return "mdcommunity_b200 0.1 (sm_100a)"; }

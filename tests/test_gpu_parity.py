@@ -170,3 +170,78 @@ def test_spmm_operator():
         out = spmm(torch.stack([row, col]), val, m, n, x)
         assert out.shape == (m, D)
         torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_large_three_layer_env_vs_oracle():
+    """Config-C4-shaped case at test size: 3 layers, N = 30000 (cooperative global-memory env kernel, no override),
+    random removals: LMCC sizes, AUDC, counters and the active set must equal the CPU oracle bit for bit."""
+    from oracle import md_oracle as orc
+    from mdcommunity_b200 import gmm
+    mdb = _mdb()
+    N, L = 30000, 3
+    layers = gmm.random_sparse_layers(N, L, 3 * N // 2, seed=3)  # average degree 3: a rich component structure
+    g = mdb.Graph_test(*layers, num_nodes=N, cost="unit")
+    batch = mdb.GraphBatch([g], cost="unit")
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_unit.npz"))), batch.device)
+    ro = mdb.BatchRollout(batch, w, max_steps=64)
+    assert ro.large
+    og = orc.MultiplexGraph(N, layers)
+    assert g.max_rank == og.max_rank
+    env = orc.OracleEnv("unit")
+    env.s0(og)
+    rng = np.random.default_rng(0)
+    acts = torch.zeros(1, 1, dtype=torch.int32, device=batch.device)
+    for t in range(12):
+        n = int(ro.n_act[0])
+        active, degs, aux = env.status()
+        ids = np.nonzero(active)[0]
+        assert n == len(ids)
+        assert np.array_equal(ro.act_list[:n].cpu().numpy(), ids)
+        assert np.array_equal(ro.aux[0].cpu().numpy(), aux)
+        for l in range(L):
+            assert np.array_equal(ro.deg[l][:N].cpu().numpy(), degs[l])
+            # alive CSR in compact order
+            ap = ro.aptr[l][:n + 1].cpu().numpy()
+            assert np.array_equal(np.diff(ap), degs[l][ids])
+        # remove a high-degree active node (splits more) or a random one
+        a = int(ids[np.argmax(degs[0][ids])]) if t % 2 == 0 else int(rng.choice(ids))
+        acts[0, 0] = a
+        ro.step(acts, 0)
+        env.stepWithoutReward(a)
+        assert int(ro.rank[0]) == env.rank_list[-1]
+        assert float(ro.score[0]) == env.score
+        assert list(ro.cov_edges[:, 0].cpu().numpy()) == list(env.numCoveredEdges)
+    # one 3-layer forward runs and produces finite Q values for every active node (L = 3 is an extension of the
+    # 2-layer reference network: fusion softmax and layer gate over 3 layers with the layer-shared weights)
+    ro.forward()
+    ids, q = ro.q_values(0)
+    assert len(ids) == int(ro.n_act[0]) and np.all(np.isfinite(q))
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] shape (degree cost, N = 1000) on a 64-graph batch: size-independent properties."""
+    from mdcommunity_b200 import gmm
+    mdb = _mdb()
+    graphs = [gmm.gmm_graph(1000, 100 + i, cost="degree") for i in range(64)]
+    batch = mdb.GraphBatch(graphs, cost="degree")
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_degree.npz"))), batch.device)
+    ro = mdb.BatchRollout(batch, w)
+    r1 = ro.run()
+    ro.reset()
+    r2 = ro.run()
+    assert ro.num_done() == 64
+    for k in ("score", "n_steps", "actions", "ranks"):
+        assert np.array_equal(r1[k], r2[k]), "rollouts must be bit-reproducible run to run"
+    for i, g in enumerate(graphs):
+        n = int(r1["n_steps"][i])
+        assert 0 < n < g.num_nodes
+        rk = r1["ranks"][i, :n]
+        assert rk[0] <= g.max_rank and np.all(np.diff(rk) <= 0) and rk[-1] == 1  # LMCC never grows; terminal <=> 1
+        assert len(set(r1["actions"][i, :n])) == n and np.all(r1["actions"][i, n:] == -1)
+        assert np.all(r1["maxcc"][i, :n] == rk / g.max_rank)  # D/mvc_env.py:81,133
+        assert 0 < r1["score"][i] < 1
+    # a graph's rollout does not depend on its batch mates
+    solo = mdb.BatchRollout(mdb.GraphBatch(graphs[5:6], cost="degree"), w).run()
+    n = int(solo["n_steps"][0])
+    assert n == r1["n_steps"][5] and np.array_equal(solo["actions"][0, :n], r1["actions"][5, :n])
+    assert solo["score"][0] == r1["score"][5]
