@@ -179,7 +179,7 @@ def test_large_three_layer_env_vs_oracle():
     from mdcommunity_b200 import gmm
     mdb = _mdb()
     N, L = 30000, 3
-    layers = gmm.random_sparse_layers(N, L, 3 * N // 2, seed=3)  # average degree 3: a rich component structure
+    layers = gmm.random_sparse_layers(N, L, 5 * N // 2, seed=3)  # average degree 5: giant mutual component + many small ones
     g = mdb.Graph_test(*layers, num_nodes=N, cost="unit")
     batch = mdb.GraphBatch([g], cost="unit")
     w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_unit.npz"))), batch.device)
@@ -191,11 +191,12 @@ def test_large_three_layer_env_vs_oracle():
     env.s0(og)
     rng = np.random.default_rng(0)
     acts = torch.zeros(1, 1, dtype=torch.int32, device=batch.device)
+    assert og.max_rank > 1000
     for t in range(12):
         n = int(ro.n_act[0])
         active, degs, aux = env.status()
         ids = np.nonzero(active)[0]
-        assert n == len(ids)
+        assert n == len(ids) and n > 0
         assert np.array_equal(ro.act_list[:n].cpu().numpy(), ids)
         assert np.array_equal(ro.aux[0].cpu().numpy(), aux)
         for l in range(L):
