@@ -50,6 +50,7 @@ typedef struct md_graphs {
   int32_t reserved0;
   const int32_t* rowptr[MD_MAX_LAYERS];  /* [n_total + 1] per layer */
   const int32_t* col[MD_MAX_LAYERS];     /* [nnz_l] neighbour = global node id; row order = edge_list order */
+  const int32_t* src[MD_MAX_LAYERS];     /* [nnz_l] row (global node id) of every CSR entry, i.e. the COO row array */
   const int32_t* n_nodes;                /* [B] */
   const int32_t* n_edges;                /* [L][B] undirected edge counts (graph.num_edges) */
   const int32_t* max_rank;               /* [B] LMCC of the intact graph (graph.max_rank) */
@@ -145,6 +146,9 @@ int32_t md_env_uses_small_path(const md_graphs_t* g);
 void md_debug_force_large_env(int32_t on);
 /* profiling hook (results become wrong): bit 0 skips the neighbour gather, bit 1 the dense transform of md_embed_iter */
 void md_debug_set_flags(int32_t flags);
+/* profiling hook: clock64 phase times of CTA 0 of the last md_env_step (labels in, CSR staged, prune rounds,
+ * component sizes, alive CSR + degrees) and, at index 16, the number of prune rounds */
+int md_debug_read_env(long long* host, int n);
 
 /* ---- Q network ---------------------------------------------------------------------------------------- */
 

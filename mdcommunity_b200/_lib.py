@@ -25,7 +25,7 @@ class MdGraphs(C.Structure):
     _fields_ = [
         ("n_graphs", C.c_int32), ("n_layers", C.c_int32), ("stride", C.c_int32), ("n_total", C.c_int32),
         ("max_graph_nnz", C.c_int32), ("reserved0", C.c_int32),
-        ("rowptr", _vp * MAX_LAYERS), ("col", _vp * MAX_LAYERS),
+        ("rowptr", _vp * MAX_LAYERS), ("col", _vp * MAX_LAYERS), ("src", _vp * MAX_LAYERS),
         ("n_nodes", _vp), ("n_edges", _vp), ("max_rank", _vp),
         ("node_w", _vp * MAX_LAYERS), ("node_cost", _vp),
     ]
@@ -61,6 +61,7 @@ _SIGS = {
     "md_env_small_max_stride": ([], C.c_int32),
     "md_debug_force_large_env": ([C.c_int32], None),
     "md_debug_set_flags": ([C.c_int32], None),
+    "md_debug_read_env": ([_vp, C.c_int32], C.c_int),
     "md_env_uses_small_path": ([C.POINTER(MdGraphs)], C.c_int32),
     "md_embed_init": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_embed_iter": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),

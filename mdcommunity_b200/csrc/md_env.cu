@@ -11,6 +11,9 @@
 #include "md_common.cuh"
 
 namespace md {
+__device__ long long g_env_dbg[32];
+#define ENV_T0() long long t_dbg = clock64(); int k_dbg = 0
+#define ENV_TICK() do { if (blockIdx.x == 0 && tid == 0) { long long n_ = clock64(); g_env_dbg[k_dbg] = n_ - t_dbg; t_dbg = n_; } ++k_dbg; } while (0)
 
 constexpr int ENV_T = 512;
 constexpr int ENV_W = ENV_T / 32;
@@ -97,12 +100,13 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int* tmp = smem + 2 * St;         // [St] scratch; later the compact list of active nodes
   int* c_rp = smem + 3 * St;        // [L][St + 1] row offsets into c_cl / c_src
   int* c_cl = c_rp + L * (St + 1);  // [max_nnz] neighbour (graph-local id)
-  int* c_src = c_cl + max_nnz;      // [max_nnz] row of the entry
+  int* c_src = c_cl + max_nnz;      // [max_nnz] row of the entry (static, staged); later the alive prefix
   __shared__ BlockRed red;
   __shared__ int s_action;
   __shared__ int s_scan[ENV_W];
 
   if (!init && S.done[g]) return;
+  ENV_T0();
 
   // ---- pick the action -----------------------------------------------------------------------------
   if (tid == 0) {
@@ -139,6 +143,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   const int a = s_action;
   if (!init && (a < 0 || lab[a] < 0)) return;  // nothing to remove (uniform exit)
 
+  ENV_TICK();  // 0: labels in
   // ---- stage the graph's CSR in shared memory ---------------------------------------------------------
   int lay_pos[MD_MAX_LAYERS + 1];
   {
@@ -148,17 +153,15 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       const int32_t* __restrict__ cl = G.col[ll];
       const int e0 = rp[0], cnt = rp[St] - e0;
       for (int v = tid; v <= St; v += ENV_T) c_rp[ll * (St + 1) + v] = rp[v] - e0 + pos;
-      for (int e = tid; e < cnt; e += ENV_T) c_cl[pos + e] = cl[e0 + e] - base;
+      const int32_t* __restrict__ sr = G.src[ll];
+      for (int e = tid; e < cnt; e += ENV_T) {
+        c_cl[pos + e] = cl[e0 + e] - base;
+        c_src[pos + e] = sr[e0 + e] - base;
+      }
       lay_pos[ll] = pos;
       pos += cnt;
     }
     lay_pos[L] = pos;
-    __syncthreads();
-    for (int ll = 0; ll < L; ++ll) {
-      const int* rp = c_rp + ll * (St + 1);
-      for (int v = tid; v < N; v += ENV_T)
-        for (int e = rp[v]; e < rp[v + 1]; ++e) c_src[e] = v;
-    }
   }
 
   if (!init) {
@@ -168,8 +171,10 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   }
   __syncthreads();
 
+  ENV_TICK();  // 1: CSR staged
   // ---- Mcc.MCC: refine the partition layer by layer until every layer is stable ----------------------
   int stable = 0, l = 0;
+  int rounds_dbg = 0;
   while (stable < L) {
     for (int v = tid; v < N; v += ENV_T) par[v] = v;
     __syncthreads();
@@ -195,7 +200,10 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
     __syncthreads();
     stable = changed ? 1 : stable + 1;
     l = (l + 1 == L) ? 0 : l + 1;
+    ++rounds_dbg;
   }
+  ENV_TICK();  // 2: LMCC rounds
+  if (blockIdx.x == 0 && tid == 0) g_env_dbg[16] = rounds_dbg;
 
   // ---- component sizes -> LMCC rank (Mcc.find_max_set_length) ------------------------------------------
   for (int v = tid; v < N; v += ENV_T) tmp[v] = 0;
@@ -207,27 +215,61 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   for (int v = tid; v < N; v += ENV_T) mx = max(mx, tmp[v]);
   const int rank = block_max_i(mx, red);
 
-  // ---- per layer: alive degree, status counters (get_status_info), alive CSR ------------------------------
+  ENV_TICK();  // 3: component sizes
+  // ---- per layer: alive CSR, alive degree, status counters (get_status_info) -------------------------------
+  // The alive CSR is a stream compaction of the staged CSR entries by the flag "both end labels equal": one
+  // edge-parallel block scan per layer (hub rows cost nothing extra).  The running prefix is kept per entry (in the
+  // c_src slots, dead after the prune), so deg(v) = pref[row end] - pref[row start] needs no second edge sweep.
   bool terminal = false;
   int n_act = 0;
   for (int ll = 0; ll < L; ++ll) {
     const int* rp = c_rp + ll * (St + 1);
-    int dsum = 0, dmax = 0;
+    const int p0 = lay_pos[ll], cnt = lay_pos[ll + 1] - p0;
+    const int e0 = G.rowptr[ll][base];  // the graph's region of acol[ll] is its static CSR region
+    int32_t* __restrict__ aptr = S.aptr[ll] + base;
+    int32_t* __restrict__ acol = S.acol[ll];
+    int* pref = c_src + p0;  // pref[i] = number of alive entries before entry i of this layer, i in [0, cnt]
+    int running = 0;
+    for (int c0 = 0; c0 < cnt; c0 += ENV_T) {
+      const int i = c0 + tid;
+      int flag = 0, u = 0;
+      if (i < cnt) {
+        u = c_cl[p0 + i];
+        const int lv = lab[c_src[p0 + i]];
+        flag = (lv >= 0 && lab[u] == lv) ? 1 : 0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, flag);
+      __syncthreads();  // every thread has read its c_src entry before the prefixes overwrite the slots
+      if (lane == 0) s_scan[wid] = __popc(bal);
+      __syncthreads();
+      int woff = 0, total = 0;
+#pragma unroll
+      for (int k = 0; k < ENV_W; ++k) {
+        const int c = s_scan[k];
+        if (k < wid) woff += c;
+        total += c;
+      }
+      const int pos = running + woff + __popc(bal & ((1u << lane) - 1u));
+      if (i < cnt) {
+        pref[i] = pos;
+        if (flag) acol[e0 + pos] = u + base;
+      }
+      running += total;
+    }
+    __syncthreads();
+    const int tot = running;  // alive directed entries of the layer (= pref[cnt], which has no slot of its own)
+    const int pend = p0 + cnt;
+#define PREF_AT(x) ((x) == pend ? tot : c_src[(x)])
+    int dmax = 0;
     long long th = 0;
     for (int v = tid; v < St; v += ENV_T) {
       int d = 0;
-      if (v < N && lab[v] >= 0) {
-        const int lv = lab[v];
-        const int e1 = rp[v + 1];
-        for (int e = rp[v]; e < e1; ++e) d += (lab[c_cl[e]] == lv);
-      }
+      if (v < N) d = PREF_AT(rp[v + 1]) - PREF_AT(rp[v]);  // rp[] offsets are absolute positions in c_cl / c_src
       S.deg[ll][base + v] = d;
       par[v] = d;
-      dsum += d;
       dmax = max(dmax, d);
       th += (long long)d * (d - 1) / 2;
     }
-    const int tot = block_sum_i(dsum, red);
     const int dm = block_max_i(dmax, red);
     const long long t2 = block_sum_ll(th, red);
     if (tid == 0) {
@@ -240,7 +282,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
 
     if (ll == 0) {
       // write labels back, compact the active nodes (ascending id, PrepareBatchGraph.py:128-138) into tmp[]
-      int running = 0;
+      int run2 = 0;
       for (int v0 = 0; v0 < St; v0 += ENV_T) {
         const int v = v0 + tid;
         int flag = 0;
@@ -259,58 +301,23 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
           total += c;
         }
         if (flag) {
-          const int p = running + woff + __popc(bal & ((1u << lane) - 1u));
+          const int p = run2 + woff + __popc(bal & ((1u << lane) - 1u));
           S.act_list[base + p] = base + v;
           tmp[p] = v;
         }
-        running += total;
+        run2 += total;
         __syncthreads();
       }
-      n_act = running;
+      n_act = run2;
     }
-
-    // alive CSR of layer ll in compact order: exclusive scan of the alive degrees, then ordered fill
-    {
-      const int e0 = G.rowptr[ll][base];  // the graph's region of acol[ll] is its static CSR region
-      int32_t* __restrict__ aptr = S.aptr[ll] + base;
-      int32_t* __restrict__ acol = S.acol[ll];
-      int running = 0;
-      for (int p0 = 0; p0 < n_act; p0 += ENV_T) {
-        const int p = p0 + tid;
-        const int v = p < n_act ? tmp[p] : -1;
-        const int d = v >= 0 ? par[v] : 0;
-        int incl = d;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int n = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += n;
-        }
-        if (lane == 31) s_scan[wid] = incl;
-        __syncthreads();
-        int woff = 0, total = 0;
-#pragma unroll
-        for (int k = 0; k < ENV_W; ++k) {
-          const int c = s_scan[k];
-          if (k < wid) woff += c;
-          total += c;
-        }
-        if (v >= 0) {
-          int o = e0 + running + woff + incl - d;
-          aptr[p] = o;
-          const int lv = lab[v];
-          const int e1 = rp[v + 1];
-          for (int e = rp[v]; e < e1; ++e) {
-            const int u = c_cl[e];
-            if (lab[u] == lv) acol[o++] = u + base;
-          }
-        }
-        running += total;
-        __syncthreads();
-      }
-      if (tid == 0) aptr[n_act] = e0 + running;
-    }
+    // row pointers of the alive CSR in compact order
+    for (int p = tid; p < n_act; p += ENV_T) aptr[p] = e0 + PREF_AT(rp[tmp[p]]);
+    if (tid == 0) aptr[n_act] = e0 + tot;
+#undef PREF_AT
+    __syncthreads();
   }
 
+  ENV_TICK();  // 4: alive CSR + degrees + compaction
   // ---- bookkeeping: reward / AUDC in f64 with the reference's operation order ---------------------------
   if (tid == 0) {
     const int B = G.n_graphs;
@@ -364,11 +371,14 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
 int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
                       int32_t forced_index, int init, md_stream_t stream);
 
+extern "C" int md_debug_read_env(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, md::g_env_dbg, sizeof(long long) * n);
+}
 static int g_force_large = 0;
 extern "C" int32_t md_env_small_max_stride(void) { return g_force_large ? 0 : md::ENV_SMALL_MAX; }
 // 1 if this batch takes the single-CTA (shared-memory) env kernel, 0 for the cooperative global-memory kernel
 extern "C" int32_t md_env_uses_small_path(const md_graphs_t* g) {
-  const size_t smem = ((size_t)3 * g->stride + (size_t)g->n_layers * (g->stride + 1) + 2 * (size_t)g->max_graph_nnz) * sizeof(int);
+  const size_t smem = ((size_t)3 * g->stride + (size_t)g->n_layers * (g->stride + 1) + 2 * (size_t)g->max_graph_nnz + 1) * sizeof(int);
   return !(g_force_large || g->stride > md::ENV_SMALL_MAX || g->max_graph_nnz <= 0 || smem > md::ENV_SMALL_SMEM);
 }
 extern "C" void md_debug_force_large_env(int32_t on) { g_force_large = on; }
@@ -378,7 +388,7 @@ static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* 
   if (!g || !s) return MD_EINVAL;
   if (g->n_layers < 1 || g->n_layers > MD_MAX_LAYERS) return MD_ELAYERS;
   if (g->stride % MD_TILE_M != 0 || g->n_total != g->n_graphs * g->stride) return MD_EINVAL;
-  const size_t smem = ((size_t)3 * g->stride + (size_t)g->n_layers * (g->stride + 1) + 2 * (size_t)g->max_graph_nnz) * sizeof(int);
+  const size_t smem = ((size_t)3 * g->stride + (size_t)g->n_layers * (g->stride + 1) + 2 * (size_t)g->max_graph_nnz + 1) * sizeof(int);
   if (g_force_large || g->stride > md::ENV_SMALL_MAX || g->max_graph_nnz <= 0 || smem > md::ENV_SMALL_SMEM)
     return md_env_step_large(g, s, forced, forced_stride, forced_index, init, stream);
   static size_t configured = 0;

@@ -115,7 +115,7 @@ class GraphBatch:
         S = max(TILE_M, (nmax + TILE_M - 1) // TILE_M * TILE_M)
         if B * S >= 2 ** 31:
             raise ValueError("batch too large for int32 node ids")
-        rowptr, col, nnz = [], [], []
+        rowptr, col, src, nnz = [], [], [], []
         for l in range(L):
             rp = np.zeros(B * S + 1, np.int64)
             cols = []
@@ -132,10 +132,12 @@ class GraphBatch:
             c = np.concatenate(cols) if pos else np.zeros(1, np.int64)
             rowptr.append(_pin(torch.from_numpy(rp.astype(np.int32))))
             col.append(_pin(torch.from_numpy(c.astype(np.int32))))
+            sr = np.repeat(np.arange(B * S, dtype=np.int32), np.diff(rp)) if pos else np.zeros(1, np.int32)
+            src.append(_pin(torch.from_numpy(sr)))
         gnnz = np.zeros(B, np.int64)
         for l in range(L):
             gnnz += 2 * np.array([g.num_edges[l] for g in graphs], np.int64)
-        out = dict(B=B, L=L, S=S, rowptr=rowptr, col=col, nnz=nnz, cost=cost, max_graph_nnz=int(gnnz.max()),
+        out = dict(B=B, L=L, S=S, rowptr=rowptr, col=col, src=src, nnz=nnz, cost=cost, max_graph_nnz=int(gnnz.max()),
                    n_nodes=_pin(torch.tensor([g.num_nodes for g in graphs], dtype=torch.int32)),
                    n_edges=_pin(torch.tensor([[g.num_edges[l] for g in graphs] for l in range(L)], dtype=torch.int32)))
         if cost == "degree":
@@ -178,6 +180,7 @@ class GraphBatch:
         up = lambda t: t.to(dev, non_blocking=True)
         self.rowptr = [up(t) for t in host["rowptr"]]
         self.col = [up(t) for t in host["col"]]
+        self.src = [up(t) for t in host["src"]]
         self.n_nodes, self.n_edges = up(host["n_nodes"]), up(host["n_edges"])
         self.max_rank = torch.ones(B, dtype=torch.int32, device=dev)
         self.node_w, self.node_cost = [], None
@@ -185,7 +188,7 @@ class GraphBatch:
             self.node_w = [up(t) for t in host["node_w"]]
             self.node_cost = up(host["node_cost"])
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in
-                             host["rowptr"] + host["col"] + [host["n_nodes"], host["n_edges"]] +
+                             host["rowptr"] + host["col"] + host["src"] + [host["n_nodes"], host["n_edges"]] +
                              (host["node_w"] + [host["node_cost"]] if self.cost == "degree" else []))
         st = _lib.MdGraphs()
         st.n_graphs, st.n_layers, st.stride, st.n_total = B, L, S, B * S
@@ -193,6 +196,7 @@ class GraphBatch:
         for l in range(L):
             st.rowptr[l] = self.rowptr[l].data_ptr()
             st.col[l] = self.col[l].data_ptr()
+            st.src[l] = self.src[l].data_ptr()
             if self.node_w:
                 st.node_w[l] = self.node_w[l].data_ptr()
         st.n_nodes = self.n_nodes.data_ptr()
