@@ -117,6 +117,8 @@ typedef struct md_work {
   float* psum;                  /* [MD_BP_ITERS][L][n_total / MD_TILE_M][64] per-tile partial sums of H (subgsum) */
   float* gconst;                /* [B][MD_GCONST] per-graph constants for the Q head */
   float* q;                     /* [n_total] Q value per node slot (valid for active nodes) */
+  void* fused_ws;               /* md_fused_ws_bytes() bytes, 1024-byte aligned: scratch of md_embed_fused (weight images,
+                                   unit counter, per-SM L2-resident column-half images); NULL = resident path not used */
 } md_work_t;
 #define MD_GCONST 16 /* s[L], gate_softmax[L], aux_dot[L] padded */
 
@@ -144,7 +146,8 @@ int32_t md_env_small_max_stride(void);
 int32_t md_env_uses_small_path(const md_graphs_t* g);
 /* test hook: route every batch through the multi-CTA (global-memory, cooperative) env kernel */
 void md_debug_force_large_env(int32_t on);
-/* profiling hook (results become wrong): bit 0 skips the neighbour gather, bit 1 the dense transform of md_embed_iter */
+/* profiling hook: bit 0 skips the neighbour gather, bit 1 the dense transform of md_embed_iter (results become wrong);
+ * bit 2 makes md_rollout_steps use the unfused embedding kernels even where md_embed_fused applies */
 void md_debug_set_flags(int32_t flags);
 /* profiling hook: clock64 phase times of CTA 0 of the last md_env_step (labels in, CSR staged, prune rounds,
  * component sizes, alive CSR + degrees) and, at index 16, the number of prune rounds */
@@ -161,6 +164,16 @@ int md_embed_init(const md_graphs_t* g, const md_state_t* s, const md_weights_t*
  * (spmm subgsum, :297-298) as per-tile partials.  iter = 0..2; reads h[iter&1], writes h[(iter+1)&1]. */
 int md_embed_iter(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                   int32_t iter, md_stream_t stream);
+
+/* md_embed_init + the MD_BP_ITERS md_embed_iter calls in ONE launch for batches with stride <= md_fused_max_stride():
+ * a persistent CTA per (graph, layer) keeps the embeddings resident in shared memory (one 32-column half at a time),
+ * gathers neighbour rows from there and runs the dense transforms on the tensor cores (tcgen05, 3-term tf32/bf16
+ * split, accumulators in tensor memory).  Same outputs as the unfused sequence: h[MD_BP_ITERS & 1] and psum.
+ * Returns MD_ETOOBIG for larger strides and MD_EINVAL when k->fused_ws is NULL. */
+int md_embed_fused(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
+                   md_stream_t stream);
+int32_t md_fused_max_stride(void);
+int64_t md_fused_ws_bytes(void);
 
 /* Virtual (graph) node chain y0..y3 (:272-287,301-321), its inter-layer fusion rows
  * (BitwiseMultipyLogis, U/MRGNN/mutil_layer_weight.py:266-313) and the per-graph Q-head constants. */

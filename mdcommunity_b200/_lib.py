@@ -49,7 +49,7 @@ class MdWeights(C.Structure):
 
 
 class MdWork(C.Structure):
-    _fields_ = [("h", (_vp * MAX_LAYERS) * 2), ("psum", _vp), ("gconst", _vp), ("q", _vp)]
+    _fields_ = [("h", (_vp * MAX_LAYERS) * 2), ("psum", _vp), ("gconst", _vp), ("q", _vp), ("fused_ws", _vp)]
 
 
 _LIB = None
@@ -65,6 +65,9 @@ _SIGS = {
     "md_env_uses_small_path": ([C.POINTER(MdGraphs)], C.c_int32),
     "md_embed_init": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_embed_iter": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),
+    "md_embed_fused": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
+    "md_fused_max_stride": ([], C.c_int32),
+    "md_fused_ws_bytes": ([], C.c_int64),
     "md_graph_embed": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_qhead": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_rollout_steps": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),

@@ -61,7 +61,9 @@ class BatchRollout:
     results after run(): score [B] f64 (AUDC), n_steps [B], actions [B, T] (-1 padded), ranks [B, T], maxcc [B, T].
     """
 
-    def __init__(self, batch: GraphBatch, weights: QWeights = None, max_steps=None):
+    def __init__(self, batch: GraphBatch, weights: QWeights = None, max_steps=None, fused=None):
+        """fused: None = use md_embed_fused whenever the batch qualifies (stride <= md_fused_max_stride());
+        False = always the unfused md_embed_init + md_embed_iter kernels (A/B tests, large graphs)."""
         self.batch = batch
         self.lib = batch.lib
         self.w = weights
@@ -114,6 +116,15 @@ class BatchRollout:
             for l in range(L):
                 k.h[i][l] = self.h[i][l].data_ptr()
         k.psum, k.gconst, k.q = self.psum.data_ptr(), self.gconst.data_ptr(), self.q.data_ptr()
+        self.fused = (fused is not False) and S <= int(self.lib.md_fused_max_stride())
+        if fused and not self.fused:
+            raise ValueError("md_embed_fused handles strides up to %d, this batch has %d" % (self.lib.md_fused_max_stride(), S))
+        if self.fused:
+            nbytes = int(self.lib.md_fused_ws_bytes())
+            self.fused_ws = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=dev)
+            k.fused_ws = (self.fused_ws.data_ptr() + 1023) // 1024 * 1024
+        else:
+            k.fused_ws = None
         self.k = k
         self._pinned_done = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.kernel_launches = 0
@@ -148,12 +159,17 @@ class BatchRollout:
     def forward(self):
         """One Q-network evaluation for all non-terminal graphs (test_forward + the Predict mask + arg-max key)."""
         lib, g, s, w, k, st = self.lib, self._g(), C.byref(self.s), self.w.ptr(), C.byref(self.k), self._stream()
-        _lib.check(lib.md_embed_init(g, s, w, k, st), "md_embed_init")
-        for it in range(_lib.BP_ITERS):
-            _lib.check(lib.md_embed_iter(g, s, w, k, it, st), "md_embed_iter")
+        if self.fused:
+            _lib.check(lib.md_embed_fused(g, s, w, k, st), "md_embed_fused")
+            self.kernel_launches += 2
+        else:
+            _lib.check(lib.md_embed_init(g, s, w, k, st), "md_embed_init")
+            for it in range(_lib.BP_ITERS):
+                _lib.check(lib.md_embed_iter(g, s, w, k, it, st), "md_embed_iter")
+            self.kernel_launches += 1 + _lib.BP_ITERS
         _lib.check(lib.md_graph_embed(g, s, w, k, st), "md_graph_embed")
         _lib.check(lib.md_qhead(g, s, w, k, st), "md_qhead")
-        self.kernel_launches += 3 + _lib.BP_ITERS
+        self.kernel_launches += 2
 
     def step(self, actions=None, index=-1):
         """stepWithoutReward for every non-terminal graph.  actions: None -> arg-max of the last forward();
@@ -183,7 +199,7 @@ class BatchRollout:
             if step == 1:
                 _lib.check(self.lib.md_rollout_steps(self._g(), C.byref(self.s), self.w.ptr(), C.byref(self.k), chunk,
                                                      self._stream()), "md_rollout_steps")
-                self.kernel_launches += chunk * (4 + _lib.BP_ITERS)
+                self.kernel_launches += chunk * ((5 if self.fused else 4 + _lib.BP_ITERS))
             else:
                 for _ in range(chunk):
                     self.forward()

@@ -21,12 +21,14 @@ ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--skip", type=int, default=0, help="un-profiled steps after the reset")
 ap.add_argument("--dbg", type=int, default=0, help="md_debug_set_flags value for the measured region")
 ap.add_argument("--iters", type=int, default=0, help="time N md_embed_iter launches alone instead of full steps")
+ap.add_argument("--fused-cmp", type=int, default=0, help="time N embedding stages: md_embed_fused vs md_embed_init + 3 md_embed_iter")
+ap.add_argument("--unfused", action="store_true", help="use the unfused embedding kernels in the rollout")
 args = ap.parse_args()
 
 graphs = [gmm.gmm_graph(args.n, i, cost=args.cost) for i in range(args.graphs)]
 batch = mdb.GraphBatch(graphs, "cuda:0", args.cost)
 w = mdb.QWeights(dict(np.load(os.path.join(ROOT, "tests", "golden", "weights_%s.npz" % args.cost))), batch.device)
-ro = mdb.BatchRollout(batch, w)
+ro = mdb.BatchRollout(batch, w, fused=False if args.unfused else None)
 ro.run()
 ro.reset()
 lib = ro.lib
@@ -35,6 +37,26 @@ if args.skip:
 torch.cuda.synchronize()
 print("active nodes", int(ro.n_act.sum()), "alive directed edges", (2 * ro.alive_edges.sum(1)).tolist())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if args.fused_cmp:
+    for name in ("fused", "unfused"):
+        for rep in range(3):
+            torch.cuda.synchronize()
+            if rep == 2 and name == "fused":
+                torch.cuda.profiler.start()
+            e0.record()
+            for i in range(args.fused_cmp):
+                if name == "fused":
+                    _lib.check(lib.md_embed_fused(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()), "fused")
+                else:
+                    _lib.check(lib.md_embed_init(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()), "init")
+                    for it in range(3):
+                        _lib.check(lib.md_embed_iter(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), it, ro._stream()), "iter")
+            e1.record()
+            torch.cuda.synchronize()
+            if rep == 2 and name == "fused":
+                torch.cuda.profiler.stop()
+        print("%s: %.1f us per embedding stage (first embedding + 3 iterations)" % (name, 1e3 * e0.elapsed_time(e1) / args.fused_cmp))
+    sys.exit(0)
 if args.iters:
     _lib.check(lib.md_embed_init(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()), "init")
     for dbg in ((args.dbg,) if args.dbg else (0, 1, 2, 3)):

@@ -76,12 +76,15 @@ def test_env_random_actions_bit_exact(variant, env_path):
     assert ro.num_done() == len(zs)
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
 @pytest.mark.parametrize("variant", ["unit", "degree"])
-def test_q_teacher_forced(variant):
-    """Feed the reference's greedy actions; per step compare active set + aux (exact) and Q (1e-4 rel + 1e-6)."""
+def test_q_teacher_forced(variant, fused):
+    """Feed the reference's greedy actions; per step compare active set + aux (exact) and Q (1e-4 rel + 1e-6).
+    fused: md_embed_fused (shared-memory resident embeddings, tcgen05 transforms); unfused: md_embed_init/_iter."""
     mdb = _mdb()
     zs, graphs, batch, w = _load_batch(variant)
-    ro = mdb.BatchRollout(batch, w)
+    ro = mdb.BatchRollout(batch, w, fused=fused)
+    assert ro.fused == fused
     acts, T = _forced(zs, "greedy_actions", batch.device)
     worst = 0.0
     agree = total = 0
@@ -246,3 +249,38 @@ def test_full_size_batch_properties():
     n = int(solo["n_steps"][0])
     assert n == r1["n_steps"][5] and np.array_equal(solo["actions"][0, :n], r1["actions"][5, :n])
     assert solo["score"][0] == r1["score"][5]
+
+
+@pytest.mark.parametrize("variant", ["unit", "degree"])
+def test_fused_embedding_matches_unfused(variant):
+    """md_embed_fused vs md_embed_init + 3 x md_embed_iter on identical env states (ragged batch, several removal
+    depths): final node embeddings within 2e-5 absolute (rows are unit vectors), per-graph sums within 1e-4 relative,
+    Q within the north-star tolerance of the unfused kernels' Q."""
+    mdb = _mdb()
+    zs, graphs, batch, w = _load_batch(variant)
+    a = mdb.BatchRollout(batch, w, fused=True)
+    b = mdb.BatchRollout(batch, w, fused=False)
+    acts, T = _forced(zs, "greedy_actions", batch.device)
+    S, L = batch.S, batch.L
+    worst_h = worst_q = 0.0
+    for t in range(min(T, 12)):
+        a.forward()
+        b.forward()
+        n_act = a.n_act.cpu().numpy()
+        assert np.array_equal(n_act, b.n_act.cpu().numpy())
+        for i in range(batch.B):
+            n = int(n_act[i])
+            if n == 0:
+                continue
+            ids = a.act_list[i * S:i * S + n].long()
+            for l in range(L):
+                ha, hb = a.h[1][l][ids], b.h[1][l][ids]
+                worst_h = max(worst_h, float((ha - hb).abs().max()))
+            qa, qb = a.q[ids], b.q[ids]
+            err = (qa - qb).abs() - (Q_RTOL * qb.abs() + Q_ATOL)
+            worst_q = max(worst_q, float(((qa - qb).abs() / (qb.abs() + 1e-2)).max()))
+            assert float(err.max()) <= 0, (variant, i, t)
+        assert worst_h <= 2e-5, (variant, t, worst_h)
+        a.step(acts)
+        b.step(acts)
+    print("fused vs unfused: worst |dH| %.3e, worst scaled |dQ| %.3e" % (worst_h, worst_q))
