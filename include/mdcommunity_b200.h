@@ -117,7 +117,7 @@ typedef struct md_work {
   float* psum;                  /* [MD_BP_ITERS][L][n_total / MD_TILE_M][64] per-tile partial sums of H (subgsum) */
   float* gconst;                /* [B][MD_GCONST] per-graph constants for the Q head */
   float* q;                     /* [n_total] Q value per node slot (valid for active nodes) */
-  void* fused_ws;               /* md_fused_ws_bytes() bytes, 1024-byte aligned: scratch of md_embed_fused (weight images,
+  void* fused_ws;               /* md_fused_ws_bytes(g) bytes, 1024-byte aligned: scratch of md_embed_fused (weight images,
                                    unit counter, per-SM L2-resident column-half images); NULL = resident path not used */
 } md_work_t;
 #define MD_GCONST 16 /* s[L], gate_softmax[L], aux_dot[L] padded */
@@ -152,6 +152,16 @@ void md_debug_set_flags(int32_t flags);
 /* profiling hook: clock64 phase times of CTA 0 of the last md_env_step (labels in, CSR staged, prune rounds,
  * component sizes, alive CSR + degrees) and, at index 16, the number of prune rounds */
 int md_debug_read_env(long long* host, int n);
+/* profiling hook: clock64 phase sums of CTA 0 of the last md_embed_fused launch.  Gather warp 0: [0] unit setup,
+ * [1] first-embedding fill, [2] column-half reload, [3] gather, [4] wait for the staging tile, [5] end-of-pass wait,
+ * [6] epilogue, [7] idle between units; MMA thread: [8] weight-image wait, [9] wait for a full tile, [10] MMA issue,
+ * [11] end-of-pass completion wait; [15] units processed */
+int md_debug_read_fused(long long* host, int n);
+/* profiling hook: per CTA (up to 160) of the last md_embed_fused launch: {cycles in the unit loop, units processed} */
+int md_debug_read_fused_ctas(unsigned* host320);
+/* profiling hook: gather sub-phase cycles of CTA 0 / warp 0: row setup, neighbour loop, own rows, staging stores,
+ * long rows, proxy fence + arrive */
+int md_debug_read_fused_gather(unsigned* host8);
 
 /* ---- Q network ---------------------------------------------------------------------------------------- */
 
@@ -165,7 +175,7 @@ int md_embed_init(const md_graphs_t* g, const md_state_t* s, const md_weights_t*
 int md_embed_iter(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                   int32_t iter, md_stream_t stream);
 
-/* md_embed_init + the MD_BP_ITERS md_embed_iter calls in ONE launch for batches with stride <= md_fused_max_stride():
+/* md_embed_init + the MD_BP_ITERS md_embed_iter calls in ONE launch for batches that satisfy md_fused_applies():
  * a persistent CTA per (graph, layer) keeps the embeddings resident in shared memory (one 32-column half at a time),
  * gathers neighbour rows from there and runs the dense transforms on the tensor cores (tcgen05, 3-term tf32/bf16
  * split, accumulators in tensor memory).  Same outputs as the unfused sequence: h[MD_BP_ITERS & 1] and psum.
@@ -173,7 +183,9 @@ int md_embed_iter(const md_graphs_t* g, const md_state_t* s, const md_weights_t*
 int md_embed_fused(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                    md_stream_t stream);
 int32_t md_fused_max_stride(void);
-int64_t md_fused_ws_bytes(void);
+/* 1 if md_embed_fused handles this batch: stride <= md_fused_max_stride() and < 65536 CSR entries per graph */
+int32_t md_fused_applies(const md_graphs_t* g);
+int64_t md_fused_ws_bytes(const md_graphs_t* g);
 
 /* Virtual (graph) node chain y0..y3 (:272-287,301-321), its inter-layer fusion rows
  * (BitwiseMultipyLogis, U/MRGNN/mutil_layer_weight.py:266-313) and the per-graph Q-head constants. */

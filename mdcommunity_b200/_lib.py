@@ -62,12 +62,16 @@ _SIGS = {
     "md_debug_force_large_env": ([C.c_int32], None),
     "md_debug_set_flags": ([C.c_int32], None),
     "md_debug_read_env": ([_vp, C.c_int32], C.c_int),
+    "md_debug_read_fused": ([_vp, C.c_int32], C.c_int),
+    "md_debug_read_fused_ctas": ([_vp], C.c_int),
+    "md_debug_read_fused_gather": ([_vp], C.c_int),
     "md_env_uses_small_path": ([C.POINTER(MdGraphs)], C.c_int32),
     "md_embed_init": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_embed_iter": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),
     "md_embed_fused": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_fused_max_stride": ([], C.c_int32),
-    "md_fused_ws_bytes": ([], C.c_int64),
+    "md_fused_applies": ([C.POINTER(MdGraphs)], C.c_int32),
+    "md_fused_ws_bytes": ([C.POINTER(MdGraphs)], C.c_int64),
     "md_graph_embed": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_qhead": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_rollout_steps": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),

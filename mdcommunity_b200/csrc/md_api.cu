@@ -7,7 +7,7 @@ extern int g_md_debug_flags;
 extern "C" int md_rollout_steps(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                                 int32_t n_steps, md_stream_t stream) {
   if (!g || !k) return MD_EINVAL;
-  const bool fused = k->fused_ws != nullptr && g->stride <= md_fused_max_stride() && !(g_md_debug_flags & 4);
+  const bool fused = k->fused_ws != nullptr && md_fused_applies(g) && !(g_md_debug_flags & 4);
   for (int i = 0; i < n_steps; ++i) {
     int rc;
     if (fused) {

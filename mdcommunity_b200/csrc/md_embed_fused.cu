@@ -14,10 +14,13 @@
 //               SWIZZLE_128B K-major tile layout (a 128-byte row is exactly one swizzle span), so the very same bytes
 //               serve the gather (8 lanes x LDS.128 per neighbour row, conflict-free) and, as MMA operand A, the
 //               "own embedding" term of the transform.
-//     gather    16 warps; 8 lanes per row; neighbour lists are read from a shared-memory copy of the unit's alive CSR
-//               (compact uint16 indices, translated once per unit); sums in CSR order; rows longer than FZ_LONG are
-//               spread over the warp's four lane groups.  Per 128-row tile the warps write P = A_adj.H (raw fp32) and
-//               the bf16 remainders [P - tf32(P) | H - tf32(H)] into a staging tile.
+//     gather    8 warps; 8 lanes per row (4 rows per warp instruction); neighbour lists come from a shared-memory copy of
+//               the unit's alive CSR (uint16 entries, translated once per unit).  Rows are re-ordered per unit by
+//               descending alive degree (deterministic counting sort) and dealt to the lane groups so that the four
+//               rows a warp walks together have (nearly) equal length: without this the power-law degree spread made
+//               every step wait for its longest row.  Sums stay in CSR order; rows longer than FZ_LONG are spread over
+//               the warp's four lane groups.  Per 128-row tile the warps write P = A_adj.H (raw fp32) and the bf16
+//               remainders [P - tf32(P) | H - tf32(H)] into a staging tile.
 //     transform one elected thread issues tcgen05.mma: D_tile += P.W13[32p:32p+32] + H.W23[32p:32p+32] as
 //               kind::tf32 (operands are truncated to tf32 by the tensor core -- measured, scripts/microbench/umma_probe.cu)
 //               with hi and lo planes of the weights, plus one kind::f16 (bf16) pass for the operand remainders:
@@ -38,11 +41,11 @@ namespace md {
 using namespace umma;
 
 constexpr int FZ_ROWS = 1024;          // largest stride (node slots per graph) the resident path handles
-constexpr int FZ_GW = 16;              // gather / epilogue warps
+constexpr int FZ_GW = 8;               // gather / epilogue warps
 constexpr int FZ_GT = FZ_GW * 32;
 constexpr int FZ_T = FZ_GT + 32;       // + the MMA / bulk-copy warp
 constexpr int FZ_IDX_CAP = 8192;       // alive directed edges of one unit cached in shared memory
-constexpr int FZ_LONG = 24;            // rows with more alive neighbours are summed by the whole warp
+constexpr int FZ_LONG = 24;            // rows with more alive neighbours are summed by the whole warp (< 31: exact sort buckets)
 constexpr uint32_t FZ_TILE_B = 16384;  // one 128-row x 128-byte tile
 constexpr uint32_t FZ_WPASS_B = 40960; // B operands of one pass: W13 hi, W13 lo, W23 hi, W23 lo (tf32), [W13|W23] bf16
 constexpr size_t FZ_WS_CTR = 2 * FZ_WPASS_B;
@@ -54,17 +57,33 @@ struct FusedSmem {
   unsigned char P[FZ_TILE_B];       // staging: neighbour sums of one tile, raw fp32
   unsigned char LO[FZ_TILE_B];      // staging: bf16 remainders, row = [P_lo (32) | H_lo (32)]
   unsigned char Wt[FZ_WPASS_B];     // B operands of the running pass
-  uint16_t idx[FZ_IDX_CAP];         // compact neighbour rows of the unit's alive CSR
-  uint16_t pos[FZ_ROWS];            // graph-local node id -> compact row
-  uint16_t rptr[FZ_ROWS + 8];       // row pointers into idx
+  uint16_t idx[FZ_IDX_CAP + 64];    // neighbour entries of the unit's alive CSR (see nbrJ); setup: sort counters
+  uint16_t pos[FZ_ROWS];            // graph-local node id -> row (degree-sorted compact order)
+  uint32_t rbe[FZ_ROWS];            // row -> first | (one-past-last << 16) entry of its neighbour list
+  uint16_t rowv[FZ_ROWS];           // row -> graph-local node id
   float red[FZ_GW][32];
-  float wn2l[2 * D];
-  uint64_t bar_full, bar_empty, bar_w, bar_h;
+  alignas(16) float wn2l[2 * D];
+  uint16_t bbase[32];
+  uint64_t bar_full, bar_empty, bar_w, bar_h, bar_res;
   uint32_t tmem;
   int unit;
 };
+static_assert(sizeof(FusedSmem) <= 232448, "FusedSmem exceeds the 227 KB shared memory of one CTA");
+
+// phase clocks of CTA 0 (profiling): gather warp 0 -> [0..7], MMA warp -> [8..11], units processed -> [15]
+__device__ long long g_fz_dbg[16];
+__device__ unsigned g_fz_gath[8];  // gather sub-phases of CTA 0 warp 0: setup, main loop, own rows, stores, long rows, fence+arrive
+__device__ unsigned g_fz_cta[160][2];  // per CTA: cycles from start to end of the unit loop, units processed
+#define FZ_CLK(acc)                   \
+  do {                                \
+    const uint32_t n_ = clock();      \
+    acc += n_ - t_dbg;                \
+    t_dbg = n_;                       \
+  } while (0)
 
 __device__ __forceinline__ void gw_sync() { asm volatile("bar.sync 1, %0;" ::"n"(FZ_GT) : "memory"); }
+// the four warps that share one TMEM lane quadrant set / staging tile in the epilogue (quad = warp / 4)
+__device__ __forceinline__ void quad_sync(int quad) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quad) : "memory"); }
 
 __device__ __forceinline__ void add4(float4& a, const float4& b) {
   a.x += b.x;
@@ -77,9 +96,67 @@ __device__ __forceinline__ uint2 lo_bf16x4(const float4& v) {
   const __nv_bfloat162 b = __floats2bfloat162_rn(v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
   return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+struct F4P {  // a float4 as two packed f32x2 registers (for FADD2)
+  uint64_t lo, hi;
+};
+__device__ __forceinline__ F4P lds128p(uint32_t addr) {
+  F4P v;
+  asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void add4p(F4P& a, const F4P& b) {
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a.lo) : "l"(b.lo));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a.hi) : "l"(b.hi));
+}
+__device__ __forceinline__ float4 unpack4(const F4P& a) {
+  return make_float4(__uint_as_float((uint32_t)a.lo), __uint_as_float((uint32_t)(a.lo >> 32)), __uint_as_float((uint32_t)a.hi),
+                     __uint_as_float((uint32_t)(a.hi >> 32)));
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
 
-// Weight images (both passes) in the exact shared-memory layout + reset of the unit counter.
-__global__ void __launch_bounds__(256) fused_prep_kernel(md_weights_t W, unsigned char* ws) {
+constexpr int FZ_ORDER_MAX = 8192;  // units ranked by work (O(U^2) ranking); larger batches run in index order
+
+// Per launch: weight images (both passes) in the exact shared-memory layout, reset of the unit counter, and the order in
+// which the persistent CTAs take the (graph, layer) units: heaviest first (alive entries + 4 per active node), so the
+// tail of the launch is made of the cheap units.  Block b ranks units [256 b, 256 b + 256).
+__global__ void __launch_bounds__(256) fused_prep_kernel(md_graphs_t G, md_state_t S, md_weights_t W, unsigned char* ws,
+                                                         int* order, int n_units) {
+  __shared__ int key[FZ_ORDER_MAX];
+  const int L = G.n_layers;
+  if (n_units <= FZ_ORDER_MAX) {
+    for (int u = threadIdx.x; u < n_units; u += 256) {
+      const int g = u / L, l = u - g * L, n = S.n_act[g], base = g * G.stride;
+      key[u] = n > 0 ? (S.aptr[l][base + n] - S.aptr[l][base]) + 4 * n : 0;
+    }
+    __syncthreads();
+    const int u = blockIdx.x * 256 + threadIdx.x;
+    if (u < n_units) {
+      const int k = key[u];
+      int rank = 0;
+      for (int v = 0; v < n_units; ++v) rank += (key[v] > k) || (key[v] == k && v < u);
+      order[rank] = u;
+    }
+  } else {
+    const int u = blockIdx.x * 256 + threadIdx.x;
+    if (u < n_units) order[u] = u;
+  }
+  if (blockIdx.x != 0) return;
   if (threadIdx.x == 0) *reinterpret_cast<int*>(ws + FZ_WS_CTR) = 0;
   for (int i = threadIdx.x; i < 2 * 64 * 32; i += 256) {
     const int p = i >> 11, n = (i >> 5) & 63, k = i & 31;
@@ -96,10 +173,14 @@ __global__ void __launch_bounds__(256) fused_prep_kernel(md_weights_t W, unsigne
 }
 
 __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K,
-                                                             unsigned char* ws, int n_units) {
+                                                             unsigned char* ws, const int* __restrict__ order,
+                                                             int n_units) {
+  // NOTE: no pointer arithmetic on the base -- the compiler must keep seeing the shared state space, otherwise every
+  // access below turns into a generic LD/ST (measured: 4x slower gather).  Alignment is asserted instead.
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  FusedSmem& sm = *reinterpret_cast<FusedSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   const int L = G.n_layers, St = G.stride, B = G.n_graphs;
   const int tpg = St / TILE_M, tiles_per_layer = B * tpg;
   if (tid == 0) {
@@ -107,10 +188,12 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     mbar_init(&sm.bar_empty, 1);
     mbar_init(&sm.bar_w, 1);
     mbar_init(&sm.bar_h, 1);
+    mbar_init(&sm.bar_res, 1);
     mbar_fence_init();
   }
   if (warp == FZ_GW) tmem_alloc(&sm.tmem, 512);
   if (tid < 2 * D) sm.wn2l[tid] = W.w_n2l[tid];
+  for (int i = tid; i < FZ_IDX_CAP + 64; i += FZ_T) sm.idx[i] = 0;  // every entry is always a valid J (< 8192)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -120,20 +203,28 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
   int* const counter = reinterpret_cast<int*>(ws + FZ_WS_CTR);
   const bool degree_cost = G.node_w[0] != nullptr;
 
+  const long long t_start = clock64();
+  uint32_t t_dbg = clock(), c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0, c9 = 0;  // phase clocks (FZ_CLK)
+  uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0;  // gather sub-phases
+  int n_units_done = 0;
   uint32_t uses = 0;    // staging-tile hand-offs so far (same sequence in the gather warps and the MMA warp)
   uint32_t wloads = 0;  // weight images consumed (MMA warp)
   uint32_t hloads = 0;  // resident-half reloads consumed (gather warps)
-  if (warp == FZ_GW && lane == 0) {
+  uint32_t passes = 0;  // passes started (MMA warp: phases of bar_res)
+  if (warp == FZ_GW && elect_one()) {
     mbar_arrive_expect_tx(&sm.bar_w, FZ_WPASS_B);
     bulk_g2s(sm.Wt, wimg, FZ_WPASS_B, &sm.bar_w);
   }
 
   for (;;) {
-    if (tid == 0) sm.unit = atomicAdd(counter, 1);
+    if (tid == 0) {
+      const int slot = atomicAdd(counter, 1);
+      sm.unit = slot < n_units ? order[slot] : -1;
+    }
     __syncthreads();
     const int unit = sm.unit;
     __syncthreads();
-    if (unit >= n_units) break;
+    if (unit < 0) break;
     const int g = unit / L, l = unit - g * L;
     const int n = S.n_act[g];
     if (n <= 0) continue;
@@ -141,110 +232,209 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     const int base = g * St;
 
     if (warp == FZ_GW) {
-      // ============================== MMA / bulk-copy warp ==============================
-      if (lane == 0) {
-        const uint32_t idt = idesc(FMT_TF32, 128, 64), idb = idesc(FMT_BF16, 128, 64);
-        const uint64_t dP = desc_k_sw128(smem_u32(sm.P), 0), dLO = desc_k_sw128(smem_u32(sm.LO), 0);
-        const uint64_t dH0 = desc_k_sw128(smem_u32(sm.Hs), 0);
-        const uint64_t b13h = desc_k_sw128(smem_u32(sm.Wt), 0), b13l = desc_k_sw128(smem_u32(sm.Wt) + 8192, 0);
-        const uint64_t b23h = desc_k_sw128(smem_u32(sm.Wt) + 16384, 0), b23l = desc_k_sw128(smem_u32(sm.Wt) + 24576, 0);
-        const uint64_t bbf = desc_k_sw128(smem_u32(sm.Wt) + 32768, 0);
-        for (int it = 0; it < MD_BP_ITERS; ++it) {
-          for (int pass = 0; pass < 2; ++pass) {
-            mbar_wait(&sm.bar_w, wloads & 1);
-            ++wloads;
+      // ============================== MMA / bulk-copy warp (warp-uniform control flow) ==============================
+      const uint32_t idt = idesc(FMT_TF32, 128, 64), idb = idesc(FMT_BF16, 128, 64);
+      const uint64_t dP = desc_k_sw128(smem_u32(sm.P), 0), dLO = desc_k_sw128(smem_u32(sm.LO), 0);
+      const uint64_t dH0 = desc_k_sw128(smem_u32(sm.Hs), 0);
+      const uint64_t b13h = desc_k_sw128(smem_u32(sm.Wt), 0), b13l = desc_k_sw128(smem_u32(sm.Wt) + 8192, 0);
+      const uint64_t b23h = desc_k_sw128(smem_u32(sm.Wt) + 16384, 0), b23l = desc_k_sw128(smem_u32(sm.Wt) + 24576, 0);
+      const uint64_t bbf = desc_k_sw128(smem_u32(sm.Wt) + 32768, 0);
+      for (int it = 0; it < MD_BP_ITERS; ++it) {
+        for (int pass = 0; pass < 2; ++pass) {
+          FZ_CLK(c3);
+          mbar_wait(&sm.bar_w, wloads & 1);
+          ++wloads;
+          mbar_wait(&sm.bar_res, passes & 1);  // resident half in place, accumulators of the previous iteration drained
+          ++passes;
+          FZ_CLK(c0);
+          tc_fence_after();
+          // own-embedding term first: it needs nothing from the gather
+          if (elect_one()) {
             for (int t = 0; t < ntile; ++t) {
-              mbar_wait(&sm.bar_full, uses & 1);
-              tc_fence_after();
               const uint32_t d = tbase + 64 * t;
               const uint64_t dH = dH0 + (uint64_t)((t * FZ_TILE_B) >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t ko = 2 * k;  // 32 bytes per K step, in 16-byte units
-                mma_tf32(d, dP + ko, b13h + ko, idt, (pass | k) != 0);
-                mma_tf32(d, dP + ko, b13l + ko, idt, 1);
-                mma_tf32(d, dH + ko, b23h + ko, idt, 1);
+                mma_tf32(d, dH + ko, b23h + ko, idt, (pass | k) != 0);
                 mma_tf32(d, dH + ko, b23l + ko, idt, 1);
+              }
+            }
+          }
+          __syncwarp();
+          for (int t = 0; t < ntile; ++t) {
+            FZ_CLK(c1);
+            mbar_wait(&sm.bar_full, uses & 1);
+            FZ_CLK(c2);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t d = tbase + 64 * t;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ko = 2 * k;
+                mma_tf32(d, dP + ko, b13h + ko, idt, 1);
+                mma_tf32(d, dP + ko, b13l + ko, idt, 1);
                 mma_bf16(d, dLO + ko, bbf + ko, idb, 1);
               }
               mma_commit(&sm.bar_empty);
-              ++uses;
             }
-            // pass complete -> the weight tile is free: fetch the other pass's image
-            mbar_wait(&sm.bar_empty, (uses - 1) & 1);
+            __syncwarp();
+            ++uses;
+          }
+          FZ_CLK(c1);
+          // pass complete -> the weight tile is free: fetch the other pass's image
+          mbar_wait(&sm.bar_empty, (uses - 1) & 1);
+          if (elect_one()) {
             mbar_arrive_expect_tx(&sm.bar_w, FZ_WPASS_B);
             bulk_g2s(sm.Wt, wimg + (size_t)(pass ^ 1) * FZ_WPASS_B, FZ_WPASS_B, &sm.bar_w);
           }
+          __syncwarp();
         }
-      } else {
-        uses += 2 * MD_BP_ITERS * ntile;
       }
-      uses = __shfl_sync(0xffffffffu, uses, 0);
-      wloads = __shfl_sync(0xffffffffu, wloads, 0);
       continue;
     }
 
     // ================================== gather / epilogue warps ==================================
-    const int gtid = tid;  // 0..511
+    FZ_CLK(c7);
+    ++n_units_done;
+    const int gtid = tid;  // 0..FZ_GT-1
     const int gi = lane >> 3, q = lane & 7;
     const int e0 = S.aptr[l][base];
     const int nnz = S.aptr[l][base + n] - e0;
-    const bool cached = nnz <= FZ_IDX_CAP;
     const int32_t* __restrict__ aptr_g = S.aptr[l] + base;
     const int32_t* __restrict__ acol_g = S.acol[l] + e0;
-    for (int p = gtid; p < n; p += FZ_GT) sm.pos[S.act_list[base + p] - base] = (uint16_t)p;
-    if (cached)
-      for (int p = gtid; p <= n; p += FZ_GT) sm.rptr[p] = (uint16_t)(aptr_g[p] - e0);
-    gw_sync();
-    if (cached)
-      for (int e = gtid; e < nnz; e += FZ_GT) sm.idx[e] = sm.pos[acol_g[e] - base];
-    // (visibility of idx / rptr: the barrier after the first resident-half fill below)
 
-    auto row_ptr = [&](int r) -> int { return cached ? (int)sm.rptr[r] : aptr_g[r] - e0; };
-    auto nbr = [&](int e) -> int { return cached ? (int)sm.idx[e] : (int)sm.pos[acol_g[e] - base]; };
-    auto ld_h = [&](int j) -> float4 {
-      return *reinterpret_cast<const float4*>(sm.Hs + (uint32_t)j * 128u + (uint32_t)((q ^ (j & 7)) << 4));
+    // ---- row order: descending alive degree (buckets 31+, 30, ..., 1), stable inside a bucket => deterministic ----
+    {
+      uint16_t* cnt = sm.idx;  // [32 chunks of 32 rows][32 buckets], reused by the neighbour cache afterwards
+      for (int i = gtid; i < 1024; i += FZ_GT) cnt[i] = 0;
+      gw_sync();
+      int b_[4], rank_[4], beg_[4], d_[4], v_[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = warp + FZ_GW * k, p = 32 * c + lane;
+        const bool valid = p < n;
+        int a0 = 0, a1 = 0;
+        if (valid) {
+          a0 = aptr_g[p] - e0;
+          a1 = aptr_g[p + 1] - e0;
+          v_[k] = S.act_list[base + p] - base;
+        }
+        d_[k] = a1 - a0;
+        beg_[k] = a0;
+        b_[k] = valid ? min(d_[k], 31) : 32;
+        const unsigned m = __match_any_sync(0xffffffffu, b_[k]);
+        rank_[k] = __popc(m & ((1u << lane) - 1u));
+        if (valid && rank_[k] == 0) cnt[c * 32 + b_[k]] = (uint16_t)__popc(m);
+      }
+      gw_sync();
+      if (warp == 0) {  // lane = bucket: exclusive scan over chunks, then suffix scan over buckets (descending order)
+        int running = 0;
+        for (int c = 0; c < 32; ++c) {
+          const int t = cnt[c * 32 + lane];
+          cnt[c * 32 + lane] = (uint16_t)running;
+          running += t;
+        }
+        int x = running;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_down_sync(0xffffffffu, x, o);
+          if (lane + o < 32) x += y;
+        }
+        sm.bbase[lane] = (uint16_t)(x - running);
+      }
+      gw_sync();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = warp + FZ_GW * k;
+        if (b_[k] < 32) {
+          const int r = sm.bbase[b_[k]] + cnt[c * 32 + b_[k]] + rank_[k];
+          sm.pos[v_[k]] = (uint16_t)r;
+          sm.rowv[r] = (uint16_t)v_[k];
+          sm.rbe[r] = (uint32_t)beg_[k] | ((uint32_t)(beg_[k] + d_[k]) << 16);
+        }
+      }
+      gw_sync();
+    }
+    // neighbour entries are stored as J = 8*j | (j & 7) (j = row of the neighbour): the 16-byte chunk `q` of row j then
+    // sits at byte ((J ^ q) << 4) of the resident buffer (SWIZZLE_128B: chunk ^= row & 7)
+    {
+      const int ncache = min(nnz, FZ_IDX_CAP);
+      for (int e = gtid; e < ncache; e += FZ_GT) {
+        const uint32_t j = sm.pos[acol_g[e] - base];
+        sm.idx[e] = (uint16_t)((j << 3) | (j & 7));
+      }
+    }
+    // (visibility of idx: the barrier after the first resident-half fill below)
+    const int n_long = sm.bbase[FZ_LONG];  // rows whose bucket exceeds FZ_LONG, i.e. alive degree > FZ_LONG
+    const uint32_t hs_a = smem_u32(sm.Hs), idx_a = smem_u32(sm.idx);
+    auto nbrJ = [&](int e) -> uint32_t {  // entries beyond the cache (units with > FZ_IDX_CAP alive entries) come from L2
+      if (e < FZ_IDX_CAP) return lds16(idx_a + 2 * e);
+      const uint32_t j = sm.pos[acol_g[e] - base];
+      return (j << 3) | (j & 7);
     };
+    auto ld_J = [&](uint32_t J) -> F4P { return lds128p(hs_a + ((J ^ (uint32_t)q) << 4)); };
 
+    FZ_CLK(c0);
     for (int it = 0; it < MD_BP_ITERS; ++it) {
       for (int pass = 0; pass < 2; ++pass) {
         // ---------------- resident column half ----------------
         if (it == 0) {
           if (uses > 0) mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // every earlier MMA (they read Hs) has completed
           const float dmax = (float)S.max_deg[l * B + g];
-          for (int r = gtid; r < ntile * TILE_M; r += FZ_GT) {
+          float xf[4];  // the thread's (up to) 4 rows: fetch the features first, the loads are independent
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = gtid + FZ_GT * k;
+            xf[k] = 0.f;
+            if (r < n) {
+              const int v = base + sm.rowv[r];
+              xf[k] = degree_cost ? G.node_w[l][v] : (float)S.deg[l][v];
+            }
+          }
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k) {
+            const int r = gtid + FZ_GT * k;
+            if (r >= ntile * TILE_M) break;
             float x0 = 0.f, x1 = 0.f;
             if (r < n) {
-              const int v = S.act_list[base + r];
               if (degree_cost) {
-                x0 = G.node_w[l][v];
+                x0 = xf[k];
                 x1 = 1.0f;
               } else {
-                x0 = (float)S.deg[l][v] / dmax;
+                x0 = xf[k] / dmax;  // degree / degree_max, both exact small integers in f32
                 x1 = x0;
               }
             }
+            const float4* w0v = reinterpret_cast<const float4*>(sm.wn2l);
+            const float4* w1v = reinterpret_cast<const float4*>(sm.wn2l + D);
             float ss = 0.f;
-#pragma unroll 8
-            for (int c = 0; c < D; ++c) {
-              const float a = fmaxf(fmaf(x1, sm.wn2l[D + c], x0 * sm.wn2l[c]), 0.f);
-              ss = fmaf(a, a, ss);
+#pragma unroll
+            for (int c4 = 0; c4 < D / 4; ++c4) {
+              const float4 w0 = w0v[c4], w1 = w1v[c4];
+              const float a0 = fmaxf(fmaf(x1, w1.x, x0 * w0.x), 0.f), a1 = fmaxf(fmaf(x1, w1.y, x0 * w0.y), 0.f);
+              const float a2 = fmaxf(fmaf(x1, w1.z, x0 * w0.z), 0.f), a3 = fmaxf(fmaf(x1, w1.w, x0 * w0.w), 0.f);
+              ss = fmaf(a0, a0, ss);
+              ss = fmaf(a1, a1, ss);
+              ss = fmaf(a2, a2, ss);
+              ss = fmaf(a3, a3, ss);
             }
-            const float den = fmaxf(sqrtf(ss), 1e-12f);
+            const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
             unsigned char* rowp = sm.Hs + (uint32_t)r * 128u;
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
+              const float4 w0 = w0v[8 * pass + ch], w1 = w1v[8 * pass + ch];
               float4 o;
-              const int c = 32 * pass + 4 * ch;
-              o.x = fmaxf(fmaf(x1, sm.wn2l[D + c], x0 * sm.wn2l[c]), 0.f) / den;
-              o.y = fmaxf(fmaf(x1, sm.wn2l[D + c + 1], x0 * sm.wn2l[c + 1]), 0.f) / den;
-              o.z = fmaxf(fmaf(x1, sm.wn2l[D + c + 2], x0 * sm.wn2l[c + 2]), 0.f) / den;
-              o.w = fmaxf(fmaf(x1, sm.wn2l[D + c + 3], x0 * sm.wn2l[c + 3]), 0.f) / den;
+              o.x = fmaxf(fmaf(x1, w1.x, x0 * w0.x), 0.f) * inv;
+              o.y = fmaxf(fmaf(x1, w1.y, x0 * w0.y), 0.f) * inv;
+              o.z = fmaxf(fmaf(x1, w1.z, x0 * w0.z), 0.f) * inv;
+              o.w = fmaxf(fmaf(x1, w1.w, x0 * w0.w), 0.f) * inv;
               *reinterpret_cast<float4*>(rowp + ((ch ^ (r & 7)) << 4)) = o;
             }
           }
           fence_proxy_async_smem();
           gw_sync();
+          FZ_CLK(c1);
         } else if (pass == 1) {
           mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // pass 0 of this iteration: all gathers and MMAs done
           if (gtid == 0) {
@@ -253,68 +443,134 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           }
           mbar_wait(&sm.bar_h, hloads & 1);
           ++hloads;
+          FZ_CLK(c2);
         }  // it > 0, pass 0: written by the epilogue below
+        if (gtid == 0) mbar_arrive(&sm.bar_res);
 
         // ---------------- tiles: gather -> staging -> MMA ----------------
+        // Tile row 32*k + 8*gi + warp (k = 0..3): a lane group walks FOUR rows at once, one neighbour of each per step
+        // (four independent load chains; the rows are 32 apart in the degree-sorted order, so they end together), and
+        // consecutive rows go to different warps.  Rows longer than FZ_LONG (the first n_long rows of the unit) are summed
+        // afterwards by whole warps.
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = 0; t < ntile; ++t) {
-#pragma unroll 1
-          for (int round = 0; round < 2; ++round) {
-            const int rt = 8 * warp + 4 * round + gi;
-            const int r = TILE_M * t + rt;
-            const bool valid = r < n;
-            int beg = 0, end = 0;
-            if (valid) {
-              beg = row_ptr(r);
-              end = row_ptr(r + 1);
-            }
-            const bool is_long = end - beg > FZ_LONG;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!is_long) {
-              int e = beg;
-              for (; e + 1 < end; e += 2) {
-                const int j0 = nbr(e), j1 = nbr(e + 1);
-                const float4 v0 = ld_h(j0), v1 = ld_h(j1);
-                add4(acc, v0);
-                add4(acc, v1);
-              }
-              if (e < end) add4(acc, ld_h(nbr(e)));
-            }
-            unsigned longmask = __ballot_sync(0xffffffffu, is_long && q == 0);
-            while (longmask) {  // warp-uniform
-              const int src = __ffs(longmask) - 1;
-              longmask &= longmask - 1;
-              const int b = __shfl_sync(0xffffffffu, beg, src), en = __shfl_sync(0xffffffffu, end, src);
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              for (int e = b + gi; e < en; e += 4) add4(a, ld_h(nbr(e)));
-              // fixed combination order: (g0 + g1) + (g2 + g3)
-              a.x += __shfl_xor_sync(0xffffffffu, a.x, 8);
-              a.y += __shfl_xor_sync(0xffffffffu, a.y, 8);
-              a.z += __shfl_xor_sync(0xffffffffu, a.z, 8);
-              a.w += __shfl_xor_sync(0xffffffffu, a.w, 8);
-              a.x += __shfl_xor_sync(0xffffffffu, a.x, 16);
-              a.y += __shfl_xor_sync(0xffffffffu, a.y, 16);
-              a.z += __shfl_xor_sync(0xffffffffu, a.z, 16);
-              a.w += __shfl_xor_sync(0xffffffffu, a.w, 16);
-              if (gi == (src >> 3)) acc = a;
-            }
-            float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-              own = ld_h(r);
-              add4(csum, own);
-            }
-            if (round == 0 && uses > 0) mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // staging tile free again
-            const uint32_t ro = (uint32_t)rt * 128u;
-            *reinterpret_cast<float4*>(sm.P + ro + ((q ^ (rt & 7)) << 4)) = acc;
-            *reinterpret_cast<uint2*>(sm.LO + ro + (((q >> 1) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_bf16x4(acc);
-            *reinterpret_cast<uint2*>(sm.LO + ro + (((4 + (q >> 1)) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_bf16x4(own);
+          const int nl_t = min(max(n_long - TILE_M * t, 0), TILE_M);
+          uint32_t ia[4];
+          int m[4];
+          F4P a4[4];
+          int cnt = 0;
+          bool all_cached = true;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rt = 32 * k + 8 * gi + warp, r = TILE_M * t + rt;
+            uint32_t be = 0;
+            if (r < n && rt >= nl_t) be = sm.rbe[r];
+            ia[k] = idx_a + 2 * (be & 0xffffu);
+            m[k] = (int)(be >> 16) - (int)(be & 0xffffu);
+            all_cached &= (be >> 16) <= (uint32_t)FZ_IDX_CAP;
+            cnt = max(cnt, m[k]);
+            a4[k].lo = 0ull, a4[k].hi = 0ull;
           }
+          FZ_CLK(d0);
+          if (all_cached) {
+            // branch-free: every step loads one entry of each of the four rows (a finished row re-reads entries just past
+            // its end -- always some valid J inside the cache, see the zero fill at kernel start) and only the add is
+            // predicated, so the four load chains overlap
+#pragma unroll 2
+            for (int i = 0; i < cnt; ++i) {
+              uint32_t J[4];
+              F4P v[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) J[k] = lds16(ia[k] + 2 * i);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[k] = ld_J(J[k]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (i < m[k]) add4p(a4[k], v[k]);
+            }
+          } else {  // units with more alive entries than the cache holds
+            for (int i = 0; i < cnt; ++i) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (i < m[k]) add4p(a4[k], ld_J(nbrJ((int)((ia[k] - idx_a) >> 1) + i)));
+            }
+          }
+          FZ_CLK(d1);
+          float4 own4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rt = 32 * k + 8 * gi + warp, r = TILE_M * t + rt;
+            own4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < n && rt >= nl_t) own4[k] = unpack4(ld_J((uint32_t)((r << 3) | (r & 7))));
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) add4(csum, own4[k]);
+          FZ_CLK(d2);
+          if (uses > 0) {
+            mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // staging tile free again (MMAs of the previous tile complete)
+            FZ_CLK(c4);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rt = 32 * k + 8 * gi + warp;
+            if (rt >= nl_t) {
+              const float4 accf = unpack4(a4[k]);
+              const uint32_t ro = (uint32_t)rt * 128u;
+              *reinterpret_cast<float4*>(sm.P + ro + ((q ^ (rt & 7)) << 4)) = accf;
+              *reinterpret_cast<uint2*>(sm.LO + ro + (((q >> 1) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_bf16x4(accf);
+              *reinterpret_cast<uint2*>(sm.LO + ro + (((4 + (q >> 1)) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_bf16x4(own4[k]);
+            }
+          }
+          FZ_CLK(d3);
+          // long rows of this tile: one warp per row, lane group gi takes every 4th neighbour
+          for (int rt = warp; rt < nl_t; rt += FZ_GW) {
+            const int r = TILE_M * t + rt;
+            const uint32_t be = sm.rbe[r];
+            const int en = (int)(be >> 16);
+            F4P ap = {0ull, 0ull};
+            int e = (int)(be & 0xffffu) + gi;
+            if (en <= FZ_IDX_CAP) {
+              for (; e + 12 < en; e += 16) {  // four independent loads in flight per lane group
+                const uint32_t ea = idx_a + 2 * e;
+                const uint32_t J0 = lds16(ea), J1 = lds16(ea + 8), J2 = lds16(ea + 16), J3 = lds16(ea + 24);
+                const F4P v0 = ld_J(J0), v1 = ld_J(J1), v2 = ld_J(J2), v3 = ld_J(J3);
+                add4p(ap, v0);
+                add4p(ap, v1);
+                add4p(ap, v2);
+                add4p(ap, v3);
+              }
+              for (; e < en; e += 4) add4p(ap, ld_J(lds16(idx_a + 2 * e)));
+            } else {
+              for (; e < en; e += 4) add4p(ap, ld_J(nbrJ(e)));
+            }
+            float4 a = unpack4(ap);
+            // fixed combination order: (g0 + g1) + (g2 + g3)
+            a.x += __shfl_xor_sync(0xffffffffu, a.x, 8);
+            a.y += __shfl_xor_sync(0xffffffffu, a.y, 8);
+            a.z += __shfl_xor_sync(0xffffffffu, a.z, 8);
+            a.w += __shfl_xor_sync(0xffffffffu, a.w, 8);
+            a.x += __shfl_xor_sync(0xffffffffu, a.x, 16);
+            a.y += __shfl_xor_sync(0xffffffffu, a.y, 16);
+            a.z += __shfl_xor_sync(0xffffffffu, a.z, 16);
+            a.w += __shfl_xor_sync(0xffffffffu, a.w, 16);
+            if (gi == 0) {
+              const float4 own = unpack4(ld_J((uint32_t)((r << 3) | (r & 7))));
+              add4(csum, own);
+              const uint32_t ro = (uint32_t)rt * 128u;
+              *reinterpret_cast<float4*>(sm.P + ro + ((q ^ (rt & 7)) << 4)) = a;
+              *reinterpret_cast<uint2*>(sm.LO + ro + (((q >> 1) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_bf16x4(a);
+              *reinterpret_cast<uint2*>(sm.LO + ro + (((4 + (q >> 1)) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_bf16x4(own);
+            }
+          }
+          FZ_CLK(d4);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.bar_full);
           ++uses;
+          FZ_CLK(d5);
         }
         // ---------------- end of pass ----------------
+        FZ_CLK(c3);
         mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // all MMAs of the pass (hence all gathers) are complete
         // column sums of this half of the iteration's input embeddings (spmm subgsum): groups, then warps, fixed order
         csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 8);
@@ -335,13 +591,22 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           ps[0] = s;
           for (int t = 1; t < ntile; ++t) ps[(size_t)t * D] = 0.f;
         }
+        FZ_CLK(c5);
       }
 
       // ---------------- epilogue: TMEM -> relu -> normalise -> next resident half / scratch / HBM ----------------
+      // One thread per row holds the 64 outputs.  Columns 0..31 go straight into the resident buffer.  Everything bound for
+      // global memory is first laid out in the (now idle) staging tiles -- P for warps 0..3, LO for warps 4..7 -- because
+      // 16-byte stores scattered at a 128-byte stride cost ~1 cycle each on the SM (measured: 10 k cycles per epilogue):
+      // the scratch image leaves as ONE bulk copy per tile, the final embeddings as fully coalesced 128-byte row pieces.
       tc_fence_after();
       {
         const int quad = warp >> 2, lg = warp & 3;
-        for (int t = quad; t < ntile; t += 4) {
+        unsigned char* const stg = quad ? sm.LO : sm.P;
+        const uint32_t stg_a = smem_u32(stg);
+        const bool last = it + 1 == MD_BP_ITERS;
+        const bool issuer = lg == 0 && lane == 0;
+        for (int t = quad; t < ntile; t += FZ_GW / 4) {
           const uint32_t taddr = tbase + ((uint32_t)(32 * lg) << 16) + 64 * t;
           float x[64];
 #pragma unroll
@@ -355,32 +620,71 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           }
           const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
           const int rt = 32 * lg + lane, r = TILE_M * t + rt;
-          if (it + 1 < MD_BP_ITERS) {
+          FZ_CLK(c6);
+          if (!last) {
             unsigned char* hp = sm.Hs + (uint32_t)r * 128u;
-            unsigned char* sp = spill + (size_t)r * 128u;
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              const uint32_t o = (uint32_t)((ch ^ (rt & 7)) << 4);
-              *reinterpret_cast<float4*>(hp + o) = make_float4(x[4 * ch] * inv, x[4 * ch + 1] * inv, x[4 * ch + 2] * inv, x[4 * ch + 3] * inv);
-              *reinterpret_cast<float4*>(sp + o) =
-                  make_float4(x[32 + 4 * ch] * inv, x[33 + 4 * ch] * inv, x[34 + 4 * ch] * inv, x[35 + 4 * ch] * inv);
+            for (int ch = 0; ch < 8; ++ch)
+              *reinterpret_cast<float4*>(hp + ((ch ^ (rt & 7)) << 4)) =
+                  make_float4(x[4 * ch] * inv, x[4 * ch + 1] * inv, x[4 * ch + 2] * inv, x[4 * ch + 3] * inv);
+            if (t != quad) {  // the previous tile's bulk copy must have read the staging tile
+              if (issuer) bulk_wait_read0();
+              quad_sync(quad);
             }
-          } else if (r < n) {
-            float* out = K.h[MD_BP_ITERS & 1][l] + (size_t)S.act_list[base + r] * D;
 #pragma unroll
-            for (int ch = 0; ch < 16; ++ch)
-              *reinterpret_cast<float4*>(out + 4 * ch) = make_float4(x[4 * ch] * inv, x[4 * ch + 1] * inv, x[4 * ch + 2] * inv, x[4 * ch + 3] * inv);
+            for (int ch = 0; ch < 8; ++ch)
+              *reinterpret_cast<float4*>(stg + (uint32_t)rt * 128u + ((ch ^ (rt & 7)) << 4)) =
+                  make_float4(x[32 + 4 * ch] * inv, x[33 + 4 * ch] * inv, x[34 + 4 * ch] * inv, x[35 + 4 * ch] * inv);
+            fence_proxy_async_smem();
+            quad_sync(quad);
+            if (issuer) {
+              bulk_s2g(spill + (size_t)t * FZ_TILE_B, stg, FZ_TILE_B);
+              bulk_commit();
+            }
+          } else {
+            float* const outb = K.h[MD_BP_ITERS & 1][l];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch)
+                *reinterpret_cast<float4*>(stg + (uint32_t)rt * 128u + ((ch ^ (rt & 7)) << 4)) = make_float4(
+                    x[32 * h + 4 * ch] * inv, x[32 * h + 4 * ch + 1] * inv, x[32 * h + 4 * ch + 2] * inv, x[32 * h + 4 * ch + 3] * inv);
+              quad_sync(quad);
+              // copy-out: 8 lanes per row, 4 rows per instruction, 128 contiguous bytes per row
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = 32 * lg + 4 * i + gi, rg = TILE_M * t + rr;
+                if (rg < n) {
+                  const float4 v = lds128(stg_a + (uint32_t)rr * 128u + (uint32_t)((q ^ (rr & 7)) << 4));
+                  *reinterpret_cast<float4*>(outb + (size_t)(base + sm.rowv[rg]) * D + 32 * h + 4 * q) = v;
+                }
+              }
+              quad_sync(quad);
+            }
           }
+          FZ_CLK(c8);
         }
+        if (!last && issuer) bulk_wait0();  // scratch image complete before it is fetched back for pass 1
       }
-      fence_proxy_async_all();  // resident half (shared) and scratch image (global) are read by the async proxy next
+      fence_proxy_async_smem();  // the resident half is read by the tensor core (async proxy) next
       tc_fence_before();
       gw_sync();
+      FZ_CLK(c9);
     }
   }
+  if (tid == 0 && blockIdx.x < 160) g_fz_cta[blockIdx.x][0] = (unsigned)(clock64() - t_start), g_fz_cta[blockIdx.x][1] = n_units_done;
+  // gather warp 0: [0] setup [1] fill [2] reload [3] gather [4] stage wait [5] pass end [6] epilogue TMEM+math [7] idle
+  //                [12] epilogue stores [13] epilogue fences + barrier
+  // MMA warp:      [8] W + resident wait [9] full-tile wait [10] MMA issue [11] completion wait + misc
+  if (blockIdx.x == 0 && tid == 0) {
+    g_fz_dbg[0] = c0, g_fz_dbg[1] = c1, g_fz_dbg[2] = c2, g_fz_dbg[3] = c3, g_fz_dbg[4] = c4;
+    g_fz_dbg[5] = c5, g_fz_dbg[6] = c6, g_fz_dbg[7] = c7, g_fz_dbg[12] = c8, g_fz_dbg[13] = c9, g_fz_dbg[15] = n_units_done;
+    g_fz_gath[0] = d0, g_fz_gath[1] = d1, g_fz_gath[2] = d2, g_fz_gath[3] = d3, g_fz_gath[4] = d4, g_fz_gath[5] = d5;
+  }
+  if (blockIdx.x == 0 && tid == FZ_GT) g_fz_dbg[8] = c0, g_fz_dbg[9] = c1, g_fz_dbg[10] = c2, g_fz_dbg[11] = c3;
 
   // teardown: the MMA warp still has one weight-image copy in flight
-  if (warp == FZ_GW && lane == 0) mbar_wait(&sm.bar_w, wloads & 1);
+  if (warp == FZ_GW) mbar_wait(&sm.bar_w, wloads & 1);
   tc_fence_before();
   __syncthreads();
   if (warp == FZ_GW) tmem_dealloc(tbase, 512);
@@ -390,7 +694,22 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
 
 extern int g_md_debug_flags;
 
+extern "C" int md_debug_read_fused(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, md::g_fz_dbg, sizeof(long long) * (n < 16 ? n : 16));
+}
+
+extern "C" int md_debug_read_fused_gather(unsigned* host8) {
+  return (int)cudaMemcpyFromSymbol(host8, md::g_fz_gath, sizeof(unsigned) * 8);
+}
+extern "C" int md_debug_read_fused_ctas(unsigned* host) {
+  return (int)cudaMemcpyFromSymbol(host, md::g_fz_cta, sizeof(unsigned) * 320);
+}
+
 extern "C" int32_t md_fused_max_stride(void) { return md::FZ_ROWS; }
+// row pointers of one unit are kept as uint16 offsets: a graph's CSR entries (all layers) must stay below 65536
+extern "C" int32_t md_fused_applies(const md_graphs_t* g) {
+  return g && g->stride <= md::FZ_ROWS && g->max_graph_nnz > 0 && g->max_graph_nnz < 65536;
+}
 
 static int fused_sm_count() {
   static int nsm = 0;
@@ -403,8 +722,11 @@ static int fused_sm_count() {
   return nsm;
 }
 
-extern "C" int64_t md_fused_ws_bytes(void) {
-  return (int64_t)(md::FZ_WS_SPILL + (size_t)fused_sm_count() * md::FZ_SPILL_B);
+static size_t fused_order_off() { return md::FZ_WS_SPILL + (size_t)fused_sm_count() * md::FZ_SPILL_B; }
+
+extern "C" int64_t md_fused_ws_bytes(const md_graphs_t* g) {
+  if (!g) return 0;
+  return (int64_t)(fused_order_off() + sizeof(int) * (size_t)g->n_graphs * (size_t)g->n_layers);
 }
 
 extern "C" int md_embed_fused(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
@@ -412,9 +734,9 @@ extern "C" int md_embed_fused(const md_graphs_t* g, const md_state_t* s, const m
   if (!g || !s || !w || !k || !k->fused_ws) return MD_EINVAL;
   if (g->n_layers < 1 || g->n_layers > MD_MAX_LAYERS) return MD_ELAYERS;
   if (g->stride % MD_TILE_M != 0 || g->n_total != g->n_graphs * g->stride) return MD_EINVAL;
-  if (g->stride > md::FZ_ROWS) return MD_ETOOBIG;
+  if (!md_fused_applies(g)) return MD_ETOOBIG;
   static bool configured = false;
-  const int smem = (int)sizeof(md::FusedSmem) + 1024;
+  const int smem = (int)sizeof(md::FusedSmem);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(md::embed_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
@@ -424,9 +746,10 @@ extern "C" int md_embed_fused(const md_graphs_t* g, const md_state_t* s, const m
   const int n_units = g->n_graphs * g->n_layers;
   const int nsm = fused_sm_count();
   const int grid = nsm < n_units ? nsm : n_units;
-  md::fused_prep_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*w, ws);
+  int* order = reinterpret_cast<int*>(ws + fused_order_off());
+  md::fused_prep_kernel<<<(n_units + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*g, *s, *w, ws, order, n_units);
   MD_CHECK_LAUNCH();
-  md::embed_fused_kernel<<<grid, md::FZ_T, smem, (cudaStream_t)stream>>>(*g, *s, *w, *k, ws, n_units);
+  md::embed_fused_kernel<<<grid, md::FZ_T, smem, (cudaStream_t)stream>>>(*g, *s, *w, *k, ws, order, n_units);
   MD_CHECK_LAUNCH();
   return 0;
 }

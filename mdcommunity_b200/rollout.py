@@ -116,11 +116,11 @@ class BatchRollout:
             for l in range(L):
                 k.h[i][l] = self.h[i][l].data_ptr()
         k.psum, k.gconst, k.q = self.psum.data_ptr(), self.gconst.data_ptr(), self.q.data_ptr()
-        self.fused = (fused is not False) and S <= int(self.lib.md_fused_max_stride())
+        self.fused = (fused is not False) and bool(self.lib.md_fused_applies(batch.ptr()))
         if fused and not self.fused:
-            raise ValueError("md_embed_fused handles strides up to %d, this batch has %d" % (self.lib.md_fused_max_stride(), S))
+            raise ValueError("md_embed_fused handles strides up to %d (this batch: %d) and < 65536 CSR entries per graph" % (self.lib.md_fused_max_stride(), S))
         if self.fused:
-            nbytes = int(self.lib.md_fused_ws_bytes())
+            nbytes = int(self.lib.md_fused_ws_bytes(batch.ptr()))
             self.fused_ws = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=dev)
             k.fused_ws = (self.fused_ws.data_ptr() + 1023) // 1024 * 1024
         else:

@@ -56,6 +56,20 @@ if args.fused_cmp:
             if rep == 2 and name == "fused":
                 torch.cuda.profiler.stop()
         print("%s: %.1f us per embedding stage (first embedding + 3 iterations)" % (name, 1e3 * e0.elapsed_time(e1) / args.fused_cmp))
+        if name == "fused":
+            buf = np.zeros(16, np.int64)
+            lib.md_debug_read_fused(buf.ctypes.data_as(C.c_void_p), 16)
+            print("fused CTA0 cycles: gather warp [setup, fill, reload, gather, stage wait, pass-end wait, epi TMEM+math, idle] =", buf[:8].tolist(),
+                  "[epi stores, epi fence+sync] =", buf[12:14].tolist(),
+                  "\n   MMA warp [W+resident wait, issue, full-tile wait, completion wait] =", buf[8:12].tolist(), "; units", int(buf[15]))
+            gb = np.zeros(8, np.uint32)
+            lib.md_debug_read_fused_gather(gb.ctypes.data_as(C.c_void_p))
+            print("   gather sub-phases [row setup, neighbour loop, own rows, stores, long rows, fence+arrive] =", gb[:6].tolist())
+            cb = np.zeros((160, 2), np.uint32)
+            lib.md_debug_read_fused_ctas(cb.ctypes.data_as(C.c_void_p))
+            cb = cb[cb[:, 1] > 0]
+            print("   per-CTA loop cycles: min %d mean %d max %d; units/CTA min %d max %d; cycles/unit mean %d" % (
+                cb[:, 0].min(), cb[:, 0].mean(), cb[:, 0].max(), cb[:, 1].min(), cb[:, 1].max(), cb[:, 0].sum() / cb[:, 1].sum()))
     sys.exit(0)
 if args.iters:
     _lib.check(lib.md_embed_init(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()), "init")
