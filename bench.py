@@ -145,28 +145,40 @@ def run_reference(args, cost, n, desc):
 # our arm
 # --------------------------------------------------------------------------------------------------------------
 def roofline_pass(mdb, batch, w):
-    """Instrumented replay: CUDA events around every md_embed_iter launch of one rollout; algorithmic bytes per
-    launch = L layer-iterations of the SURVEY 8(d) compulsory floor 4(n+1) + 4 nnz + 8 D n (H tiles of N<=1000
-    graphs are L2-resident, so the floor is the figure of record) with n = active nodes, nnz = alive directed edges."""
+    """Instrumented replay of one rollout with CUDA events around the dominant kernel of every step.
+
+    Fused path (stride <= 1024): md_embed_fused, ONE launch = first embedding + 3 message-passing iterations of all L
+    layers; algorithmic bytes per launch = 3 * sum_l (4(n+1) + 4 nnz_l + 8 D n), i.e. the SURVEY 8(d) compulsory floor
+    of the three layer-iterations it replaces (H tiles of N<=1000 graphs are cache-resident, so the floor is the figure
+    of record), n = active nodes, nnz_l = alive directed edges.  Unfused path: one md_embed_iter launch = one iteration
+    of all layers, bytes = sum_l floor."""
     import ctypes as C
     from mdcommunity_b200 import _lib
     ro = mdb.BatchRollout(batch, w)
     lib = ro.lib
     evs, byts = [], []
-    tot_other = []
     D = 64
     while ro.num_done() < batch.B and len(evs) < 3000:
         n = int(ro.n_act.sum())
         nnz = 2 * ro.alive_edges.sum(1).cpu().numpy()
+        floor = sum(4 * (n + 1) + 4 * int(nnz[l]) + 8 * D * n for l in range(batch.L))
         g, s, wp, k, st = ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()
-        _lib.check(lib.md_embed_init(g, s, wp, k, st), "init")
-        for it in range(3):
+        if ro.fused:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _lib.check(lib.md_embed_iter(g, s, wp, k, it, st), "iter")
+            _lib.check(lib.md_embed_fused(g, s, wp, k, st), "fused")
             e1.record()
             evs.append((e0, e1))
-            byts.append(sum(4 * (n + 1) + 4 * int(nnz[l]) + 8 * D * n for l in range(batch.L)))
+            byts.append(3 * floor)
+        else:
+            _lib.check(lib.md_embed_init(g, s, wp, k, st), "init")
+            for it in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.check(lib.md_embed_iter(g, s, wp, k, it, st), "iter")
+                e1.record()
+                evs.append((e0, e1))
+                byts.append(floor)
         _lib.check(lib.md_graph_embed(g, s, wp, k, st), "gembed")
         _lib.check(lib.md_qhead(g, s, wp, k, st), "qhead")
         ro.step()
@@ -175,13 +187,20 @@ def roofline_pass(mdb, batch, w):
     tot_ms, tot_b = float(sum(ms)), float(sum(byts))
     peak, how = measured_peak()
     ach = tot_b / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "fused_dram_traffic.json")
+    if ro.fused and os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+        traffic = json.load(open(tpath))
+    name = ("embed_fused_kernel (first embedding + 3 x [SpMM aggregation + dense transforms + normalise], one launch)"
+            if ro.fused else "embed_iter_kernel (fused SpMM aggregation + dense transforms + normalise)")
+    model = ("sum over launches of 3 * sum_l (4(n+1)+4nnz_l+8*64*n)" if ro.fused else "sum over launches of sum_l (4(n+1)+4nnz_l+8*64*n)")
     # the first (intact-graph) launches are the heaviest: report them too
-    return {"bound": "hbm", "kernel": "embed_iter_kernel (fused SpMM aggregation + dense transforms + normalise)",
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    return {"bound": "hbm", "kernel": name,
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "peak_source": how, "launches": len(ms), "avg_launch_ms": tot_ms / max(1, len(ms)),
             "first_launch_ms": ms[0] if ms else None,
             "first_launch_gbs": byts[0] / (ms[0] * 1e-3) / 1e9 if ms else None,
-            "algorithmic_bytes_model": "sum over launches of L*(4(n+1)+4nnz+8*64*n), n=active nodes, nnz=alive directed edges"}
+            "algorithmic_bytes_model": model + ", n=active nodes, nnz=alive directed edges"}
 
 
 def run_ours(args, cost, n, per_gpu, desc):

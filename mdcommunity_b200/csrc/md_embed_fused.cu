@@ -63,6 +63,7 @@ struct FusedSmem {
   uint16_t rowv[FZ_ROWS];           // row -> graph-local node id
   float red[FZ_GW][32];
   alignas(16) float wn2l[2 * D];
+  alignas(128) float zrow[32];      // one all-zero 128-byte row: where a finished row's lane group points its loads
   uint16_t bbase[32];
   uint64_t bar_full, bar_empty, bar_w, bar_h, bar_res;
   uint32_t tmem;
@@ -134,27 +135,27 @@ constexpr int FZ_ORDER_MAX = 8192;  // units ranked by work (O(U^2) ranking); la
 
 // Per launch: weight images (both passes) in the exact shared-memory layout, reset of the unit counter, and the order in
 // which the persistent CTAs take the (graph, layer) units: heaviest first (alive entries + 4 per active node), so the
-// tail of the launch is made of the cheap units.  Block b ranks units [256 b, 256 b + 256).
+// tail of the launch is made of the cheap units.  One warp ranks one unit (block b: units [8 b, 8 b + 8)).
 __global__ void __launch_bounds__(256) fused_prep_kernel(md_graphs_t G, md_state_t S, md_weights_t W, unsigned char* ws,
                                                          int* order, int n_units) {
   __shared__ int key[FZ_ORDER_MAX];
   const int L = G.n_layers;
+  const int lane = threadIdx.x & 31, u = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n_units <= FZ_ORDER_MAX) {
-    for (int u = threadIdx.x; u < n_units; u += 256) {
-      const int g = u / L, l = u - g * L, n = S.n_act[g], base = g * G.stride;
-      key[u] = n > 0 ? (S.aptr[l][base + n] - S.aptr[l][base]) + 4 * n : 0;
+    for (int v = threadIdx.x; v < n_units; v += 256) {
+      const int g = v / L, l = v - g * L, n = S.n_act[g], base = g * G.stride;
+      key[v] = n > 0 ? (S.aptr[l][base + n] - S.aptr[l][base]) + 4 * n : 0;
     }
     __syncthreads();
-    const int u = blockIdx.x * 256 + threadIdx.x;
     if (u < n_units) {
       const int k = key[u];
       int rank = 0;
-      for (int v = 0; v < n_units; ++v) rank += (key[v] > k) || (key[v] == k && v < u);
-      order[rank] = u;
+      for (int v = lane; v < n_units; v += 32) rank += (key[v] > k) || (key[v] == k && v < u);
+      rank = warp_sum_i(rank);
+      if (lane == 0) order[rank] = u;
     }
-  } else {
-    const int u = blockIdx.x * 256 + threadIdx.x;
-    if (u < n_units) order[u] = u;
+  } else if (u < n_units && lane == 0) {
+    order[u] = u;
   }
   if (blockIdx.x != 0) return;
   if (threadIdx.x == 0) *reinterpret_cast<int*>(ws + FZ_WS_CTR) = 0;
@@ -193,7 +194,8 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
   }
   if (warp == FZ_GW) tmem_alloc(&sm.tmem, 512);
   if (tid < 2 * D) sm.wn2l[tid] = W.w_n2l[tid];
-  for (int i = tid; i < FZ_IDX_CAP + 64; i += FZ_T) sm.idx[i] = 0;  // every entry is always a valid J (< 8192)
+  for (int i = tid; i < FZ_IDX_CAP + 64; i += FZ_T) sm.idx[i] = 0;
+  if (tid < 32) sm.zrow[tid] = 0.f;  // every entry is always a valid J (< 8192)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -368,6 +370,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     // (visibility of idx: the barrier after the first resident-half fill below)
     const int n_long = sm.bbase[FZ_LONG];  // rows whose bucket exceeds FZ_LONG, i.e. alive degree > FZ_LONG
     const uint32_t hs_a = smem_u32(sm.Hs), idx_a = smem_u32(sm.idx);
+    const uint32_t Jz = (smem_u32(sm.zrow) - hs_a) >> 4;  // "row" of zeros (any chunk of it)
     auto nbrJ = [&](int e) -> uint32_t {  // entries beyond the cache (units with > FZ_IDX_CAP alive entries) come from L2
       if (e < FZ_IDX_CAP) return lds16(idx_a + 2 * e);
       const uint32_t j = sm.pos[acol_g[e] - base];
@@ -448,9 +451,10 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
         if (gtid == 0) mbar_arrive(&sm.bar_res);
 
         // ---------------- tiles: gather -> staging -> MMA ----------------
-        // Tile row 32*k + 8*gi + warp (k = 0..3): a lane group walks FOUR rows at once, one neighbour of each per step
-        // (four independent load chains; the rows are 32 apart in the degree-sorted order, so they end together), and
-        // consecutive rows go to different warps.  Rows longer than FZ_LONG (the first n_long rows of the unit) are summed
+        // Tile row 32*k + 4*warp + gi (k = 0..3): a lane group walks FOUR rows at once, one neighbour of each per step
+        // (four independent load chains; the rows are 32 apart in the degree-sorted order, so they end together); the four
+        // groups of a warp take adjacent rows (equal degree, and four different swizzle phases: no bank conflicts when
+        // they store their staging rows).  Rows longer than FZ_LONG (the first n_long rows of the unit) are summed
         // afterwards by whole warps.
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = 0; t < ntile; ++t) {
@@ -462,7 +466,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           bool all_cached = true;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int rt = 32 * k + 8 * gi + warp, r = TILE_M * t + rt;
+            const int rt = 32 * k + 4 * warp + gi, r = TILE_M * t + rt;
             uint32_t be = 0;
             if (r < n && rt >= nl_t) be = sm.rbe[r];
             ia[k] = idx_a + 2 * (be & 0xffffu);
@@ -474,19 +478,21 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           FZ_CLK(d0);
           if (all_cached) {
             // branch-free: every step loads one entry of each of the four rows (a finished row re-reads entries just past
-            // its end -- always some valid J inside the cache, see the zero fill at kernel start) and only the add is
-            // predicated, so the four load chains overlap
+            // its end -- always inside the cache array) and a finished row is pointed at the all-zero row, so the four
+            // load chains overlap and the adds need no predicate
 #pragma unroll 2
             for (int i = 0; i < cnt; ++i) {
               uint32_t J[4];
               F4P v[4];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) J[k] = lds16(ia[k] + 2 * i);
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t Jl = lds16(ia[k] + 2 * i);
+                J[k] = i < m[k] ? Jl : Jz;
+              }
 #pragma unroll
               for (int k = 0; k < 4; ++k) v[k] = ld_J(J[k]);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (i < m[k]) add4p(a4[k], v[k]);
+              for (int k = 0; k < 4; ++k) add4p(a4[k], v[k]);
             }
           } else {  // units with more alive entries than the cache holds
             for (int i = 0; i < cnt; ++i) {
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           float4 own4[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int rt = 32 * k + 8 * gi + warp, r = TILE_M * t + rt;
+            const int rt = 32 * k + 4 * warp + gi, r = TILE_M * t + rt;
             own4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < n && rt >= nl_t) own4[k] = unpack4(ld_J((uint32_t)((r << 3) | (r & 7))));
           }
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int rt = 32 * k + 8 * gi + warp;
+            const int rt = 32 * k + 4 * warp + gi;
             if (rt >= nl_t) {
               const float4 accf = unpack4(a4[k]);
               const uint32_t ro = (uint32_t)rt * 128u;
@@ -747,7 +753,7 @@ extern "C" int md_embed_fused(const md_graphs_t* g, const md_state_t* s, const m
   const int nsm = fused_sm_count();
   const int grid = nsm < n_units ? nsm : n_units;
   int* order = reinterpret_cast<int*>(ws + fused_order_off());
-  md::fused_prep_kernel<<<(n_units + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*g, *s, *w, ws, order, n_units);
+  md::fused_prep_kernel<<<(n_units + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*g, *s, *w, ws, order, n_units);
   MD_CHECK_LAUNCH();
   md::embed_fused_kernel<<<grid, md::FZ_T, smem, (cudaStream_t)stream>>>(*g, *s, *w, *k, ws, order, n_units);
   MD_CHECK_LAUNCH();
