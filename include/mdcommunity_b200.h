@@ -207,6 +207,15 @@ int md_rollout_steps(const md_graphs_t* g, const md_state_t* s, const md_weights
 int md_select_topk(const md_graphs_t* g, const md_state_t* s, const md_work_t* k, int32_t* out_local_ids,
                    int32_t topk, md_stream_t stream);
 
+/* ---- heuristic baselines ------------------------------------------------------------------------------ */
+
+/* Selection step of the heuristic baselines (U/baseline/HDA/hda_2max.py:50-69, hda_add.py; U/baseline/CI/ci_max.py:52-90,
+ * ci_add.py) on the current environment state: kind 0 = HDA (alive degree), 1 = CI (radius-1 collective influence);
+ * combine 0 = max over layers, 1 = sum.  Leaves the arg-max key (lowest id among the maxima) in s->best, exactly as
+ * md_qhead does, so md_env_step(actions = NULL) applies it: one md_heuristic_select + one md_env_step = one iteration of
+ * critical_number (hda_2max.py:71-93). */
+int md_heuristic_select(const md_graphs_t* g, const md_state_t* s, int32_t kind, int32_t combine, md_stream_t stream);
+
 /* ---- operator boundary -------------------------------------------------------------------------------- */
 
 /* torch_sparse.spmm replacement (call sites net_graphsage.py:290,297,350,377): Y[r] = sum_e val[e] * X[col[e]]

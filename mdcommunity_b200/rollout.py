@@ -213,6 +213,22 @@ class BatchRollout:
                 break
         return self.results()
 
+    def run_heuristic(self, kind="hda", combine="max", chunk=8):
+        """critical_number of the reference's baseline scripts (U/baseline/HDA/hda_2max.py:71-93, CI/ci_max.py:92-110)
+        for every graph of the batch: select by alive degree ("hda") or collective influence ("ci"), combined over the
+        layers by "max" or "add", remove, recompute the LMCC, until LMCC == 1.  Needs no weights."""
+        k, c = {"hda": 0, "ci": 1}[kind], {"max": 0, "add": 1}[combine]
+        it = 0
+        while True:
+            for _ in range(chunk):
+                _lib.check(self.lib.md_heuristic_select(self._g(), C.byref(self.s), k, c, self._stream()), "md_heuristic_select")
+                self.step()
+                self.kernel_launches += 1
+            it += chunk
+            if self.num_done() >= self.batch.B or it > self.max_steps + chunk:
+                break
+        return self.results()
+
     def results(self):
         torch.cuda.current_stream(self.batch.device).synchronize()
         return dict(score=self.score.cpu().numpy(), n_steps=self.n_steps.cpu().numpy(),

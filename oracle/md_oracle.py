@@ -361,3 +361,51 @@ def rollout(w, g, variant, step=1, forced_actions=None, record=False):
             t += 1
     return dict(score=env.score, sol=sol, ranks=list(env.rank_list), maxcc=list(env.MaxCCList),
                 q=qs, active=acts, env=env)
+
+
+# ----------------------------------------------------------------------------------------------
+# heuristic baselines on the same environment
+#   HDA : U/baseline/HDA/hda_2max.py:50-69 (delnode: key = max(deg_1, deg_2) in the pruned layers),
+#         hda_add.py:50-69 (key = deg_1 + deg_2)
+#   CI  : U/baseline/CI/ci_max.py:52-90 (basic_ci: (deg(v) - 1) * sum_{u in N(v)} (deg(u) - 1), -1 for
+#         isolated nodes; key = max(ci_1, ci_2)), ci_add.py (key = ci_1 + ci_2)
+#   loop: critical_number (hda_2max.py:71-93): remove the arg-max, MCC, until LMCC == 1;
+#         score += LMCC / (LMCC_0 * N)  (same as the unit-cost AUDC, U/mvc_env.py:133-137)
+# Tie rule: `sorted(..., reverse=True)[0]` is stable, i.e. the FIRST node in G.nodes() order (= lowest id) among
+# the maxima.  The *_add.py scripts break ties with random.choice instead; the restatement (and the CUDA path)
+# uses the lowest id there too, which is one admissible outcome of that random choice.
+# ----------------------------------------------------------------------------------------------
+def heuristic_scores(env: OracleEnv, kind: str, combine: str) -> np.ndarray:
+    """Selection key of every node (int64), -1 for removed nodes / nodes the key cannot select."""
+    g = env.graph
+    per_layer = []
+    for l in range(g.num_layers):
+        d = env.alive_degree(l).astype(np.int64)
+        if kind == "hda":
+            s = d.copy()
+        else:
+            e = g.edges[l][env.alive_edge_mask(l)]
+            nb = np.zeros(g.num_nodes, np.int64)  # sum over alive neighbours of (deg - 1)
+            np.add.at(nb, e[:, 0], d[e[:, 1]] - 1)
+            np.add.at(nb, e[:, 1], d[e[:, 0]] - 1)
+            s = np.where(d == 0, -1, nb * (d - 1))
+        per_layer.append(s)
+    key = per_layer[0].copy()
+    for s in per_layer[1:]:
+        key = np.maximum(key, s) if combine == "max" else key + s
+    key[env.removed] = np.iinfo(np.int64).min
+    return key
+
+
+def heuristic_rollout(g: MultiplexGraph, kind="hda", combine="max"):
+    """critical_number of the baseline scripts on the oracle environment.  Returns dict(score, sol, ranks, maxcc)."""
+    assert kind in ("hda", "ci") and combine in ("max", "add")
+    env = OracleEnv("unit")
+    env.s0(g)
+    sol = []
+    while not env.isTerminal():
+        key = heuristic_scores(env, kind, combine)
+        a = int(np.argmax(key))  # first (lowest id) maximum
+        env.stepWithoutReward(a)
+        sol.append(a)
+    return dict(score=env.score, sol=sol, ranks=list(env.rank_list), maxcc=list(env.MaxCCList), env=env)
