@@ -157,9 +157,8 @@ __global__ void __launch_bounds__(256) fused_prep_kernel(md_graphs_t G, md_state
   } else if (u < n_units && lane == 0) {
     order[u] = u;
   }
-  if (blockIdx.x != 0) return;
-  if (threadIdx.x == 0) *reinterpret_cast<int*>(ws + FZ_WS_CTR) = 0;
-  for (int i = threadIdx.x; i < 2 * 64 * 32; i += 256) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int*>(ws + FZ_WS_CTR) = 0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < 2 * 64 * 32; i += gridDim.x * 256) {  // spread over the blocks
     const int p = i >> 11, n = (i >> 5) & 63, k = i & 31;
     const float w13 = W.w13[(32 * p + k) * D + n], w23 = W.w23[(32 * p + k) * D + n];
     unsigned char* img = ws + (size_t)p * FZ_WPASS_B;
