@@ -85,6 +85,9 @@ __device__ __forceinline__ long long block_sum_ll(long long v, BlockRed& r) {
 // Besides the labels / degrees / counters the kernel emits, per layer, the CSR of the *alive* edges of the active
 // nodes in compact (act_list) order: aptr[l][g*S + p] .. aptr[l][g*S + p + 1] indexes acol[l].  The three
 // message-passing iterations of the next forward stream it without re-checking labels.
+// IdxT: uint16_t when every graph of the batch has fewer than 65536 CSR entries (halves the staged CSR, so two CTAs fit
+// one SM and a 256-graph batch runs in one wave instead of two), int32_t otherwise.
+template <typename IdxT>
 __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_t S, const int32_t* forced,
                                                        int forced_stride, int forced_index, int init, int max_nnz) {
   extern __shared__ int smem[];
@@ -99,8 +102,8 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int* par = smem + St;             // [St] union-find parent; later the alive degree of the current layer
   int* tmp = smem + 2 * St;         // [St] scratch; later the compact list of active nodes
   int* c_rp = smem + 3 * St;        // [L][St + 1] row offsets into c_cl / c_src
-  int* c_cl = c_rp + L * (St + 1);  // [max_nnz] neighbour (graph-local id)
-  int* c_src = c_cl + max_nnz;      // [max_nnz] row of the entry (static, staged); later the alive prefix
+  IdxT* c_cl = reinterpret_cast<IdxT*>(c_rp + L * (St + 1));  // [max_nnz] neighbour (graph-local id)
+  IdxT* c_src = c_cl + max_nnz;     // [max_nnz] row of the entry (static, staged); later the alive prefix
   __shared__ BlockRed red;
   __shared__ int s_action;
   __shared__ int s_scan[ENV_W];
@@ -155,8 +158,8 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       for (int v = tid; v <= St; v += ENV_T) c_rp[ll * (St + 1) + v] = rp[v] - e0 + pos;
       const int32_t* __restrict__ sr = G.src[ll];
       for (int e = tid; e < cnt; e += ENV_T) {
-        c_cl[pos + e] = cl[e0 + e] - base;
-        c_src[pos + e] = sr[e0 + e] - base;
+        c_cl[pos + e] = (IdxT)(cl[e0 + e] - base);
+        c_src[pos + e] = (IdxT)(sr[e0 + e] - base);
       }
       lay_pos[ll] = pos;
       pos += cnt;
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
     const int e0 = G.rowptr[ll][base];  // the graph's region of acol[ll] is its static CSR region
     int32_t* __restrict__ aptr = S.aptr[ll] + base;
     int32_t* __restrict__ acol = S.acol[ll];
-    int* pref = c_src + p0;  // pref[i] = number of alive entries before entry i of this layer, i in [0, cnt]
+    IdxT* pref = c_src + p0;  // pref[i] = number of alive entries before entry i of this layer, i in [0, cnt]
     int running = 0;
     for (int c0 = 0; c0 < cnt; c0 += ENV_T) {
       const int i = c0 + tid;
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       }
       const int pos = running + woff + __popc(bal & ((1u << lane) - 1u));
       if (i < cnt) {
-        pref[i] = pos;
+        pref[i] = (IdxT)pos;
         if (flag) acol[e0 + pos] = u + base;
       }
       running += total;
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
     __syncthreads();
     const int tot = running;  // alive directed entries of the layer (= pref[cnt], which has no slot of its own)
     const int pend = p0 + cnt;
-#define PREF_AT(x) ((x) == pend ? tot : c_src[(x)])
+#define PREF_AT(x) ((x) == pend ? tot : (int)c_src[(x)])
     int dmax = 0;
     long long th = 0;
     for (int v = tid; v < St; v += ENV_T) {
@@ -377,9 +380,14 @@ extern "C" int md_debug_read_env(long long* host, int n) {
 static int g_force_large = 0;
 extern "C" int32_t md_env_small_max_stride(void) { return g_force_large ? 0 : md::ENV_SMALL_MAX; }
 // 1 if this batch takes the single-CTA (shared-memory) env kernel, 0 for the cooperative global-memory kernel
+static bool env_idx16(const md_graphs_t* g) { return g->max_graph_nnz < 65536 && g->stride < 65536; }
+static size_t env_small_smem(const md_graphs_t* g) {
+  const size_t idx_bytes = env_idx16(g) ? 2 : 4;
+  return ((size_t)3 * g->stride + (size_t)g->n_layers * (g->stride + 1)) * sizeof(int) +
+         ((2 * (size_t)g->max_graph_nnz * idx_bytes + 15) & ~(size_t)15);
+}
 extern "C" int32_t md_env_uses_small_path(const md_graphs_t* g) {
-  const size_t smem = ((size_t)3 * g->stride + (size_t)g->n_layers * (g->stride + 1) + 2 * (size_t)g->max_graph_nnz + 1) * sizeof(int);
-  return !(g_force_large || g->stride > md::ENV_SMALL_MAX || g->max_graph_nnz <= 0 || smem > md::ENV_SMALL_SMEM);
+  return !(g_force_large || g->stride > md::ENV_SMALL_MAX || g->max_graph_nnz <= 0 || env_small_smem(g) > md::ENV_SMALL_SMEM);
 }
 extern "C" void md_debug_force_large_env(int32_t on) { g_force_large = on; }
 
@@ -388,21 +396,25 @@ static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* 
   if (!g || !s) return MD_EINVAL;
   if (g->n_layers < 1 || g->n_layers > MD_MAX_LAYERS) return MD_ELAYERS;
   if (g->stride % MD_TILE_M != 0 || g->n_total != g->n_graphs * g->stride) return MD_EINVAL;
-  const size_t smem = ((size_t)3 * g->stride + (size_t)g->n_layers * (g->stride + 1) + 2 * (size_t)g->max_graph_nnz + 1) * sizeof(int);
-  if (g_force_large || g->stride > md::ENV_SMALL_MAX || g->max_graph_nnz <= 0 || smem > md::ENV_SMALL_SMEM)
-    return md_env_step_large(g, s, forced, forced_stride, forced_index, init, stream);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(md::env_step_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = env_small_smem(g);
+  if (!md_env_uses_small_path(g)) return md_env_step_large(g, s, forced, forced_stride, forced_index, init, stream);
+  const bool i16 = env_idx16(g);
+  static size_t configured[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > configured[i16]) {
+    cudaError_t e = i16 ? cudaFuncSetAttribute(md::env_step_small<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(md::env_step_small<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
+    configured[i16] = smem;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (init) {
     cudaError_t e = cudaMemsetAsync(s->n_done, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return (int)e;
   }
-  md::env_step_small<<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz);
+  if (i16)
+    md::env_step_small<uint16_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz);
+  else
+    md::env_step_small<int32_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz);
   MD_CHECK_LAUNCH();
   return 0;
 }
