@@ -87,7 +87,7 @@ typedef struct md_state {
   /* scratch for the large-graph (multi-CTA) LMCC path, may be NULL when stride <= md_env_small_max_stride() */
   int32_t* parent;       /* [n_total] */
   int32_t* comp_size;    /* [n_total] */
-  int32_t* flags;        /* [8] */
+  int32_t* flags;        /* [8] scratch: [0..3] grid barrier / change flags of the multi-CTA env kernel, [4] tile queue of md_qhead */
   int32_t* cur_action;   /* [B] action applied in the running step (-1 = graph untouched) */
 } md_state_t;
 
@@ -147,7 +147,8 @@ int32_t md_env_uses_small_path(const md_graphs_t* g);
 /* test hook: route every batch through the multi-CTA (global-memory, cooperative) env kernel */
 void md_debug_force_large_env(int32_t on);
 /* profiling hook: bit 0 skips the neighbour gather, bit 1 the dense transform of md_embed_iter (results become wrong);
- * bit 2 makes md_rollout_steps use the unfused embedding kernels even where md_embed_fused applies */
+ * bit 2 makes md_rollout_steps use the unfused embedding kernels even where md_embed_fused applies;
+ * bit 3 makes md_qhead use its FP32-FMA kernel instead of the tensor-core kernel */
 void md_debug_set_flags(int32_t flags);
 /* profiling hook: clock64 phase times of CTA 0 of the last md_env_step (labels in, CSR staged, prune rounds,
  * component sizes, alive CSR + degrees) and, at index 16, the number of prune rounds */

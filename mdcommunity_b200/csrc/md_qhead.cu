@@ -275,10 +275,19 @@ __global__ void __launch_bounds__(256) topk_kernel(md_graphs_t G, md_state_t S, 
 
 }  // namespace md
 
+int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, cudaStream_t st,
+                       int* launched);
+
 extern "C" int md_qhead(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                         md_stream_t stream) {
   if (!g || !s || !w || !k) return MD_EINVAL;
   if (g->stride % MD_TILE_M != 0 || g->n_total != g->n_graphs * g->stride) return MD_EINVAL;
+  {  // tensor-core kernel (md_qhead_tc.cu) unless md_debug_set_flags bit 3 asks for the FP32-FMA kernel below
+    int launched = 0;
+    const int rc = md_qhead_tc_launch(g, s, w, k, (cudaStream_t)stream, &launched);
+    if (rc) return rc;
+    if (launched) return 0;
+  }
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);

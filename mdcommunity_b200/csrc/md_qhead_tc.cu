@@ -1,0 +1,385 @@
+// md_qhead on the tensor cores: inter-layer fusion of the node rows + Q head + masked arg-max (same maths and the same
+// reference lines as md_qhead.cu: MRGNN/mutil_layer_weight.py:266-313, MultiDismantler_net_graphsage.py:323-393,
+// MultiDismantler_torch.py:286-300,799-807), restructured after the FP32-FMA kernel had become the largest share of a
+// rollout (ncu: 36 % FMA-pipe utilisation, static tile -> CTA map idle for most of the rollout).
+//
+//   persistent CTA per SM, 11 warps, dynamic tile queue (live (graph, 128-row) tiles only):
+//   warps 8..9  loaders : gather the tile's H_l rows from HBM/L2 (16 row fetches per warp in flight), store them as raw
+//                         fp32 into SWIZZLE_128B K-major operand tiles + the bf16 remainders (x - tf32(x))
+//   warp  10    MMA     : T_pre_l = H_l @ trans as the 3-term product (tf32 hi x hi, hi x lo, bf16 remainder pass), one
+//                         elected thread, accumulators double-buffered in tensor memory; the operand tile is released to
+//                         the loaders as soon as the MMAs have read it, so the next tile's gather overlaps the epilogue
+//   warps 0..7  epilogue: two threads per node row (column halves for the tanh, hidden-unit halves for h1): tcgen05.ld, tanh(. + bias), the pairwise (T_k . T_p . lw) gates,
+//                         softmax-of-sigmoid mix, normalise, scale by the per-graph s_p, relu(e_p @ h1) . h2 (FP32 FMA from
+//                         registers, h1 broadcast from shared memory), layer-gate mix, q[v], packed arg-max key.
+#include <cuda_bf16.h>
+#include "md_common.cuh"
+#include "md_umma.cuh"
+
+namespace md {
+using namespace umma;
+
+constexpr int QT_T = 352;         // 8 epilogue + 2 loader + 1 MMA warps
+constexpr int QT_EPI = 256;
+constexpr uint32_t QT_KB = 16384;  // one 128-row x 128-byte operand tile
+
+template <int L>
+struct QTSmem {
+  unsigned char A[L][2][QT_KB];  // raw fp32 rows of H_l, two K blocks of 32 columns
+  unsigned char ALO[L][QT_KB];   // bf16 remainders of H_l, 64 columns per row
+  unsigned char Bt[40960];       // trans^T: tf32 hi (2 K blocks), tf32 lo (2 K blocks), bf16 (64 columns)
+  alignas(16) float h1[D * MD_HIDDEN];
+  alignas(16) float bias[D];
+  alignas(16) float lw[D];
+  alignas(16) float h2[MD_HIDDEN];
+  float Ts[L][D][TILE_M];        // epilogue: tanh outputs, column-major so that a thread owns one conflict-free column
+  float hq[L][TILE_M];           // epilogue: partial hidden sums of the second thread of each row
+  int vrow[2][TILE_M];           // [slot] global node id of the row, -1 = padding
+  int desc[2][4];                // [slot] tile, graph
+  int next_tile;
+  uint64_t a_full, a_empty, d_full[2], d_empty[2];
+  uint32_t tmem;
+};
+
+__device__ __forceinline__ float4 qt_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ bool qt_elect() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+  return pred != 0;
+}
+
+template <int L>
+__global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K,
+                                                          int* counter) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  QTSmem<L>& sm = *reinterpret_cast<QTSmem<L>*>(smem_raw);  // (no pointer arithmetic: keep the shared state space)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  constexpr uint32_t NCOL = 64 * L;                    // accumulator columns per stage
+  constexpr uint32_t TCOLS = (2 * NCOL <= 256) ? 256 : 512;
+  const int tpg = G.stride / TILE_M;
+  const int n_tiles = G.n_graphs * tpg;
+
+  if (tid == 0) {
+    mbar_init(&sm.a_full, 2);
+    mbar_init(&sm.a_empty, 1);
+    mbar_init(&sm.d_full[0], 1);
+    mbar_init(&sm.d_full[1], 1);
+    mbar_init(&sm.d_empty[0], 8);
+    mbar_init(&sm.d_empty[1], 8);
+    mbar_fence_init();
+  }
+  if (warp == 10) tmem_alloc(&sm.tmem, TCOLS);
+  // ---- weights: trans^T operand images, h1, bias, lw, h2 ------------------------------------------------------
+  {
+    float t[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const int i = tid + QT_T * j;
+      t[j] = i < D * D ? W.trans[i] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const int i = tid + QT_T * j;
+      if (i < D * D) {
+        const int k = i >> 6, n = i & 63, kb = k >> 5, kk = k & 31;
+        const uint32_t off = sw128_off(n, kk >> 2) + 4 * (kk & 3);
+        *reinterpret_cast<float*>(sm.Bt + kb * 8192 + off) = tf32_hi(t[j]);
+        *reinterpret_cast<float*>(sm.Bt + 16384 + kb * 8192 + off) = t[j] - tf32_hi(t[j]);
+        *reinterpret_cast<__nv_bfloat16*>(sm.Bt + 32768 + sw128_off(n, k >> 3) + 2 * (k & 7)) = __float2bfloat16_rn(t[j]);
+      }
+    }
+    for (int i = tid; i < D * MD_HIDDEN / 4; i += QT_T)
+      reinterpret_cast<float4*>(sm.h1)[i] = reinterpret_cast<const float4*>(W.h1)[i];
+    if (tid < D) {
+      sm.bias[tid] = W.bias[tid];
+      sm.lw[tid] = W.logis_w[tid];
+    }
+    if (tid < MD_HIDDEN) sm.h2[tid] = W.h2[tid];
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = sm.tmem;
+  const int hsel = MD_BP_ITERS & 1;
+
+  if (warp == 8 || warp == 9) {
+    // ================================ loaders ================================
+    const int lw_ = warp - 8, ltid = tid - QT_EPI;
+    for (uint32_t i = 0;; ++i) {
+      const uint32_t slot = i & 1, use = i >> 1;
+      if (ltid == 0) {  // next live tile
+        int t;
+        for (;;) {
+          t = atomicAdd(counter, 1);
+          if (t >= n_tiles) {
+            t = -1;
+            break;
+          }
+          const int g = t / tpg;
+          if ((t - g * tpg) * TILE_M < S.n_act[g]) break;
+        }
+        sm.next_tile = t;
+      }
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+      const int tile = sm.next_tile;
+      if (use >= 1) mbar_wait(&sm.d_empty[slot], (use - 1) & 1);  // epilogue of tile i-2 is done with vrow / desc [slot]
+      const int g = tile >= 0 ? tile / tpg : 0, tt = tile >= 0 ? tile - g * tpg : 0;
+      if (tile >= 0) {
+        const int rows = min(TILE_M, S.n_act[g] - tt * TILE_M);
+        sm.vrow[slot][ltid] = ltid < rows ? S.act_list[g * G.stride + tt * TILE_M + ltid] : -1;
+        sm.vrow[slot][ltid + 64] = ltid + 64 < rows ? S.act_list[g * G.stride + tt * TILE_M + ltid + 64] : -1;
+      }
+      if (ltid == 0) sm.desc[slot][0] = tile, sm.desc[slot][1] = g;
+      asm volatile("bar.sync 1, 64;" ::: "memory");  // vrow visible to all loaders; next_tile may be overwritten
+      if (tile < 0) {
+        if (lane == 0) mbar_arrive(&sm.a_full);
+        break;
+      }
+      if (i >= 1) mbar_wait(&sm.a_empty, (i - 1) & 1);  // MMAs of the previous tile have read the operand tiles
+      const int c = lane & 15, half = lane >> 4;
+#pragma unroll
+      for (int lb2 = 0; lb2 < 2 * L; ++lb2) {  // (layer, half of the warp's 64 rows)
+        const int l = lb2 >> 1, r0 = 64 * lw_ + 32 * (lb2 & 1);
+        const float* __restrict__ H = K.h[hsel][l];
+        float4 val[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int r = r0 + 2 * j + half;
+          const int v = sm.vrow[slot][r];
+          val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (v >= 0) val[j] = __ldg(reinterpret_cast<const float4*>(H + (size_t)v * D) + c);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t r = r0 + 2 * j + half;
+          *reinterpret_cast<float4*>(sm.A[l][c >> 3] + r * 128u + (((c & 7) ^ (r & 7)) << 4)) = val[j];
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(val[j].x - tf32_hi(val[j].x), val[j].y - tf32_hi(val[j].y));
+          const __nv_bfloat162 p1 = __floats2bfloat162_rn(val[j].z - tf32_hi(val[j].z), val[j].w - tf32_hi(val[j].w));
+          *reinterpret_cast<uint2*>(sm.ALO[l] + r * 128u + (((c >> 1) ^ (r & 7)) << 4) + 8 * (c & 1)) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.a_full);
+    }
+  } else if (warp == 10) {
+    // ================================ MMA issuer ================================
+    const uint32_t idt = idesc(FMT_TF32, 128, 64), idb = idesc(FMT_BF16, 128, 64);
+    const uint32_t bt = smem_u32(sm.Bt);
+    const uint64_t bh0 = desc_k_sw128(bt, 0), bh1 = desc_k_sw128(bt + 8192, 0);
+    const uint64_t bl0 = desc_k_sw128(bt + 16384, 0), bl1 = desc_k_sw128(bt + 24576, 0);
+    const uint64_t bbf = desc_k_sw128(bt + 32768, 0);
+    for (uint32_t i = 0;; ++i) {
+      const uint32_t slot = i & 1, use = i >> 1;
+      mbar_wait(&sm.a_full, i & 1);
+      const int tile = sm.desc[slot][0];
+      if (tile < 0) {
+        if (lane == 0) mbar_arrive(&sm.d_full[slot]);
+        break;
+      }
+      if (use >= 1) mbar_wait(&sm.d_empty[slot], (use - 1) & 1);  // accumulator stage drained
+      tc_fence_after();
+      if (qt_elect()) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          const uint32_t d = tbase + slot * NCOL + 64 * l;
+          const uint64_t a0 = desc_k_sw128(smem_u32(sm.A[l][0]), 0), a1 = desc_k_sw128(smem_u32(sm.A[l][1]), 0);
+          const uint64_t alo = desc_k_sw128(smem_u32(sm.ALO[l]), 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ko = 2 * k;
+            mma_tf32(d, a0 + ko, bh0 + ko, idt, k != 0);
+            mma_tf32(d, a0 + ko, bl0 + ko, idt, 1);
+            mma_tf32(d, a1 + ko, bh1 + ko, idt, 1);
+            mma_tf32(d, a1 + ko, bl1 + ko, idt, 1);
+            mma_bf16(d, alo + ko, bbf + ko, idb, 1);
+          }
+        }
+        mma_commit(&sm.a_empty);
+        mma_commit(&sm.d_full[slot]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================ epilogue: two threads per row ================================
+    // Warps w and w + 4 share TMEM lane quadrant w & 3.  The row's tanh outputs go to a column of shared memory
+    // (Ts[l][c][row]: conflict-free) instead of registers: with everything unrolled the straight-line code no longer fit the
+    // instruction cache (ncu: 44 % of the stall samples were instruction fetch), and rolled loops need an indexable T.
+    // Half h of a row pair does the tanh of columns [32h, 32h+32) and the hidden units [16h, 16h+16) of relu(e @ h1);
+    // the small reductions in between (gates, norms) are recomputed by both from the shared T.
+    const float lb = W.logis_b[0];
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = 32 * quad + lane;
+    const uint32_t h1_a = smem_u32(sm.h1);
+    for (uint32_t i = 0;; ++i) {
+      const uint32_t slot = i & 1, use = i >> 1;
+      mbar_wait(&sm.d_full[slot], use & 1);
+      const int tile = sm.desc[slot][0];
+      if (tile < 0) break;
+      const int g = sm.desc[slot][1];
+      tc_fence_after();
+      const int v = sm.vrow[slot][r];
+#pragma unroll 1
+      for (int lc = 0; lc < L * 2; ++lc) {
+        const int l = lc >> 1, c0 = 32 * half + (lc & 1) * 16;
+        float x[16];
+        tmem_ld16(tbase + ((uint32_t)(32 * quad) << 16) + slot * NCOL + 64 * l + c0, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sm.Ts[l][c0 + j][r] = tanhf(x[j] + sm.bias[c0 + j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.d_empty[slot]);  // accumulators consumed: release the stage early
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // both column halves of T are in shared memory
+      float part[L];
+#pragma unroll
+      for (int p = 0; p < L; ++p) part[p] = 0.f;
+      float gwp[L], aqp[L];
+      if (v >= 0) {
+        float dot[L][L];
+#pragma unroll
+        for (int p = 0; p < L; ++p)
+#pragma unroll
+          for (int k = 0; k < L; ++k) dot[p][k] = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < D; ++c) {
+          float t[L];
+#pragma unroll
+          for (int l = 0; l < L; ++l) t[l] = sm.Ts[l][c][r];
+          const float w1 = sm.lw[c];
+#pragma unroll
+          for (int p = 0; p < L; ++p)
+#pragma unroll
+            for (int k = 0; k <= p; ++k) dot[p][k] = fmaf(t[k] * t[p], w1, dot[p][k]);
+        }
+#pragma unroll
+        for (int p = 0; p < L; ++p)
+#pragma unroll
+          for (int k = 0; k < p; ++k) dot[k][p] = dot[p][k];
+#pragma unroll
+        for (int p = 0; p < L; ++p) {
+          float a[L], mx = -1e30f, den = 0.f;
+#pragma unroll
+          for (int k = 0; k < L; ++k) {
+            a[k] = 1.f / (1.f + expf(-(dot[p][k] + lb)));
+            mx = fmaxf(mx, a[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < L; ++k) {
+            a[k] = expf(a[k] - mx);
+            den += a[k];
+          }
+#pragma unroll
+          for (int k = 0; k < L; ++k) a[k] = a[k] / den;
+          // X_p = T_p + sum_{k != p} a_k T_k ; |X_p| ; then e_p = X_p / |X_p| * s_p feeds relu(e_p @ h1) . h2
+          float ss = 0.f;
+#pragma unroll 4
+          for (int c = 0; c < D; ++c) {
+            float x = sm.Ts[p][c][r];
+#pragma unroll
+            for (int k = 0; k < L; ++k)
+              if (k != p) x = fmaf(a[k], sm.Ts[k][c][r], x);
+            ss = fmaf(x, x, ss);
+          }
+          const float sc = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
+          const float sg = K.gconst[(size_t)g * MD_GCONST + p];
+          gwp[p] = K.gconst[(size_t)g * MD_GCONST + 4 + p];
+          aqp[p] = K.gconst[(size_t)g * MD_GCONST + 8 + p];
+          float hid[MD_HIDDEN / 2];
+#pragma unroll
+          for (int j = 0; j < MD_HIDDEN / 2; ++j) hid[j] = 0.f;
+#pragma unroll 2
+          for (int c = 0; c < D; ++c) {
+            float x = sm.Ts[p][c][r];
+#pragma unroll
+            for (int k = 0; k < L; ++k)
+              if (k != p) x = fmaf(a[k], sm.Ts[k][c][r], x);
+            const float e = x * sc * sg;
+#pragma unroll
+            for (int j4 = 0; j4 < MD_HIDDEN / 8; ++j4) {
+              const float4 h = qt_lds128(h1_a + 4 * (c * MD_HIDDEN + 16 * half + 4 * j4));
+              hid[4 * j4] = fmaf(e, h.x, hid[4 * j4]);
+              hid[4 * j4 + 1] = fmaf(e, h.y, hid[4 * j4 + 1]);
+              hid[4 * j4 + 2] = fmaf(e, h.z, hid[4 * j4 + 2]);
+              hid[4 * j4 + 3] = fmaf(e, h.w, hid[4 * j4 + 3]);
+            }
+          }
+          float hq = 0.f;
+#pragma unroll
+          for (int j = 0; j < MD_HIDDEN / 2; ++j) hq = fmaf(fmaxf(hid[j], 0.f), sm.h2[16 * half + j], hq);
+          part[p] = hq;
+        }
+      }
+      if (half == 1) {
+#pragma unroll
+        for (int p = 0; p < L; ++p) sm.hq[p][r] = part[p];
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // partial hidden sums exchanged; every Ts read of this tile is done
+      unsigned long long key = 0ull;
+      if (half == 0 && v >= 0) {
+        float q = 0.f;
+#pragma unroll
+        for (int p = 0; p < L; ++p) q = fmaf(gwp[p], (part[p] + sm.hq[p][r]) + aqp[p], q);
+        K.q[v] = q;
+        const uint32_t local = (uint32_t)(v - g * G.stride);
+        key = ((unsigned long long)orderable(q) << 32) | (0xffffffffu - local);
+      }
+      if (half == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+          key = other > key ? other : key;
+        }
+        if (lane == 0 && key != 0ull) atomicMax(&S.best[g], key);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) tmem_dealloc(tbase, TCOLS);
+}
+
+}  // namespace md
+
+extern int g_md_debug_flags;
+
+// *launched = 1 when the tensor-core kernel was enqueued, 0 when the caller must use the FP32-FMA kernel; returns an error code
+int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, cudaStream_t st,
+                       int* launched) {
+  *launched = 0;
+  if ((g_md_debug_flags & 8) || !s->flags || g->n_layers != 2) return 0;  // L = 3 (C4) keeps the FP32-FMA kernel
+  static int nsm = 0;
+  if (nsm <= 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm <= 0) nsm = 148;
+  }
+  const int n_tiles = g->n_graphs * (g->stride / MD_TILE_M);
+  const int grid = nsm < n_tiles ? nsm : n_tiles;
+  int* counter = s->flags + 4;
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  {
+    static bool configured = false;
+    const int smem = (int)sizeof(md::QTSmem<2>);
+    if (!configured) {
+      e = cudaFuncSetAttribute(md::qhead_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+    md::qhead_tc_kernel<2><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  *launched = 1;
+  return 0;
+}

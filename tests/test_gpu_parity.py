@@ -284,3 +284,47 @@ def test_fused_embedding_matches_unfused(variant):
         a.step(acts)
         b.step(acts)
     print("fused vs unfused: worst |dH| %.3e, worst scaled |dQ| %.3e" % (worst_h, worst_q))
+
+
+@pytest.mark.parametrize("variant", ["unit", "degree"])
+def test_qhead_tensor_core_matches_fma(variant):
+    """md_qhead: tensor-core kernel (tcgen05, 3-term tf32/bf16 product for the fusion transform) vs the FP32-FMA kernel
+    (md_debug_set_flags bit 3) on identical embeddings: Q within the north-star tolerance, identical arg-max keys except
+    on sub-tolerance ties."""
+    from mdcommunity_b200 import _lib
+    mdb = _mdb()
+    zs, graphs, batch, w = _load_batch(variant)
+    ro = mdb.BatchRollout(batch, w)
+    acts, T = _forced(zs, "greedy_actions", batch.device)
+    lib = _lib.lib()
+    worst = 0.0
+    try:
+        for t in range(min(T, 10)):
+            lib.md_debug_set_flags(0)
+            ro.forward()
+            q_tc = ro.q.clone()
+            best_tc = ro.best.clone()
+            ro.best.zero_()
+            lib.md_debug_set_flags(8)
+            import ctypes as C
+            _lib.check(lib.md_qhead(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()), "md_qhead")
+            q_fma = ro.q.clone()
+            best_fma = ro.best.clone()
+            for i in range(batch.B):
+                n = int(ro.n_act[i])
+                if n == 0:
+                    continue
+                ids = ro.act_list[i * batch.S:i * batch.S + n].long()
+                a, b = q_tc[ids], q_fma[ids]
+                err = (a - b).abs() - (Q_RTOL * b.abs() + Q_ATOL)
+                worst = max(worst, float(((a - b).abs() / (b.abs() + 1e-2)).max()))
+                assert float(err.max()) <= 0, (variant, i, t)
+                if int(best_tc[i]) != int(best_fma[i]):
+                    pa = 0xFFFFFFFF - (int(best_tc[i]) & 0xFFFFFFFF)
+                    pb = 0xFFFFFFFF - (int(best_fma[i]) & 0xFFFFFFFF)
+                    qa, qb = float(q_fma[i * batch.S + pa]), float(q_fma[i * batch.S + pb])
+                    assert abs(qa - qb) <= Q_RTOL * abs(qb) + Q_ATOL, (variant, i, t)
+            ro.step(acts)
+    finally:
+        lib.md_debug_set_flags(0)
+    print("qhead tensor-core vs FMA: worst scaled |dQ| %.3e" % worst)
