@@ -213,6 +213,8 @@ def run_ours(args, cost, n, per_gpu, desc):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line the driver parses
         dist.init_process_group("nccl", device_id=dev)
     import mdcommunity_b200 as mdb
 

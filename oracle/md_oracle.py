@@ -230,6 +230,14 @@ def forward_q(w, envs, variant, trace=None):
     Unit cost builds node features from the alive degree (net_graphsage.py:248-261); degree cost
     uses [w_l(v), 1] (D/PrepareBatchGraph.py:133-136).
     """
+    with torch.no_grad():
+        q, act_ids, off, _ = forward_torch(w, envs, variant, trace)
+    return q[:, 0].numpy(), act_ids, off
+
+
+def forward_torch(w, envs, variant, trace=None):
+    """The network as torch ops (differentiable in the weights): returns (q [n,1], active ids, offsets,
+    dict(fused=[L x [n+B,64]], row=[L], col=[L], n=n)).  forward_q / train_loss are thin wrappers."""
     L = envs[0].graph.num_layers
     assert L == 2, "the reference network is hard-wired to two layers (net_graphsage.py:251)"
     B = len(envs)
@@ -241,6 +249,7 @@ def forward_q(w, envs, variant, trace=None):
     aux = torch.from_numpy(np.stack([s[2] for s in stats]))  # [B, L, 4]
     gid = torch.from_numpy(np.repeat(np.arange(B), cnt))
     node_emb, y_emb = [], []
+    coo_rows, coo_cols = [], []
     for l in range(L):
         rows, cols, x = [], [], []
         for b, e in enumerate(envs):
@@ -265,11 +274,13 @@ def forward_q(w, envs, variant, trace=None):
         row = torch.from_numpy(np.concatenate(rows)) if rows else torch.zeros(0, dtype=torch.long)
         col = torch.from_numpy(np.concatenate(cols)) if cols else torch.zeros(0, dtype=torch.long)
         node_input = torch.cat(x, 0) if x else torch.zeros((0, 2))
+        coo_rows.append(row)
+        coo_cols.append(col)
         h = F.normalize(torch.relu(torch.matmul(node_input, w["w_n2l"])), p=2, dim=1)
         y = F.normalize(torch.relu(torch.matmul(torch.ones((B, 2)), w["w_n2l"])), p=2, dim=1)
         if trace is not None:
-            trace.setdefault("h", {})[(l, 0)] = h.numpy().copy()
-            trace.setdefault("y", {})[(l, 0)] = y.numpy().copy()
+            trace.setdefault("h", {})[(l, 0)] = h.detach().numpy().copy()
+            trace.setdefault("y", {})[(l, 0)] = y.detach().numpy().copy()
         for _ in range(MAX_BP_ITER):
             pool = spmm_coo(row, col, n, h)
             node_linear = torch.matmul(pool, w["p_node_conv"])
@@ -280,16 +291,16 @@ def forward_q(w, envs, variant, trace=None):
             y_merged = torch.cat([y_linear, torch.matmul(y, w["p_node_conv2"])], 1)
             y = F.normalize(torch.relu(torch.matmul(y_merged, w["p_node_conv3"])), p=2, dim=1)
             if trace is not None:
-                trace["h"][(l, _ + 1)] = h.numpy().copy()
-                trace["y"][(l, _ + 1)] = y.numpy().copy()
-                trace.setdefault("ypool", {})[(l, _)] = y_pool.numpy().copy()
+                trace["h"][(l, _ + 1)] = h.detach().numpy().copy()
+                trace["y"][(l, _ + 1)] = y.detach().numpy().copy()
+                trace.setdefault("ypool", {})[(l, _)] = y_pool.detach().numpy().copy()
         node_emb.append(h)
         y_emb.append(y)
     e0 = torch.cat([node_emb[0], y_emb[0]], 0)
     e1 = torch.cat([node_emb[1], y_emb[1]], 0)
     fused = [F.normalize(_fuse(w, e0, e1, p), p=2, dim=1) for p in range(L)]
     if trace is not None:
-        trace["fused"] = [f.numpy().copy() for f in fused]
+        trace["fused"] = [f.detach().numpy().copy() for f in fused]
         trace["n"] = n
     qs, gates = [], []
     for l in range(L):
@@ -307,9 +318,9 @@ def forward_q(w, envs, variant, trace=None):
     sm = F.softmax(torch.cat(gates, 1), dim=1)
     q = sm[:, 0:1] * qs[0] + sm[:, 1:2] * qs[1]
     if trace is not None:
-        trace["gate_softmax"] = sm.numpy().copy()
-        trace["q_layers"] = [x.numpy().copy() for x in qs]
-    return q[:, 0].numpy(), act_ids, off
+        trace["gate_softmax"] = sm.detach().numpy().copy()
+        trace["q_layers"] = [x.detach().numpy().copy() for x in qs]
+    return q, act_ids, off, dict(fused=fused, row=coo_rows, col=coo_cols, n=n)
 
 
 def predict(w, envs, variant):
@@ -409,3 +420,60 @@ def heuristic_rollout(g: MultiplexGraph, kind="hda", combine="max"):
         env.stepWithoutReward(a)
         sol.append(a)
     return dict(score=env.score, sol=sol, ranks=list(env.rank_list), maxcc=list(env.MaxCCList), env=env)
+
+
+# ----------------------------------------------------------------------------------------------
+# DQN training step
+#   fit        U/MultiDismantler_torch.py:381-408  (SetupTrain, train_forward, calc_loss, backward, Adam step)
+#   train_forward U/MultiDismantler_net_graphsage.py:92-241: the same network as test_forward; Q is read only at
+#              the chosen action's row of each graph (action_select spmm, :199-203)
+#   calc_loss  :410-431: MSE(target, q_pred) + Alpha * sum_l 2 trace(H_l^T Lap_l H_l) / edge_num_l with
+#              Lap_l = D - A of the alive layer (PrepareBatchGraph.n2n_construct :217-249), H_l = the fused, normalised
+#              node embeddings returned as cur_message_layer, edge_num_l = sum of the n2n values (directed alive entries)
+# ----------------------------------------------------------------------------------------------
+ALPHA = 0.001  # U/MultiDismantler_torch.py:40
+LEARNING_RATE = 0.0001  # :38
+GAMMA = 1  # :33
+N_STEP = 5  # :48
+
+
+def train_loss(w, envs, actions, targets, variant="unit"):
+    """loss, q_pred [B,1], [H_0, H_1] for a batch of (state, action, target); w may hold requires_grad tensors."""
+    q, act_ids, off, ex = forward_torch(w, envs, variant)
+    rows = []
+    for b, (ids, a) in enumerate(zip(act_ids, actions)):
+        pos = np.nonzero(ids == int(a))[0]
+        assert pos.size == 1, "the action must be an active node of its state (PrepareBatchGraph.py:141)"
+        rows.append(int(off[b] + pos[0]))
+    q_pred = q.index_select(0, torch.tensor(rows, dtype=torch.long))
+    n = ex["n"]
+    loss2 = torch.zeros(1)
+    embs = []
+    for l in range(len(ex["fused"])):
+        h = ex["fused"][l][:n]
+        embs.append(h)
+        row, col = ex["row"][l], ex["col"][l]
+        deg = torch.bincount(row, minlength=n).to(h.dtype)
+        lap_h = deg.unsqueeze(1) * h - spmm_coo(row, col, n, h)
+        recons = 2 * torch.trace(torch.matmul(h.t(), lap_h))
+        loss2 = loss2 + recons / float(row.numel())
+    tgt = torch.as_tensor(np.asarray(targets, dtype=np.float64).reshape(-1, 1)).type(torch.FloatTensor)
+    loss1 = F.mse_loss(tgt, q_pred)
+    return loss1 + ALPHA * loss2, q_pred, embs
+
+
+def nstep_returns(rewards, n_step=N_STEP):
+    """NStepReplayMem.add_from_env (U/nstep_replay_mem.py:57-80): per step i the n-step reward sum, the index of the
+    successor state (None = terminal) -- states are prefixes of the removal sequence."""
+    T = len(rewards)
+    sums = [0.0] * T
+    sums[T - 1] = rewards[T - 1]
+    for i in range(T - 2, -1, -1):
+        sums[i] = sums[i + 1] + rewards[i]
+    out = []
+    for i in range(T):
+        if i + n_step >= T:
+            out.append((sums[i], None, True))
+        else:
+            out.append((sums[i] - sums[i + n_step], i + n_step, False))
+    return out

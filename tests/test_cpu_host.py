@@ -158,3 +158,43 @@ def test_bench_reference_arm_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "graphs/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _allreduce_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("md_train_host", os.path.join(ROOT, "mdcommunity_b200", "train.py"),
+                                                  submodule_search_locations=None)
+    # allreduce_gradients is pure torch.distributed host logic: exercise it without the CUDA-only package import
+    src = open(os.path.join(ROOT, "mdcommunity_b200", "train.py")).read()
+    ns = {"torch": torch, "dist": dist}
+    start = src.index("def allreduce_gradients(params):")
+    end = src.index("# ----", start)
+    exec(src[start:end], ns)
+    ps = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5))]
+    ps[0].grad = torch.full((3, 2), float(rank + 1))
+    ps[1].grad = torch.arange(5, dtype=torch.float32) * (rank + 1)
+    flat = ns["allreduce_gradients"](ps)
+    if rank == 0:
+        out.put((flat.tolist(), ps[0].grad.tolist(), ps[1].grad.tolist()))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_gloo_world2():
+    """Data-parallel training step: ONE flat gradient buffer, SUM all-reduce (world 2, gloo)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    flat, g0, g1 = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert flat == [3.0] * 6 + [0.0, 3.0, 6.0, 9.0, 12.0]
+    assert g0 == [[3.0, 3.0]] * 3 and g1 == [0.0, 3.0, 6.0, 9.0, 12.0]

@@ -1,0 +1,101 @@
+"""DQN training step / replay / simulator on the device vs the golden vectors recorded from the reference
+(tests/golden/train_unit.npz) and the pinned oracle."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _sample():
+    import mdcommunity_b200 as mdb
+    z = np.load(os.path.join(GOLDEN, "train_unit.npz"))
+    g_list, covered = [], []
+    cache = {}
+    for case, t in zip(z["cases"], z["t"]):
+        zc = np.load(os.path.join(GOLDEN, str(case) + ".npz"))
+        if str(case) not in cache:
+            cache[str(case)] = mdb.Graph_test(zc["edges0"], zc["edges1"], num_nodes=int(zc["num_nodes"]), cost="unit")
+        g_list.append(cache[str(case)])
+        covered.append([int(a) for a in zc["greedy_actions"][:int(t)]])
+    return z, g_list, covered
+
+
+def test_train_step_matches_reference():
+    """train_forward + calc_loss + backward + Adam on the device: q_pred, embeddings, loss, every gradient and the updated
+    parameters against the reference's own numbers."""
+    from mdcommunity_b200 import train
+    z, g_list, covered = _sample()
+    tr = train.DQNTrainer("unit")
+    tr.LoadModel(dict(np.load(os.path.join(GOLDEN, "weights_unit.npz"))))
+    tr.optimizer.zero_grad()
+    q_pred, fused, tb = tr.train_forward(g_list, covered, [int(a) for a in z["actions"]])
+    assert np.allclose(q_pred.detach().cpu().numpy(), z["q_pred"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(fused[0][:tb.n].detach().cpu().numpy(), z["emb0"], rtol=0, atol=5e-6)
+    assert np.allclose(fused[1][:tb.n].detach().cpu().numpy(), z["emb1"], rtol=0, atol=5e-6)
+    tgt = torch.as_tensor(z["targets"]).float().to(tr.device)
+    loss = train.calc_loss(q_pred, fused, tb, tgt)
+    assert abs(float(loss) - float(z["loss"])) <= 1e-5 * abs(float(z["loss"])) + 1e-9
+    loss.backward()
+    for k in z.files:
+        if k.startswith("grad/"):
+            g_ref = z[k]
+            g = tr.net.p(k[5:]).grad.cpu().numpy().reshape(g_ref.shape)
+            scale = np.abs(g_ref).max() + 1e-12
+            assert np.abs(g - g_ref).max() <= 1e-3 * scale + 1e-9, (k, np.abs(g - g_ref).max(), scale)
+    tr.optimizer.step()
+    for k in z.files:
+        if k.startswith("after/"):
+            assert np.allclose(tr.net.p(k[6:]).detach().cpu().numpy().reshape(z[k].shape), z[k], rtol=0, atol=2e-6), k
+
+
+def test_fit_reduces_loss_and_matches_single_call():
+    from mdcommunity_b200 import train
+    z, g_list, covered = _sample()
+    tr = train.DQNTrainer("unit")
+    tr.LoadModel(dict(np.load(os.path.join(GOLDEN, "weights_unit.npz"))))
+    l0 = tr.fit(g_list, covered, [int(a) for a in z["actions"]], z["targets"])
+    assert abs(l0 - float(z["loss"])) <= 1e-5 * abs(float(z["loss"])) + 1e-9
+    for _ in range(20):
+        l1 = tr.fit(g_list, covered, [int(a) for a in z["actions"]], z["targets"])
+    assert l1 < l0
+
+
+def test_simulator_replay_and_targets():
+    """epsilon-greedy episodes on the device env -> n-step replay entries whose rewards / successor states follow
+    nstep_replay_mem.add_from_env (checked against the oracle's restatement), then Fit-style targets and one fit()."""
+    from oracle import md_oracle as orc
+    from mdcommunity_b200 import train, gmm
+    graphs = [gmm.gmm_graph(40 + 3 * i, 100 + i, cost="unit") for i in range(6)]
+    tr = train.DQNTrainer("unit", seed=1)
+    tr.LoadModel(dict(np.load(os.path.join(GOLDEN, "weights_unit.npz"))))
+    sim = train.Simulator(tr, graphs, rng=random.Random(3))
+    mem = train.NStepReplayMem(10000)
+    for eps in (1.0, 0.5, 0.0):
+        sim.play(eps, mem)
+    assert mem.count > 20
+    # every stored episode: replay its removal sequence in the oracle env, recompute rewards and n-step sums
+    seen = {}
+    for it in mem.items[:mem.count]:
+        g, seq, t, a, r, tp, term = it
+        key = (id(g), tuple(seq))
+        if key not in seen:
+            og = orc.MultiplexGraph(g.num_nodes, g.edge_list)
+            env = orc.OracleEnv("unit")
+            env.s0(og)
+            rew = [env.stepWithoutReward(x) for x in seq]
+            assert env.isTerminal()
+            seen[key] = orc.nstep_returns(rew, train.N_STEP)
+        r_ref, tp_ref, term_ref = seen[key][t]
+        assert a == seq[t] and term == term_ref and abs(r - r_ref) <= 1e-12
+        assert tp == (len(seq) if tp_ref is None else tp_ref)
+    sample = mem.sampling(16, random.Random(5))
+    target = train.fit_targets(tr, sample)
+    assert target.shape == (16, 1) and np.all(np.isfinite(target))
+    loss = tr.fit(sample.g_list, sample.list_st, sample.list_at, target)
+    assert np.isfinite(loss)
