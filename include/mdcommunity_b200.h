@@ -67,6 +67,7 @@ typedef struct md_state {
   int32_t* n_act;        /* [B] */
   int32_t* aptr[MD_MAX_LAYERS]; /* [n_total + 1] CSR of the ALIVE edges in compact order: row g*S + p is active node p of graph g */
   int32_t* acol[MD_MAX_LAYERS]; /* [nnz_l] alive neighbours (global ids); graph g uses its static CSR region */
+  int32_t* asrc[MD_MAX_LAYERS]; /* [nnz_l] row (global node id) of every alive entry: the next env step starts from the alive CSR */
   int32_t* n_removed;    /* [B] |covered_set| */
   int32_t* cov_edges;    /* [L][B] numCoveredEdges */
   int32_t* alive_edges;  /* [L][B] */

@@ -33,7 +33,7 @@ class MdGraphs(C.Structure):
 
 class MdState(C.Structure):
     _fields_ = [
-        ("label", _vp), ("deg", _vp * MAX_LAYERS), ("act_list", _vp), ("n_act", _vp), ("aptr", _vp * MAX_LAYERS), ("acol", _vp * MAX_LAYERS), ("n_removed", _vp),
+        ("label", _vp), ("deg", _vp * MAX_LAYERS), ("act_list", _vp), ("n_act", _vp), ("aptr", _vp * MAX_LAYERS), ("acol", _vp * MAX_LAYERS), ("asrc", _vp * MAX_LAYERS), ("n_removed", _vp),
         ("cov_edges", _vp), ("alive_edges", _vp), ("max_deg", _vp), ("twohop", _vp), ("rank", _vp),
         ("done", _vp), ("n_steps", _vp), ("score", _vp), ("aux", _vp), ("best", _vp),
         ("trace_action", _vp), ("trace_rank", _vp), ("trace_maxcc", _vp), ("n_done", _vp),

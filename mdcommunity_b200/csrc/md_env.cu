@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int* lab = smem;                  // [St] graph-local label, -1 = removed / padding
   int* par = smem + St;             // [St] union-find parent; later the alive degree of the current layer
   int* tmp = smem + 2 * St;         // [St] scratch; later the compact list of active nodes
-  int* c_rp = smem + 3 * St;        // [L][St + 1] row offsets into c_cl / c_src
+  int* arow = smem + 3 * St;        // [St] node (graph-local id) of input row p
+  int* c_rp = smem + 4 * St;        // [L][St + 1] row offsets into c_cl / c_src
   IdxT* c_cl = reinterpret_cast<IdxT*>(c_rp + L * (St + 1));  // [max_nnz] neighbour (graph-local id)
   IdxT* c_src = c_cl + max_nnz;     // [max_nnz] row of the entry (static, staged); later the alive prefix
   __shared__ BlockRed red;
@@ -148,16 +149,23 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
 
   ENV_TICK();  // 0: labels in
   // ---- stage the graph's CSR in shared memory ---------------------------------------------------------
+  // A step starts from the ALIVE CSR the previous step emitted (rows = previous active nodes, entries = edges that were
+  // still alive): dead edges never come back, so staging, hooking and compaction cost shrink with the graph.  s0 /
+  // set_state start from the static CSR (rows = all nodes).  Either way row p stands for node arow[p].
+  const bool from_alive = init == 0;
+  const int nprev = from_alive ? S.n_act[g] : N;
+  for (int p = tid; p < nprev; p += ENV_T) arow[p] = from_alive ? S.act_list[base + p] - base : p;
   int lay_pos[MD_MAX_LAYERS + 1];
   {
     int pos = 0;
     for (int ll = 0; ll < L; ++ll) {
-      const int32_t* __restrict__ rp = G.rowptr[ll] + base;
-      const int32_t* __restrict__ cl = G.col[ll];
-      const int e0 = rp[0], cnt = rp[St] - e0;
-      for (int v = tid; v <= St; v += ENV_T) c_rp[ll * (St + 1) + v] = rp[v] - e0 + pos;
-      const int32_t* __restrict__ sr = G.src[ll];
-      for (int e = tid; e < cnt; e += ENV_T) {
+      const int32_t* __restrict__ rp = (from_alive ? S.aptr[ll] : G.rowptr[ll]) + base;
+      const int32_t* __restrict__ cl = from_alive ? S.acol[ll] : G.col[ll];
+      const int32_t* __restrict__ sr = from_alive ? S.asrc[ll] : G.src[ll];
+      const int e0 = rp[0], cnt = rp[nprev] - e0;
+      for (int p = tid; p <= nprev; p += ENV_T) c_rp[ll * (St + 1) + p] = rp[p] - e0 + pos;
+#pragma unroll 4
+      for (int e = tid; e < cnt; e += ENV_T) {  // unrolled: the independent loads of four trips are in flight together
         c_cl[pos + e] = (IdxT)(cl[e0 + e] - base);
         c_src[pos + e] = (IdxT)(sr[e0 + e] - base);
       }
@@ -178,9 +186,11 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   // ---- Mcc.MCC: refine the partition layer by layer until every layer is stable ----------------------
   int stable = 0, l = 0;
   int rounds_dbg = 0;
+  long long hook_dbg = 0, flat_dbg = 0, tq = 0;
   while (stable < L) {
     for (int v = tid; v < N; v += ENV_T) par[v] = v;
     __syncthreads();
+    tq = clock64();
     for (int e = lay_pos[l] + tid; e < lay_pos[l + 1]; e += ENV_T) {  // edge-parallel hooking
       const int v = c_src[e], u = c_cl[e];
       if (u < v) {
@@ -189,6 +199,8 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       }
     }
     __syncthreads();
+    hook_dbg += clock64() - tq;
+    tq = clock64();
     int changed = 0;
     for (int v = tid; v < N; v += ENV_T) {
       int r = -1;
@@ -201,12 +213,13 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
     changed = __syncthreads_or(changed);
     for (int v = tid; v < N; v += ENV_T) lab[v] = tmp[v];
     __syncthreads();
+    flat_dbg += clock64() - tq;
     stable = changed ? 1 : stable + 1;
     l = (l + 1 == L) ? 0 : l + 1;
     ++rounds_dbg;
   }
   ENV_TICK();  // 2: LMCC rounds
-  if (blockIdx.x == 0 && tid == 0) g_env_dbg[16] = rounds_dbg;
+  if (blockIdx.x == 0 && tid == 0) g_env_dbg[16] = rounds_dbg, g_env_dbg[17] = hook_dbg, g_env_dbg[18] = flat_dbg;
 
   // ---- component sizes -> LMCC rank (Mcc.find_max_set_length) ------------------------------------------
   for (int v = tid; v < N; v += ENV_T) tmp[v] = 0;
@@ -228,36 +241,50 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   for (int ll = 0; ll < L; ++ll) {
     const int* rp = c_rp + ll * (St + 1);
     const int p0 = lay_pos[ll], cnt = lay_pos[ll + 1] - p0;
-    const int e0 = G.rowptr[ll][base];  // the graph's region of acol[ll] is its static CSR region
+    const int e0 = G.rowptr[ll][base];  // the graph's region of acol[ll] / asrc[ll] is its static CSR region
     int32_t* __restrict__ aptr = S.aptr[ll] + base;
     int32_t* __restrict__ acol = S.acol[ll];
+    int32_t* __restrict__ asrc = S.asrc[ll];
     IdxT* pref = c_src + p0;  // pref[i] = number of alive entries before entry i of this layer, i in [0, cnt]
-    int running = 0;
-    for (int c0 = 0; c0 < cnt; c0 += ENV_T) {
-      const int i = c0 + tid;
-      int flag = 0, u = 0;
-      if (i < cnt) {
-        u = c_cl[p0 + i];
-        const int lv = lab[c_src[p0 + i]];
-        flag = (lv >= 0 && lab[u] == lv) ? 1 : 0;
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, flag);
-      __syncthreads();  // every thread has read its c_src entry before the prefixes overwrite the slots
-      if (lane == 0) s_scan[wid] = __popc(bal);
-      __syncthreads();
-      int woff = 0, total = 0;
+    // thread t owns the contiguous entries [i0, i1): count, one block-wide exclusive scan of the 512 counts, then write.
+    // (Reads and the in-place prefix writes of a thread stay inside its own range, so the two passes need no barrier
+    // between them besides the scan's; the chunk-at-a-time version spent 2 barriers per 512 entries: 28 k cycles / step.)
+    const int per = (cnt + ENV_T - 1) / ENV_T;
+    const int i0 = min(cnt, tid * per), i1 = min(cnt, i0 + per);
+    int mine = 0;
+    for (int i = i0; i < i1; ++i) {
+      const int lv = lab[c_src[p0 + i]];
+      mine += (lv >= 0 && lab[c_cl[p0 + i]] == lv) ? 1 : 0;
+    }
+    int incl = mine;
 #pragma unroll
-      for (int k = 0; k < ENV_W; ++k) {
-        const int c = s_scan[k];
-        if (k < wid) woff += c;
-        total += c;
-      }
-      const int pos = running + woff + __popc(bal & ((1u << lane) - 1u));
-      if (i < cnt) {
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    __syncthreads();  // s_scan is free (previous layer's readers are done)
+    if (lane == 31) s_scan[wid] = incl;
+    __syncthreads();
+    int woff = 0, running = 0;
+#pragma unroll
+    for (int k = 0; k < ENV_W; ++k) {
+      const int c = s_scan[k];
+      if (k < wid) woff += c;
+      running += c;
+    }
+    {
+      int pos = woff + incl - mine;
+      for (int i = i0; i < i1; ++i) {
+        const int u = c_cl[p0 + i], sv = c_src[p0 + i];
+        const int lv = lab[sv];
+        const bool flag = lv >= 0 && lab[u] == lv;
         pref[i] = (IdxT)pos;
-        if (flag) acol[e0 + pos] = u + base;
+        if (flag) {
+          acol[e0 + pos] = u + base;
+          asrc[e0 + pos] = sv + base;
+          ++pos;
+        }
       }
-      running += total;
     }
     __syncthreads();
     const int tot = running;  // alive directed entries of the layer (= pref[cnt], which has no slot of its own)
@@ -265,11 +292,10 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
 #define PREF_AT(x) ((x) == pend ? tot : (int)c_src[(x)])
     int dmax = 0;
     long long th = 0;
-    for (int v = tid; v < St; v += ENV_T) {
-      int d = 0;
-      if (v < N) d = PREF_AT(rp[v + 1]) - PREF_AT(rp[v]);  // rp[] offsets are absolute positions in c_cl / c_src
-      S.deg[ll][base + v] = d;
-      par[v] = d;
+    for (int p = tid; p < nprev; p += ENV_T) {  // nodes outside the input rows keep their degree 0
+      const int d = PREF_AT(rp[p + 1]) - PREF_AT(rp[p]);  // rp[] offsets are absolute positions in c_cl / c_src
+      S.deg[ll][base + arow[p]] = d;
+      par[p] = d;
       dmax = max(dmax, d);
       th += (long long)d * (d - 1) / 2;
     }
@@ -284,15 +310,13 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
     __syncthreads();
 
     if (ll == 0) {
-      // write labels back, compact the active nodes (ascending id, PrepareBatchGraph.py:128-138) into tmp[]
+      // write labels back; compact the rows that are still active (ascending id, PrepareBatchGraph.py:128-138): tmp[q] =
+      // input row of new row q
+      for (int v = tid; v < St; v += ENV_T) S.label[base + v] = (v < N && lab[v] >= 0) ? lab[v] + base : -1;
       int run2 = 0;
-      for (int v0 = 0; v0 < St; v0 += ENV_T) {
-        const int v = v0 + tid;
-        int flag = 0;
-        if (v < St) {
-          S.label[base + v] = (v < N && lab[v] >= 0) ? lab[v] + base : -1;
-          flag = (v < N && par[v] > 0) ? 1 : 0;
-        }
+      for (int p0r = 0; p0r < nprev; p0r += ENV_T) {
+        const int p = p0r + tid;
+        const int flag = (p < nprev && par[p] > 0) ? 1 : 0;
         const unsigned bal = __ballot_sync(0xffffffffu, flag);
         if (lane == 0) s_scan[wid] = __popc(bal);
         __syncthreads();
@@ -304,9 +328,9 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
           total += c;
         }
         if (flag) {
-          const int p = run2 + woff + __popc(bal & ((1u << lane) - 1u));
-          S.act_list[base + p] = base + v;
-          tmp[p] = v;
+          const int q = run2 + woff + __popc(bal & ((1u << lane) - 1u));
+          S.act_list[base + q] = base + arow[p];
+          tmp[q] = p;
         }
         run2 += total;
         __syncthreads();
@@ -383,7 +407,7 @@ extern "C" int32_t md_env_small_max_stride(void) { return g_force_large ? 0 : md
 static bool env_idx16(const md_graphs_t* g) { return g->max_graph_nnz < 65536 && g->stride < 65536; }
 static size_t env_small_smem(const md_graphs_t* g) {
   const size_t idx_bytes = env_idx16(g) ? 2 : 4;
-  return ((size_t)3 * g->stride + (size_t)g->n_layers * (g->stride + 1)) * sizeof(int) +
+  return ((size_t)4 * g->stride + (size_t)g->n_layers * (g->stride + 1)) * sizeof(int) +
          ((2 * (size_t)g->max_graph_nnz * idx_bytes + 15) & ~(size_t)15);
 }
 extern "C" int32_t md_env_uses_small_path(const md_graphs_t* g) {

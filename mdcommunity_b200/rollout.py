@@ -76,6 +76,7 @@ class BatchRollout:
         self.act_list = i32(nt)
         self.aptr = [i32(nt + 1) for _ in range(L)]
         self.acol = [i32(max(1, batch.nnz[l])) for l in range(L)]
+        self.asrc = [i32(max(1, batch.nnz[l])) for l in range(L)]
         self.n_act, self.n_removed, self.rank, self.done, self.n_steps = i32(B), i32(B), i32(B), i32(B), i32(B)
         self.cov_edges, self.alive_edges, self.max_deg = i32(L, B), i32(L, B), i32(L, B)
         self.twohop = torch.zeros(L, B, dtype=torch.int64, device=dev)
@@ -97,6 +98,7 @@ class BatchRollout:
             s.deg[l] = self.deg[l].data_ptr()
             s.aptr[l] = self.aptr[l].data_ptr()
             s.acol[l] = self.acol[l].data_ptr()
+            s.asrc[l] = self.asrc[l].data_ptr()
         for name in ("act_list", "n_act", "n_removed", "cov_edges", "alive_edges", "max_deg", "twohop", "rank", "done",
                      "n_steps", "score", "aux", "best", "trace_action", "trace_rank", "trace_maxcc", "n_done", "flags",
                      "cur_action"):

@@ -99,4 +99,4 @@ torch.cuda.profiler.stop()
 print("%d steps: %.3f ms (%.3f ms/step)" % (args.steps, e0.elapsed_time(e1), e0.elapsed_time(e1) / args.steps))
 buf = np.zeros(32, np.int64)
 lib.md_debug_read_env(buf.ctypes.data_as(C.c_void_p), 32)
-print("env CTA0 phase cycles [labels, stage CSR, prune rounds, comp sizes, alive CSR+deg]:", buf[:5].tolist(), "rounds", int(buf[16]))
+print("env CTA0 phase cycles [labels, stage CSR, prune rounds, comp sizes, alive CSR+deg]:", buf[:5].tolist(), "rounds", int(buf[16]), "hook / flatten cycles", buf[17:19].tolist())
