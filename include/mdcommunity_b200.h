@@ -203,6 +203,14 @@ int md_qhead(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, c
 int md_rollout_steps(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                      int32_t n_steps, md_stream_t stream);
 
+/* The same n_steps iterations captured once into a CUDA graph and replayed (launch-bound tail of a rollout).  Call
+ * md_rollout_steps at least once before md_rollout_graph_create; the graph bakes in the struct values (device pointers),
+ * so it is valid while the caller keeps the same buffers.  Small-graph (single-CTA env) batches only: MD_ETOOBIG else. */
+int md_rollout_graph_create(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
+                            int32_t n_steps, md_stream_t stream, void** exec_out);
+int md_rollout_graph_launch(void* exec, md_stream_t stream);
+int md_rollout_graph_destroy(void* exec);
+
 /* Top-k selection for GetSolution's stepRatio mode (np.argsort(-pred)[:step], U/MultiDismantler_torch.py:725):
  * out_local_ids[g][0..topk) = graph g's active nodes ranked by (q descending, id ascending), -1 padded.
  * Feed it to md_env_step(actions = out_local_ids, action_stride = topk, action_index = j) for j = 0..topk-1. */

@@ -76,6 +76,10 @@ _SIGS = {
     "md_qhead": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_rollout_steps": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),
     "md_heuristic_select": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_rollout_graph_create": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp,
+                                 C.POINTER(C.c_void_p)], C.c_int),
+    "md_rollout_graph_launch": ([_vp, _vp], C.c_int),
+    "md_rollout_graph_destroy": ([_vp], C.c_int),
     "md_select_topk": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWork), _vp, C.c_int32, _vp], C.c_int),
     "md_spmm_csr_f32": ([_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
     "md_psum_floats": ([C.c_int32, C.c_int32], C.c_int64),

@@ -345,6 +345,14 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
   tc_fence_before();
   __syncthreads();
   if (warp == 10) tmem_dealloc(tbase, TCOLS);
+  // the last CTA to leave re-arms the tile queue for the next launch (no memset node between launches)
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(counter + 1, 1) == (int)gridDim.x - 1) {
+      counter[0] = 0;
+      counter[1] = 0;
+    }
+  }
 }
 
 }  // namespace md
@@ -365,9 +373,8 @@ int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weigh
   }
   const int n_tiles = g->n_graphs * (g->stride / MD_TILE_M);
   const int grid = nsm < n_tiles ? nsm : n_tiles;
-  int* counter = s->flags + 4;
-  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), st);
-  if (e != cudaSuccess) return (int)e;
+  int* counter = s->flags + 4;  // [4] next tile, [5] CTAs finished; zero between launches (the kernel re-arms them)
+  cudaError_t e = cudaSuccess;
   {
     static bool configured = false;
     const int smem = (int)sizeof(md::QTSmem<2>);

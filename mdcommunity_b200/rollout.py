@@ -129,6 +129,9 @@ class BatchRollout:
             k.fused_ws = None
         self.k = k
         self._pinned_done = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._graph, self._graph_chunk, self._graph_w = None, 0, None
+        self.use_graph = True
+        self._runs = 0
         self.kernel_launches = 0
         self.reset()
 
@@ -199,8 +202,18 @@ class BatchRollout:
             topk = torch.empty(B, step, dtype=torch.int32, device=self.batch.device)
         while True:
             if step == 1:
-                _lib.check(self.lib.md_rollout_steps(self._g(), C.byref(self.s), self.w.ptr(), C.byref(self.k), chunk,
-                                                     self._stream()), "md_rollout_steps")
+                if self._graph is None and self._runs > 0 and it > 0 and not self.large and self.use_graph:
+                    # a chunk of iterations as ONE CUDA graph, built when the rollout object is re-used (instantiation costs
+                    # about as much as one small rollout); the first chunk ran eagerly: one-time kernel attributes are set
+                    ex = C.c_void_p()
+                    _lib.check(self.lib.md_rollout_graph_create(self._g(), C.byref(self.s), self.w.ptr(), C.byref(self.k), chunk,
+                                                                self._stream(), C.byref(ex)), "md_rollout_graph_create")
+                    self._graph, self._graph_chunk, self._graph_w = ex, chunk, self.w
+                if self._graph is not None and self._graph_chunk == chunk and self._graph_w is self.w:
+                    _lib.check(self.lib.md_rollout_graph_launch(self._graph, self._stream()), "md_rollout_graph_launch")
+                else:
+                    _lib.check(self.lib.md_rollout_steps(self._g(), C.byref(self.s), self.w.ptr(), C.byref(self.k), chunk,
+                                                         self._stream()), "md_rollout_steps")
                 self.kernel_launches += chunk * ((5 if self.fused else 4 + _lib.BP_ITERS))
             else:
                 for _ in range(chunk):
@@ -213,6 +226,7 @@ class BatchRollout:
             it += chunk
             if self.num_done() >= B or it > self.max_steps + chunk:
                 break
+        self._runs += 1
         return self.results()
 
     def run_heuristic(self, kind="hda", combine="max", chunk=8):
@@ -230,6 +244,13 @@ class BatchRollout:
             if self.num_done() >= self.batch.B or it > self.max_steps + chunk:
                 break
         return self.results()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_graph", None) is not None:
+                self.lib.md_rollout_graph_destroy(self._graph)
+        except Exception:
+            pass
 
     def results(self):
         torch.cuda.current_stream(self.batch.device).synchronize()

@@ -328,3 +328,21 @@ def test_qhead_tensor_core_matches_fma(variant):
     finally:
         lib.md_debug_set_flags(0)
     print("qhead tensor-core vs FMA: worst scaled |dQ| %.3e" % worst)
+
+
+def test_cuda_graph_rollout_matches_eager():
+    """BatchRollout.run(): the second run of the same object replays chunks of iterations as one CUDA graph
+    (md_rollout_graph_*); removal sequences, LMCC traces and AUDC must equal the eager first run bit for bit."""
+    mdb = _mdb()
+    zs, graphs, batch, w = _load_batch("degree")
+    ro = mdb.BatchRollout(batch, w)
+    r1 = ro.run()
+    assert ro._graph is None
+    ro.reset()
+    r2 = ro.run()
+    assert ro._graph is not None
+    ro.reset()
+    r3 = ro.run()
+    for r in (r2, r3):
+        assert np.array_equal(r1["n_steps"], r["n_steps"]) and np.array_equal(r1["actions"], r["actions"])
+        assert np.array_equal(r1["ranks"], r["ranks"]) and np.array_equal(r1["score"], r["score"])
