@@ -154,6 +154,8 @@ void md_debug_set_flags(int32_t flags);
 /* profiling hook: clock64 phase times of CTA 0 of the last md_env_step (labels in, CSR staged, prune rounds,
  * component sizes, alive CSR + degrees) and, at index 16, the number of prune rounds */
 int md_debug_read_env(long long* host, int n);
+/* profiling hook: per graph (first 1024) of the last md_env_step: {cycles, prune rounds, staged CSR entries, SM id} */
+int md_debug_read_env_ctas(unsigned* host4096);
 /* profiling hook: clock64 phase sums of CTA 0 of the last md_embed_fused launch.  Gather warp 0: [0] unit setup,
  * [1] first-embedding fill, [2] column-half reload, [3] gather, [4] wait for the staging tile, [5] end-of-pass wait,
  * [6] epilogue, [7] idle between units; MMA thread: [8] weight-image wait, [9] wait for a full tile, [10] MMA issue,

@@ -12,6 +12,7 @@
 
 namespace md {
 __device__ long long g_env_dbg[32];
+__device__ unsigned g_env_cta[1024][4];  // per graph of the last step: cycles, prune rounds, staged entries, SM id
 #define ENV_T0() long long t_dbg = clock64(); int k_dbg = 0
 #define ENV_TICK() do { if (blockIdx.x == 0 && tid == 0) { long long n_ = clock64(); g_env_dbg[k_dbg] = n_ - t_dbg; t_dbg = n_; } ++k_dbg; } while (0)
 
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
 
   if (!init && S.done[g]) return;
   ENV_T0();
+  const long long t_cta0 = clock64();
 
   // ---- pick the action -----------------------------------------------------------------------------
   if (tid == 0) {
@@ -345,6 +347,11 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   }
 
   ENV_TICK();  // 4: alive CSR + degrees + compaction
+  if (tid == 0 && g < 1024) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_env_cta[g][0] = (unsigned)(clock64() - t_cta0), g_env_cta[g][1] = rounds_dbg, g_env_cta[g][2] = lay_pos[L], g_env_cta[g][3] = smid;
+  }
   // ---- bookkeeping: reward / AUDC in f64 with the reference's operation order ---------------------------
   if (tid == 0) {
     const int B = G.n_graphs;
@@ -398,6 +405,9 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
 int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
                       int32_t forced_index, int init, md_stream_t stream);
 
+extern "C" int md_debug_read_env_ctas(unsigned* host4096) {
+  return (int)cudaMemcpyFromSymbol(host4096, md::g_env_cta, sizeof(unsigned) * 4096);
+}
 extern "C" int md_debug_read_env(long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, md::g_env_dbg, sizeof(long long) * n);
 }

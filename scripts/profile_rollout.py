@@ -100,3 +100,13 @@ print("%d steps: %.3f ms (%.3f ms/step)" % (args.steps, e0.elapsed_time(e1), e0.
 buf = np.zeros(32, np.int64)
 lib.md_debug_read_env(buf.ctypes.data_as(C.c_void_p), 32)
 print("env CTA0 phase cycles [labels, stage CSR, prune rounds, comp sizes, alive CSR+deg]:", buf[:5].tolist(), "rounds", int(buf[16]), "hook / flatten cycles", buf[17:19].tolist())
+cb = np.zeros((1024, 4), np.uint32)
+lib.md_debug_read_env_ctas(cb.ctypes.data_as(C.c_void_p))
+cb = cb[:args.graphs]
+cb = cb[cb[:, 0] > 0]
+if len(cb):
+    order = np.argsort(-cb[:, 0].astype(np.int64))[:5]
+    print("env per-graph cycles: min %d median %d max %d; rounds min %d max %d; slowest (cycles, rounds, entries, sm):" % (
+        cb[:, 0].min(), np.median(cb[:, 0]), cb[:, 0].max(), cb[:, 1].min(), cb[:, 1].max()), cb[order].tolist())
+    sm, cnt = np.unique(cb[:, 3], return_counts=True)
+    print("graphs per SM: max %d, SMs used %d" % (cnt.max(), len(sm)))
