@@ -19,12 +19,14 @@
 //               descending alive degree (deterministic counting sort) and dealt to the lane groups so that the four
 //               rows a warp walks together have (nearly) equal length: without this the power-law degree spread made
 //               every step wait for its longest row.  Sums stay in CSR order; rows longer than FZ_LONG are spread over
-//               the warp's four lane groups.  Per 128-row tile the warps write P = A_adj.H (raw fp32) and the bf16
+//               the warp's four lane groups.  Per 128-row tile the warps write P = A_adj.H (raw fp32) and the fp16
 //               remainders [P - tf32(P) | H - tf32(H)] into a staging tile.
 //     transform one elected thread issues tcgen05.mma: D_tile += P.W13[32p:32p+32] + H.W23[32p:32p+32] as
 //               kind::tf32 (operands are truncated to tf32 by the tensor core -- measured, scripts/microbench/umma_probe.cu)
-//               with hi and lo planes of the weights, plus one kind::f16 (bf16) pass for the operand remainders:
-//               a.w ~= a_hi.w_hi + a_hi.w_lo + a_lo.w   (error ~2^-20 relative; the probe measures 1.3e-6 of max |D|).
+//               with hi and lo planes of the weights, plus one kind::f16 (fp16) pass for the operand remainders:
+//               a.w ~= a_hi.w_hi + a_hi.w_lo + a_lo.w.  The remainders are kept in fp16, not bf16: a_lo <= 2^-10 |a| is far
+//               from fp16's range limits and keeps 11 bits there (error ~2^-21 relative instead of 2^-19, which showed
+//               as 1.6e-4 relative Q differences on dense graphs; the bf16 probe measured 1.3e-6 of max |D|).
 //               Accumulators for ALL tiles of the unit (<= 8 x 64 columns = the whole 512-column TMEM) stay in tensor
 //               memory across the two passes, which is what makes the column split free: no partial sums are exchanged.
 //   epilogue    tcgen05.ld (one thread per row holds the 64 outputs): relu, L2 normalise; columns 0..31 go straight into
@@ -33,7 +35,7 @@
 //               md_qhead.  Per-graph column sums of every iteration's input (the subgsum spmm) fall out of the gather.
 //
 // HBM traffic per unit and forward: alive CSR once + final H once (+ features); everything else stays on chip / in L2.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "md_common.cuh"
 #include "md_umma.cuh"
 
@@ -47,7 +49,7 @@ constexpr int FZ_T = FZ_GT + 32;       // + the MMA / bulk-copy warp
 constexpr int FZ_IDX_CAP = 8192;       // alive directed edges of one unit cached in shared memory
 constexpr int FZ_LONG = 24;            // rows with more alive neighbours are summed by the whole warp (< 31: exact sort buckets)
 constexpr uint32_t FZ_TILE_B = 16384;  // one 128-row x 128-byte tile
-constexpr uint32_t FZ_WPASS_B = 40960; // B operands of one pass: W13 hi, W13 lo, W23 hi, W23 lo (tf32), [W13|W23] bf16
+constexpr uint32_t FZ_WPASS_B = 40960; // B operands of one pass: W13 hi, W13 lo, W23 hi, W23 lo (tf32), [W13|W23] fp16
 constexpr size_t FZ_WS_CTR = 2 * FZ_WPASS_B;
 constexpr size_t FZ_WS_SPILL = FZ_WS_CTR + 1024;
 constexpr size_t FZ_SPILL_B = 8 * FZ_TILE_B;
@@ -55,7 +57,7 @@ constexpr size_t FZ_SPILL_B = 8 * FZ_TILE_B;
 struct FusedSmem {
   unsigned char Hs[8 * FZ_TILE_B];  // resident column half of the unit's embeddings (SWIZZLE_128B tiles)
   unsigned char P[FZ_TILE_B];       // staging: neighbour sums of one tile, raw fp32
-  unsigned char LO[FZ_TILE_B];      // staging: bf16 remainders, row = [P_lo (32) | H_lo (32)]
+  unsigned char LO[FZ_TILE_B];      // staging: fp16 remainders, row = [P_lo (32) | H_lo (32)]
   unsigned char Wt[FZ_WPASS_B];     // B operands of the running pass
   uint16_t idx[FZ_IDX_CAP + 64];    // neighbour entries of the unit's alive CSR (see nbrJ); setup: sort counters
   uint16_t pos[FZ_ROWS];            // graph-local node id -> row (degree-sorted compact order)
@@ -92,9 +94,9 @@ __device__ __forceinline__ void add4(float4& a, const float4& b) {
   a.z += b.z;
   a.w += b.w;
 }
-__device__ __forceinline__ uint2 lo_bf16x4(const float4& v) {
-  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y));
-  const __nv_bfloat162 b = __floats2bfloat162_rn(v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+__device__ __forceinline__ uint2 lo_f16x4(const float4& v) {
+  const __half2 a = __floats2half2_rn(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y));
+  const __half2 b = __floats2half2_rn(v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
   return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
 __device__ __forceinline__ bool elect_one() {
@@ -167,8 +169,8 @@ __global__ void __launch_bounds__(256) fused_prep_kernel(md_graphs_t G, md_state
     *reinterpret_cast<float*>(img + 8192 + off) = w13 - tf32_hi(w13);
     *reinterpret_cast<float*>(img + 16384 + off) = tf32_hi(w23);
     *reinterpret_cast<float*>(img + 24576 + off) = w23 - tf32_hi(w23);
-    *reinterpret_cast<__nv_bfloat16*>(img + 32768 + sw128_off(n, k >> 3) + 2 * (k & 7)) = __float2bfloat16_rn(w13);
-    *reinterpret_cast<__nv_bfloat16*>(img + 32768 + sw128_off(n, 4 + (k >> 3)) + 2 * (k & 7)) = __float2bfloat16_rn(w23);
+    *reinterpret_cast<__half*>(img + 32768 + sw128_off(n, k >> 3) + 2 * (k & 7)) = __float2half_rn(w13);
+    *reinterpret_cast<__half*>(img + 32768 + sw128_off(n, 4 + (k >> 3)) + 2 * (k & 7)) = __float2half_rn(w23);
   }
 }
 
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
 
     if (warp == FZ_GW) {
       // ============================== MMA / bulk-copy warp (warp-uniform control flow) ==============================
-      const uint32_t idt = idesc(FMT_TF32, 128, 64), idb = idesc(FMT_BF16, 128, 64);
+      const uint32_t idt = idesc(FMT_TF32, 128, 64), idb = idesc(FMT_F16, 128, 64);
       const uint64_t dP = desc_k_sw128(smem_u32(sm.P), 0), dLO = desc_k_sw128(smem_u32(sm.LO), 0);
       const uint64_t dH0 = desc_k_sw128(smem_u32(sm.Hs), 0);
       const uint64_t b13h = desc_k_sw128(smem_u32(sm.Wt), 0), b13l = desc_k_sw128(smem_u32(sm.Wt) + 8192, 0);
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
                 const uint64_t ko = 2 * k;
                 mma_tf32(d, dP + ko, b13h + ko, idt, 1);
                 mma_tf32(d, dP + ko, b13l + ko, idt, 1);
-                mma_bf16(d, dLO + ko, bbf + ko, idb, 1);
+                mma_f16(d, dLO + ko, bbf + ko, idb, 1);
               }
               mma_commit(&sm.bar_empty);
             }
@@ -522,8 +524,8 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
               const float4 accf = unpack4(a4[k]);
               const uint32_t ro = (uint32_t)rt * 128u;
               *reinterpret_cast<float4*>(sm.P + ro + ((q ^ (rt & 7)) << 4)) = accf;
-              *reinterpret_cast<uint2*>(sm.LO + ro + (((q >> 1) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_bf16x4(accf);
-              *reinterpret_cast<uint2*>(sm.LO + ro + (((4 + (q >> 1)) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_bf16x4(own4[k]);
+              *reinterpret_cast<uint2*>(sm.LO + ro + (((q >> 1) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_f16x4(accf);
+              *reinterpret_cast<uint2*>(sm.LO + ro + (((4 + (q >> 1)) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_f16x4(own4[k]);
             }
           }
           FZ_CLK(d3);
@@ -563,8 +565,8 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
               add4(csum, own);
               const uint32_t ro = (uint32_t)rt * 128u;
               *reinterpret_cast<float4*>(sm.P + ro + ((q ^ (rt & 7)) << 4)) = a;
-              *reinterpret_cast<uint2*>(sm.LO + ro + (((q >> 1) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_bf16x4(a);
-              *reinterpret_cast<uint2*>(sm.LO + ro + (((4 + (q >> 1)) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_bf16x4(own);
+              *reinterpret_cast<uint2*>(sm.LO + ro + (((q >> 1) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_f16x4(a);
+              *reinterpret_cast<uint2*>(sm.LO + ro + (((4 + (q >> 1)) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_f16x4(own);
             }
           }
           FZ_CLK(d4);

@@ -5,14 +5,14 @@
 //
 //   persistent CTA per SM, 11 warps, dynamic tile queue (live (graph, 128-row) tiles only):
 //   warps 8..9  loaders : gather the tile's H_l rows from HBM/L2 (16 row fetches per warp in flight), store them as raw
-//                         fp32 into SWIZZLE_128B K-major operand tiles + the bf16 remainders (x - tf32(x))
-//   warp  10    MMA     : T_pre_l = H_l @ trans as the 3-term product (tf32 hi x hi, hi x lo, bf16 remainder pass), one
+//                         fp32 into SWIZZLE_128B K-major operand tiles + the fp16 remainders (x - tf32(x))
+//   warp  10    MMA     : T_pre_l = H_l @ trans as the 3-term product (tf32 hi x hi, hi x lo, fp16 remainder pass), one
 //                         elected thread, accumulators double-buffered in tensor memory; the operand tile is released to
 //                         the loaders as soon as the MMAs have read it, so the next tile's gather overlaps the epilogue
 //   warps 0..7  epilogue: two threads per node row (column halves for the tanh, hidden-unit halves for h1): tcgen05.ld, tanh(. + bias), the pairwise (T_k . T_p . lw) gates,
 //                         softmax-of-sigmoid mix, normalise, scale by the per-graph s_p, relu(e_p @ h1) . h2 (FP32 FMA from
 //                         registers, h1 broadcast from shared memory), layer-gate mix, q[v], packed arg-max key.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "md_common.cuh"
 #include "md_umma.cuh"
 
@@ -26,8 +26,8 @@ constexpr uint32_t QT_KB = 16384;  // one 128-row x 128-byte operand tile
 template <int L>
 struct QTSmem {
   unsigned char A[L][2][QT_KB];  // raw fp32 rows of H_l, two K blocks of 32 columns
-  unsigned char ALO[L][QT_KB];   // bf16 remainders of H_l, 64 columns per row
-  unsigned char Bt[40960];       // trans^T: tf32 hi (2 K blocks), tf32 lo (2 K blocks), bf16 (64 columns)
+  unsigned char ALO[L][QT_KB];   // fp16 remainders of H_l, 64 columns per row
+  unsigned char Bt[40960];       // trans^T: tf32 hi (2 K blocks), tf32 lo (2 K blocks), fp16 (64 columns)
   alignas(16) float h1[D * MD_HIDDEN];
   alignas(16) float bias[D];
   alignas(16) float lw[D];
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
         const uint32_t off = sw128_off(n, kk >> 2) + 4 * (kk & 3);
         *reinterpret_cast<float*>(sm.Bt + kb * 8192 + off) = tf32_hi(t[j]);
         *reinterpret_cast<float*>(sm.Bt + 16384 + kb * 8192 + off) = t[j] - tf32_hi(t[j]);
-        *reinterpret_cast<__nv_bfloat16*>(sm.Bt + 32768 + sw128_off(n, k >> 3) + 2 * (k & 7)) = __float2bfloat16_rn(t[j]);
+        *reinterpret_cast<__half*>(sm.Bt + 32768 + sw128_off(n, k >> 3) + 2 * (k & 7)) = __float2half_rn(t[j]);
       }
     }
     for (int i = tid; i < D * MD_HIDDEN / 4; i += QT_T)
@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
         for (int j = 0; j < 16; ++j) {
           const uint32_t r = r0 + 2 * j + half;
           *reinterpret_cast<float4*>(sm.A[l][c >> 3] + r * 128u + (((c & 7) ^ (r & 7)) << 4)) = val[j];
-          const __nv_bfloat162 p0 = __floats2bfloat162_rn(val[j].x - tf32_hi(val[j].x), val[j].y - tf32_hi(val[j].y));
-          const __nv_bfloat162 p1 = __floats2bfloat162_rn(val[j].z - tf32_hi(val[j].z), val[j].w - tf32_hi(val[j].w));
+          const __half2 p0 = __floats2half2_rn(val[j].x - tf32_hi(val[j].x), val[j].y - tf32_hi(val[j].y));
+          const __half2 p1 = __floats2half2_rn(val[j].z - tf32_hi(val[j].z), val[j].w - tf32_hi(val[j].w));
           *reinterpret_cast<uint2*>(sm.ALO[l] + r * 128u + (((c >> 1) ^ (r & 7)) << 4) + 8 * (c & 1)) =
               make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
         }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
     }
   } else if (warp == 10) {
     // ================================ MMA issuer ================================
-    const uint32_t idt = idesc(FMT_TF32, 128, 64), idb = idesc(FMT_BF16, 128, 64);
+    const uint32_t idt = idesc(FMT_TF32, 128, 64), idb = idesc(FMT_F16, 128, 64);
     const uint32_t bt = smem_u32(sm.Bt);
     const uint64_t bh0 = desc_k_sw128(bt, 0), bh1 = desc_k_sw128(bt + 8192, 0);
     const uint64_t bl0 = desc_k_sw128(bt + 16384, 0), bl1 = desc_k_sw128(bt + 24576, 0);
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
             mma_tf32(d, a0 + ko, bl0 + ko, idt, 1);
             mma_tf32(d, a1 + ko, bh1 + ko, idt, 1);
             mma_tf32(d, a1 + ko, bl1 + ko, idt, 1);
-            mma_bf16(d, alo + ko, bbf + ko, idb, 1);
+            mma_f16(d, alo + ko, bbf + ko, idb, 1);
           }
         }
         mma_commit(&sm.a_empty);

@@ -85,11 +85,11 @@ __device__ __forceinline__ uint64_t desc_k_sw128(uint32_t tile_smem_addr, uint32
   d |= (uint64_t)2 << 61;                                          // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor: D f32, A/B both `fmt` (1 = bf16, 2 = tf32), K-major A and B, M x N tile.
+// Instruction descriptor: D f32, A/B both `fmt` (0 = f16, 1 = bf16, 2 = tf32), K-major A and B, M x N tile.
 __host__ __device__ constexpr uint32_t idesc(uint32_t fmt, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-constexpr uint32_t FMT_BF16 = 1, FMT_TF32 = 2;
+constexpr uint32_t FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2;
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
@@ -99,7 +99,7 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(id), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),

@@ -6,6 +6,7 @@
 // (c) the accuracy of the 3-term product against an f64 reference, (d) MMA issue->commit latency.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I mdcommunity_b200/csrc -I include -o umma_probe umma_probe.cu
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -48,11 +49,18 @@ __global__ void __launch_bounds__(160, 1) probe(const float* P, const float* H, 
       // remainders as bf16: LO row = [P_lo (32) | H_lo (32)], 8 bytes per 4 values
       float pl[4] = {p.x - tf32_hi(p.x), p.y - tf32_hi(p.y), p.z - tf32_hi(p.z), p.w - tf32_hi(p.w)};
       float hl[4] = {h.x - tf32_hi(h.x), h.y - tf32_hi(h.y), h.z - tf32_hi(h.z), h.w - tf32_hi(h.w)};
-      __nv_bfloat162 a0 = __floats2bfloat162_rn(pl[0], pl[1]), a1 = __floats2bfloat162_rn(pl[2], pl[3]);
-      __nv_bfloat162 b0 = __floats2bfloat162_rn(hl[0], hl[1]), b1 = __floats2bfloat162_rn(hl[2], hl[3]);
-      // 4 values = 8 bytes: chunk (16 B) index ch/2, half (ch&1)
-      uint2 pa = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
-      uint2 hb = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
+      uint2 pa, hb;  // 4 values = 8 bytes: chunk (16 B) index ch/2, half (ch&1)
+      if (mode == 2) {
+        __half2 a0 = __floats2half2_rn(pl[0], pl[1]), a1 = __floats2half2_rn(pl[2], pl[3]);
+        __half2 b0 = __floats2half2_rn(hl[0], hl[1]), b1 = __floats2half2_rn(hl[2], hl[3]);
+        pa = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
+        hb = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
+      } else {
+        __nv_bfloat162 a0 = __floats2bfloat162_rn(pl[0], pl[1]), a1 = __floats2bfloat162_rn(pl[2], pl[3]);
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(hl[0], hl[1]), b1 = __floats2bfloat162_rn(hl[2], hl[3]);
+        pa = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
+        hb = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
+      }
       *reinterpret_cast<uint2*>(sm.LO + sw128_off(r, ch >> 1) + 8 * (ch & 1)) = pa;
       *reinterpret_cast<uint2*>(sm.LO + sw128_off(r, 4 + (ch >> 1)) + 8 * (ch & 1)) = hb;
     }
@@ -67,8 +75,13 @@ __global__ void __launch_bounds__(160, 1) probe(const float* P, const float* H, 
         *reinterpret_cast<float*>(sm.B23hi + off) = tf32_hi(w23);
         *reinterpret_cast<float*>(sm.B23lo + off) = w23 - tf32_hi(w23);
         // bf16 plane [n][64]: k < 32 -> W13, k >= 32 -> W23
-        *reinterpret_cast<__nv_bfloat16*>(sm.Bbf + sw128_off(n, (2 * k) >> 4) + ((2 * k) & 15)) = __float2bfloat16_rn(w13);
-        *reinterpret_cast<__nv_bfloat16*>(sm.Bbf + sw128_off(n, (2 * (k + 32)) >> 4) + ((2 * (k + 32)) & 15)) = __float2bfloat16_rn(w23);
+        if (mode == 2) {
+          *reinterpret_cast<__half*>(sm.Bbf + sw128_off(n, (2 * k) >> 4) + ((2 * k) & 15)) = __float2half_rn(w13);
+          *reinterpret_cast<__half*>(sm.Bbf + sw128_off(n, (2 * (k + 32)) >> 4) + ((2 * (k + 32)) & 15)) = __float2half_rn(w23);
+        } else {
+          *reinterpret_cast<__nv_bfloat16*>(sm.Bbf + sw128_off(n, (2 * k) >> 4) + ((2 * k) & 15)) = __float2bfloat16_rn(w13);
+          *reinterpret_cast<__nv_bfloat16*>(sm.Bbf + sw128_off(n, (2 * (k + 32)) >> 4) + ((2 * (k + 32)) & 15)) = __float2bfloat16_rn(w23);
+        }
       }
     }
     fence_proxy_async_smem();
@@ -80,7 +93,7 @@ __global__ void __launch_bounds__(160, 1) probe(const float* P, const float* H, 
   if (warp == 4) {
     if (lane == 0) {
       const long long t0 = clock64();
-      const uint32_t idt = idesc(FMT_TF32, 128, 64), idb = idesc(FMT_BF16, 128, 64);
+      const uint32_t idt = idesc(FMT_TF32, 128, 64), idb = idesc(mode == 2 ? FMT_F16 : FMT_BF16, 128, 64);
       uint32_t acc = 0;
       for (int k = 0; k < 4; ++k) {
         mma_tf32(tbase, desc_k_sw128(smem_u32(sm.P), 32 * k), desc_k_sw128(smem_u32(sm.B13hi), 32 * k), idt, acc);
@@ -90,7 +103,7 @@ __global__ void __launch_bounds__(160, 1) probe(const float* P, const float* H, 
       if (mode >= 1) {
         for (int k = 0; k < 4; ++k) mma_tf32(tbase, desc_k_sw128(smem_u32(sm.P), 32 * k), desc_k_sw128(smem_u32(sm.B13lo), 32 * k), idt, 1);
         for (int k = 0; k < 4; ++k) mma_tf32(tbase, desc_k_sw128(smem_u32(sm.H), 32 * k), desc_k_sw128(smem_u32(sm.B23lo), 32 * k), idt, 1);
-        for (int k = 0; k < 4; ++k) mma_bf16(tbase, desc_k_sw128(smem_u32(sm.LO), 32 * k), desc_k_sw128(smem_u32(sm.Bbf), 32 * k), idb, 1);
+        for (int k = 0; k < 4; ++k) mma_f16(tbase, desc_k_sw128(smem_u32(sm.LO), 32 * k), desc_k_sw128(smem_u32(sm.Bbf), 32 * k), idb, 1);
       }
       const long long t1 = clock64();
       mma_commit(&sm.bar);
@@ -149,7 +162,7 @@ int main() {
   cudaMemcpy(dW23, W23.data(), W23.size() * 4, cudaMemcpyHostToDevice);
   const int smem = sizeof(Smem) + 1024;
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int mode = 0; mode < 2; ++mode) {
+  for (int mode = 0; mode < 3; ++mode) {  // 0: tf32 hi x hi only, 1: 3-term with bf16 remainders, 2: 3-term with fp16 remainders
     cudaMemset(dD, 0, D.size() * 4);
     probe<<<1, 160, smem>>>(dP, dH, dW13, dW23, dD, mode, dC);
     cudaError_t e = cudaDeviceSynchronize();

@@ -346,3 +346,32 @@ def test_cuda_graph_rollout_matches_eager():
     for r in (r2, r3):
         assert np.array_equal(r1["n_steps"], r["n_steps"]) and np.array_equal(r1["actions"], r["actions"])
         assert np.array_equal(r1["ranks"], r["ranks"]) and np.array_equal(r1["score"], r["score"])
+
+
+def test_fused_embedding_dense_graphs_beyond_index_cache():
+    """Graphs whose alive CSR exceeds the fused kernel's shared-memory neighbour cache (8192 entries per layer) and
+    whose hub rows exceed the whole-warp threshold: fused vs unfused embeddings / Q, and an oracle-replayed rollout."""
+    from mdcommunity_b200 import gmm
+    mdb = _mdb()
+    graphs = [gmm.gmm_graph(1000, 900 + i, cost="unit", kbar=(14.0, 11.0)) for i in range(3)]
+    graphs.append(gmm.gmm_graph(700, 950, cost="unit", kbar=(16.0, 16.0)))
+    batch = mdb.GraphBatch(graphs, cost="unit")
+    assert max(batch.nnz) // len(graphs) > 8192
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_unit.npz"))), batch.device)
+    a = mdb.BatchRollout(batch, w, fused=True)
+    b = mdb.BatchRollout(batch, w, fused=False)
+    S = batch.S
+    for t in range(6):
+        a.forward()
+        b.forward()
+        for i in range(batch.B):
+            n = int(a.n_act[i])
+            ids = a.act_list[i * S:i * S + n].long()
+            for l in range(batch.L):
+                assert float((a.h[1][l][ids] - b.h[1][l][ids]).abs().max()) <= 2e-5, (i, t, l)
+            qa, qb = a.q[ids], b.q[ids]
+            assert float(((qa - qb).abs() - (Q_RTOL * qb.abs() + Q_ATOL)).max()) <= 0, (i, t)
+        b.best.copy_(a.best)  # same action on both (sub-tolerance ties could differ)
+        a.step()
+        b.step()
+    assert torch.equal(a.label, b.label) and torch.equal(a.rank, b.rank)
