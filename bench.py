@@ -157,10 +157,14 @@ def roofline_pass(mdb, batch, w):
     ro = mdb.BatchRollout(batch, w)
     lib = ro.lib
     evs, byts = [], []
+    env_evs, env_byts = [], []
     D = 64
+    N_nodes = torch.as_tensor([g.num_nodes for g in batch.graphs], dtype=torch.float64)
+    E_static = batch.n_edges.cpu().double()  # [L, B] undirected edges
     while ro.num_done() < batch.B and len(evs) < 3000:
         n = int(ro.n_act.sum())
         nnz = 2 * ro.alive_edges.sum(1).cpu().numpy()
+        live = (ro.done == 0).cpu().double()
         floor = sum(4 * (n + 1) + 4 * int(nnz[l]) + 8 * D * n for l in range(batch.L))
         g, s, wp, k, st = ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()
         if ro.fused:
@@ -181,8 +185,15 @@ def roofline_pass(mdb, batch, w):
                 byts.append(floor)
         _lib.check(lib.md_graph_embed(g, s, wp, k, st), "gembed")
         _lib.check(lib.md_qhead(g, s, wp, k, st), "qhead")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         ro.step()
+        e1.record()
+        env_evs.append((e0, e1))
+        # SURVEY 8(d), whole-rollout small graphs: per graph-step floor L(4(N+1) + 4 nnz0) + 4N over the live graphs
+        env_byts.append(float((live * (4 * N_nodes + sum(4 * (N_nodes + 1) + 8 * E_static[l] for l in range(batch.L)))).sum()))
     torch.cuda.synchronize()
+    env_ms = [a.elapsed_time(b) for a, b in env_evs]
     ms = [a.elapsed_time(b) for a, b in evs]
     tot_ms, tot_b = float(sum(ms)), float(sum(byts))
     peak, how = measured_peak()
@@ -196,7 +207,14 @@ def roofline_pass(mdb, batch, w):
             if ro.fused else "embed_iter_kernel (fused SpMM aggregation + dense transforms + normalise)")
     model = ("sum over launches of 3 * sum_l (4(n+1)+4nnz_l+8*64*n)" if ro.fused else "sum over launches of sum_l (4(n+1)+4nnz_l+8*64*n)")
     # the first (intact-graph) launches are the heaviest: report them too
-    return {"bound": "hbm", "kernel": name,
+    env_tot = float(sum(env_ms))
+    env_ach = float(sum(env_byts)) / (env_tot * 1e-3) / 1e9 if env_tot > 0 else 0.0
+    lmcc = {"bound": "latency (shared-memory union-find, one CTA per graph); reported against HBM as the north star asks",
+            "kernel": "env_step_small (node removal + LMCC recompute + AUDC + status counters)", "achieved": env_ach,
+            "peak": peak, "unit": "GB/s", "frac": env_ach / peak, "launches": len(env_ms),
+            "avg_launch_ms": env_tot / max(1, len(env_ms)), "first_launch_ms": env_ms[0] if env_ms else None,
+            "algorithmic_bytes_model": "sum over launches and live graphs of L*(4(N+1)+4*nnz0_l)+4N (static CSR + state)"}
+    return {"bound": "hbm", "kernel": name, "lmcc": lmcc,
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "traffic_unit": "bytes per launch (first, intact-state launch; compare with first_launch_algorithmic_bytes)",
             "traffic_detail": traffic_detail, "first_launch_algorithmic_bytes": byts[0] if byts else None,
