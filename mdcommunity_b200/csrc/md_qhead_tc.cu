@@ -25,8 +25,8 @@ constexpr uint32_t QT_KB = 16384;  // one 128-row x 128-byte operand tile
 
 template <int L>
 struct QTSmem {
-  unsigned char A[L][2][QT_KB];  // raw fp32 rows of H_l, two K blocks of 32 columns
-  unsigned char ALO[L][QT_KB];   // fp16 remainders of H_l, 64 columns per row
+  unsigned char A[2][QT_KB];     // raw fp32 rows of ONE layer's H_l (the layers of a tile pass through in turn), two K blocks
+  unsigned char ALO[QT_KB];      // fp16 remainders of the same rows, 64 columns per row
   unsigned char Bt[40960];       // trans^T: tf32 hi (2 K blocks), tf32 lo (2 K blocks), fp16 (64 columns)
   alignas(16) float h1[D * MD_HIDDEN];
   alignas(16) float bias[D];
@@ -141,33 +141,37 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
         if (lane == 0) mbar_arrive(&sm.a_full);
         break;
       }
-      if (i >= 1) mbar_wait(&sm.a_empty, (i - 1) & 1);  // MMAs of the previous tile have read the operand tiles
       const int c = lane & 15, half = lane >> 4;
-#pragma unroll
-      for (int lb2 = 0; lb2 < 2 * L; ++lb2) {  // (layer, half of the warp's 64 rows)
-        const int l = lb2 >> 1, r0 = 64 * lw_ + 32 * (lb2 & 1);
+#pragma unroll 1
+      for (int l = 0; l < L; ++l) {
+        const uint32_t ld = i * L + l;                       // operand-tile hand-off number
+        if (ld >= 1) mbar_wait(&sm.a_empty, (ld - 1) & 1);   // the MMAs of the previous layer / tile have read the tiles
         const float* __restrict__ H = K.h[hsel][l];
-        float4 val[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int r = r0 + 2 * j + half;
-          const int v = sm.vrow[slot][r];
-          val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (v >= 0) val[j] = __ldg(reinterpret_cast<const float4*>(H + (size_t)v * D) + c);
-        }
+        for (int hb = 0; hb < 2; ++hb) {                     // the warp's 64 rows in two batches of 16 fetches per lane
+          const int r0 = 64 * lw_ + 32 * hb;
+          float4 val[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t r = r0 + 2 * j + half;
-          *reinterpret_cast<float4*>(sm.A[l][c >> 3] + r * 128u + (((c & 7) ^ (r & 7)) << 4)) = val[j];
-          const __half2 p0 = __floats2half2_rn(val[j].x - tf32_hi(val[j].x), val[j].y - tf32_hi(val[j].y));
-          const __half2 p1 = __floats2half2_rn(val[j].z - tf32_hi(val[j].z), val[j].w - tf32_hi(val[j].w));
-          *reinterpret_cast<uint2*>(sm.ALO[l] + r * 128u + (((c >> 1) ^ (r & 7)) << 4) + 8 * (c & 1)) =
-              make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+          for (int j = 0; j < 16; ++j) {
+            const int r = r0 + 2 * j + half;
+            const int v = sm.vrow[slot][r];
+            val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v >= 0) val[j] = __ldg(reinterpret_cast<const float4*>(H + (size_t)v * D) + c);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t r = r0 + 2 * j + half;
+            *reinterpret_cast<float4*>(sm.A[c >> 3] + r * 128u + (((c & 7) ^ (r & 7)) << 4)) = val[j];
+            const __half2 p0 = __floats2half2_rn(val[j].x - tf32_hi(val[j].x), val[j].y - tf32_hi(val[j].y));
+            const __half2 p1 = __floats2half2_rn(val[j].z - tf32_hi(val[j].z), val[j].w - tf32_hi(val[j].w));
+            *reinterpret_cast<uint2*>(sm.ALO + r * 128u + (((c >> 1) ^ (r & 7)) << 4) + 8 * (c & 1)) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+          }
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.a_full);
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.a_full);
     }
   } else if (warp == 10) {
     // ================================ MMA issuer ================================
@@ -176,22 +180,23 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
     const uint64_t bh0 = desc_k_sw128(bt, 0), bh1 = desc_k_sw128(bt + 8192, 0);
     const uint64_t bl0 = desc_k_sw128(bt + 16384, 0), bl1 = desc_k_sw128(bt + 24576, 0);
     const uint64_t bbf = desc_k_sw128(bt + 32768, 0);
+    const uint64_t a0 = desc_k_sw128(smem_u32(sm.A[0]), 0), a1 = desc_k_sw128(smem_u32(sm.A[1]), 0);
+    const uint64_t alo = desc_k_sw128(smem_u32(sm.ALO), 0);
     for (uint32_t i = 0;; ++i) {
       const uint32_t slot = i & 1, use = i >> 1;
-      mbar_wait(&sm.a_full, i & 1);
+      mbar_wait(&sm.a_full, (i * L) & 1);  // first layer of the tile (or the end marker) is in place
       const int tile = sm.desc[slot][0];
       if (tile < 0) {
         if (lane == 0) mbar_arrive(&sm.d_full[slot]);
         break;
       }
       if (use >= 1) mbar_wait(&sm.d_empty[slot], (use - 1) & 1);  // accumulator stage drained
-      tc_fence_after();
-      if (qt_elect()) {
-#pragma unroll
-        for (int l = 0; l < L; ++l) {
+#pragma unroll 1
+      for (int l = 0; l < L; ++l) {
+        if (l > 0) mbar_wait(&sm.a_full, (i * L + l) & 1);
+        tc_fence_after();
+        if (qt_elect()) {
           const uint32_t d = tbase + slot * NCOL + 64 * l;
-          const uint64_t a0 = desc_k_sw128(smem_u32(sm.A[l][0]), 0), a1 = desc_k_sw128(smem_u32(sm.A[l][1]), 0);
-          const uint64_t alo = desc_k_sw128(smem_u32(sm.ALO[l]), 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ko = 2 * k;
@@ -201,11 +206,11 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
             mma_tf32(d, a1 + ko, bl1 + ko, idt, 1);
             mma_f16(d, alo + ko, bbf + ko, idb, 1);
           }
+          mma_commit(&sm.a_empty);
+          if (l == L - 1) mma_commit(&sm.d_full[slot]);
         }
-        mma_commit(&sm.a_empty);
-        mma_commit(&sm.d_full[slot]);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ================================ epilogue: two threads per row ================================
@@ -363,7 +368,7 @@ extern int g_md_debug_flags;
 int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, cudaStream_t st,
                        int* launched) {
   *launched = 0;
-  if ((g_md_debug_flags & 8) || !s->flags || g->n_layers != 2) return 0;  // L = 3 (C4) keeps the FP32-FMA kernel
+  if ((g_md_debug_flags & 8) || !s->flags || (g->n_layers != 2 && g->n_layers != 3)) return 0;
   static int nsm = 0;
   if (nsm <= 0) {
     int dev = 0;
@@ -375,7 +380,7 @@ int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weigh
   const int grid = nsm < n_tiles ? nsm : n_tiles;
   int* counter = s->flags + 4;  // [4] next tile, [5] CTAs finished; zero between launches (the kernel re-arms them)
   cudaError_t e = cudaSuccess;
-  {
+  if (g->n_layers == 2) {
     static bool configured = false;
     const int smem = (int)sizeof(md::QTSmem<2>);
     if (!configured) {
@@ -384,6 +389,15 @@ int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weigh
       configured = true;
     }
     md::qhead_tc_kernel<2><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
+  } else {
+    static bool configured = false;
+    const int smem = (int)sizeof(md::QTSmem<3>);
+    if (!configured) {
+      e = cudaFuncSetAttribute(md::qhead_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+    md::qhead_tc_kernel<3><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;

@@ -220,6 +220,24 @@ def test_large_three_layer_env_vs_oracle():
     ro.forward()
     ids, q = ro.q_values(0)
     assert len(ids) == int(ro.n_act[0]) and np.all(np.isfinite(q))
+    # the same 3-layer Q head through the FP32-FMA kernel (md_debug_set_flags bit 3) agrees with the tensor-core kernel
+    import ctypes as C
+    from mdcommunity_b200 import _lib
+    lib = _lib.lib()
+    best_tc = int(ro.best[0])
+    ro.best.zero_()
+    lib.md_debug_set_flags(8)
+    try:
+        _lib.check(lib.md_qhead(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()), "md_qhead")
+    finally:
+        lib.md_debug_set_flags(0)
+    ids2, q2 = ro.q_values(0)
+    assert np.array_equal(ids, ids2)
+    assert np.all(np.abs(q - q2) <= Q_RTOL * np.abs(q2) + Q_ATOL), float(np.abs(q - q2).max())
+    if int(ro.best[0]) != best_tc:
+        pa, pb = 0xFFFFFFFF - (best_tc & 0xFFFFFFFF), 0xFFFFFFFF - (int(ro.best[0]) & 0xFFFFFFFF)
+        qa, qb = q2[list(ids).index(pa)], q2[list(ids).index(pb)]
+        assert abs(qa - qb) <= Q_RTOL * abs(qb) + Q_ATOL
 
 
 def test_full_size_batch_properties():
