@@ -149,7 +149,8 @@ int32_t md_env_uses_small_path(const md_graphs_t* g);
 void md_debug_force_large_env(int32_t on);
 /* profiling hook: bit 0 skips the neighbour gather, bit 1 the dense transform of md_embed_iter (results become wrong);
  * bit 2 makes md_rollout_steps use the unfused embedding kernels even where md_embed_fused applies;
- * bit 3 makes md_qhead use its FP32-FMA kernel instead of the tensor-core kernel */
+ * bit 3 makes md_qhead use its FP32-FMA kernel instead of the tensor-core kernel;
+ * bit 4 makes md_embed_iter use its tensor-core variant (measured no faster than the FP32-FMA kernel: gather bound) */
 void md_debug_set_flags(int32_t flags);
 /* profiling hook: clock64 phase times of CTA 0 of the last md_env_step (labels in, CSR staged, prune rounds,
  * component sizes, alive CSR + degrees) and, at index 16, the number of prune rounds */

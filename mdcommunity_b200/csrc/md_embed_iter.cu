@@ -398,12 +398,21 @@ __global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_s
 int g_md_debug_flags = 0;
 extern "C" void md_debug_set_flags(int32_t f) { g_md_debug_flags = f; }
 
+int md_embed_iter_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, int iter,
+                            cudaStream_t st, int* launched);
+
 extern "C" int md_embed_iter(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                              int32_t iter, md_stream_t stream) {
   if (!g || !s || !w || !k) return MD_EINVAL;
   if (g->n_layers < 1 || g->n_layers > MD_MAX_LAYERS) return MD_ELAYERS;
   if (g->stride % MD_TILE_M != 0 || g->n_total != g->n_graphs * g->stride) return MD_EINVAL;
   if (iter < 0 || iter >= MD_BP_ITERS) return MD_EINVAL;
+  {  // tensor-core variant (md_embed_iter_tc.cu) only when md_debug_set_flags bit 4 asks for it (no faster: gather bound)
+    int launched = 0;
+    const int rc = md_embed_iter_tc_launch(g, s, w, k, iter, (cudaStream_t)stream, &launched);
+    if (rc) return rc;
+    if (launched) return 0;
+  }
   static bool configured = false;
   static int nsm = 0;
   const int smem = (int)sizeof(md::IterSmem);

@@ -1,0 +1,499 @@
+// md_embed_iter on the tensor cores: the unfused message-passing iteration (graphs too large for md_embed_fused, i.e. the
+// N = 1M configuration) with the dense transform moved from FP32 FMA to tcgen05.
+// Same reference lines as md_embed_iter.cu (MultiDismantler_net_graphsage.py:288-310) and the same warp-autonomous
+// neighbour gather (descriptor prefetch one tile ahead, barrier-free short rows, cooperative hub rows); what changes:
+//   * the 16 gather warps write the tile's operands straight into tcgen05 SWIZZLE_128B K-major tiles: P = A_adj.H and the
+//     own rows H as raw fp32 (two 32-column K blocks each) plus their fp16 remainders (x - tf32(x));
+//   * one MMA warp issues the 3-term product [P|H] @ [W13;W23] (tf32 hi x hi, hi x lo, fp16 remainder pass: 40 small MMAs
+//     per tile) into one of two TMEM accumulator stages and releases the operand tiles as soon as they have been read;
+//   * 4 epilogue warps (one thread per row) read the accumulators, relu, L2 normalise and store H' while the gather of
+//     the next tile is already running.  With the FP32-FMA consumers gone the gather no longer shares issue slots with
+//     a GEMM (measured on the FMA kernel: gather alone 298 us, GEMM alone 269 us, together 417 us per launch at C2).
+#include <cuda_fp16.h>
+#include "md_common.cuh"
+#include "md_umma.cuh"
+
+namespace md {
+using namespace umma;
+
+constexpr int IT_GATH = 512;  // 16 gather warps
+constexpr int NGW = IT_GATH / 32;
+constexpr int TC_T = IT_GATH + 32 + 128;  // + MMA warp (16) + 4 epilogue warps (17..20)
+constexpr int LONG = 16;      // rows with more alive neighbours are handled cooperatively
+constexpr int WSTG = 8 * LONG;
+constexpr int MAXLONG = TILE_M;
+constexpr int MAXXS = 64;     // extra (2nd..) segments per tile; more -> whole-row fallback
+constexpr int NACT_CACHE = 256;
+constexpr uint32_t KB16 = 16384;
+
+struct IterTcSmem {
+  unsigned char P[2][KB16];    // neighbour sums, raw fp32, K blocks of 32 columns
+  unsigned char H[2][KB16];    // own rows, raw fp32
+  unsigned char LO[2][KB16];   // fp16 remainders: block 0 = P_lo (64 columns), block 1 = H_lo
+  unsigned char Wb[5][KB16];   // B operands: W13 hi, W13 lo, W23 hi, W23 lo (2 K blocks of 8 KB each), fp16 [W13 | W23]
+  float extra[MAXXS * D];      // partial sums of the 2nd.. segments of long rows
+  float cs[NGW][D];            // per-warp column sums of the tile's own rows
+  int wstg[2][NGW][WSTG];
+  int wptr[2][NGW][12];
+  int wv[2][NGW][8];
+  int v[2][TILE_M];            // global node id of the row, -1 = padding row
+  int nact[NACT_CACHE];
+  int long_row[MAXLONG];
+  int long_beg[MAXLONG];
+  int long_n[MAXLONG];
+  int long_x[MAXLONG];
+  int nlong, nxtra;
+  uint64_t a_full, a_empty, d_full[2], d_empty[2];
+  uint32_t tmem;
+};
+static_assert(sizeof(IterTcSmem) <= 232448, "IterTcSmem exceeds the shared memory of one CTA");
+
+enum { BAR_GATH = 5 };
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ bool it_elect() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+  return pred != 0;
+}
+
+struct TileIterTc {  // the tile sequence all roles walk in lock step
+  int tile, n_tiles, tiles_per_layer, tpg;
+  int l, gt, g, t, nact;
+  const int* nact_tab;
+  __device__ __forceinline__ bool next() {
+    for (; tile < n_tiles; tile += gridDim.x) {
+      l = tile / tiles_per_layer;
+      gt = tile - l * tiles_per_layer;
+      g = gt / tpg;
+      t = gt - g * tpg;
+      nact = nact_tab[g];
+      if (t * TILE_M < nact) return true;
+    }
+    return false;
+  }
+};
+
+__global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K, int iter) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  IterTcSmem& sm = *reinterpret_cast<IterTcSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  const bool cached = G.n_graphs <= NACT_CACHE;
+  if (cached)
+    for (int i = tid; i < G.n_graphs; i += TC_T) sm.nact[i] = S.n_act[i];
+  if (tid == 0) {
+    sm.nlong = 0, sm.nxtra = 0;
+    mbar_init(&sm.a_full, NGW);
+    mbar_init(&sm.a_empty, 1);
+    mbar_init(&sm.d_full[0], 1);
+    mbar_init(&sm.d_full[1], 1);
+    mbar_init(&sm.d_empty[0], 4);
+    mbar_init(&sm.d_empty[1], 4);
+    mbar_fence_init();
+  }
+  if (warp == NGW) tmem_alloc(&sm.tmem, 128);
+  // weight operand images: element (k, n) of W13 / W23 -> row n of K block k / 32, tf32 hi and lo planes + fp16 plane
+  {
+    float t13[13], t23[13];
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+      const int i = tid + TC_T * j;
+      t13[j] = i < D * D ? W.w13[i] : 0.f;
+      t23[j] = i < D * D ? W.w23[i] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+      const int i = tid + TC_T * j;
+      if (i < D * D) {
+        const int k = i >> 6, n = i & 63, kb = k >> 5, kk = k & 31;
+        const uint32_t off = kb * 8192 + sw128_off(n, kk >> 2) + 4 * (kk & 3);
+        *reinterpret_cast<float*>(sm.Wb[0] + off) = tf32_hi(t13[j]);
+        *reinterpret_cast<float*>(sm.Wb[1] + off) = t13[j] - tf32_hi(t13[j]);
+        *reinterpret_cast<float*>(sm.Wb[2] + off) = tf32_hi(t23[j]);
+        *reinterpret_cast<float*>(sm.Wb[3] + off) = t23[j] - tf32_hi(t23[j]);
+        *reinterpret_cast<__half*>(sm.Wb[4] + sw128_off(n, k >> 3) + 2 * (k & 7)) = __float2half_rn(t13[j]);
+        *reinterpret_cast<__half*>(sm.Wb[4] + 8192 + sw128_off(n, k >> 3) + 2 * (k & 7)) = __float2half_rn(t23[j]);
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = sm.tmem;
+  TileIterTc ti;
+  ti.tpg = G.stride / TILE_M;
+  ti.tiles_per_layer = G.n_graphs * ti.tpg;
+  ti.n_tiles = ti.tiles_per_layer * G.n_layers;
+  ti.tile = blockIdx.x;
+  ti.nact_tab = cached ? sm.nact : S.n_act;
+  int n_tiles_done = 0;
+
+  if (tid < IT_GATH) {
+    // byte offset of the 16-byte chunk holding columns 4*l16.. of row r inside its 32-column K block
+    auto p_off = [](int r, int c16) -> uint32_t { return (uint32_t)r * 128u + (uint32_t)(((c16 & 7) ^ (r & 7)) << 4); };
+    const int l16_ = lane & 15;
+    auto lo4 = [](const float4& x) -> uint2 {
+      const __half2 a = __floats2half2_rn(x.x - tf32_hi(x.x), x.y - tf32_hi(x.y));
+      const __half2 b = __floats2half2_rn(x.z - tf32_hi(x.z), x.w - tf32_hi(x.w));
+      return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    };
+    // this lane's float4 (columns 4*l16..) of row r: raw value + fp16 remainder (64 fp16 per row = one 128-byte row)
+    auto st_p = [&](int r, const float4& x) {
+      *reinterpret_cast<float4*>(sm.P[l16_ >> 3] + p_off(r, l16_)) = x;
+      *reinterpret_cast<uint2*>(sm.LO[0] + (uint32_t)r * 128u + (((l16_ >> 1) ^ (r & 7)) << 4) + 8 * (l16_ & 1)) = lo4(x);
+    };
+    auto st_h = [&](int r, const float4& x) {
+      *reinterpret_cast<float4*>(sm.H[l16_ >> 3] + p_off(r, l16_)) = x;
+      *reinterpret_cast<uint2*>(sm.LO[1] + (uint32_t)r * 128u + (((l16_ >> 1) ^ (r & 7)) << 4) + 8 * (l16_ & 1)) = lo4(x);
+    };
+    // ===================================== GATHER WARPS =====================================
+    const int half = lane >> 4, l16 = lane & 15;
+    const int hw = warp * 2 + half;
+    const int r0 = warp * 8;  // this warp's rows of every tile
+
+    // descriptor prefetch of a tile into staging slot `par`: row pointers, node ids, neighbour ids of short rows
+    auto prefetch = [&](const TileIterTc& tt, int par) {
+      const int rows = min(TILE_M, tt.nact - tt.t * TILE_M);
+      const int32_t* __restrict__ aptr = S.aptr[tt.l] + tt.g * G.stride + tt.t * TILE_M;
+      int ap = 0;
+      if (lane < 9) ap = aptr[min(r0 + lane, rows)];
+      const int b = __shfl_sync(0xffffffffu, ap, 0);
+      if (lane < 9) sm.wptr[par][warp][lane] = ap - b;
+      if (lane == 9) sm.wptr[par][warp][9] = b;
+      // neighbour ids of the rows that are short; a long row's ids are fetched cooperatively later
+      const int32_t* __restrict__ acol = S.acol[tt.l];
+      const int nxt = __shfl_down_sync(0xffffffffu, ap, 1);
+      int n = (lane < 8) ? nxt - ap : 0;
+      if (n > LONG) n = 0;
+      // exclusive scan of the short-row lengths over lanes 0..7 -> packed position in the staging area
+      int incl = n;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += x;
+      }
+      const int excl = incl - n;
+      if (lane < 8) sm.wv[par][warp][lane] = (r0 + lane < rows) ? S.act_list[tt.g * G.stride + tt.t * TILE_M + r0 + lane] : -1;
+      // every row r copies its n ids: lanes cooperate, 8 rows x up to 32 ids
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int nr = __shfl_sync(0xffffffffu, n, r);
+        const int src0 = __shfl_sync(0xffffffffu, ap, r);
+        const int dst0 = __shfl_sync(0xffffffffu, excl, r);
+        if (lane < nr) sm.wstg[par][warp][dst0 + lane] = acol[src0 + lane];
+      }
+    };
+
+    int it = 0;
+    bool have = ti.next();
+    if (have) prefetch(ti, 0);
+    while (have) {
+      const int buf = it & 1;
+      const TileIterTc cur = ti;
+      // advance to the next tile and prefetch its descriptors (other parity) before touching this tile's rows
+      ti.tile += gridDim.x;
+      have = ti.next();
+      if (have) prefetch(ti, buf ^ 1);
+      __syncwarp();
+
+      const int l = cur.l, g = cur.g, t = cur.t;
+      const int rows = min(TILE_M, cur.nact - t * TILE_M);
+      const int32_t* __restrict__ acol = S.acol[l];
+      const float4* __restrict__ H4 = reinterpret_cast<const float4*>(K.h[iter & 1][l]);
+      float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (it >= 2) mbar_wait(&sm.d_empty[buf], ((it >> 1) - 1) & 1);  // epilogue of tile it-2 is done with v[buf]
+      if (it >= 1) mbar_wait(&sm.a_empty, (it - 1) & 1);              // MMAs of the previous tile have read the operand tiles
+
+      const int* wp = sm.wptr[buf][warp];
+      const int* ws = sm.wstg[buf][warp];
+      const int base_e = wp[9];
+      if (lane < 8) sm.v[buf][r0 + lane] = sm.wv[buf][warp][lane];
+      __syncwarp();
+      // ---- short rows: 4 row pairs, one row per half-warp, no barrier --------------------------------------
+      int spos = 0;  // running position in the packed staging area (same in both halves: recomputed per pair)
+      {
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int ra = 2 * i, rb = 2 * i + 1;
+          int na = wp[ra + 1] - wp[ra], nb = wp[rb + 1] - wp[rb];
+          const bool la = na > LONG, lb = nb > LONG;
+          if (la && lane == 0) {
+            const int k = atomicAdd(&sm.nlong, 1);
+            sm.long_row[k] = r0 + ra;
+            sm.long_beg[k] = base_e + wp[ra];
+            sm.long_n[k] = na;
+            sm.long_x[k] = atomicAdd(&sm.nxtra, (na - 1) / LONG);
+          }
+          if (lb && lane == 0) {
+            const int k = atomicAdd(&sm.nlong, 1);
+            sm.long_row[k] = r0 + rb;
+            sm.long_beg[k] = base_e + wp[rb];
+            sm.long_n[k] = nb;
+            sm.long_x[k] = atomicAdd(&sm.nxtra, (nb - 1) / LONG);
+          }
+          if (la) na = 0;
+          if (lb) nb = 0;
+          const int pa = spos, pb = spos + na;
+          spos += na + nb;
+          const int n = half ? nb : na;
+          const int p = half ? pb : pa;
+          const int nmax = max(na, nb);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k0 = 0; k0 < nmax; k0 += 8) {
+            float4 val[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (k0 + j < n) val[j] = __ldg(H4 + (size_t)ws[p + k0 + j] * (D / 4) + l16);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // in CSR order
+              if (k0 + j < n) {
+                acc.x += val[j].x;
+                acc.y += val[j].y;
+                acc.z += val[j].z;
+                acc.w += val[j].w;
+              }
+            }
+          }
+          const bool is_long = half ? lb : la;
+          if (!is_long) st_p(r0 + 2 * i + half, acc);
+        }
+        // own rows -> A[:, 64:128]
+        float4 own[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int v = sm.v[buf][r0 + 2 * i + half];
+          own[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (v >= 0) own[i] = __ldg(H4 + (size_t)v * (D / 4) + l16);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          st_h(r0 + 2 * i + half, own[i]);
+          csum.x += own[i].x, csum.y += own[i].y, csum.z += own[i].z, csum.w += own[i].w;
+        }
+      }
+      // ---- long (hub) rows: cooperative, only when the tile has any ---------------------------------------------
+      bar_sync(BAR_GATH, IT_GATH);
+      const int nlong = sm.nlong;
+      const bool whole_rows = sm.nxtra > MAXXS;  // too many segments for the scratch area: one half-warp per long row
+      if (nlong > 0) {
+        // segment s of long row k: entries [s*LONG, min(n, (s+1)*LONG)); flat segment index over all long rows
+        int sidx = hw;
+        int k = 0, sbase = 0;  // walk the (short) long-row list
+        for (;;) {
+          int sseg = 0, n = 0, beg = 0, nrep = 1;
+          bool valid;
+          if (whole_rows) {
+            k = sidx;
+            valid = k < nlong;
+            if (valid) nrep = (sm.long_n[k] + LONG - 1) / LONG;
+          } else {
+            while (k < nlong && sidx >= sbase + (sm.long_n[k] + LONG - 1) / LONG) {
+              sbase += (sm.long_n[k] + LONG - 1) / LONG;
+              ++k;
+            }
+            valid = k < nlong;
+            if (valid) sseg = sidx - sbase;
+          }
+          if (!__any_sync(0xffffffffu, valid)) break;
+          const int nrep_max = max(nrep, __shfl_xor_sync(0xffffffffu, nrep, 16));
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int rep = 0; rep < nrep_max; ++rep) {
+            const int sg = whole_rows ? rep : sseg;
+            n = 0;
+            if (valid && rep < nrep) {
+              beg = sm.long_beg[k] + sg * LONG;
+              n = min(LONG, sm.long_n[k] - sg * LONG);
+            }
+            // the half-warp fetches its <= 16 neighbour ids (one per lane), then the rows, 8 in flight
+            int id0 = 0;
+            if (l16 < n) id0 = acol[beg + l16];
+            const int nmax = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
+            for (int k0 = 0; k0 < nmax; k0 += 8) {
+              float4 val[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int e = k0 + j;
+                const int u = __shfl_sync(0xffffffffu, id0, (half << 4) | (e & 15));
+                val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e < n) val[j] = __ldg(H4 + (size_t)u * (D / 4) + l16);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (k0 + j < n) {
+                  acc.x += val[j].x;
+                  acc.y += val[j].y;
+                  acc.z += val[j].z;
+                  acc.w += val[j].w;
+                }
+              }
+            }
+          }
+          if (valid) {
+            if (whole_rows) st_p(sm.long_row[k], acc);
+            else if (sseg == 0) *reinterpret_cast<float4*>(sm.P[l16 >> 3] + p_off(sm.long_row[k], l16)) = acc;  // raw; LO after the fold
+            else *reinterpret_cast<float4*>(sm.extra + (size_t)(sm.long_x[k] + sseg - 1) * D + 4 * l16) = acc;
+          }
+          sidx += 2 * NGW;
+        }
+        bar_sync(BAR_GATH, IT_GATH);
+        if (tid == 0) sm.nlong = 0, sm.nxtra = 0;  // everybody has read them; the next tile registers after the last barrier
+        if (!whole_rows) {
+          for (int k2 = hw; k2 < nlong; k2 += 2 * NGW) {  // fold in segment order
+            const int r = sm.long_row[k2];
+            float4 a4 = *reinterpret_cast<const float4*>(sm.P[l16 >> 3] + p_off(r, l16));
+            const int nx = (sm.long_n[k2] - 1) / LONG, xb = sm.long_x[k2];
+            for (int q = 0; q < nx; ++q) {
+              const float4 x = *reinterpret_cast<const float4*>(sm.extra + (size_t)(xb + q) * D + 4 * l16);
+              a4.x += x.x;
+              a4.y += x.y;
+              a4.z += x.z;
+              a4.w += x.w;
+            }
+            st_p(r, a4);
+          }
+        }
+        bar_sync(BAR_GATH, IT_GATH);
+      }
+      // per-tile column sums of the old embeddings (spmm subgsum): half-warps, then warps, in a fixed order
+      csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 16);
+      csum.y += __shfl_xor_sync(0xffffffffu, csum.y, 16);
+      csum.z += __shfl_xor_sync(0xffffffffu, csum.z, 16);
+      csum.w += __shfl_xor_sync(0xffffffffu, csum.w, 16);
+      if (lane < 16) *reinterpret_cast<float4*>(&sm.cs[warp][4 * l16]) = csum;
+      bar_sync(BAR_GATH, IT_GATH);
+      if (tid < D) {
+        float s = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < NGW; ++w2) s += sm.cs[w2][tid];
+        K.psum[(((size_t)iter * G.n_layers + l) * cur.tiles_per_layer + cur.gt) * D + tid] = s;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.a_full);  // hand the operand tiles to the MMA warp
+      ++it;
+    }
+    n_tiles_done = it;
+  } else if (warp == NGW) {
+    // ===================================== MMA ISSUER =====================================
+    const uint32_t idt = idesc(FMT_TF32, 128, 64), idf = idesc(FMT_F16, 128, 64);
+    uint64_t aP[2], aH[2], aLO[2], b13h[2], b13l[2], b23h[2], b23l[2], bf[2];
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      aP[kb] = desc_k_sw128(smem_u32(sm.P[kb]), 0);
+      aH[kb] = desc_k_sw128(smem_u32(sm.H[kb]), 0);
+      aLO[kb] = desc_k_sw128(smem_u32(sm.LO[kb]), 0);
+      b13h[kb] = desc_k_sw128(smem_u32(sm.Wb[0]) + kb * 8192, 0);
+      b13l[kb] = desc_k_sw128(smem_u32(sm.Wb[1]) + kb * 8192, 0);
+      b23h[kb] = desc_k_sw128(smem_u32(sm.Wb[2]) + kb * 8192, 0);
+      b23l[kb] = desc_k_sw128(smem_u32(sm.Wb[3]) + kb * 8192, 0);
+      bf[kb] = desc_k_sw128(smem_u32(sm.Wb[4]) + kb * 8192, 0);
+    }
+    uint32_t it = 0;
+    for (; ti.next(); ti.tile += gridDim.x, ++it) {
+      const uint32_t stage = it & 1;
+      mbar_wait(&sm.a_full, it & 1);
+      if (it >= 2) mbar_wait(&sm.d_empty[stage], ((it >> 1) - 1) & 1);  // accumulator stage drained by the epilogue
+      tc_fence_after();
+      if (it_elect()) {
+        const uint32_t d = tbase + 64 * stage;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ko = 2 * k;
+            mma_tf32(d, aP[kb] + ko, b13h[kb] + ko, idt, (kb | k) != 0);
+            mma_tf32(d, aP[kb] + ko, b13l[kb] + ko, idt, 1);
+            mma_tf32(d, aH[kb] + ko, b23h[kb] + ko, idt, 1);
+            mma_tf32(d, aH[kb] + ko, b23l[kb] + ko, idt, 1);
+            mma_f16(d, aLO[kb] + ko, bf[kb] + ko, idf, 1);
+          }
+        mma_commit(&sm.a_empty);
+        mma_commit(&sm.d_full[stage]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================================== EPILOGUE: one thread per row =====================================
+    const int q = warp - NGW - 1;  // TMEM lane quadrant (warps 17..20 -> 1, 2, 3, 0 ... use warp % 4)
+    const int quad = warp & 3;
+    (void)q;
+    const int row = 32 * quad + lane;
+    uint32_t it = 0;
+    for (; ti.next(); ti.tile += gridDim.x, ++it) {
+      const uint32_t stage = it & 1;
+      float* __restrict__ Hout = K.h[(iter + 1) & 1][ti.l];
+      mbar_wait(&sm.d_full[stage], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tbase + ((uint32_t)(32 * quad) << 16) + 64 * stage;
+      const int v = sm.v[stage][row];
+      float ss = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < D; c0 += 16) {
+        float x[16];
+        tmem_ld16(taddr + c0, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float r = fmaxf(x[j], 0.f);
+          ss = fmaf(r, r, ss);
+        }
+      }
+      const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
+#pragma unroll 1
+      for (int c0 = 0; c0 < D; c0 += 16) {
+        float x[16];
+        tmem_ld16(taddr + c0, x);
+        tmem_ld_wait();
+        if (v >= 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(Hout + (size_t)v * D + c0 + j) =
+                make_float4(fmaxf(x[j], 0.f) * inv, fmaxf(x[j + 1], 0.f) * inv, fmaxf(x[j + 2], 0.f) * inv, fmaxf(x[j + 3], 0.f) * inv);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.d_empty[stage]);
+    }
+  }
+  (void)n_tiles_done;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NGW) tmem_dealloc(tbase, 128);
+}
+
+}  // namespace md
+
+extern int g_md_debug_flags;
+
+// *launched = 1 when the tensor-core kernel was enqueued: only on request (md_debug_set_flags bit 4).  Measured: no gain
+// over the FP32-FMA kernel (C2 unfused 450 vs 417 us per launch, C4 9.2 vs 9.0 ms per step): the iteration is bound by the
+// L2 / HBM row gather, whose warps the FMA consumers overlapped for free; kept as the A/B reference of that finding.
+int md_embed_iter_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, int iter,
+                            cudaStream_t st, int* launched) {
+  *launched = 0;
+  if (!(g_md_debug_flags & 16) || (g_md_debug_flags & (1 | 2))) return 0;
+  static bool configured = false;
+  static int nsm = 0;
+  const int smem = (int)sizeof(md::IterTcSmem);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(md::embed_iter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm <= 0) nsm = 148;
+    configured = true;
+  }
+  const int n_tiles = g->n_graphs * (g->stride / MD_TILE_M) * g->n_layers;
+  const int grid = nsm < n_tiles ? nsm : n_tiles;
+  md::embed_iter_tc_kernel<<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  *launched = 1;
+  return 0;
+}

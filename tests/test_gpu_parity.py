@@ -393,3 +393,29 @@ def test_fused_embedding_dense_graphs_beyond_index_cache():
         a.step()
         b.step()
     assert torch.equal(a.label, b.label) and torch.equal(a.rank, b.rank)
+
+
+def test_unfused_iteration_tensor_core_variant_matches_fma():
+    """md_embed_iter: the tcgen05 variant (md_debug_set_flags bit 4) against the default FP32-FMA kernel on the same
+    states: embeddings within 2e-5 absolute (unit rows), per-tile column sums within 1e-4 relative."""
+    from mdcommunity_b200 import _lib
+    mdb = _mdb()
+    zs, graphs, batch, w = _load_batch("degree")
+    a = mdb.BatchRollout(batch, w, fused=False)
+    b = mdb.BatchRollout(batch, w, fused=False)
+    acts, T = _forced(zs, "greedy_actions", batch.device)
+    lib = _lib.lib()
+    try:
+        for t in range(5):
+            lib.md_debug_set_flags(16)
+            a.forward()
+            lib.md_debug_set_flags(0)
+            b.forward()
+            for l in range(batch.L):
+                assert float((a.h[1][l] - b.h[1][l]).abs().max()) <= 2e-5, (t, l)
+            torch.testing.assert_close(a.psum, b.psum, rtol=1e-4, atol=1e-5)
+            torch.testing.assert_close(a.q, b.q, rtol=Q_RTOL, atol=Q_ATOL)
+            a.step(acts)
+            b.step(acts)
+    finally:
+        lib.md_debug_set_flags(0)
