@@ -419,3 +419,39 @@ def test_unfused_iteration_tensor_core_variant_matches_fma():
             b.step(acts)
     finally:
         lib.md_debug_set_flags(0)
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
+def test_edge_case_graphs(fused):
+    """Ragged batch of degenerate inputs: a layer without edges (terminal at s0), a single mutual edge, isolated nodes,
+    disconnected layers whose mutual components are all singletons, a star (hub row > 24 neighbours) -- rollouts must
+    terminate and replay bit-exactly in the oracle."""
+    from oracle import md_oracle as orc
+    mdb = _mdb()
+    e = lambda *p: np.array(p, dtype=np.int64).reshape(-1, 2)
+    star = e(*[(0, i) for i in range(1, 40)])
+    ring = e(*[(i, (i + 1) % 40) for i in range(40)])
+    specs = [
+        (5, e((0, 1), (1, 2)), e()),                          # second layer empty: LMCC 1, terminal immediately
+        (2, e((0, 1)), e((0, 1))),                            # one mutual edge
+        (9, e((0, 1), (1, 2), (2, 0)), e((0, 1), (1, 2), (2, 0), (5, 6))),  # isolated nodes 3,4,7,8; 5-6 only in layer 2
+        (6, e((0, 1), (2, 3), (4, 5)), e((1, 2), (3, 4), (5, 0))),          # connected union, singleton mutual components
+        (40, star, ring),                                     # hub row of 39 neighbours
+        (130, e(*[(i, i + 1) for i in range(129)]), e(*[(i, i + 1) for i in range(129)])),  # path: stride 256, long chains
+    ]
+    graphs = [mdb.Graph_test(a, b, num_nodes=n, cost="unit") for n, a, b in specs]
+    batch = mdb.GraphBatch(graphs, cost="unit")
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_unit.npz"))), batch.device)
+    ro = mdb.BatchRollout(batch, w, fused=fused)
+    res = ro.run()
+    ow = orc.load_weights(os.path.join(GOLDEN, "weights_unit.npz"))
+    for i, (n, a, b) in enumerate(specs):
+        og = orc.MultiplexGraph(n, [a, b])
+        assert graphs[i].max_rank == og.max_rank, i
+        T = int(res["n_steps"][i])
+        sol = [int(x) for x in res["actions"][i, :T]]
+        r = orc.rollout(ow, og, "unit", forced_actions=sol)
+        assert r["sol"] == sol and r["ranks"] == [int(x) for x in res["ranks"][i, :T]], i
+        assert r["score"] == float(res["score"][i]), i
+        if og.max_rank <= 1:
+            assert T == 0
