@@ -1,0 +1,366 @@
+// md_agg: neighbour aggregation for graphs whose embeddings do not fit on chip (the N = 1M configuration):
+//   P[v, :] = sum over the alive neighbours u of v (CSR order) of H[u, :]      -- torch_sparse.spmm(n2nsum_param, H)
+// (/root/reference/code/MultiDismantler_unit_cost/MultiDismantler_net_graphsage.py:290), written into the rows of the
+// OTHER ping-pong embedding buffer, where the dense-transform kernel (md_embed_iter_tc.cu, PRE mode) picks it up, tile by
+// tile, and overwrites it with the new embeddings.
+//
+// Why a kernel of its own: with H_l = 256 MB the gather is a stream of random 256-byte row reads from HBM.  Measured on
+// B200 (scripts/microbench/gather_bw.cu): such reads reach 7.4-9.1 TB/s of gathered rows (L2 catches part of a 256 MB
+// table) once >= 64 KB per SM are in flight; the fused iteration kernel, which shares the SM with the transform (16
+// gather warps, one row pair at a time, shared memory full of operand tiles), sustained 2.3 TB/s.
+//
+// agg_ring_kernel (default): 8 warps per SM, every warp streams the neighbour rows of its 32-row chunks through a private
+// shared-memory ring with cp.async (16 bytes per lane, one 256-byte row per half-warp, no registers held while the bytes
+// are in flight): 3 slots of 2 x 16 rows, two slots (16 KB per warp, 128 KB per SM) always in flight, independent of the
+// row lengths -- the entries of a half-warp's 16 destination rows form one flat stream, summed from shared memory in CSR
+// order with a flush at every row boundary.  Descriptors (row pointers, node ids, neighbour ids) of the next chunk are
+// fetched while the ring is full.
+// agg_rows_kernel: the register-load version (32 warps, 8 loads per lane), kept as the A/B reference (md_debug_set_flags
+// bit 9): 1.69 ms per launch at C4 against the ring's figure in DESIGN 6.
+#include "md_common.cuh"
+
+namespace md {
+
+constexpr int AG_T = 1024;
+constexpr int AG_W = AG_T / 32;
+constexpr int AG_IDS = 352;  // staged neighbour ids of one 32-row chunk (mean 256 at degree 8); larger chunks read L2
+
+__global__ void __launch_bounds__(AG_T, 1) agg_rows_kernel(md_graphs_t G, md_state_t S, md_work_t K, int iter) {
+  __shared__ int ids[AG_W][AG_IDS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15;
+  const int St = G.stride, B = G.n_graphs, L = G.n_layers;
+  const int cpg = St / 32;  // 32-row chunks per graph (the stride is a multiple of 128)
+  const long long per_layer = (long long)B * cpg, n_chunks = per_layer * L;
+  for (long long c = (long long)blockIdx.x * AG_W + warp; c < n_chunks; c += (long long)gridDim.x * AG_W) {
+    const int l = (int)(c / per_layer);
+    const int rem = (int)(c - (long long)l * per_layer);
+    const int g = rem / cpg, p0 = (rem - g * cpg) * 32;
+    const int n = S.n_act[g];
+    if (p0 >= n) continue;  // warp-uniform
+    const int rows = min(32, n - p0);
+    const int32_t* __restrict__ aptr = S.aptr[l] + (size_t)g * St + p0;
+    const int32_t* __restrict__ acol = S.acol[l];
+    const int ap = aptr[min(lane, rows)], ap_hi = aptr[min(lane + 1, rows)];
+    const int v = lane < rows ? S.act_list[(size_t)g * St + p0 + lane] : -1;
+    const int e_begin = __shfl_sync(0xffffffffu, ap, 0);
+    const int total = __shfl_sync(0xffffffffu, ap_hi, 31) - e_begin;
+    const bool staged = total <= AG_IDS;
+    if (staged)
+      for (int k = lane; k < total; k += 32) ids[warp][k] = acol[e_begin + k];
+    __syncwarp();
+    const float4* __restrict__ Hin = reinterpret_cast<const float4*>(K.h[iter & 1][l]);
+    float4* __restrict__ Pout = reinterpret_cast<float4*>(K.h[(iter + 1) & 1][l]);
+#pragma unroll 1
+    for (int i = 0; 2 * i < rows; ++i) {
+      const int r = 2 * i + half;
+      const int e0 = __shfl_sync(0xffffffffu, ap, r), e1 = __shfl_sync(0xffffffffu, ap_hi, r);
+      const int vv = __shfl_sync(0xffffffffu, v, r);
+      const int nr = r < rows ? e1 - e0 : 0;
+      const int nmax = max(nr, __shfl_xor_sync(0xffffffffu, nr, 16));
+      const int* my = &ids[warp][e0 - e_begin];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k0 = 0; k0 < nmax; k0 += 8) {
+        float4 val[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k0 + j < nr) {
+            const int u = staged ? my[k0 + j] : acol[e0 + k0 + j];
+            val[j] = __ldg(Hin + (size_t)u * (D / 4) + l16);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // CSR order: the f32 sum is deterministic and equals a sequential scatter-add
+          if (k0 + j < nr) {
+            acc.x += val[j].x;
+            acc.y += val[j].y;
+            acc.z += val[j].z;
+            acc.w += val[j].w;
+          }
+        }
+      }
+      if (vv >= 0) Pout[(size_t)vv * (D / 4) + l16] = acc;
+    }
+    __syncwarp();
+  }
+}
+
+
+// ---- cp.async ring version ---------------------------------------------------------------------------------------------
+constexpr int RG_W = 8;
+constexpr int RG_T = RG_W * 32;
+constexpr int RG_R = 3;      // ring slots per warp
+constexpr int RG_IDS = 304;  // staged neighbour entries of one chunk (mean 256 at degree 8, sd 16)
+constexpr int RG_DB = 3;     // descriptor buffers per warp (the issue cursor runs at most two chunks ahead)
+constexpr int RG_IDBITS = 27;  // entry = neighbour id | destination row (0..31) << 27
+constexpr uint32_t RG_SLOT_B = 8192;
+
+struct RingDesc {
+  int ent[RG_IDS];  // staged entries (see RG_IDBITS), CSR order
+  int rptr[36];     // [0..32] row pointers relative to the chunk's first entry; [34] layer; [35] rows
+  int vrow[32];     // node (global id) of the row, -1 = none
+};
+struct RingSmem {
+  float4 ring[RG_W][RG_R][2][16][16];  // [warp][slot][half-warp][entry][16 x float4] = 8 KB per slot
+  RingDesc desc[RG_W][RG_DB];
+  int fifo[RG_W][4];                   // per in-flight slot: descriptor buffer | step << 8, -1 = nothing issued
+};
+static_assert(sizeof(RingSmem) <= 232448, "RingSmem exceeds the shared memory of one CTA");
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+
+__global__ void __launch_bounds__(RG_T, 1) agg_ring_kernel(md_graphs_t G, md_state_t S, md_work_t K, int iter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RingSmem& sm = *reinterpret_cast<RingSmem*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15;
+  const int St = G.stride, B = G.n_graphs, L = G.n_layers;
+  const int cpg = St / 32;  // 32-row chunks per graph (the stride is a multiple of 128)
+  const long long per_layer = (long long)B * cpg, n_chunks = per_layer * L;
+  const long long cstride = (long long)gridDim.x * RG_W;
+  long long c_next = (long long)blockIdx.x * RG_W + warp;  // next chunk index to look at
+  // this lane's 16-byte column chunk of the input / output embedding rows, per layer (no dynamic indexing of the params)
+  auto hin_of = [&](int l) -> const float4* {
+    const float* p = K.h[iter & 1][0];
+    if (l == 1) p = K.h[iter & 1][1];
+    if (l == 2) p = K.h[iter & 1][2];
+    if (l == 3) p = K.h[iter & 1][3];
+    return reinterpret_cast<const float4*>(p) + l16;
+  };
+  auto pout_of = [&](int l) -> float4* {
+    float* p = K.h[(iter + 1) & 1][0];
+    if (l == 1) p = K.h[(iter + 1) & 1][1];
+    if (l == 2) p = K.h[(iter + 1) & 1][2];
+    if (l == 3) p = K.h[(iter + 1) & 1][3];
+    return reinterpret_cast<float4*>(p) + l16;
+  };
+  auto acol_of = [&](int l) -> const int32_t* {
+    const int32_t* p = S.acol[0];
+    if (l == 1) p = S.acol[1];
+    if (l == 2) p = S.acol[2];
+    if (l == 3) p = S.acol[3];
+    return p;
+  };
+  auto aptr_of = [&](int l) -> const int32_t* {
+    const int32_t* p = S.aptr[0];
+    if (l == 1) p = S.aptr[1];
+    if (l == 2) p = S.aptr[2];
+    if (l == 3) p = S.aptr[3];
+    return p;
+  };
+
+  // Fetch the descriptors of the warp's next chunk into buffer b; false when the sequence is exhausted.  Chunks whose
+  // entries do not fit the staging area (hub rows) are summed right here with register loads and skipped.
+  auto load_desc = [&](int b) -> bool {
+    for (; c_next < n_chunks; c_next += cstride) {
+      const int l = (int)(c_next / per_layer);
+      const int rem = (int)(c_next - (long long)l * per_layer);
+      const int g = rem / cpg, p0 = (rem - g * cpg) * 32;
+      const int n = S.n_act[g];
+      if (p0 >= n) continue;
+      const int rows = min(32, n - p0);
+      const int32_t* __restrict__ aptr = aptr_of(l) + (size_t)g * St + p0;
+      const int ap = aptr[min(lane, rows)], ap_hi = aptr[min(lane + 1, rows)];
+      const int v = lane < rows ? S.act_list[(size_t)g * St + p0 + lane] : -1;
+      const int e_begin = __shfl_sync(0xffffffffu, ap, 0);
+      const int total = __shfl_sync(0xffffffffu, ap_hi, 31) - e_begin;
+      const int32_t* __restrict__ acol = acol_of(l) + e_begin;
+      if (total > RG_IDS) {
+        const float4* __restrict__ Hin = hin_of(l);
+        float4* __restrict__ Pout = pout_of(l);
+        for (int i = 0; 2 * i < rows; ++i) {
+          const int r = 2 * i + half;
+          const int e0 = __shfl_sync(0xffffffffu, ap, r) - e_begin, e1 = __shfl_sync(0xffffffffu, ap_hi, r) - e_begin;
+          const int vv = __shfl_sync(0xffffffffu, v, r);
+          const int nr = r < rows ? e1 - e0 : 0;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k0 = 0; k0 < nr; k0 += 4) {
+            float4 val[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (k0 + j < nr) val[j] = __ldg(Hin + (size_t)acol[e0 + k0 + j] * (D / 4));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (k0 + j < nr) acc.x += val[j].x, acc.y += val[j].y, acc.z += val[j].z, acc.w += val[j].w;
+          }
+          if (vv >= 0) Pout[(size_t)vv * (D / 4)] = acc;
+        }
+        continue;
+      }
+      RingDesc& d = sm.desc[warp][b];
+      d.rptr[lane] = ap - e_begin;
+      d.vrow[lane] = v;
+      if (lane == 0) d.rptr[32] = total, d.rptr[34] = l, d.rptr[35] = rows;
+      for (int k = lane; k < total; k += 32) d.ent[k] = acol[k];
+      __syncwarp();
+      for (int e = ap - e_begin; e < ap_hi - e_begin; ++e) d.ent[e] |= lane << RG_IDBITS;  // lane = destination row
+      __syncwarp();
+      c_next += cstride;
+      return true;
+    }
+    return false;
+  };
+  // number of 16-entry steps of the chunk in buffer b (>= 1: a chunk without entries still flushes its rows)
+  auto n_steps = [&](int b) -> int {
+    const RingDesc& d = sm.desc[warp][b];
+    const int len = max(d.rptr[16], d.rptr[32] - d.rptr[16]);
+    return max(1, (len + 15) >> 4);
+  };
+  const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(&sm.ring[warp][0][half][0][l16]);
+  const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+  // this half-warp's entries of step si: lane j holds entry j (0 beyond the end of the half's stream)
+  auto step_entry = [&](const RingDesc& d, int si, int& nv) -> int {
+    const int sb = d.rptr[16 * half];
+    nv = d.rptr[16 * half + 16] - sb - si * 16;
+    return l16 < nv ? d.ent[sb + si * 16 + l16] : 0;
+  };
+  auto issue = [&](int b, int si, int slot) {
+    const RingDesc& d = sm.desc[warp][b];
+    int nv;
+    const int w = step_entry(d, si, nv);
+    const float4* __restrict__ Hin = hin_of(d.rptr[34]);
+    const uint32_t dst = ring_a + (uint32_t)slot * RG_SLOT_B;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int wj = __shfl_sync(0xffffffffu, w, 16 * half + j);
+      if (j < nv) cp_async16(dst + 256u * j, Hin + (size_t)(wj & ((1 << RG_IDBITS) - 1)) * (D / 4));
+    }
+  };
+
+  // consumer state of this half-warp: destination row being summed (0..31 within the chunk), accumulator
+  int row = 0, row_last = 0;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4* __restrict__ Pout = nullptr;
+  auto begin_chunk = [&](int b) {
+    const RingDesc& d = sm.desc[warp][b];
+    row = 16 * half;
+    row_last = min(16 * half + 16, d.rptr[35]);  // one past this half's last row
+    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    Pout = pout_of(d.rptr[34]);
+  };
+  auto flush_to = [&](const RingDesc& d, int target) {  // store rows [row, target): the first holds acc, the rest are empty
+    while (row < target) {
+      const int v = d.vrow[row];
+      if (v >= 0) Pout[(size_t)v * (D / 4)] = acc;
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      ++row;
+    }
+  };
+  auto consume = [&](int b, int si, int slot, bool last) {
+    const RingDesc& d = sm.desc[warp][b];
+    int nv;
+    const int w = step_entry(d, si, nv);
+    const int rj = (int)((unsigned)w >> RG_IDBITS);
+    // entries that start a new destination row (relative to the previous entry of the stream; entry 0: to `row`)
+    const int rprev = __shfl_up_sync(0xffffffffu, rj, 1);
+    const bool nr = l16 < nv && rj != (l16 == 0 ? row : rprev);
+    const unsigned starts = (__ballot_sync(0xffffffffu, nr) & hmask) >> (16 * half);
+    const uint32_t src = ring_a + (uint32_t)slot * RG_SLOT_B;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < nv) {
+        if ((starts >> j) & 1u) flush_to(d, __shfl_sync(hmask, rj, 16 * half + j));
+        const float4 x = lds_f4(src + 256u * j);
+        acc.x += x.x;
+        acc.y += x.y;
+        acc.z += x.z;
+        acc.w += x.w;
+      }
+    }
+    if (last) flush_to(d, row_last);
+  };
+
+  // ---- the step stream: issue runs RG_R - 1 steps ahead of consume -----------------------------------------------
+  // Chunk k uses descriptor buffer k % RG_DB.  The issue cursor fetches the next chunk's descriptors lazily, right before
+  // its first step is issued: by then the consume cursor is at most one chunk behind, so the buffer being overwritten
+  // (chunk k - 2's) is no longer read.
+  int ib = 0, is = 0, in = 0;  // issue cursor: descriptor buffer, step, steps of that chunk
+  int cs = 0, cn = 0;          // consume cursor: step, steps of its chunk
+  if (!load_desc(0)) return;
+  in = n_steps(0);
+  cn = in;
+  begin_chunk(0);
+  bool issue_done = false;
+  unsigned q = 0;  // stream positions issued so far (ring slot = position % RG_R)
+  auto issue_next = [&]() {
+    int tag = -1;
+    if (!issue_done && is == in) {
+      const int nb = (ib + 1) % RG_DB;
+      if (load_desc(nb)) ib = nb, is = 0, in = n_steps(nb);
+      else issue_done = true;
+    }
+    if (!issue_done) {
+      issue(ib, is, (int)(q % RG_R));
+      tag = ib | (is << 8);
+      ++is;
+    }
+    cp_async_commit();
+    if (lane == 0) sm.fifo[warp][q % RG_R] = tag;
+    ++q;
+  };
+  for (int k = 0; k < RG_R - 1; ++k) issue_next();
+  for (unsigned qc = 0;; ++qc) {
+    issue_next();
+    cp_async_wait<RG_R - 1>();
+    __syncwarp();
+    const int tag = sm.fifo[warp][qc % RG_R];
+    if (tag < 0) break;  // nothing was issued for this position: the stream is exhausted
+    const int b = tag & 0xff;
+    consume(b, tag >> 8, (int)(qc % RG_R), cs + 1 == cn);
+    if (++cs == cn) {  // next chunk (its first step is already in flight, so its descriptors are in place)
+      const int nt = sm.fifo[warp][(qc + 1) % RG_R];
+      if (nt >= 0) {
+        cs = 0;
+        cn = n_steps(nt & 0xff);
+        begin_chunk(nt & 0xff);
+      }
+    }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+}
+
+}  // namespace md
+
+extern int g_md_debug_flags;
+
+// enqueue P = A_adj . H for every layer (internal: called by md_embed_iter when the two-kernel path applies)
+int md_agg_rows_launch(const md_graphs_t* g, const md_state_t* s, const md_work_t* k, int iter, cudaStream_t st) {
+  static int nsm = 0;
+  if (nsm <= 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm <= 0) nsm = 148;
+  }
+  const long long n_chunks = (long long)g->n_graphs * (g->stride / 32) * g->n_layers;
+  if ((g_md_debug_flags & 512) || g->n_total >= (1 << md::RG_IDBITS)) {  // (the ring packs the row into the id's top bits)
+    const long long want = (n_chunks + md::AG_W - 1) / md::AG_W;
+    const int grid = (int)(want < nsm ? want : nsm);
+    md::agg_rows_kernel<<<grid, md::AG_T, 0, st>>>(*g, *s, *k, iter);
+  } else {
+    static bool configured = false;
+    const int smem = (int)sizeof(md::RingSmem);
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(md::agg_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+    const long long want = (n_chunks + md::RG_W - 1) / md::RG_W;
+    const int grid = (int)(want < nsm ? want : nsm);
+    md::agg_ring_kernel<<<grid, md::RG_T, smem, st>>>(*g, *s, *k, iter);
+  }
+  MD_CHECK_LAUNCH();
+  return 0;
+}

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_s
     const int r0 = warp * 8;  // this warp's rows of every tile
 
     // descriptor prefetch of a tile into staging slot `par`: row pointers, node ids, neighbour ids of short rows
+    const bool pf_l2 = !(dbg & 64) && (size_t)G.n_total * (D * 4) * G.n_layers > (size_t)(96u << 20);
     auto prefetch = [&](const TileIter& tt, int par) {
       const int rows = min(TILE_M, tt.nact - tt.t * TILE_M);
       const int32_t* __restrict__ aptr = S.aptr[tt.l] + tt.g * G.stride + tt.t * TILE_M;
@@ -155,7 +156,15 @@ __global__ void __launch_bounds__(IT_T, 1) embed_iter_kernel(md_graphs_t G, md_s
         const int nr = __shfl_sync(0xffffffffu, n, r);
         const int src0 = __shfl_sync(0xffffffffu, ap, r);
         const int dst0 = __shfl_sync(0xffffffffu, excl, r);
-        if (lane < nr) sm.wstg[par][warp][dst0 + lane] = acol[src0 + lane];
+        if (lane < nr) {
+          const int u = acol[src0 + lane];
+          sm.wstg[par][warp][dst0 + lane] = u;
+          if (pf_l2) {  // embeddings larger than L2: start the DRAM -> L2 fetch of the neighbour row one tile ahead
+            const char* hp = reinterpret_cast<const char*>(K.h[iter & 1][tt.l]) + (size_t)u * (D * 4);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(hp));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + 128));
+          }
+        }
       }
     };
 

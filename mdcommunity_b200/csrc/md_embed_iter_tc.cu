@@ -32,7 +32,7 @@ struct IterTcSmem {
   unsigned char LO[2][KB16];   // fp16 remainders: block 0 = P_lo (64 columns), block 1 = H_lo
   unsigned char Wb[5][KB16];   // B operands: W13 hi, W13 lo, W23 hi, W23 lo (2 K blocks of 8 KB each), fp16 [W13 | W23]
   float extra[MAXXS * D];      // partial sums of the 2nd.. segments of long rows
-  float cs[NGW][D];            // per-warp column sums of the tile's own rows
+  float cs[2][NGW][D];         // [tile parity] per-warp column sums of the tile's own rows
   int wstg[2][NGW][WSTG];
   int wptr[2][NGW][12];
   int wv[2][NGW][8];
@@ -73,6 +73,9 @@ struct TileIterTc {  // the tile sequence all roles walk in lock step
   }
 };
 
+// PRE: the neighbour sums were computed by md_agg (agg_rows_kernel) into the rows of the output buffer; the gather warps only
+// stream P and H rows in (contiguous 256-byte rows, all loads of a tile in flight before the operand tiles are touched).
+template <bool PRE>
 __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K, int iter) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   IterTcSmem& sm = *reinterpret_cast<IterTcSmem*>(smem_raw);
@@ -156,6 +159,10 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
     // descriptor prefetch of a tile into staging slot `par`: row pointers, node ids, neighbour ids of short rows
     auto prefetch = [&](const TileIterTc& tt, int par) {
       const int rows = min(TILE_M, tt.nact - tt.t * TILE_M);
+      if constexpr (PRE) {
+        if (lane < 8) sm.wv[par][warp][lane] = (r0 + lane < rows) ? S.act_list[tt.g * G.stride + tt.t * TILE_M + r0 + lane] : -1;
+        return;
+      }
       const int32_t* __restrict__ aptr = S.aptr[tt.l] + tt.g * G.stride + tt.t * TILE_M;
       int ap = 0;
       if (lane < 9) ap = aptr[min(r0 + lane, rows)];
@@ -203,6 +210,30 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
       const int32_t* __restrict__ acol = S.acol[l];
       const float4* __restrict__ H4 = reinterpret_cast<const float4*>(K.h[iter & 1][l]);
       float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (PRE) {
+        const float4* __restrict__ P4 = reinterpret_cast<const float4*>(K.h[(iter + 1) & 1][l]);
+        float4 pv[4], own[4];
+        int vr[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // all 8 row loads of this lane are in flight before anything is waited for
+          vr[i] = sm.wv[buf][warp][2 * i + half];
+          pv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          own[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (vr[i] >= 0) {
+            pv[i] = __ldcg(P4 + (size_t)vr[i] * (D / 4) + l16);  // other rows of this buffer are being overwritten: no .nc
+            own[i] = __ldg(H4 + (size_t)vr[i] * (D / 4) + l16);
+          }
+        }
+        if (it >= 2) mbar_wait(&sm.d_empty[buf], ((it >> 1) - 1) & 1);  // epilogue of tile it-2 is done with v[buf]
+        if (it >= 1) mbar_wait(&sm.a_empty, (it - 1) & 1);              // MMAs of the previous tile have read the operand tiles
+        if (lane < 8) sm.v[buf][r0 + lane] = sm.wv[buf][warp][lane];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          st_p(r0 + 2 * i + half, pv[i]);
+          st_h(r0 + 2 * i + half, own[i]);
+          csum.x += own[i].x, csum.y += own[i].y, csum.z += own[i].z, csum.w += own[i].w;
+        }
+      } else {
       if (it >= 2) mbar_wait(&sm.d_empty[buf], ((it >> 1) - 1) & 1);  // epilogue of tile it-2 is done with v[buf]
       if (it >= 1) mbar_wait(&sm.a_empty, (it - 1) & 1);              // MMAs of the previous tile have read the operand tiles
 
@@ -358,17 +389,18 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
         }
         bar_sync(BAR_GATH, IT_GATH);
       }
+      }  // !PRE
       // per-tile column sums of the old embeddings (spmm subgsum): half-warps, then warps, in a fixed order
       csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 16);
       csum.y += __shfl_xor_sync(0xffffffffu, csum.y, 16);
       csum.z += __shfl_xor_sync(0xffffffffu, csum.z, 16);
       csum.w += __shfl_xor_sync(0xffffffffu, csum.w, 16);
-      if (lane < 16) *reinterpret_cast<float4*>(&sm.cs[warp][4 * l16]) = csum;
+      if (lane < 16) *reinterpret_cast<float4*>(&sm.cs[buf][warp][4 * l16]) = csum;
       bar_sync(BAR_GATH, IT_GATH);
       if (tid < D) {
         float s = 0.f;
 #pragma unroll
-        for (int w2 = 0; w2 < NGW; ++w2) s += sm.cs[w2][tid];
+        for (int w2 = 0; w2 < NGW; ++w2) s += sm.cs[buf][w2][tid];
         K.psum[(((size_t)iter * G.n_layers + l) * cur.tiles_per_layer + cur.gt) * D + tid] = s;
       }
       fence_proxy_async_smem();
@@ -470,18 +502,30 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
 
 extern int g_md_debug_flags;
 
-// *launched = 1 when the tensor-core kernel was enqueued: only on request (md_debug_set_flags bit 4).  Measured: no gain
-// over the FP32-FMA kernel (C2 unfused 450 vs 417 us per launch, C4 9.2 vs 9.0 ms per step): the iteration is bound by the
-// L2 / HBM row gather, whose warps the FMA consumers overlapped for free; kept as the A/B reference of that finding.
+// *launched = 1 when a tensor-core kernel was enqueued.
+//  * two-kernel path (default when the embeddings exceed L2, i.e. the N = 1M configuration; md_debug_set_flags bit 8 forces
+//    it, bit 7 disables it): md_agg's high-occupancy neighbour aggregation, then this kernel in PRE mode.  C4: 9.0 -> see
+//    DESIGN 6 ms per step for the aggregation stage.
+//  * single fused tensor-core kernel: only on request (bit 4).  Measured: no gain over the FP32-FMA kernel (C2 unfused 450
+//    vs 417 us per launch, C4 9.2 vs 9.0 ms per step): with the gather inside, the iteration is bound by the 16 gather
+//    warps' row loads, which the FMA consumers overlapped for free; kept as the A/B reference of that finding.
+int md_agg_rows_launch(const md_graphs_t* g, const md_state_t* s, const md_work_t* k, int iter, cudaStream_t st);
+
 int md_embed_iter_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, int iter,
                             cudaStream_t st, int* launched) {
   *launched = 0;
-  if (!(g_md_debug_flags & 16) || (g_md_debug_flags & (1 | 2))) return 0;
+  const int f = g_md_debug_flags;
+  if (f & (1 | 2)) return 0;  // isolation runs of the FMA kernel
+  const bool beyond_l2 = (size_t)g->n_total * g->n_layers * (md::D * 4) > ((size_t)96 << 20);
+  const bool pre = !(f & 128) && ((f & 256) || beyond_l2);
+  if (!pre && !(f & 16)) return 0;
   static bool configured = false;
   static int nsm = 0;
   const int smem = (int)sizeof(md::IterTcSmem);
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(md::embed_iter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(md::embed_iter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(md::embed_iter_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -491,7 +535,13 @@ int md_embed_iter_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_
   }
   const int n_tiles = g->n_graphs * (g->stride / MD_TILE_M) * g->n_layers;
   const int grid = nsm < n_tiles ? nsm : n_tiles;
-  md::embed_iter_tc_kernel<<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter);
+  if (pre) {
+    const int rc = md_agg_rows_launch(g, s, k, iter, st);
+    if (rc) return rc;
+    md::embed_iter_tc_kernel<true><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter);
+  } else {
+    md::embed_iter_tc_kernel<false><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   *launched = 1;

@@ -23,6 +23,7 @@ ap.add_argument("--layers", type=int, default=3)
 ap.add_argument("--edges", type=int, default=4_000_000)
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--profile-steps", type=int, default=0, help="bracket this many steps with cudaProfilerStart/Stop")
+ap.add_argument("--dbg", type=int, default=0, help="md_debug_set_flags value (A/B switches of the kernels)")
 args = ap.parse_args()
 
 t0 = time.time()
@@ -35,6 +36,7 @@ torch.cuda.synchronize()
 print("setup %.1f s; max_rank %d, active %d, alive directed edges %s" % (
     time.time() - t0, g.max_rank, int(ro.n_act[0]), (2 * ro.alive_edges[:, 0]).tolist()), flush=True)
 lib = ro.lib
+lib.md_debug_set_flags(args.dbg)
 gp, sp, wp, kp, st = ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()
 ev = lambda: torch.cuda.Event(enable_timing=True)
 rows = []

@@ -421,6 +421,35 @@ def test_unfused_iteration_tensor_core_variant_matches_fma():
         lib.md_debug_set_flags(0)
 
 
+def test_two_kernel_iteration_matches_fma():
+    """md_embed_iter, large-graph path (md_agg neighbour aggregation + tensor-core transform in PRE mode; forced here with
+    md_debug_set_flags bit 8, the default only when the embeddings exceed L2) against the default FP32-FMA kernel on the
+    same states, including hub rows and ragged last tiles."""
+    from mdcommunity_b200 import _lib
+    mdb = _mdb()
+    for cost in ("degree", "unit"):
+        zs, graphs, batch, w = _load_batch(cost)
+        a = mdb.BatchRollout(batch, w, fused=False)
+        b = mdb.BatchRollout(batch, w, fused=False)
+        acts, T = _forced(zs, "greedy_actions", batch.device)
+        lib = _lib.lib()
+        try:
+            for t in range(5):
+                lib.md_debug_set_flags(256)
+                a.forward()
+                lib.md_debug_set_flags(0)
+                b.forward()
+                for l in range(batch.L):
+                    ids = torch.cat([a.act_list[g * batch.S:g * batch.S + int(a.n_act[g])] for g in range(batch.B)]).long()
+                    assert float((a.h[1][l][ids] - b.h[1][l][ids]).abs().max()) <= 2e-5, (cost, t, l)
+                torch.testing.assert_close(a.psum, b.psum, rtol=1e-4, atol=1e-5)
+                torch.testing.assert_close(a.q, b.q, rtol=Q_RTOL, atol=Q_ATOL)
+                a.step(acts)
+                b.step(acts)
+        finally:
+            lib.md_debug_set_flags(0)
+
+
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
 def test_edge_case_graphs(fused):
     """Ragged batch of degenerate inputs: a layer without edges (terminal at s0), a single mutual edge, isolated nodes,
