@@ -97,13 +97,13 @@ constexpr uint32_t RG_SLOT_B = 8192;
 
 struct RingDesc {
   int ent[RG_IDS];  // staged entries (see RG_IDBITS), CSR order
-  int rptr[36];     // [0..32] row pointers relative to the chunk's first entry; [34] layer; [35] rows
   int vrow[32];     // node (global id) of the row, -1 = none
+  int total, layer, pad[2];
 };
 struct RingSmem {
-  float4 ring[RG_W][RG_R][2][16][16];  // [warp][slot][half-warp][entry][16 x float4] = 8 KB per slot
+  unsigned char ring[RG_W][RG_R][RG_SLOT_B];  // [warp][slot][32 entries x 256 bytes]
   RingDesc desc[RG_W][RG_DB];
-  int fifo[RG_W][4];                   // per in-flight slot: descriptor buffer | step << 8, -1 = nothing issued
+  int fifo[RG_W][4];  // per in-flight slot: descriptor buffer | step << 8, -1 = nothing issued
 };
 static_assert(sizeof(RingSmem) <= 232448, "RingSmem exceeds the shared memory of one CTA");
 
@@ -113,35 +113,38 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ float4 lds_f4(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+__device__ __forceinline__ uint64_t lds_b64(uint32_t a) {
+  uint64_t v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ void add_f32x2(uint64_t& a, uint64_t b) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b)); }
 
+// One WARP per stream: the entries of a chunk's 32 destination rows form one flat list, cut into steps of 32 entries; a
+// step is 32 rows of 256 bytes, every lane copying / summing 8 bytes of each (all control flow is warp-uniform).
 __global__ void __launch_bounds__(RG_T, 1) agg_ring_kernel(md_graphs_t G, md_state_t S, md_work_t K, int iter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RingSmem& sm = *reinterpret_cast<RingSmem*>(smem_raw);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int St = G.stride, B = G.n_graphs, L = G.n_layers;
   const int cpg = St / 32;  // 32-row chunks per graph (the stride is a multiple of 128)
   const long long per_layer = (long long)B * cpg, n_chunks = per_layer * L;
   const long long cstride = (long long)gridDim.x * RG_W;
   long long c_next = (long long)blockIdx.x * RG_W + warp;  // next chunk index to look at
-  // this lane's 16-byte column chunk of the input / output embedding rows, per layer (no dynamic indexing of the params)
-  auto hin_of = [&](int l) -> const float4* {
+  // this lane's 8-byte column pair of the input / output embedding rows, per layer (no dynamic indexing of the params)
+  auto hin_of = [&](int l) -> const float2* {
     const float* p = K.h[iter & 1][0];
     if (l == 1) p = K.h[iter & 1][1];
     if (l == 2) p = K.h[iter & 1][2];
     if (l == 3) p = K.h[iter & 1][3];
-    return reinterpret_cast<const float4*>(p) + l16;
+    return reinterpret_cast<const float2*>(p) + lane;
   };
-  auto pout_of = [&](int l) -> float4* {
+  auto pout_of = [&](int l) -> uint64_t* {
     float* p = K.h[(iter + 1) & 1][0];
     if (l == 1) p = K.h[(iter + 1) & 1][1];
     if (l == 2) p = K.h[(iter + 1) & 1][2];
     if (l == 3) p = K.h[(iter + 1) & 1][3];
-    return reinterpret_cast<float4*>(p) + l16;
+    return reinterpret_cast<uint64_t*>(p) + lane;
   };
   auto acol_of = [&](int l) -> const int32_t* {
     const int32_t* p = S.acol[0];
@@ -158,8 +161,9 @@ __global__ void __launch_bounds__(RG_T, 1) agg_ring_kernel(md_graphs_t G, md_sta
     return p;
   };
 
-  // Fetch the descriptors of the warp's next chunk into buffer b; false when the sequence is exhausted.  Chunks whose
-  // entries do not fit the staging area (hub rows) are summed right here with register loads and skipped.
+  // Fetch the descriptors of the warp's next chunk into buffer b; false when the sequence is exhausted.  Rows without
+  // entries get their zeros here; chunks whose entries do not fit the staging area (hub rows) are summed right here with
+  // register loads and skipped.
   auto load_desc = [&](int b) -> bool {
     for (; c_next < n_chunks; c_next += cstride) {
       const int l = (int)(c_next / per_layer);
@@ -174,35 +178,33 @@ __global__ void __launch_bounds__(RG_T, 1) agg_ring_kernel(md_graphs_t G, md_sta
       const int e_begin = __shfl_sync(0xffffffffu, ap, 0);
       const int total = __shfl_sync(0xffffffffu, ap_hi, 31) - e_begin;
       const int32_t* __restrict__ acol = acol_of(l) + e_begin;
+      uint64_t* __restrict__ Pout = pout_of(l);
       if (total > RG_IDS) {
-        const float4* __restrict__ Hin = hin_of(l);
-        float4* __restrict__ Pout = pout_of(l);
-        for (int i = 0; 2 * i < rows; ++i) {
-          const int r = 2 * i + half;
+        const float2* __restrict__ Hin = hin_of(l);
+        for (int r = 0; r < rows; ++r) {
           const int e0 = __shfl_sync(0xffffffffu, ap, r) - e_begin, e1 = __shfl_sync(0xffffffffu, ap_hi, r) - e_begin;
           const int vv = __shfl_sync(0xffffffffu, v, r);
-          const int nr = r < rows ? e1 - e0 : 0;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int k0 = 0; k0 < nr; k0 += 4) {
-            float4 val[4];
+          float2 acc = make_float2(0.f, 0.f);
+          for (int k0 = e0; k0 < e1; k0 += 8) {
+            float2 val[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (k0 + j < nr) val[j] = __ldg(Hin + (size_t)acol[e0 + k0 + j] * (D / 4));
+            for (int j = 0; j < 8; ++j) {
+              val[j] = make_float2(0.f, 0.f);
+              if (k0 + j < e1) val[j] = __ldg(Hin + (size_t)acol[k0 + j] * (D / 2));
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (k0 + j < nr) acc.x += val[j].x, acc.y += val[j].y, acc.z += val[j].z, acc.w += val[j].w;
+            for (int j = 0; j < 8; ++j)
+              if (k0 + j < e1) acc.x += val[j].x, acc.y += val[j].y;
           }
-          if (vv >= 0) Pout[(size_t)vv * (D / 4)] = acc;
+          reinterpret_cast<float2*>(Pout)[(size_t)vv * (D / 2)] = acc;
         }
         continue;
       }
       RingDesc& d = sm.desc[warp][b];
-      d.rptr[lane] = ap - e_begin;
       d.vrow[lane] = v;
-      if (lane == 0) d.rptr[32] = total, d.rptr[34] = l, d.rptr[35] = rows;
+      if (lane == 0) d.total = total, d.layer = l;
       for (int k = lane; k < total; k += 32) d.ent[k] = acol[k];
+      if (v >= 0 && ap_hi == ap) Pout[(size_t)v * (D / 2)] = 0ull;  // (an active node has alive neighbours: defensive)
       __syncwarp();
       for (int e = ap - e_begin; e < ap_hi - e_begin; ++e) d.ent[e] |= lane << RG_IDBITS;  // lane = destination row
       __syncwarp();
@@ -211,74 +213,58 @@ __global__ void __launch_bounds__(RG_T, 1) agg_ring_kernel(md_graphs_t G, md_sta
     }
     return false;
   };
-  // number of 16-entry steps of the chunk in buffer b (>= 1: a chunk without entries still flushes its rows)
-  auto n_steps = [&](int b) -> int {
-    const RingDesc& d = sm.desc[warp][b];
-    const int len = max(d.rptr[16], d.rptr[32] - d.rptr[16]);
-    return max(1, (len + 15) >> 4);
-  };
-  const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(&sm.ring[warp][0][half][0][l16]);
-  const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
-  // this half-warp's entries of step si: lane j holds entry j (0 beyond the end of the half's stream)
-  auto step_entry = [&](const RingDesc& d, int si, int& nv) -> int {
-    const int sb = d.rptr[16 * half];
-    nv = d.rptr[16 * half + 16] - sb - si * 16;
-    return l16 < nv ? d.ent[sb + si * 16 + l16] : 0;
-  };
+  // number of 32-entry steps of the chunk in buffer b (>= 1 keeps the stream bookkeeping uniform)
+  auto n_steps = [&](int b) -> int { return max(1, (sm.desc[warp][b].total + 31) >> 5); };
+  const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(&sm.ring[warp][0][8 * lane]);
+  // issue: 16 bytes per lane, L1 bypassed (.cg) -- half-warp h copies entry 2 j + h; the consumer reads the slot with its
+  // own mapping (8 bytes of every entry per lane), so the two sides need not agree
+  const int half = lane >> 4, l16 = lane & 15;
+  const uint32_t ring_i = (uint32_t)__cvta_generic_to_shared(&sm.ring[warp][0][256 * half + 16 * l16]);
   auto issue = [&](int b, int si, int slot) {
     const RingDesc& d = sm.desc[warp][b];
-    int nv;
-    const int w = step_entry(d, si, nv);
-    const float4* __restrict__ Hin = hin_of(d.rptr[34]);
-    const uint32_t dst = ring_a + (uint32_t)slot * RG_SLOT_B;
+    const int nv = d.total - si * 32;
+    const int w = lane < nv ? d.ent[si * 32 + lane] : 0;
+    const float4* __restrict__ Hin = reinterpret_cast<const float4*>(hin_of(d.layer) - lane) + l16;
+    const uint32_t dst = ring_i + (uint32_t)slot * RG_SLOT_B;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int wj = __shfl_sync(0xffffffffu, w, 16 * half + j);
-      if (j < nv) cp_async16(dst + 256u * j, Hin + (size_t)(wj & ((1 << RG_IDBITS) - 1)) * (D / 4));
+      const int wj = __shfl_sync(0xffffffffu, w, 2 * j + half);
+      if (2 * j + half < nv) cp_async16(dst + 512u * j, Hin + (size_t)(wj & ((1 << RG_IDBITS) - 1)) * (D / 4));
     }
   };
 
-  // consumer state of this half-warp: destination row being summed (0..31 within the chunk), accumulator
-  int row = 0, row_last = 0;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4* __restrict__ Pout = nullptr;
+  // consumer state: destination row being summed (0..31 within the chunk), its accumulator (two packed floats per lane)
+  int row = 0;
+  uint64_t acc = 0ull;
+  uint64_t* __restrict__ Pout = nullptr;
   auto begin_chunk = [&](int b) {
     const RingDesc& d = sm.desc[warp][b];
-    row = 16 * half;
-    row_last = min(16 * half + 16, d.rptr[35]);  // one past this half's last row
-    acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    Pout = pout_of(d.rptr[34]);
-  };
-  auto flush_to = [&](const RingDesc& d, int target) {  // store rows [row, target): the first holds acc, the rest are empty
-    while (row < target) {
-      const int v = d.vrow[row];
-      if (v >= 0) Pout[(size_t)v * (D / 4)] = acc;
-      acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      ++row;
-    }
+    row = d.total > 0 ? (int)((unsigned)d.ent[0] >> RG_IDBITS) : -1;
+    acc = 0ull;
+    Pout = pout_of(d.layer);
   };
   auto consume = [&](int b, int si, int slot, bool last) {
     const RingDesc& d = sm.desc[warp][b];
-    int nv;
-    const int w = step_entry(d, si, nv);
+    const int nv = d.total - si * 32;
+    const int w = lane < nv ? d.ent[si * 32 + lane] : 0;
     const int rj = (int)((unsigned)w >> RG_IDBITS);
-    // entries that start a new destination row (relative to the previous entry of the stream; entry 0: to `row`)
-    const int rprev = __shfl_up_sync(0xffffffffu, rj, 1);
-    const bool nr = l16 < nv && rj != (l16 == 0 ? row : rprev);
-    const unsigned starts = (__ballot_sync(0xffffffffu, nr) & hmask) >> (16 * half);
+    int rprev = __shfl_up_sync(0xffffffffu, rj, 1);
+    if (lane == 0) rprev = row;
+    const unsigned starts = __ballot_sync(0xffffffffu, lane < nv && rj != rprev);  // entries that open a new row
     const uint32_t src = ring_a + (uint32_t)slot * RG_SLOT_B;
+    uint64_t x[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < nv) {
-        if ((starts >> j) & 1u) flush_to(d, __shfl_sync(hmask, rj, 16 * half + j));
-        const float4 x = lds_f4(src + 256u * j);
-        acc.x += x.x;
-        acc.y += x.y;
-        acc.z += x.z;
-        acc.w += x.w;
+    for (int j = 0; j < 32; ++j) x[j] = j < nv ? lds_b64(src + 256u * j) : 0ull;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if ((starts >> j) & 1u) {  // warp-uniform: the row that ends here leaves, the next one starts
+        Pout[(size_t)d.vrow[row] * (D / 2)] = acc;
+        acc = 0ull;
+        row = __shfl_sync(0xffffffffu, rj, j);
       }
+      add_f32x2(acc, x[j]);  // (+0 beyond the end of the stream)
     }
-    if (last) flush_to(d, row_last);
+    if (last && row >= 0) Pout[(size_t)d.vrow[row] * (D / 2)] = acc;
   };
 
   // ---- the step stream: issue runs RG_R - 1 steps ahead of consume -----------------------------------------------
