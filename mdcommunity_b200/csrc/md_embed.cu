@@ -49,6 +49,43 @@ __global__ void __launch_bounds__(256) embed_init_kernel(md_graphs_t G, md_state
 }
 
 // =================================================================================================
+// psum_reduce : graphs of many tiles (N = 1M: 7813 per layer) -- the per-tile column sums of one (iteration, layer, graph)
+// are folded into the slot of tile 0 by a whole CTA (16 tile groups x 64 columns, 8 independent partial sums per thread,
+// combined in a fixed order), so that graph_embed_kernel's single thread per column does not walk 3 x 7813 dependent
+// loads (0.88 ms per step at C4).  Graphs of few tiles keep the plain sequential sum inside graph_embed_kernel.
+// =================================================================================================
+constexpr int PSUM_REDUCE_MIN_TILES = 64;
+
+__global__ void __launch_bounds__(1024) psum_reduce_kernel(md_graphs_t G, md_state_t S, md_work_t K) {
+  __shared__ float part[16][D];
+  const int L = G.n_layers, B = G.n_graphs;
+  const int g = blockIdx.x % B, l = (blockIdx.x / B) % L, it = blockIdx.x / (B * L);
+  const int tpg = G.stride / TILE_M, tiles_per_layer = B * tpg;
+  const int ntile = (S.n_act[g] + TILE_M - 1) / TILE_M;
+  if (ntile <= PSUM_REDUCE_MIN_TILES) return;
+  const int c = threadIdx.x & 63, q = threadIdx.x >> 6;
+  float* ps = K.psum + (((size_t)it * L + l) * tiles_per_layer + (size_t)g * tpg) * D + c;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  for (int t0 = q; t0 < ntile; t0 += 16 * 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int t = t0 + 16 * j;
+      if (t < ntile) a[j] += ps[(size_t)t * D];
+    }
+  }
+  part[q][c] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  __syncthreads();
+  if (q == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += part[k][c];
+    ps[0] = s;
+  }
+}
+
+// =================================================================================================
 // md_graph_embed : one CTA per graph, L*64 threads
 // =================================================================================================
 __device__ __forceinline__ float group_sum64(float v, float* scratch, int l, int c) {
@@ -83,7 +120,8 @@ __global__ void __launch_bounds__(MD_MAX_LAYERS* D) graph_embed_kernel(md_graphs
   for (int it = 0; it < MD_BP_ITERS; ++it) {
     float s = 0.f;
     const float* ps = K.psum + (((size_t)it * L + l) * tiles_per_layer + (size_t)g * tpg) * D + c;
-    for (int t = 0; t < ntile; ++t) s += ps[(size_t)t * D];
+    const int nsum = ntile > PSUM_REDUCE_MIN_TILES ? 1 : ntile;  // many tiles: psum_reduce_kernel left the total in tile 0
+    for (int t = 0; t < nsum; ++t) s += ps[(size_t)t * D];
     sbuf[l][c] = s;
     __syncthreads();
     float o = 0.f;
@@ -191,6 +229,10 @@ extern "C" int md_graph_embed(const md_graphs_t* g, const md_state_t* s, const m
                               md_stream_t stream) {
   int rc = check_common(g, s, w, k);
   if (rc) return rc;
+  if (g->stride / MD_TILE_M > md::PSUM_REDUCE_MIN_TILES) {
+    md::psum_reduce_kernel<<<MD_BP_ITERS * g->n_layers * g->n_graphs, 1024, 0, (cudaStream_t)stream>>>(*g, *s, *k);
+    MD_CHECK_LAUNCH();
+  }
   md::graph_embed_kernel<<<g->n_graphs, g->n_layers * md::D, 0, (cudaStream_t)stream>>>(*g, *s, *w, *k);
   MD_CHECK_LAUNCH();
   return 0;
