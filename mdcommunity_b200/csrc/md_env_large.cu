@@ -14,11 +14,16 @@ constexpr int LG_T = 256;
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
+// Parent reads are plain (L1-cached) loads on purpose: in a graph with a giant component every find ends at the same
+// root word, and a million volatile reads of one word serialise in one L2 slice (measured: 0.6 ms per hooking sweep at
+// N = 1M, whatever the number of edges hooked).  A stale line only shows an OLDER parent, which is still an ancestor
+// (parents only ever move towards smaller ids), so find still climbs towards the root; a stale root is caught by the
+// atomicCAS in guf_unite, whose return value is always current.
 __device__ __forceinline__ int guf_find(int* par, int x) {
-  int p = ld_volatile(par + x);
+  int p = par[x];
   while (p != x) {
-    int gp = ld_volatile(par + p);
-    if (gp != p) par[x] = gp;  // path halving (benign race: parents only move towards smaller ids)
+    const int gp = par[p];
+    if (gp != p) par[x] = gp;  // path halving (benign race)
     x = p;
     p = gp;
   }
@@ -112,22 +117,61 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
   // a slot is re-cleared two rounds after its use, when every CTA has certainly read it.
   grid_barrier(bar, epoch);
 
+  // phase timers (block 0, thread 0): flags[6] = MCC rounds in ns, flags[7] = rounds << 24 | (sizes + degrees in us);
+  // flags[4..5] belong to md_qhead's tile queue
+  auto now_ns = []() -> unsigned long long {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+  };
+  unsigned long long t_ph = now_ns();
   // ---- Mcc.MCC --------------------------------------------------------------------------------------------
   int stable = 0, l = 0, round = 0;
   while (stable < L) {
     const int32_t* __restrict__ rp = G.rowptr[l];
     const int32_t* __restrict__ cl = G.col[l];
     int* chg = flags + 1 + (round % 3);
-    for (int v = gtid; v < NT; v += gsz) par[v] = v;
+    // Afforest-style round (Sutton et al.): link every node to its first two same-label neighbours, compress, find the
+    // dominant set of each graph by sampling, then finish only the rows OUTSIDE that set -- an edge between a skipped
+    // row and an outside node is still seen from the outside node's row (the CSR is symmetric), and edges inside the
+    // dominant set join nodes that are already together.  A full hooking sweep over the 8M entries of a layer cost 0.6 ms.
+    int* smp = S.comp_size;  // sample counters per root (zeroed again before the component sizes are counted)
+    for (int v = gtid; v < NT; v += gsz) {
+      par[v] = v;
+      smp[v] = 0;
+    }
+    for (int g = gtid; g < B; g += gsz) S.best[g] = 0ull;  // scratch: (samples << 32 | root) of the dominant set
     if (gtid == 0) flags[1 + ((round + 1) % 3)] = 0;  // slot of the next round (last used in round - 2)
     grid_barrier(bar, epoch);
     for (int v = gtid; v < NT; v += gsz) {
       const int lv = label[v];
       if (lv < 0) continue;
+      const int e0 = rp[v], e1 = min(rp[v + 1], e0 + 2);
+      for (int e = e0; e < e1; ++e) {
+        const int u = cl[e];
+        if (label[u] == lv) guf_unite(par, u, v);
+      }
+    }
+    grid_barrier(bar, epoch);
+    for (int v = gtid; v < NT; v += gsz) {
+      if (label[v] < 0) continue;
+      const int r = guf_find(par, v);
+      par[v] = r;
+      if ((v & 15) == 0) {
+        const unsigned long long c = (unsigned long long)(atomicAdd(smp + r, 1) + 1);
+        atomicMax(reinterpret_cast<unsigned long long*>(S.best) + v / St, (c << 32) | (unsigned)r);
+      }
+    }
+    grid_barrier(bar, epoch);
+    for (int v = gtid; v < NT; v += gsz) {
+      const int lv = label[v];
+      if (lv < 0) continue;
+      const int dom = (int)(unsigned)(ld_volatile(reinterpret_cast<const int*>(S.best + v / St)));  // low word = root
+      if (par[v] == dom) continue;  // (compressed in the previous sweep; membership never ends)
       const int e1 = rp[v + 1];
       for (int e = rp[v]; e < e1; ++e) {
         const int u = cl[e];
-        if (u < v && label[u] == lv) guf_unite(par, u, v);
+        if (label[u] == lv) guf_unite(par, u, v);
       }
     }
     grid_barrier(bar, epoch);
@@ -149,13 +193,22 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
     ++round;
   }
 
+  if (gtid == 0) {
+    const unsigned long long t = now_ns();
+    flags[6] = (int)(t - t_ph);
+    t_ph = t;
+  }
   // ---- component sizes, alive degrees, per-graph counters -------------------------------------------------
   int* csz = S.comp_size;
+  for (int g = gtid; g < B; g += gsz) S.best[g] = 0ull;  // (scratch of the MCC rounds; the arg-max key starts from 0)
   for (int v = gtid; v < NT; v += gsz) csz[v] = 0;
   grid_barrier(bar, epoch);
   for (int v = gtid; v < NT; v += gsz) {
     const int lv = label[v];
-    if (lv >= 0) atomicAdd(csz + lv, 1);
+    {  // one atomic per distinct label of the warp (the giant component would otherwise serialise ~N atomics on one word)
+      const unsigned same = __match_any_sync(__activemask(), lv);
+      if (lv >= 0 && (int)(__ffs(same) - 1) == (tid & 31)) atomicAdd(csz + lv, __popc(same));
+    }
     const int g = v / St;
     if (!init && S.cur_action[g] < 0) continue;  // untouched graph: keep its counters
     for (int ll = 0; ll < L; ++ll) {
@@ -198,6 +251,10 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
     }
   }
 
+  if (gtid == 0) {
+    const unsigned long long t = now_ns();
+    flags[7] = (round << 24) | (int)min((t - t_ph) / 1000ull, (unsigned long long)0xffffff);
+  }
   // ---- compaction of the active nodes + alive CSR: per-chunk counts / degree sums, then ordered write ---------
   // chunk c covers nodes [g*St + k*chunk, g*St + min((k+1)*chunk, St)) with g = c / cpg, k = c % cpg
   int* ccount = par;  // parents are dead now; (1 + L) * B * cpg entries: [0] active count, [1 + l] alive-degree sum

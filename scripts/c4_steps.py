@@ -59,6 +59,9 @@ for step in range(args.steps + 3):
     torch.cuda.synchronize()
     if args.profile_steps and step == 2 + args.profile_steps:
         torch.cuda.profiler.stop()
+    if step == 5:
+        f6, f7 = int(ro.flags[6]), int(ro.flags[7])
+        print("env_step_large: %d MCC rounds %.1f us, component sizes + alive degrees %d us" % (f7 >> 24, f6 / 1e3, f7 & 0xffffff), flush=True)
     if step >= 3:
         rows.append([e[i].elapsed_time(e[i + 1]) for i in range(4)] + [n, int(nnz.sum()), int(ro.rank[0])])
     if int(ro.done[0]):
