@@ -10,6 +10,7 @@
 //     the next tile is already running.  With the FP32-FMA consumers gone the gather no longer shares issue slots with
 //     a GEMM (measured on the FMA kernel: gather alone 298 us, GEMM alone 269 us, together 417 us per launch at C2).
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "md_common.cuh"
 #include "md_umma.cuh"
 
@@ -18,7 +19,7 @@ using namespace umma;
 
 constexpr int IT_GATH = 512;  // 16 gather warps
 constexpr int NGW = IT_GATH / 32;
-constexpr int TC_T = IT_GATH + 32 + 128;  // + MMA warp (16) + 4 epilogue warps (17..20)
+constexpr int TC_T = IT_GATH + 32 + 256;  // + MMA warp (16) + 8 epilogue warps (17..24): two per TMEM lane quadrant
 constexpr int LONG = 16;      // rows with more alive neighbours are handled cooperatively
 constexpr int WSTG = 8 * LONG;
 constexpr int MAXLONG = TILE_M;
@@ -76,7 +77,7 @@ struct TileIterTc {  // the tile sequence all roles walk in lock step
 // PRE: the neighbour sums were computed by md_agg (agg_rows_kernel) into the rows of the output buffer; the gather warps only
 // stream P and H rows in (contiguous 256-byte rows, all loads of a tile in flight before the operand tiles are touched).
 template <bool PRE>
-__global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K, int iter) {
+__global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K, int iter, int dbg) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   IterTcSmem& sm = *reinterpret_cast<IterTcSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -91,8 +92,8 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
     mbar_init(&sm.a_empty, 1);
     mbar_init(&sm.d_full[0], 1);
     mbar_init(&sm.d_full[1], 1);
-    mbar_init(&sm.d_empty[0], 4);
-    mbar_init(&sm.d_empty[1], 4);
+    mbar_init(&sm.d_empty[0], 8);
+    mbar_init(&sm.d_empty[1], 8);
     mbar_fence_init();
   }
   if (warp == NGW) tmem_alloc(&sm.tmem, 128);
@@ -160,7 +161,17 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
     auto prefetch = [&](const TileIterTc& tt, int par) {
       const int rows = min(TILE_M, tt.nact - tt.t * TILE_M);
       if constexpr (PRE) {
-        if (lane < 8) sm.wv[par][warp][lane] = (r0 + lane < rows) ? S.act_list[tt.g * G.stride + tt.t * TILE_M + r0 + lane] : -1;
+        const int v = (lane < 8 && r0 + lane < rows) ? S.act_list[tt.g * G.stride + tt.t * TILE_M + r0 + lane] : -1;
+        if (lane < 8) sm.wv[par][warp][lane] = v;
+        // start the DRAM -> L2 fetch of the next tile's P and H rows now (one 128-byte line per lane: 8 rows x 2 operands x
+        // 2 lines); the demand loads follow one tile period later and find the lines in L2
+        if (!(dbg & 2048)) {
+          const int vv = __shfl_sync(0xffffffffu, v, lane >> 2);
+          if (vv >= 0) {
+            const float* base = (lane & 2) ? K.h[iter & 1][tt.l] : K.h[(iter + 1) & 1][tt.l];
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)vv * D + 32 * (lane & 1)));
+          }
+        }
         return;
       }
       const int32_t* __restrict__ aptr = S.aptr[tt.l] + tt.g * G.stride + tt.t * TILE_M;
@@ -202,8 +213,10 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
       // advance to the next tile and prefetch its descriptors (other parity) before touching this tile's rows
       ti.tile += gridDim.x;
       have = ti.next();
-      if (have) prefetch(ti, buf ^ 1);
-      __syncwarp();
+      if constexpr (!PRE) {
+        if (have) prefetch(ti, buf ^ 1);
+        __syncwarp();
+      }
 
       const int l = cur.l, g = cur.g, t = cur.t;
       const int rows = min(TILE_M, cur.nact - t * TILE_M);
@@ -221,9 +234,10 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
           own[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (vr[i] >= 0) {
             pv[i] = __ldcg(P4 + (size_t)vr[i] * (D / 4) + l16);  // other rows of this buffer are being overwritten: no .nc
-            own[i] = __ldg(H4 + (size_t)vr[i] * (D / 4) + l16);
+            own[i] = __ldcg(H4 + (size_t)vr[i] * (D / 4) + l16);  // .cg: with 216 KB of shared memory the L1 is ~30 KB
           }
         }
+        if (have) prefetch(ti, buf ^ 1);  // node ids of the next tile: behind the row loads, off the critical path
         if (it >= 2) mbar_wait(&sm.d_empty[buf], ((it >> 1) - 1) & 1);  // epilogue of tile it-2 is done with v[buf]
         if (it >= 1) mbar_wait(&sm.a_empty, (it - 1) & 1);              // MMAs of the previous tile have read the operand tiles
         if (lane < 8) sm.v[buf][r0 + lane] = sm.wv[buf][warp][lane];
@@ -449,48 +463,52 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
       __syncwarp();
     }
   } else {
-    // ===================================== EPILOGUE: one thread per row =====================================
-    const int q = warp - NGW - 1;  // TMEM lane quadrant (warps 17..20 -> 1, 2, 3, 0 ... use warp % 4)
-    const int quad = warp & 3;
-    (void)q;
+    // ===================================== EPILOGUE: one thread per row and column half =====================
+    // Two warps share a TMEM lane quadrant (warp % 4): both read all 64 accumulators of their row for the norm, each
+    // writes 32 of the 64 outputs.  (With one warp per quadrant the 16 scattered 16-byte stores per thread made the
+    // epilogue the longest stage of the PRE pipeline.)
+    const int quad = warp & 3, chalf = (warp - NGW - 1) >> 2;
     const int row = 32 * quad + lane;
-    uint32_t it = 0;
-    for (; ti.next(); ti.tile += gridDim.x, ++it) {
-      const uint32_t stage = it & 1;
-      float* __restrict__ Hout = K.h[(iter + 1) & 1][ti.l];
-      mbar_wait(&sm.d_full[stage], (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tbase + ((uint32_t)(32 * quad) << 16) + 64 * stage;
-      const int v = sm.v[stage][row];
-      float ss = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += 16) {
-        float x[16];
-        tmem_ld16(taddr + c0, x);
-        tmem_ld_wait();
+    auto epilogue = [&](auto ch_tag) {
+      constexpr int CH = decltype(ch_tag)::value;  // column half, compile-time so that `keep` stays in registers
+      uint32_t it = 0;
+      for (; ti.next(); ti.tile += gridDim.x, ++it) {
+        const uint32_t stage = it & 1;
+        float* __restrict__ Hout = K.h[(iter + 1) & 1][ti.l];
+        mbar_wait(&sm.d_full[stage], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tbase + ((uint32_t)(32 * quad) << 16) + 64 * stage;
+        const int v = sm.v[stage][row];
+        float ss = 0.f;
+        float keep[2][16];  // this warp's 32 columns, kept from the norm pass
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float r = fmaxf(x[j], 0.f);
-          ss = fmaf(r, r, ss);
-        }
-      }
-      const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
-#pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += 16) {
-        float x[16];
-        tmem_ld16(taddr + c0, x);
-        tmem_ld_wait();
-        if (v >= 0) {
+        for (int c0 = 0; c0 < D; c0 += 16) {
+          float x[16];
+          tmem_ld16(taddr + c0, x);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(Hout + (size_t)v * D + c0 + j) =
-                make_float4(fmaxf(x[j], 0.f) * inv, fmaxf(x[j + 1], 0.f) * inv, fmaxf(x[j + 2], 0.f) * inv, fmaxf(x[j + 3], 0.f) * inv);
+          for (int j = 0; j < 16; ++j) {
+            const float r = fmaxf(x[j], 0.f);
+            ss = fmaf(r, r, ss);
+            if ((c0 >> 5) == CH) keep[(c0 >> 4) & 1][j] = r;
+          }
         }
+        const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
+        if (v >= 0 && !(dbg & 1024)) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(Hout + (size_t)v * D + 32 * CH + 16 * h + j) =
+                  make_float4(keep[h][j] * inv, keep[h][j + 1] * inv, keep[h][j + 2] * inv, keep[h][j + 3] * inv);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.d_empty[stage]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.d_empty[stage]);
-    }
+    };
+    if (chalf == 0) epilogue(std::integral_constant<int, 0>{});
+    else epilogue(std::integral_constant<int, 1>{});
   }
   (void)n_tiles_done;
   tc_fence_before();
@@ -538,9 +556,9 @@ int md_embed_iter_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_
   if (pre) {
     const int rc = md_agg_rows_launch(g, s, k, iter, st);
     if (rc) return rc;
-    md::embed_iter_tc_kernel<true><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter);
+    md::embed_iter_tc_kernel<true><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter, f);
   } else {
-    md::embed_iter_tc_kernel<false><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter);
+    md::embed_iter_tc_kernel<false><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter, f);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;

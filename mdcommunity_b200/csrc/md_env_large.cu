@@ -154,12 +154,17 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
     }
     grid_barrier(bar, epoch);
     for (int v = gtid; v < NT; v += gsz) {
-      if (label[v] < 0) continue;
-      const int r = guf_find(par, v);
-      par[v] = r;
-      if ((v & 15) == 0) {
-        const unsigned long long c = (unsigned long long)(atomicAdd(smp + r, 1) + 1);
-        atomicMax(reinterpret_cast<unsigned long long*>(S.best) + v / St, (c << 32) | (unsigned)r);
+      int r = -1;
+      if (label[v] >= 0) {
+        r = guf_find(par, v);
+        par[v] = r;
+      }
+      if (((v >> 5) & 15) == 0) {  // every 16th warp samples; one atomic per distinct root of the warp
+        const unsigned same = __match_any_sync(0xffffffffu, r);
+        if (r >= 0 && (int)(__ffs(same) - 1) == (tid & 31)) {
+          const unsigned long long c = (unsigned long long)(atomicAdd(smp + r, __popc(same)) + __popc(same));
+          atomicMax(reinterpret_cast<unsigned long long*>(S.best) + v / St, (c << 32) | (unsigned)r);
+        }
       }
     }
     grid_barrier(bar, epoch);
