@@ -317,6 +317,110 @@ __global__ void __launch_bounds__(RG_T, 1) agg_ring_kernel(md_graphs_t G, md_sta
   cp_async_wait<0>();
 }
 
+
+// ---- iteration 0, unit cost: no embedding gather at all ------------------------------------------------------------------
+// The first embedding of a node is a function of its alive degree only: relu([d/dmax, d/dmax] @ w_n2l), normalised
+// (MultiDismantler_net_graphsage.py:248-287 with the unit-cost features of PrepareBatchGraph.py).  So the first neighbour
+// sum needs no 256-byte row per neighbour: a table of the <= DG_CAP + 1 distinct rows of the (layer, graph) lives in shared
+// memory (built with exactly embed_init_kernel's arithmetic) and the gather reads 4 bytes (the neighbour's alive degree,
+// L2-resident) per entry.  The rows are still added one by one in CSR order.  md_embed_init is skipped altogether on this
+// path; the transform kernel forms its own-row operand from the degrees as well (md_embed_iter_tc.cu).
+constexpr int DG_T = 512;
+constexpr int DG_W = DG_T / 32;
+constexpr int DG_CAP = 63;
+constexpr int DG_IDS = 352;
+
+__device__ __forceinline__ float2 h0_pair(float x0, float w0a, float w0b, float w1a, float w1b) {  // embed_init_kernel's row
+  const float a = fmaxf(fmaf(x0, w1a, x0 * w0a), 0.f);
+  const float b = fmaxf(fmaf(x0, w1b, x0 * w0b), 0.f);
+  const float den = fmaxf(sqrtf(warp_sum(a * a + b * b)), 1e-12f);
+  return make_float2(a / den, b / den);
+}
+
+__global__ void __launch_bounds__(DG_T, 2) agg_deg_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K) {
+  __shared__ float2 tab[DG_CAP + 1][32];
+  __shared__ int du[DG_W][DG_IDS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int B = G.n_graphs, St = G.stride;
+  const int l = blockIdx.y / B, g = blockIdx.y - l * B;
+  const int n = S.n_act[g];
+  if (n <= 0) return;
+  const float w0a = W.w_n2l[2 * lane], w0b = W.w_n2l[2 * lane + 1];
+  const float w1a = W.w_n2l[D + 2 * lane], w1b = W.w_n2l[D + 2 * lane + 1];
+  const float dmax = (float)S.max_deg[l * B + g];
+  for (int d = warp; d <= DG_CAP; d += DG_W) tab[d][lane] = h0_pair((float)d / dmax, w0a, w0b, w1a, w1b);
+  __syncthreads();
+  const int32_t* __restrict__ deg = S.deg[l];
+  const int32_t* __restrict__ acol_l = S.acol[l];
+  float2* __restrict__ Pout = reinterpret_cast<float2*>(K.h[1][l]) + lane;  // iteration 0 writes buffer 1
+  const int n_chunks = (n + 31) / 32;
+  for (int c = blockIdx.x * DG_W + warp; c < n_chunks; c += gridDim.x * DG_W) {
+    const int p0 = 32 * c, rows = min(32, n - p0);
+    const int32_t* __restrict__ aptr = S.aptr[l] + (size_t)g * St + p0;
+    const int ap = aptr[min(lane, rows)], ap_hi = aptr[min(lane + 1, rows)];
+    const int v = lane < rows ? S.act_list[(size_t)g * St + p0 + lane] : -1;
+    const int e_begin = __shfl_sync(0xffffffffu, ap, 0);
+    const int total = __shfl_sync(0xffffffffu, ap_hi, 31) - e_begin;
+    const int32_t* __restrict__ acol = acol_l + e_begin;
+    bool simple = total <= DG_IDS;
+    for (int k = lane; k < min(total, DG_IDS); k += 32) {
+      const int d = deg[acol[k]];
+      du[warp][k] = d;
+      simple &= d <= DG_CAP;
+    }
+    simple = __all_sync(0xffffffffu, simple);
+    __syncwarp();
+    if (simple) {
+      // A quarter-warp per destination row (8 lanes x 32 bytes), two rows per quarter at a time: per table row added the
+      // warp issues 1.75 instructions instead of 8 (a whole warp per 256-byte row was issue-bound: 0.76 ms per launch).
+      const int q = lane >> 3, j8 = lane & 7;
+      const float4* tab4 = reinterpret_cast<const float4*>(&tab[0][0]) + 2 * j8;  // row d: tab4[16 * d], tab4[16 * d + 1]
+      float4* __restrict__ Pout4 = reinterpret_cast<float4*>(K.h[1][l]) + 2 * j8;
+      for (int pass = 0; pass < 4 && 8 * pass < rows; ++pass) {
+        const int rA = 8 * pass + q, rB = rA + 4;
+        const int e0A = __shfl_sync(0xffffffffu, ap, rA) - e_begin, e0B = __shfl_sync(0xffffffffu, ap, rB) - e_begin;
+        const int e1A = __shfl_sync(0xffffffffu, ap_hi, rA) - e_begin, e1B = __shfl_sync(0xffffffffu, ap_hi, rB) - e_begin;
+        const int lenA = rA < rows ? e1A - e0A : 0, lenB = rB < rows ? e1B - e0B : 0;  // (shuffles stay outside the selects)
+        const int vA = __shfl_sync(0xffffffffu, v, rA), vB = __shfl_sync(0xffffffffu, v, rB);
+        int maxlen = max(lenA, lenB);
+        maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 8));
+        maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 16));
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        for (int i = 0; i < maxlen; ++i) {
+          if (i < lenA) {
+            const float4* t = tab4 + 16 * du[warp][e0A + i];
+            const float4 x0 = t[0], x1 = t[1];
+            a0.x += x0.x, a0.y += x0.y, a0.z += x0.z, a0.w += x0.w;
+            a1.x += x1.x, a1.y += x1.y, a1.z += x1.z, a1.w += x1.w;
+          }
+          if (i < lenB) {
+            const float4* t = tab4 + 16 * du[warp][e0B + i];
+            const float4 x0 = t[0], x1 = t[1];
+            b0.x += x0.x, b0.y += x0.y, b0.z += x0.z, b0.w += x0.w;
+            b1.x += x1.x, b1.y += x1.y, b1.z += x1.z, b1.w += x1.w;
+          }
+        }
+        if (rA < rows) Pout4[(size_t)vA * (D / 4)] = a0, Pout4[(size_t)vA * (D / 4) + 1] = a1;
+        if (rB < rows) Pout4[(size_t)vB * (D / 4)] = b0, Pout4[(size_t)vB * (D / 4) + 1] = b1;
+      }
+    } else {  // hub rows beyond the staging area or degrees beyond the table
+      for (int r = 0; r < rows; ++r) {
+        const int e0 = __shfl_sync(0xffffffffu, ap, r) - e_begin, e1 = __shfl_sync(0xffffffffu, ap_hi, r) - e_begin;
+        const int vv = __shfl_sync(0xffffffffu, v, r);
+        float2 acc = make_float2(0.f, 0.f);
+        for (int e = e0; e < e1; ++e) {
+          const int d = e < DG_IDS ? du[warp][e] : deg[acol[e]];  // (warp-uniform)
+          const float2 x = d <= DG_CAP ? tab[d][lane] : h0_pair((float)d / dmax, w0a, w0b, w1a, w1b);
+          acc.x += x.x;
+          acc.y += x.y;
+        }
+        Pout[(size_t)vv * (D / 2)] = acc;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace md
 
 extern int g_md_debug_flags;
@@ -347,6 +451,25 @@ int md_agg_rows_launch(const md_graphs_t* g, const md_state_t* s, const md_work_
     const int grid = (int)(want < nsm ? want : nsm);
     md::agg_ring_kernel<<<grid, md::RG_T, smem, st>>>(*g, *s, *k, iter);
   }
+  MD_CHECK_LAUNCH();
+  return 0;
+}
+
+// iteration 0 of the unit-cost variant on the two-kernel path (see agg_deg_kernel)
+int md_agg_deg_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, cudaStream_t st) {
+  static int nsm = 0;
+  if (nsm <= 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm <= 0) nsm = 148;
+  }
+  const int units = g->n_graphs * g->n_layers;
+  int per = 2 * nsm / units;  // CTAs per (layer, graph): one wave of two CTAs per SM
+  const int max_per = (g->stride / 32 + md::DG_W - 1) / md::DG_W;
+  if (per > max_per) per = max_per;
+  if (per < 1) per = 1;
+  md::agg_deg_kernel<<<dim3(per, units), md::DG_T, 0, st>>>(*g, *s, *w, *k);
   MD_CHECK_LAUNCH();
   return 0;
 }

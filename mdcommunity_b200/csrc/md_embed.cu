@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(MD_MAX_LAYERS* D) graph_embed_kernel(md_graphs
 // =================================================================================================
 // host entry points
 // =================================================================================================
+bool md_h0_on_the_fly(const md_graphs_t* g);
+
 static int check_common(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k) {
   if (!g || !s || !w || !k) return MD_EINVAL;
   if (g->n_layers < 1 || g->n_layers > MD_MAX_LAYERS) return MD_ELAYERS;
@@ -219,6 +221,7 @@ extern "C" int md_embed_init(const md_graphs_t* g, const md_state_t* s, const md
                              md_stream_t stream) {
   int rc = check_common(g, s, w, k);
   if (rc) return rc;
+  if (md_h0_on_the_fly(g)) return 0;  // large unit-cost graphs: iteration 0 works from the alive degrees (md_agg.cu)
   dim3 grid(g->n_graphs * (g->stride / MD_TILE_M), g->n_layers);
   md::embed_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*g, *s, *w, *k);
   MD_CHECK_LAUNCH();

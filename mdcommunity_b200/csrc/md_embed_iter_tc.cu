@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
         // 2 lines); the demand loads follow one tile period later and find the lines in L2
         if (!(dbg & 2048)) {
           const int vv = __shfl_sync(0xffffffffu, v, lane >> 2);
-          if (vv >= 0) {
+          if (vv >= 0 && !((lane & 2) && (dbg & (1 << 20)))) {  // (no H rows to fetch when they come from the degrees)
             const float* base = (lane & 2) ? K.h[iter & 1][tt.l] : K.h[(iter + 1) & 1][tt.l];
             asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)vv * D + 32 * (lane & 1)));
           }
@@ -227,14 +227,38 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
         const float4* __restrict__ P4 = reinterpret_cast<const float4*>(K.h[(iter + 1) & 1][l]);
         float4 pv[4], own[4];
         int vr[4];
+        const bool h0_from_deg = (dbg & (1 << 20)) != 0;  // iteration 0, unit cost: H0 was never written (see md_agg.cu)
+        int dg[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {  // all 8 row loads of this lane are in flight before anything is waited for
           vr[i] = sm.wv[buf][warp][2 * i + half];
           pv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           own[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          dg[i] = 0;
           if (vr[i] >= 0) {
             pv[i] = __ldcg(P4 + (size_t)vr[i] * (D / 4) + l16);  // other rows of this buffer are being overwritten: no .nc
-            own[i] = __ldcg(H4 + (size_t)vr[i] * (D / 4) + l16);  // .cg: with 216 KB of shared memory the L1 is ~30 KB
+            if (h0_from_deg) dg[i] = S.deg[l][vr[i]];
+            else own[i] = __ldcg(H4 + (size_t)vr[i] * (D / 4) + l16);  // .cg: with 216 KB of shared memory the L1 is ~30 KB
+          }
+        }
+        if (h0_from_deg) {  // relu([x, x] @ w_n2l) normalised, x = alive degree / max alive degree (embed_init_kernel's formula)
+          const float dmax = (float)S.max_deg[l * G.n_graphs + g];
+          const float4 w0 = *reinterpret_cast<const float4*>(W.w_n2l + 4 * l16), w1 = *reinterpret_cast<const float4*>(W.w_n2l + D + 4 * l16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x0 = (float)dg[i] / dmax;  // one IEEE division + one reciprocal per row: 20 divisions per lane and
+            float4 a;                              // tile doubled this kernel's time (they compete with the loaders' issue slots)
+            a.x = fmaxf(fmaf(x0, w1.x, x0 * w0.x), 0.f);
+            a.y = fmaxf(fmaf(x0, w1.y, x0 * w0.y), 0.f);
+            a.z = fmaxf(fmaf(x0, w1.z, x0 * w0.z), 0.f);
+            a.w = fmaxf(fmaf(x0, w1.w, x0 * w0.w), 0.f);
+            float ss = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+            const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
+            own[i] = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
           }
         }
         if (have) prefetch(ti, buf ^ 1);  // node ids of the next tile: behind the row loads, off the critical path
@@ -528,14 +552,24 @@ extern int g_md_debug_flags;
 //    vs 417 us per launch, C4 9.2 vs 9.0 ms per step): with the gather inside, the iteration is bound by the 16 gather
 //    warps' row loads, which the FMA consumers overlapped for free; kept as the A/B reference of that finding.
 int md_agg_rows_launch(const md_graphs_t* g, const md_state_t* s, const md_work_t* k, int iter, cudaStream_t st);
+int md_agg_deg_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, cudaStream_t st);
+
+static bool tc_pre_path(const md_graphs_t* g) {
+  const int f = g_md_debug_flags;
+  if (f & (1 | 2)) return false;  // isolation runs of the FMA kernel
+  const bool beyond_l2 = (size_t)g->n_total * g->n_layers * (md::D * 4) > ((size_t)96 << 20);
+  return !(f & 128) && ((f & 256) || beyond_l2);
+}
+// true when the first embedding is never materialised: two-kernel path, unit cost (features = alive degree / max alive
+// degree), not switched off by md_debug_set_flags bit 12.  md_embed_init asks this to become a no-op.
+bool md_h0_on_the_fly(const md_graphs_t* g) { return tc_pre_path(g) && g->node_w[0] == nullptr && !(g_md_debug_flags & 4096); }
 
 int md_embed_iter_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, int iter,
                             cudaStream_t st, int* launched) {
   *launched = 0;
   const int f = g_md_debug_flags;
   if (f & (1 | 2)) return 0;  // isolation runs of the FMA kernel
-  const bool beyond_l2 = (size_t)g->n_total * g->n_layers * (md::D * 4) > ((size_t)96 << 20);
-  const bool pre = !(f & 128) && ((f & 256) || beyond_l2);
+  const bool pre = tc_pre_path(g);
   if (!pre && !(f & 16)) return 0;
   static bool configured = false;
   static int nsm = 0;
@@ -554,9 +588,10 @@ int md_embed_iter_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_
   const int n_tiles = g->n_graphs * (g->stride / MD_TILE_M) * g->n_layers;
   const int grid = nsm < n_tiles ? nsm : n_tiles;
   if (pre) {
-    const int rc = md_agg_rows_launch(g, s, k, iter, st);
+    const bool h0 = iter == 0 && md_h0_on_the_fly(g);
+    const int rc = h0 ? md_agg_deg_launch(g, s, w, k, st) : md_agg_rows_launch(g, s, k, iter, st);
     if (rc) return rc;
-    md::embed_iter_tc_kernel<true><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter, f);
+    md::embed_iter_tc_kernel<true><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter, (f & 0xfffff) | (h0 ? (1 << 20) : 0));
   } else {
     md::embed_iter_tc_kernel<false><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter, f);
   }
