@@ -224,6 +224,61 @@ def roofline_pass(mdb, batch, w):
             "algorithmic_bytes_model": model + ", n=active nodes, nnz=alive directed edges"}
 
 
+def c4_leg(dev, steps=20):
+    """Second part of BASELINE.json's metric: removal steps/sec on one 3-layer graph of N = 1M (config C4), timed with CUDA
+    events per stage; aggregation = the 9 layer-iterations against SURVEY 8(d)'s no-reuse byte model (H_l = 256 MB > L2)."""
+    import ctypes as C
+    import mdcommunity_b200 as mdb
+    from mdcommunity_b200 import _lib, gmm
+    N, L, E, D = 1_000_000, 3, 4_000_000, 64
+    t0 = time.time()
+    g = mdb.Graph_test(*gmm.random_sparse_layers(N, L, E, seed=0), num_nodes=N, cost="unit")
+    batch = mdb.GraphBatch([g], dev, "unit")
+    w = mdb.QWeights(load_state_dict("unit"), dev)
+    ro = mdb.BatchRollout(batch, w, max_steps=steps + 16)
+    torch.cuda.synchronize()
+    setup_s = time.time() - t0
+    lib = ro.lib
+    gp, sp, wp, kp, st = ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()
+    rows = []
+    for step in range(steps + 3):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        n_act, nnz = int(ro.n_act[0]), int(2 * ro.alive_edges[:, 0].sum())
+        e[0].record()
+        _lib.check(lib.md_embed_init(gp, sp, wp, kp, st), "init")
+        e[1].record()
+        for it in range(3):
+            _lib.check(lib.md_embed_iter(gp, sp, wp, kp, it, st), "iter")
+        e[2].record()
+        _lib.check(lib.md_graph_embed(gp, sp, wp, kp, st), "gembed")
+        _lib.check(lib.md_qhead(gp, sp, wp, kp, st), "qhead")
+        e[3].record()
+        ro.step()
+        e[4].record()
+        torch.cuda.synchronize()
+        if step >= 3:
+            rows.append([e[i].elapsed_time(e[i + 1]) for i in range(4)] + [n_act, nnz])
+        if int(ro.done[0]):
+            break
+    r = np.array(rows, dtype=np.float64)
+    med = np.median(r[:, :4], 0)
+    step_ms = float(np.median(r[:, :4].sum(1)))
+    n_act, nnz = r[0, 4], r[0, 5]
+    agg_bytes = 3 * (L * 4 * (n_act + 1) + 4 * nnz + 4 * D * nnz + L * 4 * D * n_act)
+    peak, src = measured_peak()
+    return {"workload": "C4: one synthetic 3-layer multiplex, N=1000000, 4000000 undirected edges per layer, unit cost, %d greedy steps "
+                        "from the intact graph (score all nodes + arg-max + removal + LMCC recompute per step)" % len(r),
+            "removal_steps_per_s": 1e3 / step_ms, "ms_per_step": step_ms,
+            "median_ms": {"embed_init": med[0], "aggregation_9_layer_iterations": med[1], "graph_embed+qhead": med[2],
+                          "env_step_lmcc": med[3]},
+            "aggregation_roofline": {"bound": "hbm", "achieved": agg_bytes / (med[1] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": agg_bytes / (med[1] * 1e-3) / 1e9 / peak, "peak_source": src,
+                                     "algorithmic_bytes_model": "9 x (4(n+1) + 4 nnz + 256 nnz + 256 n): SURVEY 8(d) no-reuse model; "
+                                                                "iteration 0 reads alive degrees instead of rows (see DESIGN 6.13)"},
+            "timing": "CUDA events per stage, median over the steps, 3 warm-up steps", "setup_s": setup_s,
+            "lmcc_rank_after": int(ro.rank[0])}
+
+
 def run_ours(args, cost, n, per_gpu, desc):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -335,6 +390,12 @@ def run_ours(args, cost, n, per_gpu, desc):
             line["cpu_baseline"] = {"value": k / dt, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "host_cores": cores, "steps_per_s": st / dt,
                                     "sample": "first %d graphs of the GPU batch, oracle/md_oracle.py rollout, 1 process" % k}
+        if world == 1 and args.workload == "c2" and not args.no_c4:
+            torch.cuda.empty_cache()
+            try:
+                line["c4"] = c4_leg(dev)
+            except Exception as exc:  # the headline line must survive a failure of the secondary leg
+                line["c4"] = {"error": repr(exc)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -350,6 +411,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--graphs-per-gpu", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the N = 1M removal-steps/s leg (about 30 s)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

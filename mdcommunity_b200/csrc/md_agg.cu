@@ -374,8 +374,10 @@ __global__ void __launch_bounds__(DG_T, 2) agg_deg_kernel(md_graphs_t G, md_stat
       // A quarter-warp per destination row (8 lanes x 32 bytes), two rows per quarter at a time: per table row added the
       // warp issues 1.75 instructions instead of 8 (a whole warp per 256-byte row was issue-bound: 0.76 ms per launch).
       const int q = lane >> 3, j8 = lane & 7;
-      const float4* tab4 = reinterpret_cast<const float4*>(&tab[0][0]) + 2 * j8;  // row d: tab4[16 * d], tab4[16 * d + 1]
-      float4* __restrict__ Pout4 = reinterpret_cast<float4*>(K.h[1][l]) + 2 * j8;
+      // lane j8 owns columns [4 j8, 4 j8 + 4) and [32 + 4 j8, 36 + 4 j8): every 8-lane phase of an LDS.128 / STG.128 then
+      // covers 128 contiguous bytes (no bank conflicts, full sectors)
+      const float4* tab4 = reinterpret_cast<const float4*>(&tab[0][0]) + j8;  // row d: tab4[16 * d], tab4[16 * d + 8]
+      float4* __restrict__ Pout4 = reinterpret_cast<float4*>(K.h[1][l]) + j8;
       for (int pass = 0; pass < 4 && 8 * pass < rows; ++pass) {
         const int rA = 8 * pass + q, rB = rA + 4;
         const int e0A = __shfl_sync(0xffffffffu, ap, rA) - e_begin, e0B = __shfl_sync(0xffffffffu, ap, rB) - e_begin;
@@ -389,19 +391,19 @@ __global__ void __launch_bounds__(DG_T, 2) agg_deg_kernel(md_graphs_t G, md_stat
         for (int i = 0; i < maxlen; ++i) {
           if (i < lenA) {
             const float4* t = tab4 + 16 * du[warp][e0A + i];
-            const float4 x0 = t[0], x1 = t[1];
+            const float4 x0 = t[0], x1 = t[8];
             a0.x += x0.x, a0.y += x0.y, a0.z += x0.z, a0.w += x0.w;
             a1.x += x1.x, a1.y += x1.y, a1.z += x1.z, a1.w += x1.w;
           }
           if (i < lenB) {
             const float4* t = tab4 + 16 * du[warp][e0B + i];
-            const float4 x0 = t[0], x1 = t[1];
+            const float4 x0 = t[0], x1 = t[8];
             b0.x += x0.x, b0.y += x0.y, b0.z += x0.z, b0.w += x0.w;
             b1.x += x1.x, b1.y += x1.y, b1.z += x1.z, b1.w += x1.w;
           }
         }
-        if (rA < rows) Pout4[(size_t)vA * (D / 4)] = a0, Pout4[(size_t)vA * (D / 4) + 1] = a1;
-        if (rB < rows) Pout4[(size_t)vB * (D / 4)] = b0, Pout4[(size_t)vB * (D / 4) + 1] = b1;
+        if (rA < rows) Pout4[(size_t)vA * (D / 4)] = a0, Pout4[(size_t)vA * (D / 4) + 8] = a1;
+        if (rB < rows) Pout4[(size_t)vB * (D / 4)] = b0, Pout4[(size_t)vB * (D / 4) + 8] = b1;
       }
     } else {  // hub rows beyond the staging area or degrees beyond the table
       for (int r = 0; r < rows; ++r) {

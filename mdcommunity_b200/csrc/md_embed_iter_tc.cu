@@ -46,6 +46,8 @@ struct IterTcSmem {
   int nlong, nxtra;
   uint64_t a_full, a_empty, d_full[2], d_empty[2];
   uint32_t tmem;
+  float h0_x[64], h0_inv[64];  // PRE, iteration 0 from the degrees: x = d / dmax and 1 / |relu([x, x] @ w_n2l)| per alive degree d
+  int h0_key;                  // (layer, graph, dmax) the two tables were built for
 };
 static_assert(sizeof(IterTcSmem) <= 232448, "IterTcSmem exceeds the shared memory of one CTA");
 
@@ -88,6 +90,7 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
     for (int i = tid; i < G.n_graphs; i += TC_T) sm.nact[i] = S.n_act[i];
   if (tid == 0) {
     sm.nlong = 0, sm.nxtra = 0;
+    sm.h0_key = -1;
     mbar_init(&sm.a_full, NGW);
     mbar_init(&sm.a_empty, 1);
     mbar_init(&sm.d_full[0], 1);
@@ -242,22 +245,51 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
           }
         }
         if (h0_from_deg) {  // relu([x, x] @ w_n2l) normalised, x = alive degree / max alive degree (embed_init_kernel's formula)
-          const float dmax = (float)S.max_deg[l * G.n_graphs + g];
+          // x and the reciprocal norm depend on the degree only: tables per (layer, graph), rebuilt by the 16 loader warps
+          // with embed_init_kernel's warp-per-row arithmetic when the tile sequence moves on to another layer / graph
+          // (computing them per row in every lane -- 4 divisions, square roots and reciprocals per lane and tile --
+          // made this launch 0.2 ms slower than the ones that load H).
+          const int dmax_i = S.max_deg[l * G.n_graphs + g];
+          const int key = (l * G.n_graphs + g) * 1024 + min(dmax_i, 1023);
+          if (sm.h0_key != key) {  // (uniform over the loader warps: they walk the same tiles)
+            bar_sync(BAR_GATH, IT_GATH);
+            const float w0a = W.w_n2l[2 * lane], w0b = W.w_n2l[2 * lane + 1];
+            const float w1a = W.w_n2l[D + 2 * lane], w1b = W.w_n2l[D + 2 * lane + 1];
+            for (int d = warp; d < 64; d += NGW) {
+              const float x0 = (float)d / (float)dmax_i;
+              const float a = fmaxf(fmaf(x0, w1a, x0 * w0a), 0.f), b = fmaxf(fmaf(x0, w1b, x0 * w0b), 0.f);
+              float ss = a * a + b * b;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+              if (lane == 0) sm.h0_x[d] = x0, sm.h0_inv[d] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+            }
+            if (tid == 0) sm.h0_key = key;
+            bar_sync(BAR_GATH, IT_GATH);
+          }
+          const float dmax = (float)dmax_i;
           const float4 w0 = *reinterpret_cast<const float4*>(W.w_n2l + 4 * l16), w1 = *reinterpret_cast<const float4*>(W.w_n2l + D + 4 * l16);
+          bool big = false;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) big |= dg[i] > 63;
+          big = __any_sync(0xffffffffu, big);  // hub rows beyond the tables: the whole warp takes the direct formula
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float x0 = (float)dg[i] / dmax;  // one IEEE division + one reciprocal per row: 20 divisions per lane and
-            float4 a;                              // tile doubled this kernel's time (they compete with the loaders' issue slots)
+            float x0, inv = 0.f;
+            if (!big) x0 = sm.h0_x[dg[i]], inv = sm.h0_inv[dg[i]];
+            else x0 = (float)dg[i] / dmax;
+            float4 a;
             a.x = fmaxf(fmaf(x0, w1.x, x0 * w0.x), 0.f);
             a.y = fmaxf(fmaf(x0, w1.y, x0 * w0.y), 0.f);
             a.z = fmaxf(fmaf(x0, w1.z, x0 * w0.z), 0.f);
             a.w = fmaxf(fmaf(x0, w1.w, x0 * w0.w), 0.f);
-            float ss = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
-            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-            ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-            ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-            const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
+            if (big) {
+              float ss = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+              inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+            }
             own[i] = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
           }
         }
