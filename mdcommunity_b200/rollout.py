@@ -265,3 +265,75 @@ class BatchRollout:
         S = self.batch.S
         ids = self.act_list[gi * S:gi * S + n].long()
         return (ids - gi * S).cpu().numpy(), self.q[ids].cpu().numpy()
+
+
+class MultiStreamRollout:
+    """The same lock-step rollout, with the batch cut into `parts` independent sub-batches that advance on their own CUDA
+    streams.  Graphs never interact, so this changes nothing in the results; what it buys is overlap: the env step of
+    a sub-batch waits for its slowest graph and the tail of every kernel leaves SMs idle -- the other
+    sub-batches' kernels fill them.  Sub-batch p holds graphs [p * ceil(B / parts), ...) in order."""
+
+    def __init__(self, graphs, weights, device=None, cost=None, parts=2, chunk=8):
+        graphs = list(graphs)
+        per = (len(graphs) + parts - 1) // parts
+        self.slices = [graphs[i:i + per] for i in range(0, len(graphs), per)]
+        self.batches = [GraphBatch(s, device, cost) for s in self.slices]
+        self.rollouts = [BatchRollout(b, weights) for b in self.batches]
+        self.device = self.batches[0].device
+        self.streams = [torch.cuda.Stream(self.device) for _ in self.rollouts]
+        self.events = [torch.cuda.Event() for _ in self.rollouts]
+        self.chunk = chunk
+        self._pins = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in self.rollouts]
+
+    @property
+    def kernel_launches(self):
+        return sum(r.kernel_launches for r in self.rollouts)
+
+    def _enqueue_chunk(self, ro, first):
+        """One chunk of lock-step iterations of sub-rollout `ro` on the current stream (CUDA-graph replay from its second run on)."""
+        lib, chunk = ro.lib, self.chunk
+        if ro._graph is None and ro._runs > 0 and not first and not ro.large and ro.use_graph:
+            ex = C.c_void_p()
+            _lib.check(lib.md_rollout_graph_create(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), chunk, ro._stream(), C.byref(ex)),
+                       "md_rollout_graph_create")
+            ro._graph, ro._graph_chunk, ro._graph_w = ex, chunk, ro.w
+        if ro._graph is not None and ro._graph_chunk == chunk and ro._graph_w is ro.w:
+            _lib.check(lib.md_rollout_graph_launch(ro._graph, ro._stream()), "md_rollout_graph_launch")
+        else:
+            _lib.check(lib.md_rollout_steps(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), chunk, ro._stream()), "md_rollout_steps")
+        ro.kernel_launches += chunk * (5 if ro.fused else 4 + _lib.BP_ITERS)
+
+    def run(self):
+        cur = torch.cuda.current_stream(self.device)
+        for ro, st in zip(self.rollouts, self.streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                ro.reset()
+        live = list(range(len(self.rollouts)))
+        it = 0
+        while live:
+            for i in live:
+                ro = self.rollouts[i]
+                with torch.cuda.stream(self.streams[i]):
+                    self._enqueue_chunk(ro, it == 0)
+                    self._pins[i].copy_(ro.n_done, non_blocking=True)
+                    self.events[i].record(self.streams[i])
+            nxt = []
+            for i in live:
+                self.events[i].synchronize()
+                if int(self._pins[i][0]) < self.rollouts[i].batch.B and it <= self.rollouts[i].max_steps + self.chunk:
+                    nxt.append(i)
+            live = nxt
+            it += self.chunk
+        for ro, st in zip(self.rollouts, self.streams):
+            ro._runs += 1
+            cur.wait_stream(st)
+        return self.results()
+
+    def results(self):
+        rs = [r.results() for r in self.rollouts]
+        T = max(r["actions"].shape[1] for r in rs)
+        pad = lambda a, fill: np.concatenate([a, np.full((a.shape[0], T - a.shape[1]), fill, a.dtype)], 1)
+        return dict(score=np.concatenate([r["score"] for r in rs]), n_steps=np.concatenate([r["n_steps"] for r in rs]),
+                    actions=np.concatenate([pad(r["actions"], -1) for r in rs]), ranks=np.concatenate([pad(r["ranks"], 0) for r in rs]),
+                    maxcc=np.concatenate([pad(r["maxcc"], 0) for r in rs]))

@@ -450,6 +450,45 @@ def test_two_kernel_iteration_matches_fma():
             lib.md_debug_set_flags(0)
 
 
+@pytest.mark.parametrize("cost", ["unit", "degree"])
+def test_two_kernel_iteration_dense_and_hub_graphs(cost):
+    """The large-graph aggregation kernels off their fast paths: dense graphs whose 32-row chunks exceed the staged
+    entries (md_agg ring: register-load fallback inside load_desc; agg_deg: unstaged rows) and a star whose hub has more
+    alive neighbours than the per-degree tables hold (> 63) -- against the FP32-FMA kernel, over a few greedy steps."""
+    from mdcommunity_b200 import _lib, gmm
+    mdb = _mdb()
+    graphs = [gmm.gmm_graph(900, 700 + i, cost=cost, kbar=(22.0, 18.0)) for i in range(2)]
+    n = 400
+    star = np.array([[0, i] for i in range(1, 200)] + [[i, i + 1] for i in range(1, n - 1)])
+    ring = np.array([[i, (i + 1) % n] for i in range(n)] + [[0, i] for i in range(2, 120)])
+    graphs.append(mdb.Graph_test(star, ring, num_nodes=n, cost=cost))
+    batch = mdb.GraphBatch(graphs, cost=cost)
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_%s.npz" % cost))), batch.device)
+    a = mdb.BatchRollout(batch, w, fused=False)
+    b = mdb.BatchRollout(batch, w, fused=False)
+    assert int(a.max_deg.max()) > 63 and max(batch.nnz) / (batch.B * 900 / 32) > 304
+    lib = _lib.lib()
+    S = batch.S
+    try:
+        for t in range(5):
+            lib.md_debug_set_flags(256)
+            a.forward()
+            lib.md_debug_set_flags(0)
+            b.forward()
+            for i in range(batch.B):
+                ids = a.act_list[i * S:i * S + int(a.n_act[i])].long()
+                for l in range(batch.L):
+                    assert float((a.h[1][l][ids] - b.h[1][l][ids]).abs().max()) <= 2e-5, (cost, i, t, l)
+                qa, qb = a.q[ids], b.q[ids]
+                assert float(((qa - qb).abs() - (Q_RTOL * qb.abs() + Q_ATOL)).max()) <= 0, (cost, i, t)
+            b.best.copy_(a.best)  # same action on both (sub-tolerance ties could differ)
+            a.step()
+            b.step()
+    finally:
+        lib.md_debug_set_flags(0)
+    assert torch.equal(a.label, b.label) and torch.equal(a.rank, b.rank)
+
+
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
 def test_edge_case_graphs(fused):
     """Ragged batch of degenerate inputs: a layer without edges (terminal at s0), a single mutual edge, isolated nodes,
