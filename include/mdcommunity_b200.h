@@ -150,7 +150,13 @@ void md_debug_force_large_env(int32_t on);
 /* profiling hook: bit 0 skips the neighbour gather, bit 1 the dense transform of md_embed_iter (results become wrong);
  * bit 2 makes md_rollout_steps use the unfused embedding kernels even where md_embed_fused applies;
  * bit 3 makes md_qhead use its FP32-FMA kernel instead of the tensor-core kernel;
- * bit 4 makes md_embed_iter use its tensor-core variant (measured no faster than the FP32-FMA kernel: gather bound) */
+ * bit 4 makes md_embed_iter use its single-kernel tensor-core variant (measured no faster than the FP32-FMA kernel);
+ * bit 6 switches off the L2 prefetch of the fused md_embed_iter (embeddings beyond L2);
+ * bit 7 disables / bit 8 forces the two-kernel md_embed_iter (md_agg neighbour sums + tensor-core transform; default
+ *   only when the embeddings exceed L2), bit 9 selects md_agg's register-load kernel instead of the cp.async ring,
+ *   bit 12 disables iteration 0 from the alive degrees (unit cost) so that md_embed_init writes H0 again;
+ * bits 10 / 11 (timing experiments, results become wrong / unchanged): transform kernel without its global stores /
+ *   without its L2 prefetch of the next tile */
 void md_debug_set_flags(int32_t flags);
 /* profiling hook: clock64 phase times of CTA 0 of the last md_env_step (labels in, CSR staged, prune rounds,
  * component sizes, alive CSR + degrees) and, at index 16, the number of prune rounds */
@@ -170,13 +176,17 @@ int md_debug_read_fused_gather(unsigned* host8);
 
 /* ---- Q network ---------------------------------------------------------------------------------------- */
 
-/* Node input features + first embedding (U/MultiDismantler_net_graphsage.py:248-287; D/MultiDismantler_net.py:222-240). */
+/* Node input features + first embedding (U/MultiDismantler_net_graphsage.py:248-287; D/MultiDismantler_net.py:222-240)
+ * into h[0].  A no-op for unit-cost batches whose embeddings exceed L2: there md_embed_iter(iter = 0) works from the
+ * alive degrees and never reads h[0] (call the two in sequence as md_rollout_steps does). */
 int md_embed_init(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                   md_stream_t stream);
 
 /* One message-passing iteration for all layers: neighbour sum over alive edges (torch_sparse.spmm n2n, :290-291),
  * dense transforms (:294-309), relu + L2 normalise (:309-310), and the per-graph sum of the OLD embeddings
- * (spmm subgsum, :297-298) as per-tile partials.  iter = 0..2; reads h[iter&1], writes h[(iter+1)&1]. */
+ * (spmm subgsum, :297-298) as per-tile partials.  iter = 0..2; reads h[iter&1], writes h[(iter+1)&1].
+ * Embeddings beyond L2 (N = 1M): two launches, md_agg's neighbour sums into h[(iter+1)&1] and a tensor-core transform
+ * that overwrites them in place.  md_graph_embed consumes the per-tile partials (call it once per forward). */
 int md_embed_iter(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                   int32_t iter, md_stream_t stream);
 
