@@ -155,6 +155,7 @@ void md_debug_force_large_env(int32_t on);
  * bit 7 disables / bit 8 forces the two-kernel md_embed_iter (md_agg neighbour sums + tensor-core transform; default
  *   only when the embeddings exceed L2), bit 9 selects md_agg's register-load kernel instead of the cp.async ring,
  *   bit 12 disables iteration 0 from the alive degrees (unit cost) so that md_embed_init writes H0 again;
+ * bit 13 keeps relu's argument e @ h1 of the two-layer tensor-core md_qhead on the FP32 pipes (A/B reference);
  * bits 10 / 11 (timing experiments, results become wrong / unchanged): transform kernel without its global stores /
  *   without its L2 prefetch of the next tile */
 void md_debug_set_flags(int32_t flags);

@@ -23,12 +23,16 @@ constexpr int QT_T = 352;         // 8 epilogue + 2 loader + 1 MMA warps
 constexpr int QT_EPI = 256;
 constexpr uint32_t QT_KB = 16384;  // one 128-row x 128-byte operand tile
 
-template <int L>
+// HTC: relu(e_p @ h1) on the tensor cores as well (two layers only: the extra operand tiles do not fit next to Ts[3])
+template <int L, bool HTC>
 struct QTSmem {
   unsigned char A[2][QT_KB];     // raw fp32 rows of ONE layer's H_l (the layers of a tile pass through in turn), two K blocks
   unsigned char ALO[QT_KB];      // fp16 remainders of the same rows, 64 columns per row
   unsigned char Bt[40960];       // trans^T: tf32 hi (2 K blocks), tf32 lo (2 K blocks), fp16 (64 columns)
-  alignas(16) float h1[D * MD_HIDDEN];
+  unsigned char E[HTC ? 2 : 1][HTC ? QT_KB : 16];   // HTC: e_p = fused, normalised, scaled rows of one layer (raw fp32, two K blocks)
+  unsigned char ELO[HTC ? QT_KB : 16];              // HTC: their fp16 remainders
+  unsigned char Bh[HTC ? 20480 : 16];               // HTC: h1^T (32 hidden units x 64): tf32 hi (2 x 4 KB), tf32 lo (2 x 4 KB), fp16 (4 KB)
+  alignas(16) float h1[HTC ? 4 : D * MD_HIDDEN];
   alignas(16) float bias[D];
   alignas(16) float lw[D];
   alignas(16) float h2[MD_HIDDEN];
@@ -37,7 +41,7 @@ struct QTSmem {
   int vrow[2][TILE_M];           // [slot] global node id of the row, -1 = padding
   int desc[2][4];                // [slot] tile, graph
   int next_tile;
-  uint64_t a_full, a_empty, d_full[2], d_empty[2];
+  uint64_t a_full, a_empty, d_full[2], d_empty[2], h_full;
   uint32_t tmem;
 };
 
@@ -46,21 +50,29 @@ __device__ __forceinline__ float4 qt_lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+// round-to-nearest tf32 (the tensor core truncates fp32 operands: an operand that is already a tf32 value passes unchanged,
+// and the remainder x - rn(x) is at most 2^-12 |x| instead of truncation's 2^-11: one more bit for the fp16 / tf32 remainder planes)
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ bool qt_elect() {
   uint32_t pred = 0;
   asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
   return pred != 0;
 }
 
-template <int L>
+template <int L, bool HTC>
 __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K,
                                                           int* counter) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  QTSmem<L>& sm = *reinterpret_cast<QTSmem<L>*>(smem_raw);  // (no pointer arithmetic: keep the shared state space)
+  QTSmem<L, HTC>& sm = *reinterpret_cast<QTSmem<L, HTC>*>(smem_raw);  // (no pointer arithmetic: keep the shared state space)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   constexpr uint32_t NCOL = 64 * L;                    // accumulator columns per stage
-  constexpr uint32_t TCOLS = (2 * NCOL <= 256) ? 256 : 512;
+  constexpr uint32_t TCOLS = (2 * NCOL <= 256 && !HTC) ? 256 : 512;
+  constexpr uint32_t HCOL = 2 * NCOL;                  // HTC: 4 x 32 accumulator columns of relu's argument e_p @ h1
   const int tpg = G.stride / TILE_M;
   const int n_tiles = G.n_graphs * tpg;
 
@@ -71,6 +83,7 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
     mbar_init(&sm.d_full[1], 1);
     mbar_init(&sm.d_empty[0], 8);
     mbar_init(&sm.d_empty[1], 8);
+    mbar_init(&sm.h_full, 1);
     mbar_fence_init();
   }
   if (warp == 10) tmem_alloc(&sm.tmem, TCOLS);
@@ -93,8 +106,19 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
         *reinterpret_cast<__half*>(sm.Bt + 32768 + sw128_off(n, k >> 3) + 2 * (k & 7)) = __float2half_rn(t[j]);
       }
     }
-    for (int i = tid; i < D * MD_HIDDEN / 4; i += QT_T)
-      reinterpret_cast<float4*>(sm.h1)[i] = reinterpret_cast<const float4*>(W.h1)[i];
+    if constexpr (HTC) {
+      for (int i = tid; i < D * MD_HIDDEN; i += QT_T) {  // h1[c][j] -> B operand row j (hidden unit), K index c
+        const int c = i / MD_HIDDEN, j = i - c * MD_HIDDEN, kb = c >> 5, kk = c & 31;
+        const float x = W.h1[i];
+        const uint32_t off = kb * 4096 + sw128_off(j, kk >> 2) + 4 * (kk & 3);
+        *reinterpret_cast<float*>(sm.Bh + off) = tf32_rn(x);
+        *reinterpret_cast<float*>(sm.Bh + 8192 + off) = tf32_rn(x - tf32_rn(x));
+        *reinterpret_cast<__half*>(sm.Bh + 16384 + sw128_off(j, c >> 3) + 2 * (c & 7)) = __float2half_rn(x);
+      }
+    } else {
+      for (int i = tid; i < D * MD_HIDDEN / 4; i += QT_T)
+        reinterpret_cast<float4*>(sm.h1)[i] = reinterpret_cast<const float4*>(W.h1)[i];
+    }
     if (tid < D) {
       sm.bias[tid] = W.bias[tid];
       sm.lw[tid] = W.logis_w[tid];
@@ -223,6 +247,7 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
     const int quad = warp & 3, half = warp >> 2;
     const int r = 32 * quad + lane;
     const uint32_t h1_a = smem_u32(sm.h1);
+    uint32_t hph = 0;  // HTC: uses of h_full so far
     for (uint32_t i = 0;; ++i) {
       const uint32_t slot = i & 1, use = i >> 1;
       mbar_wait(&sm.d_full[slot], use & 1);
@@ -248,6 +273,138 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
 #pragma unroll
       for (int p = 0; p < L; ++p) part[p] = 0.f;
       float gwp[L], aqp[L];
+      if constexpr (HTC) {
+        // Same maths as the branch below up to e_p; relu's argument e_p @ h1 (64 x 32 per row: the 2 x 1024 FMAs per
+        // thread that made the epilogue the longest stage of the kernel) goes to the tensor cores as the usual 3-term
+        // product: thread `half` of a row writes columns [32 half, 32 half + 32) of e_p (= K block `half`) and their fp16
+        // remainders, one elected thread issues the 20 MMAs into 32 spare accumulator columns, both read 16 units back.
+        float am[L][L];
+        if (v >= 0) {
+          float dot[L][L];
+#pragma unroll
+          for (int p = 0; p < L; ++p)
+#pragma unroll
+            for (int k = 0; k < L; ++k) dot[p][k] = 0.f;
+#pragma unroll 4
+          for (int c = 0; c < D; ++c) {
+            float t[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) t[l] = sm.Ts[l][c][r];
+            const float w1 = sm.lw[c];
+#pragma unroll
+            for (int p = 0; p < L; ++p)
+#pragma unroll
+              for (int k = 0; k <= p; ++k) dot[p][k] = fmaf(t[k] * t[p], w1, dot[p][k]);
+          }
+#pragma unroll
+          for (int p = 0; p < L; ++p)
+#pragma unroll
+            for (int k = 0; k < p; ++k) dot[k][p] = dot[p][k];
+#pragma unroll
+          for (int p = 0; p < L; ++p) {
+            float mx = -1e30f, den = 0.f;
+#pragma unroll
+            for (int k = 0; k < L; ++k) {
+              am[p][k] = 1.f / (1.f + expf(-(dot[p][k] + lb)));
+              mx = fmaxf(mx, am[p][k]);
+            }
+#pragma unroll
+            for (int k = 0; k < L; ++k) {
+              am[p][k] = expf(am[p][k] - mx);
+              den += am[p][k];
+            }
+#pragma unroll
+            for (int k = 0; k < L; ++k) am[p][k] = am[p][k] / den;
+          }
+        }
+#pragma unroll 1
+        for (int p = 0; p < L; ++p) {
+          if (v >= 0) {
+            float ss = 0.f;
+#pragma unroll 4
+            for (int c = 0; c < D; ++c) {
+              float x = sm.Ts[p][c][r];
+#pragma unroll
+              for (int k = 0; k < L; ++k)
+                if (k != p) x = fmaf(am[p][k], sm.Ts[k][c][r], x);
+              ss = fmaf(x, x, ss);
+            }
+            const float sc = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
+            const float sg = K.gconst[(size_t)g * MD_GCONST + p];
+            gwp[p] = K.gconst[(size_t)g * MD_GCONST + 4 + p];
+            aqp[p] = K.gconst[(size_t)g * MD_GCONST + 8 + p];
+            unsigned char* erow = sm.E[half] + (uint32_t)r * 128u;
+            unsigned char* lrow = sm.ELO + (uint32_t)r * 128u;
+#pragma unroll 2
+            for (int ch = 0; ch < 8; ++ch) {  // 4 columns = one 16-byte chunk of the K block
+              float e[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = 32 * half + 4 * ch + j;
+                float x = sm.Ts[p][c][r];
+#pragma unroll
+                for (int k = 0; k < L; ++k)
+                  if (k != p) x = fmaf(am[p][k], sm.Ts[k][c][r], x);
+                e[j] = x * sc * sg;
+              }
+              const float4 eh = make_float4(tf32_rn(e[0]), tf32_rn(e[1]), tf32_rn(e[2]), tf32_rn(e[3]));
+              *reinterpret_cast<float4*>(erow + ((ch ^ (r & 7)) << 4)) = eh;
+              // remainders scaled by 2^12 (exact): |e| is a few 1e-3 here, its remainder would be an fp16 subnormal with a
+              // handful of bits left (measured: 1.3e-6 absolute Q error); the scaled product has its own accumulator
+              const __half2 p0 = __floats2half2_rn((e[0] - eh.x) * 4096.f, (e[1] - eh.y) * 4096.f);
+              const __half2 p1 = __floats2half2_rn((e[2] - eh.z) * 4096.f, (e[3] - eh.w) * 4096.f);
+              // fp16 row: column c at byte 2 c -> chunk c >> 3 = 4 half + (ch >> 1), 8 bytes at (ch & 1) * 8
+              *reinterpret_cast<uint2*>(lrow + (((4 * half + (ch >> 1)) ^ (r & 7)) << 4) + 8 * (ch & 1)) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          asm volatile("bar.sync 3, 256;" ::: "memory");  // e_p complete; the previous layer's accumulator reads are done
+          if (warp == 0) {
+            tc_fence_after();
+            if (qt_elect()) {
+              const uint32_t idt = idesc(FMT_TF32, 128, 32), idb = idesc(FMT_F16, 128, 32);
+              const uint32_t bh = smem_u32(sm.Bh);
+              const uint32_t d = tbase + HCOL;
+#pragma unroll
+              for (int kb = 0; kb < 2; ++kb) {
+                const uint64_t ae = desc_k_sw128(smem_u32(sm.E[kb]), 0);
+                const uint64_t bhi = desc_k_sw128(bh + kb * 4096, 0), blo = desc_k_sw128(bh + 8192 + kb * 4096, 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  // four accumulators: the tensor core truncates when it adds into an accumulator, a bias that grows with
+                  // the number of steps (16 steps into one accumulator: 1.2e-6 absolute Q error where |q| ~ 1e-4; the
+                  // FP32 pipes: 4.5e-7).  hi x hi gets one accumulator per K block (4 steps each), the two small
+                  // products their own; the epilogue adds the four in FP32.
+                  mma_tf32(d + 32 * kb, ae + 2 * k, bhi + 2 * k, idt, k != 0);
+                  mma_tf32(d + 64, ae + 2 * k, blo + 2 * k, idt, (kb | k) != 0);
+                }
+              }
+              const uint64_t al = desc_k_sw128(smem_u32(sm.ELO), 0), bf = desc_k_sw128(bh + 16384, 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mma_f16(d + 96, al + 2 * k, bf + 2 * k, idb, k != 0);
+              mma_commit(&sm.h_full);
+            }
+            __syncwarp();
+          }
+          mbar_wait(&sm.h_full, hph & 1);
+          ++hph;
+          tc_fence_after();
+          float x[16], xb[16], xm[16], xl[16];
+          const uint32_t hta = tbase + ((uint32_t)(32 * quad) << 16) + HCOL + 16 * half;
+          tmem_ld16(hta, x);
+          tmem_ld16(hta + 32, xb);
+          tmem_ld16(hta + 64, xm);
+          tmem_ld16(hta + 96, xl);
+          tmem_ld_wait();
+          float hq = 0.f;
+#pragma unroll
+          for (int j = 0; j < MD_HIDDEN / 2; ++j)
+            hq = fmaf(fmaxf((x[j] + xb[j]) + fmaf(xl[j], 1.f / 4096.f, xm[j]), 0.f), sm.h2[16 * half + j], hq);
+          part[p] = hq;
+        }
+      } else
       if (v >= 0) {
         float dot[L][L];
 #pragma unroll
@@ -380,24 +537,33 @@ int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weigh
   const int grid = nsm < n_tiles ? nsm : n_tiles;
   int* counter = s->flags + 4;  // [4] next tile, [5] CTAs finished; zero between launches (the kernel re-arms them)
   cudaError_t e = cudaSuccess;
-  if (g->n_layers == 2) {
+  if (g->n_layers == 2 && !(g_md_debug_flags & 8192)) {  // (bit 13: hidden layer on the FP32 pipes, the A/B reference)
     static bool configured = false;
-    const int smem = (int)sizeof(md::QTSmem<2>);
+    const int smem = (int)sizeof(md::QTSmem<2, true>);
     if (!configured) {
-      e = cudaFuncSetAttribute(md::qhead_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      e = cudaFuncSetAttribute(md::qhead_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return (int)e;
       configured = true;
     }
-    md::qhead_tc_kernel<2><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
+    md::qhead_tc_kernel<2, true><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
+  } else if (g->n_layers == 2) {
+    static bool configured = false;
+    const int smem = (int)sizeof(md::QTSmem<2, false>);
+    if (!configured) {
+      e = cudaFuncSetAttribute(md::qhead_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+    md::qhead_tc_kernel<2, false><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
   } else {
     static bool configured = false;
-    const int smem = (int)sizeof(md::QTSmem<3>);
+    const int smem = (int)sizeof(md::QTSmem<3, false>);
     if (!configured) {
-      e = cudaFuncSetAttribute(md::qhead_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      e = cudaFuncSetAttribute(md::qhead_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return (int)e;
       configured = true;
     }
-    md::qhead_tc_kernel<3><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
+    md::qhead_tc_kernel<3, false><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;

@@ -304,11 +304,13 @@ def test_fused_embedding_matches_unfused(variant):
     print("fused vs unfused: worst |dH| %.3e, worst scaled |dQ| %.3e" % (worst_h, worst_q))
 
 
+@pytest.mark.parametrize("ref_flag", [8, 8192], ids=["vs_fma_kernel", "vs_fma_hidden_layer"])
 @pytest.mark.parametrize("variant", ["unit", "degree"])
-def test_qhead_tensor_core_matches_fma(variant):
-    """md_qhead: tensor-core kernel (tcgen05, 3-term tf32/bf16 product for the fusion transform) vs the FP32-FMA kernel
-    (md_debug_set_flags bit 3) on identical embeddings: Q within the north-star tolerance, identical arg-max keys except
-    on sub-tolerance ties."""
+def test_qhead_tensor_core_matches_fma(variant, ref_flag):
+    """md_qhead: tensor-core kernel (tcgen05, 3-term tf32 / fp16 products for the fusion transform and, with two layers,
+    for relu's argument e @ h1) vs the FP32-FMA kernel (md_debug_set_flags bit 3) and vs the tensor-core kernel with the
+    hidden layer on the FP32 pipes (bit 13) on identical embeddings: Q within the north-star tolerance, identical arg-max
+    keys except on sub-tolerance ties."""
     from mdcommunity_b200 import _lib
     mdb = _mdb()
     zs, graphs, batch, w = _load_batch(variant)
@@ -323,7 +325,7 @@ def test_qhead_tensor_core_matches_fma(variant):
             q_tc = ro.q.clone()
             best_tc = ro.best.clone()
             ro.best.zero_()
-            lib.md_debug_set_flags(8)
+            lib.md_debug_set_flags(ref_flag)
             import ctypes as C
             _lib.check(lib.md_qhead(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()), "md_qhead")
             q_fma = ro.q.clone()
