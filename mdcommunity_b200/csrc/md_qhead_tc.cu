@@ -38,6 +38,7 @@ struct QTSmem {
   alignas(16) float h2[MD_HIDDEN];
   float Ts[L][D][TILE_M];        // epilogue: tanh outputs, column-major so that a thread owns one conflict-free column
   float hq[L][TILE_M];           // epilogue: partial hidden sums of the second thread of each row
+  float ssq[2][2][HTC ? TILE_M : 1];  // HTC: [layer parity][thread of the row] half of |X_p|^2
   int vrow[2][TILE_M];           // [slot] global node id of the row, -1 = padding
   int desc[2][4];                // [slot] tile, graph
   int next_tile;
@@ -319,18 +320,12 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
         }
 #pragma unroll 1
         for (int p = 0; p < L; ++p) {
+          // one pass over this thread's 32 columns of X_p = T_p + sum_{k != p} a_k T_k: the UNSCALED rows go to the operand
+          // tiles and the scale 1/|X_p| * s_p is applied to the 32 products afterwards (the norm needs both threads' halves,
+          // exchanged through shared memory across the barrier that is there anyway)
+          float ssh = 0.f, sg = 0.f;
           if (v >= 0) {
-            float ss = 0.f;
-#pragma unroll 4
-            for (int c = 0; c < D; ++c) {
-              float x = sm.Ts[p][c][r];
-#pragma unroll
-              for (int k = 0; k < L; ++k)
-                if (k != p) x = fmaf(am[p][k], sm.Ts[k][c][r], x);
-              ss = fmaf(x, x, ss);
-            }
-            const float sc = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
-            const float sg = K.gconst[(size_t)g * MD_GCONST + p];
+            sg = K.gconst[(size_t)g * MD_GCONST + p];
             gwp[p] = K.gconst[(size_t)g * MD_GCONST + 4 + p];
             aqp[p] = K.gconst[(size_t)g * MD_GCONST + 8 + p];
             unsigned char* erow = sm.E[half] + (uint32_t)r * 128u;
@@ -345,12 +340,13 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
 #pragma unroll
                 for (int k = 0; k < L; ++k)
                   if (k != p) x = fmaf(am[p][k], sm.Ts[k][c][r], x);
-                e[j] = x * sc * sg;
+                ssh = fmaf(x, x, ssh);
+                e[j] = x;
               }
               const float4 eh = make_float4(tf32_rn(e[0]), tf32_rn(e[1]), tf32_rn(e[2]), tf32_rn(e[3]));
               *reinterpret_cast<float4*>(erow + ((ch ^ (r & 7)) << 4)) = eh;
-              // remainders scaled by 2^12 (exact): |e| is a few 1e-3 here, its remainder would be an fp16 subnormal with a
-              // handful of bits left (measured: 1.3e-6 absolute Q error); the scaled product has its own accumulator
+              // remainders scaled by 2^12 (exact): unscaled they reach fp16's subnormal range with a handful of bits left
+              // (measured with the scaled rows e_p, |e| ~ 1e-3: 1.3e-6 absolute Q error); their product has its own accumulator
               const __half2 p0 = __floats2half2_rn((e[0] - eh.x) * 4096.f, (e[1] - eh.y) * 4096.f);
               const __half2 p1 = __floats2half2_rn((e[2] - eh.z) * 4096.f, (e[3] - eh.w) * 4096.f);
               // fp16 row: column c at byte 2 c -> chunk c >> 3 = 4 half + (ch >> 1), 8 bytes at (ch & 1) * 8
@@ -358,6 +354,7 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
                   make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
             }
           }
+          sm.ssq[p & 1][half][r] = ssh;
           fence_proxy_async_smem();
           tc_fence_before();
           asm volatile("bar.sync 3, 256;" ::: "memory");  // e_p complete; the previous layer's accumulator reads are done
@@ -398,10 +395,12 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
           tmem_ld16(hta + 64, xm);
           tmem_ld16(hta + 96, xl);
           tmem_ld_wait();
+          const float ss = sm.ssq[p & 1][0][r] + sm.ssq[p & 1][1][r];
+          const float scale = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f)) * sg;  // e_p = X_p / |X_p| * s_p
           float hq = 0.f;
 #pragma unroll
           for (int j = 0; j < MD_HIDDEN / 2; ++j)
-            hq = fmaf(fmaxf((x[j] + xb[j]) + fmaf(xl[j], 1.f / 4096.f, xm[j]), 0.f), sm.h2[16 * half + j], hq);
+            hq = fmaf(fmaxf(((x[j] + xb[j]) + fmaf(xl[j], 1.f / 4096.f, xm[j])) * scale, 0.f), sm.h2[16 * half + j], hq);
           part[p] = hq;
         }
       } else
