@@ -350,6 +350,23 @@ def test_qhead_tensor_core_matches_fma(variant, ref_flag):
     print("qhead tensor-core vs FMA: worst scaled |dQ| %.3e" % worst)
 
 
+def test_multi_stream_rollout_matches_single_stream():
+    """MultiStreamRollout: the batch cut into sub-batches on their own CUDA streams (CUDA-graph replay from the second run
+    on) gives exactly the single-stream results: AUDC, removal sequences, LMCC traces bit for bit."""
+    from mdcommunity_b200.rollout import MultiStreamRollout
+    mdb = _mdb()
+    zs, graphs, batch, w = _load_batch("degree")
+    ref = mdb.BatchRollout(batch, w).run()
+    for parts in (2, 3):
+        mr = MultiStreamRollout(graphs, w, batch.device, "degree", parts=parts)
+        for _ in range(2):  # the second run replays captured chunks
+            r = mr.run()
+            T = min(r["actions"].shape[1], ref["actions"].shape[1])
+            assert np.array_equal(r["score"], ref["score"]) and np.array_equal(r["n_steps"], ref["n_steps"])
+            assert np.array_equal(r["actions"][:, :T], ref["actions"][:, :T])
+            assert np.array_equal(r["ranks"][:, :T], ref["ranks"][:, :T])
+
+
 def test_cuda_graph_rollout_matches_eager():
     """BatchRollout.run(): the second run of the same object replays chunks of iterations as one CUDA graph
     (md_rollout_graph_*); removal sequences, LMCC traces and AUDC must equal the eager first run bit for bit."""
