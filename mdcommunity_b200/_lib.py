@@ -103,8 +103,12 @@ def lib():
         else:
             try:
                 path = _build.build()  # no-op when the stamp matches
-            except Exception:
-                pass  # a box without nvcc still uses the prebuilt .so that travelled with the snapshot
+            except FileNotFoundError:
+                # a box without nvcc uses the prebuilt .so that travelled with the snapshot -- but only if it was built
+                # from exactly these sources (a compile ERROR is never swallowed: it propagates)
+                if not _build.up_to_date():
+                    raise RuntimeError("libmdb200.so is stale (sources changed since it was built) and nvcc is not "
+                                       "available to rebuild it")
         h = C.CDLL(path)
         for name, (args, res) in _SIGS.items():
             fn = getattr(h, name)  # AttributeError if the symbol is missing: fail loudly

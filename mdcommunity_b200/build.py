@@ -16,6 +16,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
 ]
+if os.environ.get("MDB200_PROFILE"):  # in-kernel phase clocks (md_debug_read_env / _fused*); never set for release builds
+    NVCC_FLAGS.append("-DMD_PROFILE")
 
 
 def _nvcc():
@@ -31,6 +33,12 @@ def _stamp():
             h.update(open(p, "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
+
+
+def up_to_date():
+    """True when libmdb200.so exists and its stamp matches the current sources + flags."""
+    stamp_file = LIB + ".stamp"
+    return os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == _stamp()
 
 
 def build(force=False, verbose=False):

@@ -429,7 +429,8 @@ extern int g_md_debug_flags;
 
 // enqueue P = A_adj . H for every layer (internal: called by md_embed_iter when the two-kernel path applies)
 int md_agg_rows_launch(const md_graphs_t* g, const md_state_t* s, const md_work_t* k, int iter, cudaStream_t st) {
-  static int nsm = 0;
+  static md::PerDevice<int> nsm_pd;
+  int& nsm = nsm_pd.get();
   if (nsm <= 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -442,7 +443,8 @@ int md_agg_rows_launch(const md_graphs_t* g, const md_state_t* s, const md_work_
     const int grid = (int)(want < nsm ? want : nsm);
     md::agg_rows_kernel<<<grid, md::AG_T, 0, st>>>(*g, *s, *k, iter);
   } else {
-    static bool configured = false;
+    static md::PerDevice<bool> configured_pd;
+  bool& configured = configured_pd.get();
     const int smem = (int)sizeof(md::RingSmem);
     if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(md::agg_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -459,7 +461,8 @@ int md_agg_rows_launch(const md_graphs_t* g, const md_state_t* s, const md_work_
 
 // iteration 0 of the unit-cost variant on the two-kernel path (see agg_deg_kernel)
 int md_agg_deg_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, cudaStream_t st) {
-  static int nsm = 0;
+  static md::PerDevice<int> nsm_pd;
+  int& nsm = nsm_pd.get();
   if (nsm <= 0) {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -55,4 +55,19 @@ __device__ __forceinline__ float from_orderable(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+// ---- host side: caches keyed by the current device --------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device and SM counts may differ between devices, so the
+// "configured once" flags of the launchers are kept per device (a second GPU in the same process gets its own).
+constexpr int MAX_DEVICES = 64;
+inline int cur_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d < 0 || d >= MAX_DEVICES) ? 0 : d;
+}
+template <class T>
+struct PerDevice {
+  T v[MAX_DEVICES] = {};
+  T& get() { return v[cur_device()]; }
+};
+
 }  // namespace md

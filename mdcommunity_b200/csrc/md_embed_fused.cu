@@ -77,12 +77,16 @@ static_assert(sizeof(FusedSmem) <= 232448, "FusedSmem exceeds the 227 KB shared 
 __device__ long long g_fz_dbg[16];
 __device__ unsigned g_fz_gath[8];  // gather sub-phases of CTA 0 warp 0: setup, main loop, own rows, stores, long rows, fence+arrive
 __device__ unsigned g_fz_cta[160][2];  // per CTA: cycles from start to end of the unit loop, units processed
+#ifdef MD_PROFILE
 #define FZ_CLK(acc)                   \
   do {                                \
     const uint32_t n_ = clock();      \
     acc += n_ - t_dbg;                \
     t_dbg = n_;                       \
   } while (0)
+#else
+#define FZ_CLK(acc) do { } while (0)
+#endif
 
 __device__ __forceinline__ void gw_sync() { asm volatile("bar.sync 1, %0;" ::"n"(FZ_GT) : "memory"); }
 // the four warps that share one TMEM lane quadrant set / staging tile in the epilogue (quad = warp / 4)
@@ -206,8 +210,10 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
   int* const counter = reinterpret_cast<int*>(ws + FZ_WS_CTR);
   const bool degree_cost = G.node_w[0] != nullptr;
 
+#ifdef MD_PROFILE
   const long long t_start = clock64();
-  uint32_t t_dbg = clock(), c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0, c9 = 0;  // phase clocks (FZ_CLK)
+#endif
+  uint32_t t_dbg = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0, c9 = 0;  // phase clocks (FZ_CLK)
   uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0;  // gather sub-phases
   int n_units_done = 0;
   uint32_t uses = 0;    // staging-tile hand-offs so far (same sequence in the gather warps and the MMA warp)
@@ -679,6 +685,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
       FZ_CLK(c9);
     }
   }
+#ifdef MD_PROFILE
   if (tid == 0 && blockIdx.x < 160) g_fz_cta[blockIdx.x][0] = (unsigned)(clock64() - t_start), g_fz_cta[blockIdx.x][1] = n_units_done;
   // gather warp 0: [0] setup [1] fill [2] reload [3] gather [4] stage wait [5] pass end [6] epilogue TMEM+math [7] idle
   //                [12] epilogue stores [13] epilogue fences + barrier
@@ -689,6 +696,10 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     g_fz_gath[0] = d0, g_fz_gath[1] = d1, g_fz_gath[2] = d2, g_fz_gath[3] = d3, g_fz_gath[4] = d4, g_fz_gath[5] = d5;
   }
   if (blockIdx.x == 0 && tid == FZ_GT) g_fz_dbg[8] = c0, g_fz_dbg[9] = c1, g_fz_dbg[10] = c2, g_fz_dbg[11] = c3;
+#else
+  (void)t_dbg, (void)c0, (void)c1, (void)c2, (void)c3, (void)c4, (void)c5, (void)c6, (void)c7, (void)c8, (void)c9;
+  (void)d0, (void)d1, (void)d2, (void)d3, (void)d4, (void)d5, (void)n_units_done;
+#endif
 
   // teardown: the MMA warp still has one weight-image copy in flight
   if (warp == FZ_GW) mbar_wait(&sm.bar_w, wloads & 1);
@@ -719,7 +730,8 @@ extern "C" int32_t md_fused_applies(const md_graphs_t* g) {
 }
 
 static int fused_sm_count() {
-  static int nsm = 0;
+  static md::PerDevice<int> nsm_pd;
+  int& nsm = nsm_pd.get();
   if (nsm <= 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -742,7 +754,8 @@ extern "C" int md_embed_fused(const md_graphs_t* g, const md_state_t* s, const m
   if (g->n_layers < 1 || g->n_layers > MD_MAX_LAYERS) return MD_ELAYERS;
   if (g->stride % MD_TILE_M != 0 || g->n_total != g->n_graphs * g->stride) return MD_EINVAL;
   if (!md_fused_applies(g)) return MD_ETOOBIG;
-  static bool configured = false;
+  static md::PerDevice<bool> configured_pd;
+  bool& configured = configured_pd.get();
   const int smem = (int)sizeof(md::FusedSmem);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(md::embed_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -422,8 +422,10 @@ extern "C" int md_embed_iter(const md_graphs_t* g, const md_state_t* s, const md
     if (rc) return rc;
     if (launched) return 0;
   }
-  static bool configured = false;
-  static int nsm = 0;
+  static md::PerDevice<bool> configured_pd;
+  bool& configured = configured_pd.get();
+  static md::PerDevice<int> nsm_pd;
+  int& nsm = nsm_pd.get();
   const int smem = (int)sizeof(md::IterSmem);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(md::embed_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

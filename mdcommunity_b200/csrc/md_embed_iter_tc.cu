@@ -603,8 +603,10 @@ int md_embed_iter_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_
   if (f & (1 | 2)) return 0;  // isolation runs of the FMA kernel
   const bool pre = tc_pre_path(g);
   if (!pre && !(f & 16)) return 0;
-  static bool configured = false;
-  static int nsm = 0;
+  static md::PerDevice<bool> configured_pd;
+  bool& configured = configured_pd.get();
+  static md::PerDevice<int> nsm_pd;
+  int& nsm = nsm_pd.get();
   const int smem = (int)sizeof(md::IterTcSmem);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(md::embed_iter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

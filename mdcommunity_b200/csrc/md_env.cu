@@ -11,10 +11,21 @@
 #include "md_common.cuh"
 
 namespace md {
+// phase clocks (profiling builds only: MDB200_PROFILE=1 python -m mdcommunity_b200.build --force; release builds carry
+// no clock reads and no debug globals, so concurrent launches on several streams share no written state)
 __device__ long long g_env_dbg[32];
 __device__ unsigned g_env_cta[1024][4];  // per graph of the last step: cycles, prune rounds, staged entries, SM id
+#ifdef MD_PROFILE
 #define ENV_T0() long long t_dbg = clock64(); int k_dbg = 0
 #define ENV_TICK() do { if (blockIdx.x == 0 && tid == 0) { long long n_ = clock64(); g_env_dbg[k_dbg] = n_ - t_dbg; t_dbg = n_; } ++k_dbg; } while (0)
+#define ENV_CLK() clock64()
+#define ENV_PROF(...) __VA_ARGS__
+#else
+#define ENV_T0() do { } while (0)
+#define ENV_TICK() do { } while (0)
+#define ENV_CLK() 0ll
+#define ENV_PROF(...)
+#endif
 
 constexpr int ENV_T = 512;
 constexpr int ENV_W = ENV_T / 32;
@@ -112,7 +123,8 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
 
   if (!init && S.done[g]) return;
   ENV_T0();
-  const long long t_cta0 = clock64();
+  const long long t_cta0 = ENV_CLK();
+  (void)t_cta0;
 
   // ---- pick the action -----------------------------------------------------------------------------
   if (tid == 0) {
@@ -192,7 +204,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   while (stable < L) {
     for (int v = tid; v < N; v += ENV_T) par[v] = v;
     __syncthreads();
-    tq = clock64();
+    tq = ENV_CLK();
     for (int e = lay_pos[l] + tid; e < lay_pos[l + 1]; e += ENV_T) {  // edge-parallel hooking
       const int v = c_src[e], u = c_cl[e];
       if (u < v) {
@@ -201,8 +213,8 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       }
     }
     __syncthreads();
-    hook_dbg += clock64() - tq;
-    tq = clock64();
+    hook_dbg += ENV_CLK() - tq;
+    tq = ENV_CLK();
     int changed = 0;
     for (int v = tid; v < N; v += ENV_T) {
       int r = -1;
@@ -215,13 +227,14 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
     changed = __syncthreads_or(changed);
     for (int v = tid; v < N; v += ENV_T) lab[v] = tmp[v];
     __syncthreads();
-    flat_dbg += clock64() - tq;
+    flat_dbg += ENV_CLK() - tq;
     stable = changed ? 1 : stable + 1;
     l = (l + 1 == L) ? 0 : l + 1;
     ++rounds_dbg;
   }
   ENV_TICK();  // 2: LMCC rounds
-  if (blockIdx.x == 0 && tid == 0) g_env_dbg[16] = rounds_dbg, g_env_dbg[17] = hook_dbg, g_env_dbg[18] = flat_dbg;
+  ENV_PROF(if (blockIdx.x == 0 && tid == 0) g_env_dbg[16] = rounds_dbg, g_env_dbg[17] = hook_dbg, g_env_dbg[18] = flat_dbg;)
+  (void)hook_dbg, (void)flat_dbg, (void)tq, (void)rounds_dbg;
 
   // ---- component sizes -> LMCC rank (Mcc.find_max_set_length) ------------------------------------------
   for (int v = tid; v < N; v += ENV_T) tmp[v] = 0;
@@ -347,11 +360,13 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   }
 
   ENV_TICK();  // 4: alive CSR + degrees + compaction
+#ifdef MD_PROFILE
   if (tid == 0 && g < 1024) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     g_env_cta[g][0] = (unsigned)(clock64() - t_cta0), g_env_cta[g][1] = rounds_dbg, g_env_cta[g][2] = lay_pos[L], g_env_cta[g][3] = smid;
   }
+#endif
   // ---- bookkeeping: reward / AUDC in f64 with the reference's operation order ---------------------------
   if (tid == 0) {
     const int B = G.n_graphs;
@@ -433,12 +448,13 @@ static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* 
   const size_t smem = env_small_smem(g);
   if (!md_env_uses_small_path(g)) return md_env_step_large(g, s, forced, forced_stride, forced_index, init, stream);
   const bool i16 = env_idx16(g);
-  static size_t configured[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > configured[i16]) {
+  static md::PerDevice<size_t> configured_pd[2];
+  size_t& configured_smem = configured_pd[i16].get();
+  if (smem > 48 * 1024 && smem > configured_smem) {
     cudaError_t e = i16 ? cudaFuncSetAttribute(md::env_step_small<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                         : cudaFuncSetAttribute(md::env_step_small<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured[i16] = smem;
+    configured_smem = smem;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (init) {

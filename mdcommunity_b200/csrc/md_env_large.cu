@@ -437,7 +437,8 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
 int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
                       int32_t forced_index, int init, md_stream_t stream) {
   if (!s->parent || !s->comp_size || !s->flags || !s->cur_action) return MD_EINVAL;
-  static int grid = 0;
+  static md::PerDevice<int> grid_pd;
+  int& grid = grid_pd.get();
   if (grid == 0) {
     int dev = 0, nsm = 0, occ = 0, coop = 0;
     cudaGetDevice(&dev);

@@ -294,7 +294,8 @@ extern "C" int md_qhead(const md_graphs_t* g, const md_state_t* s, const md_weig
   const int n_tiles = g->n_graphs * (g->stride / MD_TILE_M);
   cudaStream_t st = (cudaStream_t)stream;
   if (g->n_layers == 2) {
-    static bool configured = false;
+    static md::PerDevice<bool> configured_pd;
+  bool& configured = configured_pd.get();
     const int smem = (int)sizeof(md::QSmem<2>);
     if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(md::qhead_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -304,7 +305,8 @@ extern "C" int md_qhead(const md_graphs_t* g, const md_state_t* s, const md_weig
     int grid = 2 * nsm < n_tiles ? 2 * nsm : n_tiles;
     md::qhead_kernel<2><<<grid, md::QH_T, smem, st>>>(*g, *s, *w, *k);
   } else if (g->n_layers == 3) {
-    static bool configured = false;
+    static md::PerDevice<bool> configured_pd;
+  bool& configured = configured_pd.get();
     const int smem = (int)sizeof(md::QSmem<3>);
     if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(md::qhead_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -525,7 +525,8 @@ int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weigh
                        int* launched) {
   *launched = 0;
   if ((g_md_debug_flags & 8) || !s->flags || (g->n_layers != 2 && g->n_layers != 3)) return 0;
-  static int nsm = 0;
+  static md::PerDevice<int> nsm_pd;
+  int& nsm = nsm_pd.get();
   if (nsm <= 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -537,7 +538,8 @@ int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weigh
   int* counter = s->flags + 4;  // [4] next tile, [5] CTAs finished; zero between launches (the kernel re-arms them)
   cudaError_t e = cudaSuccess;
   if (g->n_layers == 2 && !(g_md_debug_flags & 8192)) {  // (bit 13: hidden layer on the FP32 pipes, the A/B reference)
-    static bool configured = false;
+    static md::PerDevice<bool> configured_pd;
+  bool& configured = configured_pd.get();
     const int smem = (int)sizeof(md::QTSmem<2, true>);
     if (!configured) {
       e = cudaFuncSetAttribute(md::qhead_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -546,7 +548,8 @@ int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weigh
     }
     md::qhead_tc_kernel<2, true><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
   } else if (g->n_layers == 2) {
-    static bool configured = false;
+    static md::PerDevice<bool> configured_pd;
+  bool& configured = configured_pd.get();
     const int smem = (int)sizeof(md::QTSmem<2, false>);
     if (!configured) {
       e = cudaFuncSetAttribute(md::qhead_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -555,7 +558,8 @@ int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weigh
     }
     md::qhead_tc_kernel<2, false><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
   } else {
-    static bool configured = false;
+    static md::PerDevice<bool> configured_pd;
+  bool& configured = configured_pd.get();
     const int smem = (int)sizeof(md::QTSmem<3, false>);
     if (!configured) {
       e = cudaFuncSetAttribute(md::qhead_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -36,14 +36,18 @@ class MvcEnv:
     def s0(self, _g):
         """Reset (mvc_env.py:31-52): clears the episode and runs the initial mutual-component prune on the GPU."""
         self.graph = _g
-        cached = getattr(_g, "_mdb_rollout", None)
-        if cached is None:
+        # The immutable device CSR is cached on the graph object; the mutable episode state (labels, counters, score,
+        # traces) belongs to THIS env: several envs may hold the same graph at once (env_list + TrainSet.Sample() with
+        # replacement, test_env next to a training env), exactly like the reference's per-env covered_set / remove_edge.
+        batch = getattr(_g, "_mdb_batch", None)
+        if batch is None or (self.device is not None and torch.device(self.device) != batch.device):
             batch = GraphBatch([_g], device=self.device, cost=_g.cost)
-            cached = BatchRollout(batch, None)
-            _g._mdb_rollout = cached
+            _g._mdb_batch = batch
+        if self._ro is not None and self._ro.batch is batch:
+            self._ro.reset()
         else:
-            cached.reset()
-        self._ro = cached
+            self._ro = BatchRollout(batch, None)
+        cached = self._ro
         L = _g.num_layers
         self.covered_set.clear()
         self.action_list.clear()

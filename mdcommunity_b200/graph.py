@@ -112,7 +112,10 @@ class GraphBatch:
         B = len(graphs)
         L = graphs[0].num_layers
         nmax = max(g.num_nodes for g in graphs)
-        S = max(TILE_M, (nmax + TILE_M - 1) // TILE_M * TILE_M)
+        # S >= nmax + 1: the alive-CSR row pointers of graph g live at aptr[g*S .. g*S + n_act] inside one
+        # (B*S + 1)-entry array, so with n_act == S the end pointer of graph g would be the same word as the start
+        # pointer of graph g + 1 (two CTAs writing different values).  One spare slot per graph rules that out.
+        S = (nmax // TILE_M + 1) * TILE_M
         if B * S >= 2 ** 31:
             raise ValueError("batch too large for int32 node ids")
         rowptr, col, src, nnz = [], [], [], []

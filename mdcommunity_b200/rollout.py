@@ -14,6 +14,18 @@ from . import _lib
 from .graph import GraphBatch
 
 
+def _on_device(fn):
+    """Run a BatchRollout method with the batch's device current: the C ABI launches on the CURRENT device, and the
+    stream handed over belongs to batch.device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        with torch.cuda.device(self.batch.device):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 class QWeights:
     """The reference's 14-tensor state_dict on the device, plus the two merged products the fused kernel uses."""
 
@@ -142,6 +154,7 @@ class BatchRollout:
     def _g(self):
         return self.batch.ptr()
 
+    @_on_device
     def reset(self):
         """MvcEnv.s0 for every graph; also fills graph.max_rank (Graph_test.ori_rank) on first use."""
         self.trace_action.fill_(-1)
@@ -154,6 +167,7 @@ class BatchRollout:
                 g.max_rank = int(r)
             self.batch._max_rank_set = True
 
+    @_on_device
     def set_state(self, removed_mask):
         """Arbitrary state: removed_mask uint8 [n_total] on the device; self.cov_edges must hold numCoveredEdges."""
         assert removed_mask.dtype == torch.uint8 and removed_mask.is_cuda and removed_mask.numel() == self.batch.n_total
@@ -161,6 +175,7 @@ class BatchRollout:
                                              self._stream()), "md_env_set_state")
         self.kernel_launches += 1
 
+    @_on_device
     def forward(self):
         """One Q-network evaluation for all non-terminal graphs (test_forward + the Predict mask + arg-max key)."""
         lib, g, s, w, k, st = self.lib, self._g(), C.byref(self.s), self.w.ptr(), C.byref(self.k), self._stream()
@@ -176,6 +191,7 @@ class BatchRollout:
         _lib.check(lib.md_qhead(g, s, w, k, st), "md_qhead")
         self.kernel_launches += 2
 
+    @_on_device
     def step(self, actions=None, index=-1):
         """stepWithoutReward for every non-terminal graph.  actions: None -> arg-max of the last forward();
         int32 device tensor [B, stride] of local node ids -> column `index` (or column n_steps[g] when index < 0)."""
@@ -193,6 +209,7 @@ class BatchRollout:
         torch.cuda.current_stream(self.batch.device).synchronize()
         return int(self._pinned_done[0])
 
+    @_on_device
     def run(self, chunk=8, step=1):
         """Greedy rollout to termination (GetSol when step == 1, GetSolution's top-`step` batches otherwise)."""
         B = self.batch.B
@@ -229,6 +246,7 @@ class BatchRollout:
         self._runs += 1
         return self.results()
 
+    @_on_device
     def run_heuristic(self, kind="hda", combine="max", chunk=8):
         """critical_number of the reference's baseline scripts (U/baseline/HDA/hda_2max.py:71-93, CI/ci_max.py:92-110)
         for every graph of the batch: select by alive degree ("hda") or collective influence ("ci"), combined over the

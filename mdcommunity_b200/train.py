@@ -62,8 +62,8 @@ class QNet(torch.nn.Module):
                 init = torch.eye(64)
             elif k.endswith(".bias") and "logis" not in k:
                 init = torch.zeros(shp)
-            else:  # net_graphsage.py:30: truncated-normal-like fmod(N(0,1), 2) * 0.01
-                init = torch.fmod(torch.randn(shp, generator=gen), 2) * 0.01
+            else:  # net_graphsage.py:30: fmod(normal(0, std = 0.01), 2) -- effectively a plain N(0, 0.01): no wrap at 2
+                init = torch.fmod(torch.normal(0.0, 0.01, size=tuple(shp), generator=gen), 2)
             name = k.replace(".", "__")
             self._names[k] = name
             self.register_parameter(name, torch.nn.Parameter(init.to(device)))

@@ -38,3 +38,28 @@ def load_golden_graph(path):
 def oracle_weights():
     from oracle import md_oracle as orc
     return {v: orc.load_weights(os.path.join(GOLDEN, "weights_%s.npz" % v)) for v in ("unit", "degree")}
+
+
+Q_RTOL, Q_ATOL = 1e-4, 1e-6  # north_star: Q within 1e-4 relative; 1e-6 absolute floor (|q| ~ 1e-3)
+
+
+def assert_sequence_parity(sol, score, z, ctx=""):
+    """The stated rule for a free-running removal sequence against the reference's golden greedy trace `z`:
+    identical sequence => identical AUDC (bit-exact); otherwise the FIRST differing pick must be a near-tie in the
+    reference's own Q vector: |q_ref_pick - q_our_pick| <= 1e-4 |q_max| + 1e-6.  Never passes vacuously."""
+    ref = [int(a) for a in z["greedy_actions"]]
+    sol = [int(a) for a in sol]
+    same = 0
+    while same < min(len(sol), len(ref)) and sol[same] == ref[same]:
+        same += 1
+    if same == len(ref) == len(sol):
+        assert score == float(z["greedy_final_score"]), (ctx, score, float(z["greedy_final_score"]))
+        return same
+    assert same < len(ref) and same < len(sol), (ctx, "one sequence is a strict prefix of the other", same, len(sol), len(ref))
+    off = z["greedy_off"]
+    qg = z["greedy_q"][off[same]:off[same + 1]]
+    ids = list(z["greedy_active"][off[same]:off[same + 1]])
+    assert sol[same] in ids, (ctx, "picked an inactive node", same, sol[same])
+    gap = abs(float(qg[ids.index(ref[same])]) - float(qg[ids.index(sol[same])]))
+    assert gap <= Q_RTOL * abs(float(qg.max())) + Q_ATOL, (ctx, same, gap)
+    return same

@@ -1,0 +1,169 @@
+"""Parity at BASELINE.json's FULL sizes, through the C ABI.
+
+  * C4: one 3-layer multiplex of N = 1 000 000 nodes, 4 000 000 undirected edges per layer -- greedy steps from the
+    intact graph: LMCC / AUDC / counters / active set / alive degrees bit-exact against the scipy oracle; the final
+    node embeddings and Q of a 100 000-node sample against the L-layer oracle network; one neighbour aggregation
+    (md_agg, cp.async ring) against scipy.sparse CSR @ H.
+  * C2: the exact bench batch (256 degree-cost GMM graphs, N = 1000, seeds 0..255) -- 8 of its rollouts replayed in
+    the oracle (LMCC / AUDC bit-exact on our sequence; free-running oracle sequence equal up to the first near-tie).
+
+L = 3 is an extension of the reference's 2-layer network (oracle/md_oracle.py: forward_torch); there is no reference
+output for it, so the L = 3 Q check is against our own CPU restatement (pinned only through its L = 2 golden vectors).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, Q_ATOL, Q_RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c4_million_node_three_layer_parity():
+    import scipy.sparse as sp
+    import mdcommunity_b200 as mdb
+    from mdcommunity_b200 import _lib, gmm
+    from oracle import md_oracle as orc
+
+    N, L, E = 1_000_000, 3, 4_000_000
+    layers = gmm.random_sparse_layers(N, L, E, seed=0)  # the bench's C4 graph
+    g = mdb.Graph_test(*layers, num_nodes=N, cost="unit")
+    batch = mdb.GraphBatch([g], cost="unit")
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_unit.npz"))), batch.device)
+    ro = mdb.BatchRollout(batch, w, max_steps=32)
+    assert ro.large and not ro.fused
+    og = orc.MultiplexGraph(N, layers)
+    assert g.max_rank == og.max_rank and og.max_rank > 900_000
+    ow = orc.load_weights(os.path.join(GOLDEN, "weights_unit.npz"))
+    env = orc.OracleEnv("unit")
+    env.s0(og)
+    rng = np.random.default_rng(1)
+    lib = ro.lib
+    n_steps = 5
+    for t in range(n_steps):
+        # ---- state before the step: active set, alive degrees, aux features, alive CSR row lengths: exact ----
+        active, degs, aux = env.status()
+        ids = np.nonzero(active)[0]
+        n = int(ro.n_act[0])
+        assert n == len(ids)
+        assert np.array_equal(ro.act_list[:n].cpu().numpy(), ids)
+        assert np.array_equal(ro.aux[0].cpu().numpy(), aux)
+        for l in range(L):
+            assert np.array_equal(ro.deg[l][:N].cpu().numpy(), degs[l])
+            assert int(ro.alive_edges[l, 0]) == int(env.alive_edge_mask(l).sum())
+            ap = ro.aptr[l][:n + 1].cpu().numpy().astype(np.int64)
+            assert np.array_equal(np.diff(ap), degs[l][ids])
+        ro.forward()
+        ids_d, q_d = ro.q_values(0)
+        assert np.array_equal(ids_d, ids)
+        pick = int(0xFFFFFFFF - (int(ro.best[0]) & 0xFFFFFFFF))
+        assert pick == int(ids[np.argmax(q_d)])  # the arg-max key decodes to the first max of the device's own Q
+        if t == 0:
+            # ---- network at full size: embeddings after the 3 iterations and Q on a 100 000-row sample --------
+            rows = np.sort(rng.choice(n, 100_000, replace=False))
+            rows[0] = int(np.nonzero(ids == pick)[0][0])  # always include the picked node
+            rows = np.unique(rows)
+            trace = {}
+            q_o, act_ids, off = orc.forward_q(ow, [env], "unit", trace=trace, head_rows=rows)
+            sel = torch.from_numpy(ids[rows]).to(batch.device)
+            for l in range(L):
+                h_o = trace["h"][(l, orc.MAX_BP_ITER)][rows]
+                h_d = ro.h[_lib.BP_ITERS & 1][l][sel].cpu().numpy()
+                assert float(np.abs(h_d - h_o).max()) <= 2e-5, (l, float(np.abs(h_d - h_o).max()))
+            err = np.abs(q_d[rows] - q_o) - (Q_RTOL * np.abs(q_o) + Q_ATOL)
+            assert float(err.max()) <= 0, float(np.abs(q_d[rows] - q_o).max())
+            # the device's pick is (within tolerance) the oracle's maximum over the sample
+            jo = int(np.nonzero(ids[rows] == pick)[0][0])
+            assert q_o.max() - q_o[jo] <= Q_RTOL * abs(float(q_o.max())) + Q_ATOL
+        # ---- the step: greedy pick of the device (steps 0..2), then a hub and a random node -----------------------
+        if t < 3:
+            a = pick
+            ro.step()
+        else:
+            a = int(ids[np.argmax(degs[1][ids])]) if t == 3 else int(rng.choice(ids))
+            acts = torch.full((1, 1), a, dtype=torch.int32, device=batch.device)
+            ro.step(acts, 0)
+        env.stepWithoutReward(a)
+        assert int(ro.rank[0]) == env.rank_list[-1], t
+        assert float(ro.score[0]) == env.score, t
+        assert list(ro.cov_edges[:, 0].cpu().numpy()) == list(env.numCoveredEdges), t
+        assert bool(int(ro.done[0])) == env.isTerminal()
+    r = ro.results()
+    assert int(r["n_steps"][0]) == n_steps
+    assert list(r["actions"][0, :n_steps]) == env.action_list
+    assert list(r["ranks"][0, :n_steps]) == env.rank_list
+    assert list(r["maxcc"][0, :n_steps]) == env.MaxCCList[1:]
+
+    # ---- one neighbour aggregation of the large-graph path against scipy.sparse CSR @ H -------------------------
+    # md_embed_iter(iter = 1) = md_agg (P = A_alive . H1 into h[0]) + the tensor-core transform that overwrites P in
+    # place; md_debug_set_flags bit 10 drops the transform's stores, which leaves P in h[0].
+    active, degs, _ = env.status()
+    ids = np.nonzero(active)[0]
+    n = len(ids)
+    gp, sp_, wp, kp, st = ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()
+    _lib.check(lib.md_embed_init(gp, sp_, wp, kp, st), "init")
+    _lib.check(lib.md_embed_iter(gp, sp_, wp, kp, 0, st), "iter0")  # h[1] = H1
+    lib.md_debug_set_flags(1024)
+    try:
+        _lib.check(lib.md_embed_iter(gp, sp_, wp, kp, 1, st), "iter1")
+    finally:
+        lib.md_debug_set_flags(0)
+    torch.cuda.synchronize()
+    for l in range(L):
+        h1 = ro.h[1][l][:N].cpu().numpy()
+        e = og.edges[l][env.alive_edge_mask(l)]
+        a_csr = sp.csr_matrix((np.ones(2 * len(e), np.float32), (np.concatenate([e[:, 0], e[:, 1]]), np.concatenate([e[:, 1], e[:, 0]]))),
+                              shape=(N, N))
+        p_ref = (a_csr @ h1)[ids]
+        p_dev = ro.h[0][l][torch.from_numpy(ids).to(batch.device)].cpu().numpy()
+        # rows of H are unit vectors, a sum of d of them is exact to ~d * 2^-24 per element
+        tol = 2e-5 * np.maximum(1.0, degs[l][ids])[:, None]
+        assert np.all(np.abs(p_dev - p_ref) <= tol), (l, float(np.abs(p_dev - p_ref).max()))
+
+
+def test_c2_bench_batch_oracle_replay():
+    """The 256-graph C2 batch of bench.py (degree cost, N = 1000, seeds 0..255): every rollout terminates; 8 of them are
+    replayed in the oracle (our removal sequence -> LMCC trace and AUDC bit-exact) and compared with the oracle's own
+    free-running sequence (equal up to the first pick whose Q gap in the oracle's Q vector is below tolerance)."""
+    import mdcommunity_b200 as mdb
+    from mdcommunity_b200 import gmm
+    from oracle import md_oracle as orc
+    cost = "degree"
+    graphs = [gmm.gmm_graph(1000, i, cost=cost) for i in range(256)]
+    batch = mdb.GraphBatch(graphs, cost=cost)
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_%s.npz" % cost))), batch.device)
+    ro = mdb.BatchRollout(batch, w)
+    res = ro.run()
+    assert ro.num_done() == 256
+    ow = orc.load_weights(os.path.join(GOLDEN, "weights_%s.npz" % cost))
+    agree = 0
+    picks = list(range(0, 256, 32))
+    for i in picks:
+        g = graphs[i]
+        og = orc.MultiplexGraph(g.num_nodes, g.edge_list, weights=g.weights)
+        assert og.max_rank == g.max_rank
+        n = int(res["n_steps"][i])
+        sol = [int(a) for a in res["actions"][i, :n]]
+        forced = orc.rollout(ow, og, cost, forced_actions=sol)
+        assert forced["sol"] == sol
+        assert forced["ranks"] == [int(x) for x in res["ranks"][i, :n]], i
+        assert forced["score"] == float(res["score"][i]), i
+        assert forced["maxcc"][1:] == [float(x) for x in res["maxcc"][i, :n]], i
+        free = orc.rollout(ow, og, cost, record=True)
+        ref = free["sol"]
+        same = 0
+        while same < min(n, len(ref)) and sol[same] == ref[same]:
+            same += 1
+        if same == n == len(ref):
+            agree += 1
+            assert free["score"] == float(res["score"][i])
+        else:
+            assert same < n and same < len(ref)
+            ids, q = list(free["active"][same]), free["q"][same]
+            assert sol[same] in ids
+            gap = abs(float(q[ids.index(ref[same])]) - float(q[ids.index(sol[same])]))
+            assert gap <= Q_RTOL * abs(float(q.max())) + Q_ATOL, (i, same, gap)
+    print("C2 batch: %d of %d sampled rollouts identical to the oracle's free-running sequence" % (agree, len(picks)))

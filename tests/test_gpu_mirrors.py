@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, golden_cases
+from conftest import GOLDEN, assert_sequence_parity, golden_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -71,8 +71,7 @@ def test_driver_getsol_and_predict(variant):
         dqn.InsertGraph(g, is_test=True)
         score, sol, cost = dqn.GetSol(gid)
         ref = [int(a) for a in z["greedy_actions"]]
-        if sol == ref:
-            assert score == float(z["greedy_final_score"])
+        assert_sequence_parity(sol, score, z, (variant, gid))
         # Predict on the reference's states (covered list + remove_edge sets rebuilt by the MvcEnv mirror)
         env = mdb.MvcEnv(50)
         env.s0(g)
@@ -120,11 +119,35 @@ def test_real_file_formats(tmp_path):
     dqn = mdb.MultiDismantler(cost="unit")
     dqn.LoadModel(os.path.join(GOLDEN, "weights_unit.npz"))
     sol, secs, score = dqn.EvaluateRealData(str(path), str(tmp_path), 0.0, int(z["num_nodes"]), (1, 2))
-    ref = [int(a) for a in z["greedy_actions"]]
-    if sol == ref:
-        assert score == float(z["greedy_final_score"])
+    assert_sequence_parity(sol, score, z, "EvaluateRealData")
     out = tmp_path / "StepRatio_0.0000"
     lines = open(out / "Soluion_toy_multiplex_12.txt").read().split()
     assert [int(x) for x in lines] == sol
     lm = open(out / "NormalizedLMCC_toy_multiplex_12.txt").read().split()
     assert len(lm) == int(z["num_nodes"]) + 2 and float(lm[0]) == 1.0
+
+
+def test_two_envs_on_one_graph_do_not_share_state():
+    """The reference keeps all episode state per env (covered_set / remove_edge / score): several MvcEnv objects may hold
+    the same graph (env_list + TrainSet.Sample() with replacement; test_env next to a training env).  Interleaved
+    episodes on one graph object must each reproduce the golden trace."""
+    import mdcommunity_b200 as mdb
+    z = np.load(os.path.join(GOLDEN, "unit_n100_s0.npz"))
+    g = _graph(mdb, z, "unit")
+    e1, e2 = mdb.MvcEnv(50), mdb.MvcEnv(50)
+    e1.s0(g)
+    e2.s0(g)
+    assert e1._ro is not e2._ro and e1._ro.batch is e2._ro.batch  # device CSR shared, episode state per env
+    acts = [int(a) for a in z["random_actions"]]
+    greedy = [int(a) for a in z["greedy_actions"]]
+    for t in range(max(len(acts), len(greedy))):
+        if t < len(acts):
+            e1.stepWithoutReward(acts[t])
+            assert e1.score == z["random_score"][t] and e1.MaxCCList[-1] == z["random_maxcc"][t]
+        if t < len(greedy):
+            e2.stepWithoutReward(greedy[t])
+            assert e2.MaxCCList[-1] == z["greedy_maxcc"][t]
+    assert e1.isTerminal() and e2.isTerminal()
+    assert e2.score == float(z["greedy_final_score"])
+    e1.s0(g)  # re-use: a fresh episode on the same env
+    assert e1.score == 0.0 and not e1.isTerminal() and e2.isTerminal()

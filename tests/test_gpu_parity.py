@@ -542,3 +542,43 @@ def test_edge_case_graphs(fused):
         assert r["score"] == float(res["score"][i]), i
         if og.max_rank <= 1:
             assert T == 0
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
+def test_node_count_multiple_of_tile(fused, env_path):
+    """N % 128 == 0 with every node in a non-singleton mutual component (n_act == N at s0): the per-graph alive-CSR row
+    pointers must not alias between neighbouring graphs (stride >= N + 1).  Two cliques joined by layer-specific cross
+    edges + rings, batched next to each other; rollouts replay bit-exactly in the oracle and equal the solo runs."""
+    from oracle import md_oracle as orc
+    mdb = _mdb()
+    e = lambda p: np.array(p, dtype=np.int64).reshape(-1, 2)
+    N = 128
+    clique = lambda lo, hi: [(i, j) for i in range(lo, hi) for j in range(i + 1, hi)]
+    ring = lambda step: [(i, (i + step) % N) for i in range(N)]
+    specs = [
+        (e(clique(0, 12) + clique(64, 76) + ring(1) + [(3, 70)]), e(clique(0, 12) + clique(64, 76) + ring(1) + [(5, 66), (20, 90)])),
+        (e(ring(1) + ring(5)), e(ring(1) + ring(7))),
+        (e(ring(1) + clique(30, 40)), e(ring(1) + ring(3))),
+    ]
+    graphs = [mdb.Graph_test(a, b, num_nodes=N, cost="unit") for a, b in specs]
+    batch = mdb.GraphBatch(graphs, cost="unit")
+    assert batch.S > N
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_unit.npz"))), batch.device)
+    ro = mdb.BatchRollout(batch, w, fused=fused)
+    assert [int(x) for x in ro.n_act.cpu()] == [N] * len(graphs)
+    for l in range(2):  # row pointers of graph g end where its alive entries end, whatever its neighbour wrote
+        ap = ro.aptr[l].cpu().numpy()
+        for i, g in enumerate(graphs):
+            assert ap[i * batch.S + N] - ap[i * batch.S] == 2 * g.num_edges[l], (l, i)
+    res = ro.run()
+    ow = orc.load_weights(os.path.join(GOLDEN, "weights_unit.npz"))
+    for i, (a, b) in enumerate(specs):
+        og = orc.MultiplexGraph(N, [a, b])
+        assert graphs[i].max_rank == og.max_rank == N
+        T = int(res["n_steps"][i])
+        sol = [int(x) for x in res["actions"][i, :T]]
+        r = orc.rollout(ow, og, "unit", forced_actions=sol)
+        assert r["ranks"] == [int(x) for x in res["ranks"][i, :T]] and r["score"] == float(res["score"][i]), i
+        solo = mdb.BatchRollout(mdb.GraphBatch(graphs[i:i + 1], cost="unit"), w, fused=fused).run()
+        assert int(solo["n_steps"][0]) == T and np.array_equal(solo["actions"][0, :T], res["actions"][i, :T]), i
+        assert solo["score"][0] == res["score"][i]
