@@ -8,7 +8,10 @@ Workload at N=1 (BASELINE.json configs[1], "c2"): degree-cost rollout, 256 two-l
 With --gpus N (torchrun, one rank per GPU) every rank owns its own 256 graphs (weak scaling, no data-path
 collective); the per-graph records are all-gathered over NCCL at the end of every step inside the timed region.
 
-One JSON line is printed by rank 0 (see the contract in the task statement); extra keys: roofline, cpu_baseline.
+One JSON line is printed by rank 0 (see the contract in the task statement); extra keys: roofline (dominant C2 kernel:
+HBM model + shared-memory model, and the LMCC kernel), cpu_baseline, c4 (removal steps/s at N = 1M with per-kernel
+rooflines and a scipy CPU baseline), c3_strong (1024 unit-cost graphs of the three testSynthetic families split over the
+ranks: strong scaling), per_rank_ms / gather_ms (multi-GPU).
 `--impl reference` times the CPU restatement of the reference path (oracle/, kind "port": the reference is pure
 Python and /root/reference does not exist on the GPU box) on the host cores.
 """
@@ -37,6 +40,42 @@ WORKLOADS = {
 def make_graphs(cost, n, count, seed0):
     from mdcommunity_b200 import gmm
     return [gmm.gmm_graph(n, seed0 + i, cost=cost) for i in range(count)]
+
+
+# C3 (BASELINE.json configs[2]): 1024 unit-cost graphs, N = 1000, the three families of testSynthetic
+# (U/testSynthetic.py:20 data_g / data_gamma / data_k; knobs of U/GMM.py:10-25), seed = graph index
+C3_TOTAL = 1024
+C3_G = (0.0, 0.25, 0.5, 0.75, 1.0)
+C3_GAMMA = (2.1, 2.5, 3.0)
+C3_KBAR = (4.0, 6.0, 8.0, 10.0)
+
+
+def c3_params(i):
+    fam, j = i % 3, i // 3
+    g, gamma, kbar = 0.5, 2.5, 6.0
+    if fam == 0:
+        g = C3_G[j % len(C3_G)]
+    elif fam == 1:
+        gamma = C3_GAMMA[j % len(C3_GAMMA)]
+    else:
+        kbar = C3_KBAR[j % len(C3_KBAR)]
+    return dict(g=g, gamma=(gamma, gamma), kbar=(kbar, kbar))
+
+
+def _c3_graph(i):
+    from mdcommunity_b200 import gmm
+    return gmm.gmm_graph(1000, 50_000 + i, cost="unit", **c3_params(i))
+
+
+def make_c3_graphs(indices):
+    """Graph i of the C3 set for every i in `indices` (host generation, outside every timed region; a process pool when
+    the shard is large -- must run before CUDA is initialised in this process)."""
+    indices = list(indices)
+    if len(indices) > 160 and (os.cpu_count() or 1) >= 4 and not torch.cuda.is_initialized():
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(16, os.cpu_count())) as pool:
+            return pool.map(_c3_graph, indices, chunksize=8)
+    return [_c3_graph(i) for i in indices]
 
 
 def load_state_dict(cost):
@@ -156,7 +195,7 @@ def roofline_pass(mdb, batch, w):
     from mdcommunity_b200 import _lib
     ro = mdb.BatchRollout(batch, w)
     lib = ro.lib
-    evs, byts = [], []
+    evs, byts, smem_b = [], [], []
     env_evs, env_byts = [], []
     D = 64
     N_nodes = torch.as_tensor([g.num_nodes for g in batch.graphs], dtype=torch.float64)
@@ -174,6 +213,7 @@ def roofline_pass(mdb, batch, w):
             e1.record()
             evs.append((e0, e1))
             byts.append(3 * floor)
+            smem_b.append(smem_model_bytes(n, [int(z) for z in nnz]))
         else:
             _lib.check(lib.md_embed_init(g, s, wp, k, st), "init")
             for it in range(3):
@@ -214,7 +254,25 @@ def roofline_pass(mdb, batch, w):
             "peak": peak, "unit": "GB/s", "frac": env_ach / peak, "launches": len(env_ms),
             "avg_launch_ms": env_tot / max(1, len(env_ms)), "first_launch_ms": env_ms[0] if env_ms else None,
             "algorithmic_bytes_model": "sum over launches and live graphs of L*(4(N+1)+4*nnz0_l)+4N (static CSR + state)"}
-    return {"bound": "hbm", "kernel": name, "lmcc": lmcc,
+    smem = None
+    if ro.fused and smem_b:
+        props = torch.cuda.get_device_properties(batch.device)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            mhz = pynvml.nvmlDeviceGetMaxClockInfo(pynvml.nvmlDeviceGetHandleByIndex(batch.device.index or 0), pynvml.NVML_CLOCK_SM)
+        except Exception:
+            mhz = 1965
+        speak = 128.0 * props.multi_processor_count * mhz * 1e6 / 1e9  # 128 B / clk / SM
+        sach = float(sum(smem_b)) / (tot_ms * 1e-3) / 1e9
+        smem = {"bound": "shared memory bandwidth (the embeddings of a (graph, layer) unit stay resident in one SM's shared "
+                         "memory: DRAM traffic is 6.5x below the HBM model, so HBM is not what limits this kernel)",
+                "achieved": sach, "peak": speak, "unit": "GB/s", "frac": sach / speak,
+                "first_launch_gbs": smem_b[0] / (ms[0] * 1e-3) / 1e9, "first_launch_frac": smem_b[0] / (ms[0] * 1e-3) / 1e9 / speak,
+                "peak_source": "128 B/clk/SM x %d SMs x %d MHz (max SM clock)" % (props.multi_processor_count, mhz),
+                "model": "per launch 3 x sum_l (256 nnz_l [neighbour rows gathered] + 4 x 256 n [own row, two MMA operand "
+                         "rows, new embedding written])"}
+    return {"bound": "hbm", "kernel": name, "lmcc": lmcc, "smem": smem,
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "traffic_unit": "bytes per launch (first, intact-state launch; compare with first_launch_algorithmic_bytes)",
             "traffic_detail": traffic_detail, "first_launch_algorithmic_bytes": byts[0] if byts else None,
@@ -224,15 +282,53 @@ def roofline_pass(mdb, batch, w):
             "algorithmic_bytes_model": model + ", n=active nodes, nnz=alive directed edges"}
 
 
-def c4_leg(dev, steps=20):
-    """Second part of BASELINE.json's metric: removal steps/sec on one 3-layer graph of N = 1M (config C4), timed with CUDA
-    events per stage; aggregation = the 9 layer-iterations against SURVEY 8(d)'s no-reuse byte model (H_l = 256 MB > L2)."""
+def c4_cpu_baseline(layers, N, D=64):
+    """SURVEY 8(d) / BASELINE.md section 3: C4 cannot run in the reference (dense [n, n] adjacency, L hard-wired to 2), so
+    the CPU figures are labelled RESTATEMENTS timed on the host: one neighbour aggregation = scipy.sparse CSR @ dense
+    [N, 64] f32, one LMCC recompute = the connected_components-based mutual-component loop of oracle/md_oracle.py after
+    removing the node of highest layer-0 degree."""
+    import scipy.sparse as sp
+    from oracle import md_oracle as orc
+    L = len(layers)
+    e = layers[0]
+    a = sp.csr_matrix((np.ones(2 * len(e), np.float32), (np.concatenate([e[:, 0], e[:, 1]]), np.concatenate([e[:, 1], e[:, 0]]))),
+                      shape=(N, N))
+    h = np.random.default_rng(0).standard_normal((N, D), dtype=np.float32)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        a @ h
+        ts.append(time.perf_counter() - t0)
+    agg_s = min(ts)
+    og = orc.MultiplexGraph(N, layers, max_rank=N)
+    removed = np.zeros(N, bool)
+    t0 = time.perf_counter()
+    lab = orc.mutual_labels(og, removed, np.zeros(N, np.int64))
+    s0_s = time.perf_counter() - t0
+    removed[int(np.argmax(np.bincount(e.ravel(), minlength=N)))] = True
+    t0 = time.perf_counter()
+    orc.mutual_labels(og, removed, lab)
+    mcc_s = time.perf_counter() - t0
+    step_s = 3 * L * agg_s + mcc_s  # the 9 aggregations + one LMCC recompute of a step (dense transforms / Q head not counted)
+    return {"kind": "port", "cores": 1, "value": 1.0 / step_s, "unit": "removal steps/s",
+            "aggregation_ms": 1e3 * agg_s, "lmcc_recompute_ms": 1e3 * mcc_s, "lmcc_s0_ms": 1e3 * s0_s,
+            "sample": "one scipy.sparse CSR[1M x 1M, 8M nnz] @ [1M, 64] f32 product (best of 3) and one mutual-component "
+                      "recompute (scipy connected_components loop) on the C4 graph; step = 9 aggregations + 1 recompute; "
+                      "labelled restatements (the reference cannot run this configuration), single-threaded scipy"}
+
+
+def c4_leg(dev, steps=100):
+    """Second part of BASELINE.json's metric: removal steps/sec on one 3-layer graph of N = 1M (config C4), >= 100
+    consecutive greedy steps from the intact graph, every kernel of the step timed with CUDA events on its stream and
+    set against its own algorithmic bytes (H_l = 256 MB > L2, so the no-reuse model is the figure of record
+    for the aggregation)."""
     import ctypes as C
     import mdcommunity_b200 as mdb
     from mdcommunity_b200 import _lib, gmm
     N, L, E, D = 1_000_000, 3, 4_000_000, 64
     t0 = time.time()
-    g = mdb.Graph_test(*gmm.random_sparse_layers(N, L, E, seed=0), num_nodes=N, cost="unit")
+    layers = gmm.random_sparse_layers(N, L, E, seed=0)
+    g = mdb.Graph_test(*layers, num_nodes=N, cost="unit")
     batch = mdb.GraphBatch([g], dev, "unit")
     w = mdb.QWeights(load_state_dict("unit"), dev)
     ro = mdb.BatchRollout(batch, w, max_steps=steps + 16)
@@ -240,43 +336,176 @@ def c4_leg(dev, steps=20):
     setup_s = time.time() - t0
     lib = ro.lib
     gp, sp, wp, kp, st = ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()
-    rows = []
-    for step in range(steps + 3):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    names = ["embed_init", "agg0", "xform0", "agg1", "xform1", "agg2", "xform2", "graph_embed", "qhead", "env_step"]
+    rows, shapes, rounds = [], [], []
+    WARM = 3
+    for step in range(steps + WARM):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
         n_act, nnz = int(ro.n_act[0]), int(2 * ro.alive_edges[:, 0].sum())
-        e[0].record()
+        k = 0
+        e[k].record()
         _lib.check(lib.md_embed_init(gp, sp, wp, kp, st), "init")
-        e[1].record()
-        for it in range(3):
-            _lib.check(lib.md_embed_iter(gp, sp, wp, kp, it, st), "iter")
-        e[2].record()
+        k += 1
+        e[k].record()
+        for it in range(3):  # the two kernels of an iteration, enqueued one by one (md_debug_set_flags bits 14 / 15)
+            lib.md_debug_set_flags(16384)
+            _lib.check(lib.md_embed_iter(gp, sp, wp, kp, it, st), "agg")
+            k += 1
+            e[k].record()
+            lib.md_debug_set_flags(32768)
+            _lib.check(lib.md_embed_iter(gp, sp, wp, kp, it, st), "xform")
+            k += 1
+            e[k].record()
+        lib.md_debug_set_flags(0)
         _lib.check(lib.md_graph_embed(gp, sp, wp, kp, st), "gembed")
+        k += 1
+        e[k].record()
         _lib.check(lib.md_qhead(gp, sp, wp, kp, st), "qhead")
-        e[3].record()
+        k += 1
+        e[k].record()
         ro.step()
-        e[4].record()
+        k += 1
+        e[k].record()
         torch.cuda.synchronize()
-        if step >= 3:
-            rows.append([e[i].elapsed_time(e[i + 1]) for i in range(4)] + [n_act, nnz])
+        if step >= WARM:
+            rows.append([e[i].elapsed_time(e[i + 1]) for i in range(len(names))])
+            shapes.append((n_act, nnz))
+            rounds.append(int(ro.flags[7]) >> 24)  # prune rounds of this step's LMCC recompute (kernel-side counter)
         if int(ro.done[0]):
             break
     r = np.array(rows, dtype=np.float64)
-    med = np.median(r[:, :4], 0)
-    step_ms = float(np.median(r[:, :4].sum(1)))
-    n_act, nnz = r[0, 4], r[0, 5]
-    agg_bytes = 3 * (L * 4 * (n_act + 1) + 4 * nnz + 4 * D * nnz + L * 4 * D * n_act)
+    med = dict(zip(names, np.median(r, 0)))
+    step_ms = float(np.median(r.sum(1)))
+    n_act = float(np.median([x[0] for x in shapes]))
+    nnz = float(np.median([x[1] for x in shapes]))  # directed alive entries, all layers
+    R = float(np.median(rounds))
     peak, src = measured_peak()
-    return {"workload": "C4: one synthetic 3-layer multiplex, N=1000000, 4000000 undirected edges per layer, unit cost, %d greedy steps "
-                        "from the intact graph (score all nodes + arg-max + removal + LMCC recompute per step)" % len(r),
-            "removal_steps_per_s": 1e3 / step_ms, "ms_per_step": step_ms,
-            "median_ms": {"embed_init": med[0], "aggregation_9_layer_iterations": med[1], "graph_embed+qhead": med[2],
-                          "env_step_lmcc": med[3]},
-            "aggregation_roofline": {"bound": "hbm", "achieved": agg_bytes / (med[1] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                     "frac": agg_bytes / (med[1] * 1e-3) / 1e9 / peak, "peak_source": src,
-                                     "algorithmic_bytes_model": "9 x (4(n+1) + 4 nnz + 256 nnz + 256 n): SURVEY 8(d) no-reuse model; "
-                                                                "iteration 0 reads alive degrees instead of rows (see DESIGN 6.13)"},
-            "timing": "CUDA events per stage, median over the steps, 3 warm-up steps", "setup_s": setup_s,
-            "lmcc_rank_after": int(ro.rank[0])}
+
+    def roof(ms, byts, **kw):
+        a = byts / (ms * 1e-3) / 1e9
+        return dict({"bound": "hbm", "ms": ms, "algorithmic_bytes": byts, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak}, **kw)
+
+    b_rows = L * 4 * (n_act + 1) + 4 * nnz + 4 * D * nnz + L * 4 * D * n_act  # one md_agg launch (all layers), no-reuse
+    b_deg = L * 4 * (n_act + 1) + 4 * nnz + 4 * nnz + L * 4 * D * n_act         # iteration 0: 4-byte degree gather per entry
+    b_xf = L * 3 * 4 * D * n_act                                                # read P, read H, write H'
+    b_xf0 = L * (2 * 4 * D * n_act + 4 * n_act)                                 # iteration 0: H0 comes from the degrees
+    b_qh = L * 4 * D * n_act + 4 * n_act + 4 * n_act                            # H_l rows, ids, q
+    b_sweep = 4 * (n_act + 1) + 2 * 4 * nnz / L + 4 * n_act + n_act / 8         # one edge sweep of one layer
+    sweeps = R + 2 * L  # R prune rounds (one Afforest pass each, modelled as one sweep) + per layer: degrees / sizes, alive CSR
+    kern = {
+        "agg_deg (iteration 0: degree gather)": roof(med["agg0"], b_deg),
+        "agg_ring (iterations 1, 2: 256-byte row gather)": roof((med["agg1"] + med["agg2"]) / 2, b_rows),
+        "embed_iter_tc<PRE> (transform, iterations 1, 2)": roof((med["xform1"] + med["xform2"]) / 2, b_xf),
+        "embed_iter_tc<PRE> (transform, iteration 0)": roof(med["xform0"], b_xf0),
+        "qhead_tc<3>": roof(med["qhead"], b_qh),
+        "env_step_large": roof(med["env_step"], sweeps * b_sweep, R=R, L=L, S=1, sweeps=sweeps, B_sweep=b_sweep,
+                               model="(R + 2L) * B_sweep: R prune rounds x 1 sweep, + per layer one sweep for alive "
+                                     "degrees / component sizes and one for the alive-CSR emission"),
+    }
+    agg_ms = sum(med[k] for k in names[1:7])
+    agg_bytes = b_deg + 2 * b_rows + b_xf0 + 2 * b_xf
+    step_bytes = agg_bytes + b_qh + sweeps * b_sweep
+    out = {"workload": "C4: one synthetic 3-layer multiplex, N=1000000, 4000000 undirected edges per layer, unit cost, %d consecutive "
+                       "greedy steps from the intact graph (score all nodes + arg-max + removal + LMCC recompute per step)" % len(r),
+           "removal_steps_per_s": 1e3 / step_ms, "ms_per_step": step_ms, "steps_timed": len(r),
+           "median_ms": {k: float(v) for k, v in med.items()},
+           "stage_ms": {"aggregation_9_layer_iterations": agg_ms, "graph_embed+qhead": med["graph_embed"] + med["qhead"],
+                        "env_step_lmcc": med["env_step"]},
+           "aggregation_roofline": dict(roof(agg_ms, agg_bytes), peak_source=src,
+                                        algorithmic_bytes_model="bytes actually required: iteration 0 = degree gather "
+                                        "(4 B per entry) + transform from degrees; iterations 1, 2 = 4(n+1) + 4 nnz + 256 nnz + 256 n "
+                                        "(SURVEY 8(d) no-reuse) + 3 x 256 n for the transform"),
+           "kernels": kern, "step_roofline": roof(step_ms, step_bytes),
+           "timing": "CUDA events around every launch, median over the steps, %d warm-up steps" % WARM, "setup_s": setup_s,
+           "lmcc_rank_after": int(ro.rank[0]), "n_act_median": n_act, "alive_directed_entries_median": nnz}
+    del ro, batch
+    torch.cuda.empty_cache()
+    try:
+        out["cpu_baseline"] = c4_cpu_baseline(layers, N)
+    except Exception as exc:
+        out["cpu_baseline"] = {"error": repr(exc)}
+    return out
+
+
+def _nccl_log_setup(rank):
+    """NCCL's INFO log goes to a FILE (one per rank) instead of being muted: stdout stays the one JSON line the driver
+    parses, and the line can still say how many ranks the communicator really had."""
+    d = os.path.join(os.environ.get("GRAFT_REPO_ROOT", ROOT), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+    except OSError:
+        d = "/tmp"
+    os.environ["NCCL_DEBUG"] = "INFO"
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    os.environ["NCCL_DEBUG_FILE"] = os.path.join(d, "nccl_bench_rank%d.log" % rank)
+    return os.environ["NCCL_DEBUG_FILE"]
+
+
+def _nccl_log_summary(path):
+    import re
+    out = {"log": path, "nranks": None, "nvls": None}
+    try:
+        txt = open(path, errors="replace").read()
+    except OSError:
+        return out
+    m = re.findall(r"nranks (\d+)", txt)
+    if m:
+        out["nranks"] = max(int(x) for x in m)
+    out["nvls"] = bool(re.search(r"NVLS", txt))
+    return out
+
+
+def smem_model_bytes(n, nnz_per_layer, D=64):
+    """Shared-memory traffic md_embed_fused cannot avoid, per launch (3 iterations, all layers): per layer-iteration the
+    gather reads one 256-byte row per alive entry (256 nnz) and each row's own embedding (256 n), the tensor core reads
+    the two operand rows P and H (2 x 256 n), the epilogue writes the new embedding (256 n)."""
+    return 3 * sum(4 * D * z + 4 * 4 * D * n for z in nnz_per_layer)
+
+
+def c3_strong_leg(mdb, dist, dev, world, rank, graphs, idx, w, steps=3, warmup=1):
+    """BASELINE.json configs[2]: 1024 unit-cost graphs (three testSynthetic families) split over the ranks
+    (sharding.shard_indices: graph i -> rank i mod W), every rank rolls out its shard, one all_gather of the per-graph
+    records (sharding.gather_records) per pass.  STRONG scaling: total work fixed, value = 1024 graphs / max-over-ranks time."""
+    from mdcommunity_b200 import sharding
+    batch = mdb.GraphBatch(graphs, dev, "unit")
+    ro = mdb.BatchRollout(batch, w, max_steps=1000)
+    per_rank_max = (C3_TOTAL + world - 1) // world
+    width = 200  # removal-sequence prefix carried in the record (the full sequences stay on the owning rank)
+    full = None
+
+    def one_pass():
+        nonlocal full
+        ro.reset()
+        ro.run()
+        rec = torch.cat([ro.score[:, None], ro.n_steps[:, None].double(), ro.trace_action[:, :width].double(),
+                         ro.trace_rank[:, :width].double()], 1)
+        full = sharding.gather_records(rec, C3_TOTAL, per_rank_max, device=dev)
+
+    for _ in range(warmup):
+        one_pass()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0]) / steps
+    score, n_steps, _, _ = sharding.unpack_records(full, width)
+    return {"workload": "C3: 1024 unit-cost 2-layer GMM graphs, N=1000; families data_g (g in %s), data_gamma (gamma in %s), "
+                        "data_k (kbar in %s), other knobs g=0.5 gamma=2.5 kbar=6, seed 50000+i; graph i -> rank i mod W" % (
+                            list(C3_G), list(C3_GAMMA), list(C3_KBAR)),
+            "scaling": "strong", "n_gpus": world, "graphs_total": C3_TOTAL, "graphs_per_gpu": len(graphs),
+            "value": C3_TOTAL / (ms * 1e-3), "unit": "graphs/s", "ms_per_pass": ms, "passes": steps,
+            "mean_removals_per_graph": float(n_steps.mean()), "max_removals": int(n_steps.max()), "mean_audc": float(score.mean()),
+            "timing": "CUDA events, reset + rollout + all_gather of the records per pass, max over ranks"}
 
 
 def run_ours(args, cost, n, per_gpu, desc):
@@ -286,15 +515,21 @@ def run_ours(args, cost, n, per_gpu, desc):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    # ---- synthetic inputs (host; before CUDA is initialised: the large C3 shard is generated by a process pool) ----
+    from mdcommunity_b200 import sharding
+    do_c3 = args.workload == "c2" and not args.no_c3
+    c3_idx = sharding.shard_indices(C3_TOTAL, rank, world) if do_c3 else []
+    c3_graphs = make_c3_graphs(c3_idx) if do_c3 else []
+    graphs = make_graphs(cost, n, per_gpu, rank * per_gpu)
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    nccl_log = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line the driver parses
+        nccl_log = _nccl_log_setup(rank)
         dist.init_process_group("nccl", device_id=dev)
     import mdcommunity_b200 as mdb
 
-    graphs = make_graphs(cost, n, per_gpu, rank * per_gpu)
     w = mdb.QWeights(load_state_dict(cost), dev)
     host = mdb.GraphBatch.prepare_host(graphs, cost)
     batch = mdb.GraphBatch(graphs, dev, cost, host=host)
@@ -302,14 +537,21 @@ def run_ours(args, cost, n, per_gpu, desc):
     T = ro.max_steps
     rec_w = 2 + 2 * T  # per-graph record: audc f64, n_steps, then actions / ranks
     gather_buf = torch.empty(world * per_gpu, rec_w, dtype=torch.float64, device=dev) if world > 1 else None
+    gather_ev = []
 
-    def one_step():
+    def one_step(timed=False):
         ro.reset()
         ro.run()
         if world > 1:  # the only collective of the path: gather per-graph AUDC + removal sequences
+            if timed:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
             rec = torch.cat([ro.score[:, None], ro.n_steps[:, None].double(), ro.trace_action.double(),
                              ro.trace_rank.double()], 1)
             dist.all_gather_into_tensor(gather_buf, rec)
+            if timed:
+                b.record()
+                gather_ev.append((a, b))
 
     for _ in range(args.warmup):
         one_step()
@@ -322,14 +564,21 @@ def run_ours(args, cost, n, per_gpu, desc):
     torch.cuda.synchronize()
     e0.record()
     for _ in range(args.steps):
-        one_step()
+        one_step(timed=True)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    my_ms = e0.elapsed_time(e1)
+    ms = torch.tensor([my_ms], device=dev)
+    per_rank_ms = [my_ms / args.steps]
+    gather_ms = None
     if world > 1:
+        allms = torch.zeros(world, device=dev)
+        dist.all_gather_into_tensor(allms, ms.clone())
+        per_rank_ms = [float(x) / args.steps for x in allms.cpu()]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        gather_ms = float(np.mean([a.elapsed_time(b) for a, b in gather_ev]))
     ms = float(ms[0])
     launches = ro.kernel_launches - launches0
     res = ro.results()
@@ -362,6 +611,17 @@ def run_ours(args, cost, n, per_gpu, desc):
     e2e_ms = float(e2e_ms[0])
     d2h = sum(int(v.nbytes) for v in out.values())
     clocks = sampler.stop() if sampler else None
+    del b, out
+
+    c3 = None
+    if do_c3:
+        try:
+            wu = mdb.QWeights(load_state_dict("unit"), dev)
+            c3 = c3_strong_leg(mdb, dist, dev, world, rank, c3_graphs, c3_idx, wu)
+        except Exception as exc:  # the headline line must survive a failure of a secondary leg
+            c3 = {"error": repr(exc)}
+            if world > 1:
+                raise
 
     if rank == 0:
         roof = roofline_pass(mdb, batch, w)
@@ -381,16 +641,22 @@ def run_ours(args, cost, n, per_gpu, desc):
                     "d2h_bytes_per_step": int(d2h), "timing": "wall clock, max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "removal_steps_per_s": world * per_gpu * mean_steps * args.steps / (ms * 1e-3),
+            "per_rank_ms_per_step": per_rank_ms, "gather_ms_per_step": gather_ms,
         }
+        if nccl_log:
+            line["nccl"] = _nccl_log_summary(nccl_log)
+        if c3 is not None:
+            line["c3_strong"] = c3
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(min(16, cores))
-            k = 4 if n >= 1000 else 16
+            k = min(len(graphs), 4 if n >= 1000 else 16)
             dt, st = oracle_rollouts(cost, graphs[:k])
             line["cpu_baseline"] = {"value": k / dt, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "host_cores": cores, "steps_per_s": st / dt,
-                                    "sample": "first %d graphs of the GPU batch, oracle/md_oracle.py rollout, 1 process" % k}
+                                    "sample": "first %d graph(s) of the GPU batch, oracle/md_oracle.py rollout, 1 process" % k}
         if world == 1 and args.workload == "c2" and not args.no_c4:
+            del ro, batch
             torch.cuda.empty_cache()
             try:
                 line["c4"] = c4_leg(dev)
@@ -412,6 +678,7 @@ def main():
     ap.add_argument("--graphs-per-gpu", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the N = 1M removal-steps/s leg (about 30 s)")
+    ap.add_argument("--no-c3", action="store_true", help="skip the 1024-graph strong-scaling leg (C3)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -14,7 +14,9 @@
  *   - one host thread per GPU process.  There is no CPU fallback.
  *
  * Node addressing: a batch holds B graphs; graph g owns the global node slots [g*S, (g+1)*S) where the stride
- * S is a multiple of MD_TILE_M.  Slots >= n_nodes[g] are padding (label -1 for ever).
+ * S is a multiple of MD_TILE_M and S > n_nodes[g] for every graph (at least one padding slot: the alive-CSR row pointers
+ * of graph g occupy aptr[g*S .. g*S + n_act[g]], which must not reach the first word of graph g + 1).
+ * Slots >= n_nodes[g] are padding (label -1 for ever).
  */
 #ifndef MDCOMMUNITY_B200_H
 #define MDCOMMUNITY_B200_H
@@ -156,6 +158,8 @@ void md_debug_force_large_env(int32_t on);
  *   only when the embeddings exceed L2), bit 9 selects md_agg's register-load kernel instead of the cp.async ring,
  *   bit 12 disables iteration 0 from the alive degrees (unit cost) so that md_embed_init writes H0 again;
  * bit 13 keeps relu's argument e @ h1 of the two-layer tensor-core md_qhead on the FP32 pipes (A/B reference);
+ * bits 14 / 15 (two-kernel md_embed_iter only): enqueue only the neighbour aggregation / only the transform, so that a
+ *   caller can time the two kernels of an iteration separately (bit 14 call followed by bit 15 call == the normal sequence);
  * bits 10 / 11 (timing experiments, results become wrong / unchanged): transform kernel without its global stores /
  *   without its L2 prefetch of the next tile */
 void md_debug_set_flags(int32_t flags);

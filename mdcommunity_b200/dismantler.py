@@ -162,19 +162,69 @@ class MultiDismantler:
             remain_score += 1 / g.max_rank * (g.weights[0][v] / tw0 + g.weights[1][v] / tw1) / 2
         return env.score + remain_score
 
-    def GetSolBatch(self, graphs, step=1):
-        """Lock-step rollouts of many graphs: returns (scores f64 [B], list of removal sequences, results dict)."""
+    def GetSolBatch(self, graphs, step=1, distributed=None):
+        """Rollouts of many independent graphs: returns (scores f64 [B], list of removal sequences, results dict).
+
+        distributed: None = shard when torch.distributed is initialised with more than one rank.  Sharded mode is the
+        product-level multi-GPU entry point of the path: graph i goes to rank i mod W (sharding.shard_indices), every rank
+        rolls out its own graphs with no data-path collective, and ONE all_gather of fixed-width per-graph records (AUDC
+        f64 bit-exact, n_steps, removal sequence, LMCC trace) returns the complete result on every rank."""
+        import torch.distributed as dist
+        from . import sharding
         assert self.weights is not None, "LoadModel first"
-        batch = GraphBatch(graphs, device=self.device, cost=self.cost)
-        ro = BatchRollout(batch, self.weights)
-        res = ro.run(step=step)
-        sols = [[int(a) for a in res["actions"][i, :int(res["n_steps"][i])]] for i in range(batch.B)]
+        graphs = list(graphs)
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if distributed is None:
+            distributed = world > 1
+        if not distributed or world == 1:
+            batch = GraphBatch(graphs, device=self.device, cost=self.cost)
+            ro = BatchRollout(batch, self.weights)
+            res = ro.run(step=step)
+        else:
+            rank = dist.get_rank()
+            mine = sharding.shard_indices(len(graphs), rank, world)
+            width = max(g.num_nodes for g in graphs)
+            per_rank_max = (len(graphs) + world - 1) // world
+            if mine:
+                batch = GraphBatch([graphs[i] for i in mine], device=self.device, cost=self.cost)
+                ro = BatchRollout(batch, self.weights, max_steps=width)
+                r = ro.run(step=step)
+                for j, i in enumerate(mine):
+                    graphs[i].max_rank = batch.graphs[j].max_rank
+                rec = sharding.pack_records(r["score"], r["n_steps"], r["actions"], r["ranks"], width)
+                rec = torch.cat([rec, torch.tensor([[float(batch.graphs[j].max_rank)] for j in range(len(mine))],
+                                                   dtype=torch.float64)], 1)
+            else:
+                rec = torch.zeros(0, 3 + 2 * width, dtype=torch.float64)
+            full = sharding.gather_records(rec, len(graphs), per_rank_max, device=self.device)
+            score, n_steps, actions, ranks = sharding.unpack_records(full[:, :2 + 2 * width], width)
+            max_rank = full[:, 2 + 2 * width].cpu().numpy().astype(np.int64)
+            for i, g in enumerate(graphs):
+                g.max_rank = int(max_rank[i])
+            res = dict(score=score, n_steps=n_steps, actions=actions, ranks=ranks, max_rank=max_rank)
+        B = len(graphs)
+        sols = [[int(a) for a in res["actions"][i, :int(res["n_steps"][i])]] for i in range(B)]
         return res["score"], sols, res
 
-    def Evaluate(self, graphs, model_file=None):
-        """(:563-600) on caller-supplied graphs: mean/std of AUDC and of the per-graph solve time."""
+    def Evaluate(self, data_test, data_test_name=None, data_type=None, model_file=None, data_root="../../data/synthetic",
+                 n_test=20):
+        """(:563-600) mean/std of AUDC, of the per-graph solve time and the mean cost over the synthetic test set
+        `{data_root}/{data_type}/syn_{data_test_name}/adj{1,2}_{i}.npy`, i < n_test (the reference hard-codes
+        data_root = "../../data/synthetic" and n_test = 20, 2 in its smoke mode; `data_test` is unused there as well).
+        Timed region per graph = GetSol, as in the reference (:588-590).
+        Convenience: `data_test` may also be a list of Graph_test objects (then no files are read)."""
         if model_file is not None:
             self.LoadModel(model_file)
+        assert self.weights is not None, "LoadModel first (the reference's findModel scans a training directory)"
+        if isinstance(data_test, (list, tuple)) and (not data_test or isinstance(data_test[0], mgraph.Graph_test)):
+            graphs = list(data_test)
+        else:
+            if data_test_name is None or data_type is None:
+                raise ValueError("Evaluate(data_test, data_test_name, data_type, model_file) as in the reference")
+            d = os.path.join(data_root, str(data_type), "syn_%s" % data_test_name)
+            graphs = [mgraph.load_npy_pair(os.path.join(d, "adj1_%s.npy" % i), os.path.join(d, "adj2_%s.npy" % i), cost=self.cost)
+                      for i in range(n_test)]
+        self.ClearTestGraphs()
         scores, times, costs = [], [], []
         for i, g in enumerate(graphs):
             self.InsertGraph(g, is_test=True)

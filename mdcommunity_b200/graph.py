@@ -61,6 +61,27 @@ class Graph_test:
             self.weights.append(deg / max(int(deg.max()), 1))
 
 
+def edges_from_dense(adj):
+    """Edge list of a dense symmetric adjacency matrix in the order the reference obtains it:
+    nx.from_numpy_array(adj) followed by G.edges() (U/MultiDismantler_torch.py:585-587) yields each undirected edge once,
+    as (u, v) with u < v, in row-major order of the upper triangle.  The order matters: neighbour rows are summed in
+    edge-list order (see build_csr).  Diagonal entries (self loops) are dropped."""
+    a = np.asarray(adj)
+    if a.ndim != 2 or a.shape[0] != a.shape[1]:
+        raise ValueError("adjacency must be a square matrix")
+    sym = (a != 0) | (a.T != 0)
+    return np.argwhere(np.triu(sym, 1)).astype(np.int64)
+
+
+def load_npy_pair(path1, path2, cost="unit"):
+    """Two dense adjacency .npy files (the synthetic test sets of testSynthetic: adj1_i.npy / adj2_i.npy,
+    U/MultiDismantler_torch.py:575-587) -> Graph_test."""
+    a1, a2 = np.load(path1), np.load(path2)
+    if a1.shape != a2.shape:
+        raise ValueError("the two layers must have the same number of nodes")
+    return Graph_test(edges_from_dense(a1), edges_from_dense(a2), num_nodes=int(a1.shape[0]), cost=cost)
+
+
 class GSet:
     """graph.GSet (U/graph.py:53-68)."""
 

@@ -198,3 +198,26 @@ def test_gradient_allreduce_gloo_world2():
         assert p.exitcode == 0
     assert flat == [3.0] * 6 + [0.0, 3.0, 6.0, 9.0, 12.0]
     assert g0 == [[3.0, 3.0]] * 3 and g1 == [0.0, 3.0, 6.0, 9.0, 12.0]
+
+
+def test_dense_adjacency_loader_matches_networkx_edge_order(tmp_path):
+    """load_npy_pair (the .npy synthetic test sets of testSynthetic, U/MultiDismantler_torch.py:575-587): the edge
+    list must come out in the order of nx.from_numpy_array(adj) -> G.edges(), which fixes the neighbour summation order."""
+    import networkx as nx
+    from mdcommunity_b200 import graph as mg
+    rng = np.random.default_rng(0)
+    n = 40
+    adjs = []
+    for k in range(2):
+        a = (rng.random((n, n)) < 0.12).astype(np.float64)
+        a = np.triu(a, 1)
+        a = a + a.T
+        adjs.append(a)
+        np.save(tmp_path / ("adj%d_0.npy" % (k + 1)), a)
+    g = mg.load_npy_pair(str(tmp_path / "adj1_0.npy"), str(tmp_path / "adj2_0.npy"))
+    assert g.num_nodes == n and g.num_layers == 2
+    for l in range(2):
+        ref = np.array(list(nx.from_numpy_array(adjs[l]).edges()), dtype=np.int64).reshape(-1, 2)
+        assert np.array_equal(g.edge_list[l], ref)
+    with pytest.raises(ValueError):
+        mg.edges_from_dense(np.zeros((3, 4)))
