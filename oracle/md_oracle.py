@@ -236,6 +236,7 @@ def _fuse(w, embs, p):
     return t[p] + z
 
 
+F64_POOL_ROWS = 1 << 16  # graphs with more active rows than this: per-graph embedding sums in f64 (see forward_torch)
 FUSE_CHUNK = 1 << 17  # rows per fusion call for very large graphs (bounds the [n, L, 64] temporaries; N = 1M only)
 
 
@@ -307,7 +308,15 @@ def forward_torch(w, envs, variant, trace=None, head_rows=None):
         for _ in range(MAX_BP_ITER):
             pool = spmm_coo(row, col, n, h)
             node_linear = torch.matmul(pool, w["p_node_conv"])
-            y_pool = spmm_coo(gid, torch.arange(n), B, h)
+            if n > F64_POOL_ROWS:
+                # torch_sparse.spmm(subgsum) is a sequential f32 scatter-add over the graph's rows.  Over ~1M rows (many of
+                # them bit-identical: the first embedding depends on the degree only) its rounding errors no longer
+                # average out -- the f32 running sum is quantised to ulp(1e5) ~ 0.008 per add and the result depends on
+                # the row order at the 1e-2 level.  The reference cannot run such graphs at all (dense [n, n] adjacency);
+                # for them the oracle forms the segment sum in f64, the exact value every f32 summation order approximates.
+                y_pool = torch.zeros((B, h.shape[1]), dtype=torch.float64).index_add_(0, gid, h.double()).float()
+            else:
+                y_pool = spmm_coo(gid, torch.arange(n), B, h)
             y_linear = torch.matmul(y_pool, w["p_node_conv"])
             merged = torch.cat([node_linear, torch.matmul(h, w["p_node_conv2"])], 1)
             h = F.normalize(torch.relu(torch.matmul(merged, w["p_node_conv3"])), p=2, dim=1)

@@ -48,10 +48,21 @@ def test_train_step_matches_reference():
             g = tr.net.p(k[5:]).grad.cpu().numpy().reshape(g_ref.shape)
             scale = np.abs(g_ref).max() + 1e-12
             assert np.abs(g - g_ref).max() <= 1e-3 * scale + 1e-9, (k, np.abs(g - g_ref).max(), scale)
+    before = {k: tr.net.p(k).detach().cpu().numpy().copy() for k in train.PARAM_SHAPES}
     tr.optimizer.step()
+    lr = 1e-4  # LEARNING_RATE, U/MultiDismantler_torch.py:38
     for k in z.files:
         if k.startswith("after/"):
-            assert np.allclose(tr.net.p(k[6:]).detach().cpu().numpy().reshape(z[k].shape), z[k], rtol=0, atol=2e-6), k
+            name = k[6:]
+            after = tr.net.p(name).detach().cpu().numpy().reshape(z[k].shape)
+            g_ref = z["grad/" + name].reshape(z[k].shape)
+            # Adam's first step moves a parameter by lr * g / (|g| + 1e-8): for |g| >> 1e-8 that is -+lr whatever the
+            # magnitude, for |g| ~ 1e-8 it depends on the last bits of g (a sign flip of rounding noise moves the
+            # parameter by 2 lr).  So: entries with a resolved gradient must match the reference's update to 2e-6; the
+            # others (gradient below 1e-2 of the tensor's largest) must simply be a bounded Adam step.
+            resolved = np.abs(g_ref) >= 1e-2 * (np.abs(g_ref).max() + 1e-30)  # 10x the gradient tolerance above
+            assert np.all(np.abs(after - z[k])[resolved] <= 2e-6), (k, float(np.abs(after - z[k])[resolved].max()))
+            assert np.all(np.abs(after - before[name].reshape(z[k].shape)) <= lr * 1.001 + 1e-9), k
 
 
 def test_fit_reduces_loss_and_matches_single_call():
