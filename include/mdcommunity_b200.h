@@ -90,8 +90,14 @@ typedef struct md_state {
   /* scratch for the large-graph (multi-CTA) LMCC path, may be NULL when stride <= md_env_small_max_stride() */
   int32_t* parent;       /* [n_total] */
   int32_t* comp_size;    /* [n_total] */
-  int32_t* flags;        /* [8] scratch: [0..3] grid barrier / change flags of the multi-CTA env kernel, [4] tile queue of md_qhead */
+  int32_t* flags;        /* [16] scratch: [0..3] grid barrier / change flags of the multi-CTA env kernel, [4..5] tile queue of
+                            md_qhead, [6..7] phase timers of the multi-CTA env kernel, [8] number of graphs that have LEFT the
+                            lock-step iteration (terminal, or handed over to md_rollout_tail) */
   int32_t* cur_action;   /* [B] action applied in the running step (-1 = graph untouched) */
+  int32_t* tail_n;       /* [B] or NULL.  Non-NULL enables the hand-over to md_rollout_tail: when a step leaves a graph with
+                            at most md_tail_max_nodes() active nodes (and md_tail_max_entries() alive entries per layer),
+                            md_env_step stores that node count here and marks the graph finished FOR THE LOCK-STEP KERNELS
+                            (n_act = 0, done = 1, n_done untouched); md_rollout_tail completes it.  Zero-initialised. */
 } md_state_t;
 
 /* The 14-tensor checkpoint (U/MultiDismantler_net_graphsage.py:42-89, U/MRGNN/mutil_layer_weight.py:252-264),
@@ -220,6 +226,23 @@ int md_qhead(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, c
 /* n_steps lock-step greedy iterations (GetSol loop body, U/MultiDismantler_torch.py:759-784): forward + env step. */
 int md_rollout_steps(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                      int32_t n_steps, md_stream_t stream);
+
+/* ---- tail of a rollout ------------------------------------------------------------------------------------------
+ * A lock-step iteration costs ~100 us of fixed latency however small the graphs have become, and most removals of a
+ * rollout happen after the graph has collapsed to a few dozen active nodes.  With s->tail_n set, such graphs leave the
+ * lock step (see md_state_t.tail_n) and ONE CTA per graph finishes the rollout on chip: the GetSol loop body
+ * (U/MultiDismantler_torch.py:759-784: Predict + arg-max + stepWithoutReward) with all state in shared memory.
+ * Two-layer batches on the single-CTA env path only (md_tail_applies). */
+int32_t md_tail_applies(const md_graphs_t* g);
+int32_t md_tail_max_nodes(void);
+int32_t md_tail_max_entries(void);
+/* hand over every non-terminal graph that is already small enough (call once after md_env_reset, before the first iteration) */
+int md_tail_handover(const md_graphs_t* g, const md_state_t* s, md_stream_t stream);
+/* Finish all handed-over graphs.  The launch is ordered AFTER everything enqueued on `stream` so far but runs on an
+ * internal low-priority stream, i.e. it does not block later work on `stream`: the lock-step iterations of the larger
+ * graphs continue while the small ones finish on idle SMs.  md_tail_join makes `stream` wait for all tail launches. */
+int md_rollout_tail(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, md_stream_t stream);
+int md_tail_join(md_stream_t stream);
 
 /* The same n_steps iterations captured once into a CUDA graph and replayed (launch-bound tail of a rollout).  Call
  * md_rollout_steps at least once before md_rollout_graph_create; the graph bakes in the struct values (device pointers),

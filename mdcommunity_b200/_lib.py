@@ -38,7 +38,7 @@ class MdState(C.Structure):
         ("done", _vp), ("n_steps", _vp), ("score", _vp), ("aux", _vp), ("best", _vp),
         ("trace_action", _vp), ("trace_rank", _vp), ("trace_maxcc", _vp), ("n_done", _vp),
         ("max_steps", C.c_int32), ("cost_mode", C.c_int32),
-        ("parent", _vp), ("comp_size", _vp), ("flags", _vp), ("cur_action", _vp),
+        ("parent", _vp), ("comp_size", _vp), ("flags", _vp), ("cur_action", _vp), ("tail_n", _vp),
     ]
 
 
@@ -76,6 +76,12 @@ _SIGS = {
     "md_graph_embed": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_qhead": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), _vp], C.c_int),
     "md_rollout_steps": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp], C.c_int),
+    "md_tail_applies": ([C.POINTER(MdGraphs)], C.c_int32),
+    "md_tail_max_nodes": ([], C.c_int32),
+    "md_tail_max_entries": ([], C.c_int32),
+    "md_tail_handover": ([C.POINTER(MdGraphs), C.POINTER(MdState), _vp], C.c_int),
+    "md_rollout_tail": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), _vp], C.c_int),
+    "md_tail_join": ([_vp], C.c_int),
     "md_heuristic_select": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.c_int32, C.c_int32, _vp], C.c_int),
     "md_rollout_graph_create": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp,
                                  C.POINTER(C.c_void_p)], C.c_int),

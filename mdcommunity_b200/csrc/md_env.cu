@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   // edge-parallel block scan per layer (hub rows cost nothing extra).  The running prefix is kept per entry (in the
   // c_src slots, dead after the prune), so deg(v) = pref[row end] - pref[row start] needs no second edge sweep.
   bool terminal = false;
-  int n_act = 0;
+  int n_act = 0, max_tot = 0;
   for (int ll = 0; ll < L; ++ll) {
     const int* rp = c_rp + ll * (St + 1);
     const int p0 = lay_pos[ll], cnt = lay_pos[ll + 1] - p0;
@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       S.twohop[ll * G.n_graphs + g] = t2;
     }
     terminal |= (tot == 0);
+    max_tot = max(max_tot, tot);
     __syncthreads();
 
     if (ll == 0) {
@@ -411,7 +412,17 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       ax[3] = 1.0f;
     }
     S.done[g] = terminal ? 1 : 0;
-    if (terminal) atomicAdd(S.n_done, 1);
+    if (terminal) {
+      atomicAdd(S.n_done, 1);
+      atomicAdd(&S.flags[FLAG_LEFT], 1);
+    } else if (S.tail_n != nullptr && init == 0 && L == 2 && n_act <= TL_N && max_tot <= TL_E) {
+      // small enough to finish on one SM: hand the graph over to md_rollout_tail.  For the lock-step kernels it is
+      // finished from here on (they skip graphs with n_act == 0 / done != 0); n_done counts it when the tail completes it.
+      S.tail_n[g] = n_act;
+      S.n_act[g] = 0;
+      S.done[g] = 1;
+      atomicAdd(&S.flags[FLAG_LEFT], 1);
+    }
   }
 }
 
@@ -460,6 +471,10 @@ static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* 
   if (init) {
     cudaError_t e = cudaMemsetAsync(s->n_done, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return (int)e;
+    if (s->flags) {
+      e = cudaMemsetAsync(s->flags + md::FLAG_LEFT, 0, sizeof(int32_t), st);
+      if (e != cudaSuccess) return (int)e;
+    }
   }
   if (i16)
     md::env_step_small<uint16_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz);

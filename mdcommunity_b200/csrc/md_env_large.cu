@@ -428,7 +428,10 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
       ax[3] = 1.0f;
     }
     S.done[g] = terminal ? 1 : 0;
-    if (terminal) atomicAdd(S.n_done, 1);
+    if (terminal) {
+      atomicAdd(S.n_done, 1);
+      atomicAdd(&S.flags[FLAG_LEFT], 1);
+    }
   }
 }
 
@@ -455,6 +458,8 @@ int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* 
   if (e != cudaSuccess) return (int)e;
   if (init) {
     e = cudaMemsetAsync(s->n_done, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(s->flags + md::FLAG_LEFT, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return (int)e;
   }
   int cpg = grid / g->n_graphs;

@@ -20,8 +20,6 @@
 
 namespace md {
 
-constexpr int TL_N = 128;           // most active nodes a graph may have at hand-over
-constexpr int TL_E = 4096;          // most alive directed entries per layer at hand-over
 constexpr int TL_T = 256;
 constexpr int TL_W = TL_T / 32;
 constexpr int TL_LD = 2 * D + 4;    // final-embedding tile: row = [H_0 (64) | H_1 (64) | pad], as in md_qhead.cu
@@ -781,7 +779,7 @@ __global__ void tail_handover_kernel(md_graphs_t G, md_state_t S) {
   S.tail_n[g] = n;
   S.n_act[g] = 0;
   S.done[g] = 1;
-  atomicAdd(&S.flags[8], 1);
+  atomicAdd(&S.flags[FLAG_LEFT], 1);
 }
 
 }  // namespace md
@@ -802,6 +800,31 @@ extern "C" int md_tail_handover(const md_graphs_t* g, const md_state_t* s, md_st
   return 0;
 }
 
+// ---- the tail stream: low priority, one per device ------------------------------------------------------------------
+namespace {
+struct TailCtx {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
+md::PerDevice<TailCtx> g_tail_ctx;
+int tail_ctx(TailCtx** out) {
+  TailCtx& c = g_tail_ctx.get();
+  if (!c.st) {
+    int least = 0, greatest = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamCreateWithPriority(&c.st, cudaStreamNonBlocking, least);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) return (int)e;
+  }
+  *out = &c;
+  return 0;
+}
+}  // namespace
+
 extern "C" int md_rollout_tail(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, md_stream_t stream) {
   if (!g || !s || !w || !s->tail_n) return MD_EINVAL;
   if (!md_tail_applies(g)) return MD_ETOOBIG;
@@ -813,7 +836,26 @@ extern "C" int md_rollout_tail(const md_graphs_t* g, const md_state_t* s, const 
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  md::rollout_tail_kernel<<<g->n_graphs, md::TL_T, smem, (cudaStream_t)stream>>>(*g, *s, *w);
+  TailCtx* c = nullptr;
+  int rc = tail_ctx(&c);
+  if (rc) return rc;
+  // fork: the tail launch sees everything enqueued on `stream` so far, `stream` itself does not wait for it
+  cudaError_t e = cudaEventRecord(c->ev_fork, (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaStreamWaitEvent(c->st, c->ev_fork, 0);
+  if (e != cudaSuccess) return (int)e;
+  md::rollout_tail_kernel<<<g->n_graphs, md::TL_T, smem, c->st>>>(*g, *s, *w);
   MD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int md_tail_join(md_stream_t stream) {
+  TailCtx* c = nullptr;
+  int rc = tail_ctx(&c);
+  if (rc) return rc;
+  cudaError_t e = cudaEventRecord(c->ev_join, c->st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaStreamWaitEvent((cudaStream_t)stream, c->ev_join, 0);
+  if (e != cudaSuccess) return (int)e;
   return 0;
 }

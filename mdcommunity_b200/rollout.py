@@ -73,9 +73,11 @@ class BatchRollout:
     results after run(): score [B] f64 (AUDC), n_steps [B], actions [B, T] (-1 padded), ranks [B, T], maxcc [B, T].
     """
 
-    def __init__(self, batch: GraphBatch, weights: QWeights = None, max_steps=None, fused=None):
+    def __init__(self, batch: GraphBatch, weights: QWeights = None, max_steps=None, fused=None, tail=None):
         """fused: None = use md_embed_fused whenever the batch qualifies (stride <= md_fused_max_stride());
-        False = always the unfused md_embed_init + md_embed_iter kernels (A/B tests, large graphs)."""
+        False = always the unfused md_embed_init + md_embed_iter kernels (A/B tests, large graphs).
+        tail: None = run() hands graphs that have shrunk to <= md_tail_max_nodes() active nodes over to md_rollout_tail
+        (one CTA finishes each of them on chip) whenever the batch qualifies; False = pure lock step to the end."""
         self.batch = batch
         self.lib = batch.lib
         self.w = weights
@@ -102,8 +104,9 @@ class BatchRollout:
         self.large = not self.lib.md_env_uses_small_path(batch.ptr())
         self.parent = i32(nt) if self.large else None
         self.comp_size = i32(nt) if self.large else None
-        self.flags = i32(8)
+        self.flags = i32(16)
         self.cur_action = i32(B)
+        self.tail_n = i32(B)
         s = _lib.MdState()
         s.label = self.label.data_ptr()
         for l in range(L):
@@ -119,7 +122,15 @@ class BatchRollout:
         s.comp_size = self.comp_size.data_ptr() if self.large else None
         s.max_steps = self.max_steps
         s.cost_mode = 1 if batch.cost == "degree" else 0
+        s.tail_n = None
         self.s = s
+        # the same state with the hand-over to md_rollout_tail switched on: only run() uses it (teacher-forced steps,
+        # forward() / q_values() inspection, top-k and heuristic rollouts keep every graph in the lock-step kernels)
+        self.tail = (tail is not False) and bool(self.lib.md_tail_applies(batch.ptr()))
+        if tail and not self.tail:
+            raise ValueError("md_rollout_tail handles two-layer batches on the single-CTA env path only")
+        self.s_tail = _lib.MdState.from_buffer_copy(s)
+        self.s_tail.tail_n = self.tail_n.data_ptr()
         # activations
         self.h = [[torch.zeros(nt, _lib.EMBED, dtype=torch.float32, device=dev) for _ in range(L)] for _ in range(2)]
         self.psum = torch.zeros(int(self.lib.md_psum_floats(L, nt)), dtype=torch.float32, device=dev)
@@ -158,6 +169,7 @@ class BatchRollout:
     def reset(self):
         """MvcEnv.s0 for every graph; also fills graph.max_rank (Graph_test.ori_rank) on first use."""
         self.trace_action.fill_(-1)
+        self.tail_n.zero_()
         _lib.check(self.lib.md_env_reset(self._g(), C.byref(self.s), self._stream()), "md_env_reset")
         self.kernel_launches += 1
         if not getattr(self.batch, "_max_rank_set", False):
@@ -209,6 +221,50 @@ class BatchRollout:
         torch.cuda.current_stream(self.batch.device).synchronize()
         return int(self._pinned_done[0])
 
+    def num_left(self):
+        """Graphs that have left the lock-step iteration (terminal, or handed over to md_rollout_tail)."""
+        self._pinned_done.copy_(self.flags[8:9], non_blocking=True)
+        torch.cuda.current_stream(self.batch.device).synchronize()
+        return int(self._pinned_done[0])
+
+    # -- greedy rollout: pieces shared by run() and MultiStreamRollout -------------------------------------------
+    def _run_state(self, step=1):
+        return self.s_tail if (self.tail and step == 1) else self.s
+
+    def _begin_run(self, step=1):
+        """Start of a greedy rollout from the current env state: graphs that are already small go to md_rollout_tail."""
+        if self.tail and step == 1:
+            st = self._stream()
+            _lib.check(self.lib.md_tail_handover(self._g(), C.byref(self.s_tail), st), "md_tail_handover")
+            _lib.check(self.lib.md_rollout_tail(self._g(), C.byref(self.s_tail), self.w.ptr(), st), "md_rollout_tail")
+            self.kernel_launches += 2
+
+    def _enqueue_chunk(self, chunk, first):
+        """`chunk` lock-step iterations on the current stream (one CUDA-graph launch from the second run of this object
+        on), then -- tail mode -- one md_rollout_tail launch for the graphs the chunk handed over."""
+        s = self._run_state()
+        if self._graph is None and self._runs > 0 and not first and not self.large and self.use_graph:
+            # a chunk of iterations as ONE CUDA graph, built when the rollout object is re-used (instantiation costs
+            # about as much as one small rollout); the first chunk ran eagerly: one-time kernel attributes are set
+            ex = C.c_void_p()
+            _lib.check(self.lib.md_rollout_graph_create(self._g(), C.byref(s), self.w.ptr(), C.byref(self.k), chunk,
+                                                        self._stream(), C.byref(ex)), "md_rollout_graph_create")
+            self._graph, self._graph_chunk, self._graph_w = ex, chunk, self.w
+        if self._graph is not None and self._graph_chunk == chunk and self._graph_w is self.w:
+            _lib.check(self.lib.md_rollout_graph_launch(self._graph, self._stream()), "md_rollout_graph_launch")
+        else:
+            _lib.check(self.lib.md_rollout_steps(self._g(), C.byref(s), self.w.ptr(), C.byref(self.k), chunk,
+                                                 self._stream()), "md_rollout_steps")
+        self.kernel_launches += chunk * ((5 if self.fused else 4 + _lib.BP_ITERS))
+        if s is self.s_tail:
+            _lib.check(self.lib.md_rollout_tail(self._g(), C.byref(s), self.w.ptr(), self._stream()), "md_rollout_tail")
+            self.kernel_launches += 1
+
+    def _finish_run(self):
+        if self.tail:
+            _lib.check(self.lib.md_tail_join(self._stream()), "md_tail_join")
+        self._runs += 1
+
     @_on_device
     def run(self, chunk=8, step=1):
         """Greedy rollout to termination (GetSol when step == 1, GetSolution's top-`step` batches otherwise)."""
@@ -217,21 +273,10 @@ class BatchRollout:
         topk = None
         if step > 1:
             topk = torch.empty(B, step, dtype=torch.int32, device=self.batch.device)
+        self._begin_run(step)
         while True:
             if step == 1:
-                if self._graph is None and self._runs > 0 and it > 0 and not self.large and self.use_graph:
-                    # a chunk of iterations as ONE CUDA graph, built when the rollout object is re-used (instantiation costs
-                    # about as much as one small rollout); the first chunk ran eagerly: one-time kernel attributes are set
-                    ex = C.c_void_p()
-                    _lib.check(self.lib.md_rollout_graph_create(self._g(), C.byref(self.s), self.w.ptr(), C.byref(self.k), chunk,
-                                                                self._stream(), C.byref(ex)), "md_rollout_graph_create")
-                    self._graph, self._graph_chunk, self._graph_w = ex, chunk, self.w
-                if self._graph is not None and self._graph_chunk == chunk and self._graph_w is self.w:
-                    _lib.check(self.lib.md_rollout_graph_launch(self._graph, self._stream()), "md_rollout_graph_launch")
-                else:
-                    _lib.check(self.lib.md_rollout_steps(self._g(), C.byref(self.s), self.w.ptr(), C.byref(self.k), chunk,
-                                                         self._stream()), "md_rollout_steps")
-                self.kernel_launches += chunk * ((5 if self.fused else 4 + _lib.BP_ITERS))
+                self._enqueue_chunk(chunk, it == 0)
             else:
                 for _ in range(chunk):
                     self.forward()
@@ -241,9 +286,9 @@ class BatchRollout:
                     for j in range(step):
                         self.step(topk, j)
             it += chunk
-            if self.num_done() >= B or it > self.max_steps + chunk:
+            if self.num_left() >= B or it > self.max_steps + chunk:
                 break
-        self._runs += 1
+        self._finish_run()
         return self.results()
 
     @_on_device
@@ -307,34 +352,21 @@ class MultiStreamRollout:
     def kernel_launches(self):
         return sum(r.kernel_launches for r in self.rollouts)
 
-    def _enqueue_chunk(self, ro, first):
-        """One chunk of lock-step iterations of sub-rollout `ro` on the current stream (CUDA-graph replay from its second run on)."""
-        lib, chunk = ro.lib, self.chunk
-        if ro._graph is None and ro._runs > 0 and not first and not ro.large and ro.use_graph:
-            ex = C.c_void_p()
-            _lib.check(lib.md_rollout_graph_create(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), chunk, ro._stream(), C.byref(ex)),
-                       "md_rollout_graph_create")
-            ro._graph, ro._graph_chunk, ro._graph_w = ex, chunk, ro.w
-        if ro._graph is not None and ro._graph_chunk == chunk and ro._graph_w is ro.w:
-            _lib.check(lib.md_rollout_graph_launch(ro._graph, ro._stream()), "md_rollout_graph_launch")
-        else:
-            _lib.check(lib.md_rollout_steps(ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), chunk, ro._stream()), "md_rollout_steps")
-        ro.kernel_launches += chunk * (5 if ro.fused else 4 + _lib.BP_ITERS)
-
     def run(self):
         cur = torch.cuda.current_stream(self.device)
         for ro, st in zip(self.rollouts, self.streams):
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 ro.reset()
+                ro._begin_run()
         live = list(range(len(self.rollouts)))
         it = 0
         while live:
             for i in live:
                 ro = self.rollouts[i]
                 with torch.cuda.stream(self.streams[i]):
-                    self._enqueue_chunk(ro, it == 0)
-                    self._pins[i].copy_(ro.n_done, non_blocking=True)
+                    ro._enqueue_chunk(self.chunk, it == 0)
+                    self._pins[i].copy_(ro.flags[8:9], non_blocking=True)
                     self.events[i].record(self.streams[i])
             nxt = []
             for i in live:
@@ -344,7 +376,8 @@ class MultiStreamRollout:
             live = nxt
             it += self.chunk
         for ro, st in zip(self.rollouts, self.streams):
-            ro._runs += 1
+            with torch.cuda.stream(st):
+                ro._finish_run()
             cur.wait_stream(st)
         return self.results()
 

@@ -582,3 +582,55 @@ def test_node_count_multiple_of_tile(fused, env_path):
         solo = mdb.BatchRollout(mdb.GraphBatch(graphs[i:i + 1], cost="unit"), w, fused=fused).run()
         assert int(solo["n_steps"][0]) == T and np.array_equal(solo["actions"][0, :T], res["actions"][i, :T]), i
         assert solo["score"][0] == res["score"][i]
+
+
+@pytest.mark.parametrize("variant", ["unit", "degree"])
+def test_tail_kernel_matches_lock_step(variant):
+    """run() with the hand-over to md_rollout_tail (one CTA finishes a graph once it has <= 128 active nodes) against the
+    pure lock-step rollout (tail=False) on the golden batch + mid-size graphs that hand over in the middle of their
+    rollout: every sequence replays bit-exactly in the oracle (LMCC trace, AUDC), and the two modes pick the same nodes
+    except on sub-tolerance ties (checked in the oracle's own Q vector at the first difference)."""
+    from oracle import md_oracle as orc
+    from mdcommunity_b200 import gmm
+    mdb = _mdb()
+    zs, graphs, _, _ = _load_batch(variant)
+    graphs = list(graphs) + [gmm.gmm_graph(n, 300 + n, cost=variant) for n in (180, 260, 400, 700)]
+    batch = mdb.GraphBatch(graphs, cost=variant)
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_%s.npz" % variant))), batch.device)
+    a = mdb.BatchRollout(batch, w, tail=True)
+    b = mdb.BatchRollout(batch, w, tail=False)
+    assert a.tail and not b.tail
+    ra, rb = a.run(), b.run()
+    assert a.num_done() == len(graphs) and b.num_done() == len(graphs)
+    assert int(a.tail_n.abs().sum()) == 0 and int(a.n_act.sum()) == 0
+    ow = orc.load_weights(os.path.join(GOLDEN, "weights_%s.npz" % variant))
+    same_all = 0
+    for i, g in enumerate(graphs):
+        og = orc.MultiplexGraph(g.num_nodes, g.edge_list, weights=g.weights if variant == "degree" else None)
+        seqs = []
+        for r in (ra, rb):
+            n = int(r["n_steps"][i])
+            sol = [int(x) for x in r["actions"][i, :n]]
+            f = orc.rollout(ow, og, variant, forced_actions=sol)
+            assert f["ranks"] == [int(x) for x in r["ranks"][i, :n]], (variant, i)
+            assert f["score"] == float(r["score"][i]), (variant, i)
+            assert f["maxcc"][1:] == [float(x) for x in r["maxcc"][i, :n]], (variant, i)
+            seqs.append(sol)
+        sa, sb = seqs
+        k = 0
+        while k < min(len(sa), len(sb)) and sa[k] == sb[k]:
+            k += 1
+        if k == len(sa) == len(sb):
+            same_all += 1
+            assert ra["score"][i] == rb["score"][i]
+            continue
+        assert k < len(sa) and k < len(sb), (variant, i)
+        env = orc.OracleEnv(variant)
+        env.s0(og)
+        for x in sa[:k]:
+            env.stepWithoutReward(x)
+        p = orc.predict(ow, [env], variant)[0]
+        assert abs(p[sa[k]] - p[sb[k]]) <= Q_RTOL * abs(p.max()) + Q_ATOL, (variant, i, k, p[sa[k]], p[sb[k]])
+    assert same_all >= len(graphs) // 2
+    # final device state of a finished graph is the same in both modes: all remaining nodes singletons
+    assert torch.equal(a.label, b.label) and torch.equal(a.rank, b.rank) and torch.equal(a.cov_edges, b.cov_edges) or same_all < len(graphs)
