@@ -13,7 +13,7 @@
 namespace md {
 
 constexpr int D = MD_EMBED;
-constexpr int TL_N = 128;   // md_rollout_tail: most active nodes a graph may have at hand-over
+constexpr int TL_N = 64;    // md_rollout_tail: most active nodes a graph may have at hand-over
 constexpr int TL_E = 4096;  //                  most alive directed entries per layer at hand-over
 constexpr int FLAG_LEFT = 8;  // md_state_t.flags slot: graphs that left the lock-step iteration
 constexpr int TILE_M = MD_TILE_M;

@@ -20,7 +20,7 @@
 
 namespace md {
 
-constexpr int TL_T = 256;
+constexpr int TL_T = 512;
 constexpr int TL_W = TL_T / 32;
 constexpr int TL_LD = 2 * D + 4;    // final-embedding tile: row = [H_0 (64) | H_1 (64) | pad], as in md_qhead.cu
 constexpr int TL_MAP = 2048;        // largest stride for which the global -> local map fits the scratch (X0 doubles as it)
@@ -32,7 +32,7 @@ struct TailSmem {
   float w13[D * D], w23[D * D], trans[D * D];
   float h1[D * MD_HIDDEN];
   float wn2l[2 * D], bias[D], lw[D], cross[D], h2[MD_HIDDEN + MD_AUX], wl2[MD_GATE];
-  float part[4][D];                 // column-sum partials
+  float part[TL_T / 64][D];         // column-sum partials
   float ssum[D];                    // per-graph sum of the current embeddings (spmm subgsum)
   float y[2][D], yT[2][D], hid[2][MD_GATE];
   float aux[2][MD_AUX];
@@ -53,6 +53,8 @@ struct TailSmem {
   uint16_t rp[2][2][TL_N + 2];      // [buffer][layer] row offsets
   uint8_t col[2][2][TL_E];          // [buffer][layer] neighbour rows
   int s_i[8];
+  int st_i[TL_W][2];               // per-warp alive-degree sum / max
+  long long st_ll[TL_W];            // per-warp two-hop sum
 };
 static_assert(sizeof(TailSmem) <= 227 * 1024, "TailSmem exceeds one CTA's shared memory");
 
@@ -84,15 +86,18 @@ __device__ __forceinline__ float half_sum16(float v) {  // over the 16 lanes tha
   return v;
 }
 
-// acc[i][c] += sum_{k < 64} A[(ty + 16 i) * lda + k] * W[k * 64 + 4 tx + c]   for the first NI row groups
+constexpr int TL_RG = TL_T / 16;    // rows per row group: thread (tx = tid & 15, ty = tid >> 4) owns rows ty + TL_RG * i, columns 4 tx .. 4 tx + 3
+constexpr int TL_NI = TL_N / TL_RG;  // row groups at most
+
+// acc[i][c] += sum_{k < 64} A[(ty + TL_RG i) * lda + k] * W[k * 64 + 4 tx + c]   for the first NI row groups
 template <int NI>
-__device__ __forceinline__ void tl_gemm64(float (&acc)[8][4], const float* __restrict__ A, int lda, const float* __restrict__ W,
+__device__ __forceinline__ void tl_gemm64(float (&acc)[TL_NI][4], const float* __restrict__ A, int lda, const float* __restrict__ W,
                                           int tx, int ty) {
 #pragma unroll 2
   for (int k0 = 0; k0 < D; k0 += 4) {
     float4 a[NI], w[4];
 #pragma unroll
-    for (int i = 0; i < NI; ++i) a[i] = *reinterpret_cast<const float4*>(A + (ty + 16 * i) * lda + k0);
+    for (int i = 0; i < NI; ++i) a[i] = *reinterpret_cast<const float4*>(A + (ty + TL_RG * i) * lda + k0);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(W + (k0 + kk) * D + 4 * tx);
 #pragma unroll
@@ -114,7 +119,7 @@ __device__ __forceinline__ void tl_gemm64(float (&acc)[8][4], const float* __res
 template <int NI>
 __device__ __forceinline__ void tl_transform(TailSmem& sm, const float* P, const float* H, float* out, int ldo, int n, int tx,
                                              int ty) {
-  float acc[8][4];
+  float acc[TL_NI][4];
 #pragma unroll
   for (int i = 0; i < NI; ++i)
 #pragma unroll
@@ -131,10 +136,10 @@ __device__ __forceinline__ void tl_transform(TailSmem& sm, const float* P, const
       ss = fmaf(acc[i][c], acc[i][c], ss);
     }
     ss = half_sum16(ss);
-    const float den = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
-    const int r = ty + 16 * i;
+    const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));  // x / max(|x|, eps) (F.normalize) as x * rcp_rn: <= 1 ulp
+    const int r = ty + TL_RG * i;
     if (r < n)
-      *reinterpret_cast<float4*>(out + r * ldo + 4 * tx) = make_float4(acc[i][0] / den, acc[i][1] / den, acc[i][2] / den, acc[i][3] / den);
+      *reinterpret_cast<float4*>(out + r * ldo + 4 * tx) = make_float4(acc[i][0] * inv, acc[i][1] * inv, acc[i][2] * inv, acc[i][3] * inv);
   }
 }
 
@@ -147,7 +152,7 @@ __device__ __forceinline__ unsigned long long tl_qhead(TailSmem& sm, int n, int 
   // T_l = tanh(H_l @ trans + bias), in place (a row is private to its half-warp)
 #pragma unroll
   for (int l = 0; l < L; ++l) {
-    float acc[8][4];
+    float acc[TL_NI][4];
 #pragma unroll
     for (int i = 0; i < NI; ++i)
 #pragma unroll
@@ -156,7 +161,7 @@ __device__ __forceinline__ unsigned long long tl_qhead(TailSmem& sm, int n, int 
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < NI; ++i)
-      *reinterpret_cast<float4*>(sm.A + (ty + 16 * i) * TL_LD + l * D + 4 * tx) =
+      *reinterpret_cast<float4*>(sm.A + (ty + TL_RG * i) * TL_LD + l * D + 4 * tx) =
           make_float4(tanhf(acc[i][0] + bv.x), tanhf(acc[i][1] + bv.y), tanhf(acc[i][2] + bv.z), tanhf(acc[i][3] + bv.w));
   }
   __syncwarp();
@@ -164,7 +169,7 @@ __device__ __forceinline__ unsigned long long tl_qhead(TailSmem& sm, int n, int 
   const float4 lwv = *reinterpret_cast<const float4*>(sm.lw + 4 * tx);
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
-    float* rowp = sm.A + (ty + 16 * i) * TL_LD + 4 * tx;
+    float* rowp = sm.A + (ty + TL_RG * i) * TL_LD + 4 * tx;
     float4 Tl[L];
 #pragma unroll
     for (int l = 0; l < L; ++l) Tl[l] = *reinterpret_cast<const float4*>(rowp + l * D);
@@ -215,13 +220,13 @@ __device__ __forceinline__ unsigned long long tl_qhead(TailSmem& sm, int n, int 
     }
   }
   __syncwarp();
-  float qrow[8];
+  float qrow[TL_NI];
 #pragma unroll
   for (int i = 0; i < NI; ++i) qrow[i] = 0.f;
   const float2 h2v = *reinterpret_cast<const float2*>(sm.h2 + 2 * tx);
 #pragma unroll
   for (int p = 0; p < L; ++p) {
-    float acc[8][2];
+    float acc[TL_NI][2];
 #pragma unroll
     for (int i = 0; i < NI; ++i) acc[i][0] = acc[i][1] = 0.f;
 #pragma unroll 2
@@ -229,7 +234,7 @@ __device__ __forceinline__ unsigned long long tl_qhead(TailSmem& sm, int n, int 
       float4 a[NI];
       float2 w[4];
 #pragma unroll
-      for (int i = 0; i < NI; ++i) a[i] = *reinterpret_cast<const float4*>(sm.A + (ty + 16 * i) * TL_LD + p * D + k0);
+      for (int i = 0; i < NI; ++i) a[i] = *reinterpret_cast<const float4*>(sm.A + (ty + TL_RG * i) * TL_LD + p * D + k0);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float2*>(sm.h1 + (k0 + kk) * MD_HIDDEN + 2 * tx);
 #pragma unroll
@@ -254,7 +259,7 @@ __device__ __forceinline__ unsigned long long tl_qhead(TailSmem& sm, int n, int 
   unsigned long long key = 0ull;
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
-    const int r = ty + 16 * i;
+    const int r = ty + TL_RG * i;
     if (r < n && tx == 0) {
       const unsigned long long k2 = ((unsigned long long)orderable(qrow[i]) << 32) | (0xffffffffu - (uint32_t)sm.node[r]);
       key = k2 > key ? k2 : key;
@@ -303,6 +308,8 @@ __device__ __forceinline__ float tl_group_sum64(TailSmem& sm, float v) {
   const int w0 = (threadIdx.x >> 6) * 2;
   return sm.red_f[w0 & (TL_W - 1)] + sm.red_f[(w0 + 1) & (TL_W - 1)];
 }
+
+static_assert(TL_N % 32 == 0 && 2 * TL_N <= TL_T && TL_N <= 256, "tail thread layout");
 
 __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md_state_t S, md_weights_t W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
   bool terminal = false;
 
   for (int guard = 0; guard <= n0 && !terminal; ++guard) {
-    const int ni = (n + 15) >> 4;  // row groups of 16 in use
+    const int ni = (n + TL_RG - 1) / TL_RG;  // row groups in use
     // ================================ forward ================================
     for (int l = 0; l < L; ++l) {
       // node features + first embedding (md_embed.cu embed_init_kernel): one warp per row, 2 columns per lane
@@ -409,17 +416,22 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
       float* Hc = sm.X0;  // current embeddings
       float* Hn = sm.X1;  // neighbour sums, then the new embeddings
       for (int it = 0; it < MD_BP_ITERS; ++it) {
-        // (a) per-graph column sums of the current embeddings (spmm subgsum): 4 row groups x 64 columns, fixed order
+        // (a) per-graph column sums of the current embeddings (spmm subgsum): TL_T / 64 row groups x 64 columns, fixed order
         {
           const int c = tid & 63, q = tid >> 6;
           float s = 0.f;
-          for (int r = q; r < n; r += 4) s += Hc[r * D + c];
+          for (int r = q; r < n; r += TL_T / 64) s += Hc[r * D + c];
           sm.part[q][c] = s;
         }
         __syncthreads();
-        if (tid < D) sm.ssum[tid] = (sm.part[0][tid] + sm.part[1][tid]) + (sm.part[2][tid] + sm.part[3][tid]);
+        if (tid < D) {
+          float s = 0.f;
+#pragma unroll
+          for (int q = 0; q < TL_T / 64; ++q) s += sm.part[q][tid];
+          sm.ssum[tid] = s;
+        }
         __syncthreads();
-        // (b) warps 0, 1: graph row  y' = normalise(relu(S @ w13 + y @ w23));  warps 2..7: P = A_alive . H, CSR order
+        // (b) warps 0, 1: graph row  y' = normalise(relu(S @ w13 + y @ w23));  the other warps: P = A_alive . H, CSR order
         float yo = 0.f;
         if (warp < 2) {
           const int c = tid;
@@ -451,10 +463,9 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
         const bool last = it + 1 == MD_BP_ITERS;
         float* out = last ? sm.A + l * D : Hn;
         const int ldo = last ? TL_LD : D;
+        static_assert(TL_NI == 2, "dispatch below assumes two row groups");
         if (ni <= 1) tl_transform<1>(sm, Hn, Hc, out, ldo, n, tx, ty);
-        else if (ni <= 2) tl_transform<2>(sm, Hn, Hc, out, ldo, n, tx, ty);
-        else if (ni <= 4) tl_transform<4>(sm, Hn, Hc, out, ldo, n, tx, ty);
-        else tl_transform<8>(sm, Hn, Hc, out, ldo, n, tx, ty);
+        else tl_transform<2>(sm, Hn, Hc, out, ldo, n, tx, ty);
         __syncthreads();
         float* t = Hc;
         Hc = Hn;
@@ -503,11 +514,13 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
         if (act && c == 0) sm.gc_s[l] = s;
       }
       {  // gate_l = relu(yf_l @ w_layer1) @ w_layer2 : thread (l2, j) for j < 128
-        const int l2 = tid >> 7, j = tid & 127;
-        float o2 = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < D; ++k) o2 = fmaf(sm.y[l2][k], __ldg(W.wl1 + k * MD_GATE + j), o2);
-        sm.hid[l2][j] = fmaxf(o2, 0.f) * sm.wl2[j];
+        const int l2 = (tid >> 7) & 1, j = tid & 127;
+        if (tid < L * MD_GATE) {
+          float o2 = 0.f;
+#pragma unroll 16
+          for (int k = 0; k < D; ++k) o2 = fmaf(sm.y[l2][k], __ldg(W.wl1 + k * MD_GATE + j), o2);
+          sm.hid[l2][j] = fmaxf(o2, 0.f) * sm.wl2[j];
+        }
       }
       __syncthreads();
       {
@@ -533,9 +546,7 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
     // ---- node rows: fusion + Q head + arg-max ----------------------------------------------------------------
     unsigned long long key;
     if (ni <= 1) key = tl_qhead<1>(sm, n, tx, ty);
-    else if (ni <= 2) key = tl_qhead<2>(sm, n, tx, ty);
-    else if (ni <= 4) key = tl_qhead<4>(sm, n, tx, ty);
-    else key = tl_qhead<8>(sm, n, tx, ty);
+    else key = tl_qhead<2>(sm, n, tx, ty);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
@@ -619,19 +630,38 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
     int alive[L];
     long long twohop[L];
     {
-      const int l = tid >> 7, r = tid & 127;
+      const int l = (tid / TL_N) & 1, r = tid % TL_N;  // threads [0, TL_N): layer 0, [TL_N, 2 TL_N): layer 1 (whole warps per layer)
       int d = 0;
-      if (r < n && sm.lab[r] >= 0) {
+      if (tid < L * TL_N && r < n && sm.lab[r] >= 0) {
         const uint16_t* rp = sm.rp[cur][l];
         const uint8_t* cl = sm.col[cur][l];
         const int lr = sm.lab[r], e1 = rp[r + 1];
         for (int e = rp[r]; e < e1; ++e) d += (sm.lab[cl[e]] == lr);
       }
-      if (r < n) sm.deg[l][r] = d;
+      if (tid < L * TL_N && r < n) sm.deg[l][r] = d;
+      const int ws = warp_sum_i(d), wm = warp_max_i(d);
+      const long long wt = warp_sum_ll((long long)d * (d - 1) / 2);
+      __syncthreads();
+      if (lane == 0) {
+        sm.st_i[warp][0] = ws;
+        sm.st_i[warp][1] = wm;
+        sm.st_ll[warp] = wt;
+      }
+      __syncthreads();
+      constexpr int WPL = TL_N / 32;  // warps per layer
+#pragma unroll
       for (int ll = 0; ll < L; ++ll) {
-        alive[ll] = tl_block_sum_i(sm, l == ll ? d : 0);
-        dmax[ll] = tl_block_max_i(sm, l == ll ? d : 0);
-        twohop[ll] = tl_block_sum_ll(sm, l == ll ? (long long)d * (d - 1) / 2 : 0ll);
+        int a = 0, m = 0;
+        long long t = 0;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+          a += sm.st_i[ll * WPL + k][0];
+          m = max(m, sm.st_i[ll * WPL + k][1]);
+          t += sm.st_ll[ll * WPL + k];
+        }
+        alive[ll] = a;
+        dmax[ll] = m;
+        twohop[ll] = t;
       }
     }
     terminal = (alive[0] == 0) || (alive[1] == 0);
@@ -702,8 +732,8 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
       }
       __syncthreads();
       {
-        const int l = tid >> 7, rr = tid & 127;
-        if (rr < n && sm.newidx[rr] >= 0) {
+        const int l = (tid / TL_N) & 1, rr = tid % TL_N;
+        if (tid < L * TL_N && rr < n && sm.newidx[rr] >= 0) {
           const uint16_t* rp = sm.rp[cur][l];
           const uint8_t* cl = sm.col[cur][l];
           uint8_t* out = sm.col[cur ^ 1][l];
