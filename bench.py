@@ -530,43 +530,51 @@ def run_ours(args, cost, n, per_gpu, desc):
         dist.init_process_group("nccl", device_id=dev)
     import mdcommunity_b200 as mdb
 
+    from mdcommunity_b200.rollout import RolloutPipeline
     w = mdb.QWeights(load_state_dict(cost), dev)
     host = mdb.GraphBatch.prepare_host(graphs, cost)
     batch = mdb.GraphBatch(graphs, dev, cost, host=host)
-    ro = mdb.BatchRollout(batch, w)
+    depth = max(1, args.depth)
+    tail = None if not args.no_tail else False
+    ros = [mdb.BatchRollout(batch, w, tail=tail) for _ in range(depth)]  # `depth` batches in flight (same graphs, own state)
+    ro = ros[0]
     T = ro.max_steps
     rec_w = 2 + 2 * T  # per-graph record: audc f64, n_steps, then actions / ranks
     gather_buf = torch.empty(world * per_gpu, rec_w, dtype=torch.float64, device=dev) if world > 1 else None
     gather_ev = []
+    pipe = RolloutPipeline(dev, depth=depth)
+    timed = [False]
 
-    def one_step(timed=False):
-        ro.reset()
-        ro.run()
-        if world > 1:  # the only collective of the path: gather per-graph AUDC + removal sequences
-            if timed:
+    def gather(r):  # the only collective of the path: per-graph AUDC + removal sequences of one finished batch
+        if world > 1:
+            if timed[0]:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-            rec = torch.cat([ro.score[:, None], ro.n_steps[:, None].double(), ro.trace_action.double(),
-                             ro.trace_rank.double()], 1)
+            rec = torch.cat([r.score[:, None], r.n_steps[:, None].double(), r.trace_action.double(), r.trace_rank.double()], 1)
             dist.all_gather_into_tensor(gather_buf, rec)
-            if timed:
+            if timed[0]:
                 b.record()
                 gather_ev.append((a, b))
 
-    for _ in range(args.warmup):
-        one_step()
+    def run_steps(k):
+        """k steps = k complete rollouts of the batch, `depth` of them in flight at a time (RolloutPipeline): a step's
+        under-occupied straggler phase overlaps the next step's full-width kernels."""
+        pipe.run(k, lambda j: ros[j % depth], lambda j, r: gather(r))
+
+    run_steps(max(args.warmup, 2 * depth))  # every rollout object has run twice: its CUDA graph exists
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = ro.kernel_launches
+    launches0 = sum(r.kernel_launches for r in ros)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    timed[0] = True
     e0.record()
-    for _ in range(args.steps):
-        one_step(timed=True)
+    run_steps(args.steps)
     e1.record()
     torch.cuda.synchronize()
+    timed[0] = False
     if world > 1:
         dist.barrier()
     my_ms = e0.elapsed_time(e1)
@@ -580,38 +588,51 @@ def run_ours(args, cost, n, per_gpu, desc):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         gather_ms = float(np.mean([a.elapsed_time(b) for a, b in gather_ev]))
     ms = float(ms[0])
-    launches = ro.kernel_launches - launches0
+    launches = sum(r.kernel_launches for r in ros) - launches0
     res = ro.results()
     mean_steps = float(res["n_steps"].mean())
     mean_audc = float(res["score"].mean())
+    # latency of ONE batch with nothing else in flight (reset + rollout), for reference next to the pipelined throughput
+    lat = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ro.reset()
+        ro.run()
+        b.record()
+        torch.cuda.synchronize()
+        lat.append(a.elapsed_time(b))
+    single_batch_ms = float(np.median(lat))
 
     # ---- end-to-end through the public API with host buffers (H2D of the CSR, D2H of the records) ------------
-    def e2e_step():
-        b = mdb.GraphBatch(graphs, dev, cost, host=host)  # H2D from pinned memory
-        r = mdb.BatchRollout(b, w)
-        out = r.run()  # D2H: score, n_steps, actions, ranks, maxcc
-        if world > 1:
-            rec = torch.cat([r.score[:, None], r.n_steps[:, None].double(), r.trace_action.double(),
-                             r.trace_rank.double()], 1)
-            dist.all_gather_into_tensor(gather_buf, rec)
-        return b, out
+    e2e_out = [None]
 
-    for _ in range(args.warmup):  # the allocator has to see the two-batches-alive pattern before the clock starts
-        e2e_step()
+    def e2e_make(j):
+        b = mdb.GraphBatch(graphs, dev, cost, host=host)  # H2D from pinned memory (on the job's stream)
+        return mdb.BatchRollout(b, w, tail=tail)
+
+    def e2e_finish(j, r):
+        e2e_out[0] = r.results()  # D2H: score, n_steps, actions, ranks, maxcc
+        gather(r)
+
+    def e2e_steps(k):
+        pipe.run(k, e2e_make, e2e_finish, reset=False)
+
+    e2e_steps(max(args.warmup, depth))  # the allocator has to see the batches-in-flight pattern before the clock starts
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        b, out = e2e_step()
+    e2e_steps(args.steps)
     torch.cuda.synchronize()
     e2e_ms = torch.tensor([1e3 * (time.perf_counter() - t0)], device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms[0])
+    out = e2e_out[0]
     d2h = sum(int(v.nbytes) for v in out.values())
     clocks = sampler.stop() if sampler else None
-    del b, out
+    del out
 
     c3 = None
     if do_c3:
@@ -636,12 +657,16 @@ def run_ours(args, cost, n, per_gpu, desc):
                        "l2": "no flush: per-step working set (4 embedding buffers, %.0f MB) exceeds the 126 MB L2"
                              % (4 * batch.n_total * 256 / 1e6),
                        "mean_removals_per_graph": mean_steps, "mean_audc": mean_audc,
-                       "sharding": "independent graphs per rank, NCCL all_gather of per-graph records"},
+                       "sharding": "independent graphs per rank, NCCL all_gather of per-graph records",
+                       "batches_in_flight": depth, "tail_kernel": bool(ro.tail),
+                       "step": "one complete rollout (s0 -> all terminal) of the batch; %d steps are in flight at a time on "
+                               "their own streams (RolloutPipeline), all of them inside the timed region" % depth},
             "e2e": {"value": total_graphs / (e2e_ms * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": int(batch.h2d_bytes),
                     "d2h_bytes_per_step": int(d2h), "timing": "wall clock, max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "removal_steps_per_s": world * per_gpu * mean_steps * args.steps / (ms * 1e-3),
             "per_rank_ms_per_step": per_rank_ms, "gather_ms_per_step": gather_ms,
+            "single_batch_latency_ms": single_batch_ms,
         }
         if nccl_log:
             line["nccl"] = _nccl_log_summary(nccl_log)
@@ -656,7 +681,7 @@ def run_ours(args, cost, n, per_gpu, desc):
                                     "host_cores": cores, "steps_per_s": st / dt,
                                     "sample": "first %d graph(s) of the GPU batch, oracle/md_oracle.py rollout, 1 process" % k}
         if world == 1 and args.workload == "c2" and not args.no_c4:
-            del ro, batch
+            del ro, ros, batch
             torch.cuda.empty_cache()
             try:
                 line["c4"] = c4_leg(dev)
@@ -679,6 +704,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the N = 1M removal-steps/s leg (about 30 s)")
     ap.add_argument("--no-c3", action="store_true", help="skip the 1024-graph strong-scaling leg (C3)")
+    ap.add_argument("--depth", type=int, default=2, help="batches in flight (RolloutPipeline); 1 = strictly one after the other")
+    ap.add_argument("--no-tail", action="store_true", help="pure lock step: no hand-over of small graphs to md_rollout_tail")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -243,6 +243,10 @@ int md_tail_handover(const md_graphs_t* g, const md_state_t* s, md_stream_t stre
  * graphs continue while the small ones finish on idle SMs.  md_tail_join makes `stream` wait for all tail launches. */
 int md_rollout_tail(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, md_stream_t stream);
 int md_tail_join(md_stream_t stream);
+/* profiling hook (profiling builds only, zeros otherwise): per graph (first 1024) of the tail launches so far
+ * {cycles, steps, nodes at hand-over, SM id, phase cycles: setup, embedding iterations, graph rows, Q head + arg-max,
+ * LMCC rounds, rest of the env step} */
+int md_debug_read_tail(unsigned long long* host10240);
 
 /* The same n_steps iterations captured once into a CUDA graph and replayed (launch-bound tail of a rollout).  Call
  * md_rollout_steps at least once before md_rollout_graph_create; the graph bakes in the struct values (device pointers),

@@ -82,6 +82,7 @@ _SIGS = {
     "md_tail_handover": ([C.POINTER(MdGraphs), C.POINTER(MdState), _vp], C.c_int),
     "md_rollout_tail": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), _vp], C.c_int),
     "md_tail_join": ([_vp], C.c_int),
+    "md_debug_read_tail": ([_vp], C.c_int),
     "md_heuristic_select": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.c_int32, C.c_int32, _vp], C.c_int),
     "md_rollout_graph_create": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWeights), C.POINTER(MdWork), C.c_int32, _vp,
                                  C.POINTER(C.c_void_p)], C.c_int),

@@ -101,8 +101,7 @@ __device__ __forceinline__ long long block_sum_ll(long long v, BlockRed& r) {
 // one SM and a 256-graph batch runs in one wave instead of two), int32_t otherwise.
 template <typename IdxT>
 __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_t S, const int32_t* forced,
-                                                       int forced_stride, int forced_index, int init, int max_nnz,
-                                                       int dbg_flags) {
+                                                       int forced_stride, int forced_index, int init, int max_nnz) {
   extern __shared__ int smem[];
   const int g = blockIdx.x;
   const int tid = threadIdx.x;
@@ -206,42 +205,11 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
     for (int v = tid; v < N; v += ENV_T) par[v] = v;
     __syncthreads();
     tq = ENV_CLK();
-    // Afforest-style hooking (Sutton et al.): a plain edge-parallel sweep of uf_unite builds deep trees inside the giant
-    // block and every find walks them (measured: ~3.7 k cycles per unite, 17 k cycles per round at the intact state).
-    // Instead every row first links to its first, then to its second alive neighbour, with the forest flattened after
-    // each pass (trees of depth 1), and the edge-parallel sweep only unites the few edges whose end points still sit in
-    // different trees.  Same result: the connected components of the label-restricted layer.
-    if (!(dbg_flags & 16384)) {
-      const int* rp = c_rp + l * (St + 1);
-      for (int k = 0; k < 2; ++k) {
-        for (int p = tid; p < nprev; p += ENV_T) {
-          const int v = arow[p];
-          const int lv = lab[v];
-          if (lv < 0) continue;
-          const int e1 = rp[p + 1];
-          int seen = 0;
-          for (int e = rp[p]; e < e1; ++e) {
-            const int u = c_cl[e];
-            if (lab[u] == lv) {
-              if (seen == k) {
-                uf_unite(par, u, v);
-                break;
-              }
-              ++seen;
-            }
-          }
-        }
-        __syncthreads();
-        for (int v = tid; v < N; v += ENV_T)
-          if (lab[v] >= 0) par[v] = uf_find(par, v);
-        __syncthreads();
-      }
-    }
-    for (int e = lay_pos[l] + tid; e < lay_pos[l + 1]; e += ENV_T) {  // edge-parallel: what the two passes left apart
+    for (int e = lay_pos[l] + tid; e < lay_pos[l + 1]; e += ENV_T) {  // edge-parallel hooking
       const int v = c_src[e], u = c_cl[e];
       if (u < v) {
         const int lv = lab[v];
-        if (lv >= 0 && lab[u] == lv && par[u] != par[v]) uf_unite(par, u, v);
+        if (lv >= 0 && lab[u] == lv) uf_unite(par, u, v);
       }
     }
     __syncthreads();
@@ -462,7 +430,6 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
 
 int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
                       int32_t forced_index, int init, md_stream_t stream);
-extern int g_md_debug_flags;  // bit 14 here: plain edge-parallel hooking (the A/B reference of the Afforest passes)
 
 extern "C" int md_debug_read_env_ctas(unsigned* host4096) {
   return (int)cudaMemcpyFromSymbol(host4096, md::g_env_cta, sizeof(unsigned) * 4096);
@@ -510,9 +477,9 @@ static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* 
     }
   }
   if (i16)
-    md::env_step_small<uint16_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz, g_md_debug_flags);
+    md::env_step_small<uint16_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz);
   else
-    md::env_step_small<int32_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz, g_md_debug_flags);
+    md::env_step_small<int32_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz);
   MD_CHECK_LAUNCH();
   return 0;
 }

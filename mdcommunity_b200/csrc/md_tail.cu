@@ -311,6 +311,20 @@ __device__ __forceinline__ float tl_group_sum64(TailSmem& sm, float v) {
 
 static_assert(TL_N % 32 == 0 && 2 * TL_N <= TL_T && TL_N <= 256, "tail thread layout");
 
+// profiling builds (MDB200_PROFILE=1): per graph {total cycles, steps, nodes at hand-over, SM id} and the phase cycles
+// {hand-over setup, embedding iterations, graph rows, Q head + arg-max, LMCC rounds, rest of the env step}
+__device__ unsigned long long g_tail_dbg[1024][10];
+#ifdef MD_PROFILE
+#define TL_CLK(slot)                           \
+  do {                                         \
+    const long long n_ = clock64();            \
+    ph[slot] += n_ - t_ph;                     \
+    t_ph = n_;                                 \
+  } while (0)
+#else
+#define TL_CLK(slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md_state_t S, md_weights_t W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TailSmem& sm = *reinterpret_cast<TailSmem*>(smem_raw);
@@ -326,6 +340,11 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
   int n = sm.s_i[0];
   if (n <= 0 || n > TL_N) return;
   const int n0 = n;
+#ifdef MD_PROFILE
+  long long ph[6] = {0, 0, 0, 0, 0, 0};
+  const long long t_begin = clock64();
+  long long t_ph = t_begin;
+#endif
   const int N = G.n_nodes[g];
   const bool degree_cost = S.cost_mode != 0;
 
@@ -383,6 +402,7 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
   const double mr = (double)G.max_rank[g];
   bool terminal = false;
 
+  TL_CLK(0);
   for (int guard = 0; guard <= n0 && !terminal; ++guard) {
     const int ni = (n + TL_RG - 1) / TL_RG;  // row groups in use
     // ================================ forward ================================
@@ -472,6 +492,7 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
         Hn = t;
       }
     }
+    TL_CLK(1);
     // ---- graph rows: fusion (BitwiseMultipyLogis), s_p = yf_p . cross, layer gate, aux . h2 (md_embed.cu graph_embed_kernel) ----
     {
       const int l = (tid >> 6) & 1, c = tid & 63;
@@ -543,6 +564,7 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
       }
       __syncthreads();
     }
+    TL_CLK(2);
     // ---- node rows: fusion + Q head + arg-max ----------------------------------------------------------------
     unsigned long long key;
     if (ni <= 1) key = tl_qhead<1>(sm, n, tx, ty);
@@ -569,6 +591,7 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
     const int a_row = sm.s_i[1], a_node = sm.s_i[2];
     if (a_row < 0) break;  // (cannot happen: n >= 2 active rows always yield a key)
 
+    TL_CLK(3);
     // ================================ environment step ================================
     // numCoveredEdges[l] += alive degree of a (mvc_env.py:81-84); remove a
     cov[0] += sm.deg[0][a_row];
@@ -614,6 +637,7 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
         l ^= 1;
       }
     }
+    TL_CLK(4);
     // component sizes -> LMCC rank (every node outside the tail's rows is removed or a singleton)
     for (int r = tid; r < n; r += TL_T) sm.tmp[r] = 0;
     __syncthreads();
@@ -769,7 +793,19 @@ __global__ void __launch_bounds__(TL_T, 1) rollout_tail_kernel(md_graphs_t G, md
       cur ^= 1;
       n = n_new;
     }
+    TL_CLK(5);
   }
+#ifdef MD_PROFILE
+  if (tid == 0 && g < 1024) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_tail_dbg[g][0] = (unsigned long long)(clock64() - t_begin);
+    g_tail_dbg[g][1] = (unsigned long long)(n_steps - S.n_steps[g]);
+    g_tail_dbg[g][2] = (unsigned long long)n0;
+    g_tail_dbg[g][3] = smid;
+    for (int i = 0; i < 6; ++i) g_tail_dbg[g][4 + i] = (unsigned long long)ph[i];
+  }
+#endif
 
   // ---- write the final state back (the graph is terminal: every remaining node is a singleton) ----------------------
   for (int r = tid; r < n0; r += TL_T) {
@@ -814,6 +850,9 @@ __global__ void tail_handover_kernel(md_graphs_t G, md_state_t S) {
 
 }  // namespace md
 
+extern "C" int md_debug_read_tail(unsigned long long* host10240) {
+  return (int)cudaMemcpyFromSymbol(host10240, md::g_tail_dbg, sizeof(unsigned long long) * 10240);
+}
 extern "C" int32_t md_tail_max_nodes(void) { return md::TL_N; }
 extern "C" int32_t md_tail_max_entries(void) { return md::TL_E; }
 
@@ -832,22 +871,26 @@ extern "C" int md_tail_handover(const md_graphs_t* g, const md_state_t* s, md_st
 
 // ---- the tail stream: low priority, one per device ------------------------------------------------------------------
 namespace {
+constexpr int TAIL_STREAMS = 4;  // round robin: a launch whose CTAs run long must not hold back the next hand-overs
 struct TailCtx {
-  cudaStream_t st = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t st[TAIL_STREAMS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[TAIL_STREAMS] = {};
+  unsigned next = 0;
 };
 md::PerDevice<TailCtx> g_tail_ctx;
 int tail_ctx(TailCtx** out) {
   TailCtx& c = g_tail_ctx.get();
-  if (!c.st) {
+  if (!c.ev_fork) {
     int least = 0, greatest = 0;
     cudaError_t e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
     if (e != cudaSuccess) return (int)e;
-    e = cudaStreamCreateWithPriority(&c.st, cudaStreamNonBlocking, least);
-    if (e != cudaSuccess) return (int)e;
+    for (int i = 0; i < TAIL_STREAMS; ++i) {
+      e = cudaStreamCreateWithPriority(&c.st[i], cudaStreamNonBlocking, least);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaEventCreateWithFlags(&c.ev_join[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) return (int)e;
+    }
     e = cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) return (int)e;
   }
   *out = &c;
@@ -870,11 +913,12 @@ extern "C" int md_rollout_tail(const md_graphs_t* g, const md_state_t* s, const 
   int rc = tail_ctx(&c);
   if (rc) return rc;
   // fork: the tail launch sees everything enqueued on `stream` so far, `stream` itself does not wait for it
+  cudaStream_t ts = c->st[c->next++ % TAIL_STREAMS];
   cudaError_t e = cudaEventRecord(c->ev_fork, (cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
-  e = cudaStreamWaitEvent(c->st, c->ev_fork, 0);
+  e = cudaStreamWaitEvent(ts, c->ev_fork, 0);
   if (e != cudaSuccess) return (int)e;
-  md::rollout_tail_kernel<<<g->n_graphs, md::TL_T, smem, c->st>>>(*g, *s, *w);
+  md::rollout_tail_kernel<<<g->n_graphs, md::TL_T, smem, ts>>>(*g, *s, *w);
   MD_CHECK_LAUNCH();
   return 0;
 }
@@ -883,9 +927,11 @@ extern "C" int md_tail_join(md_stream_t stream) {
   TailCtx* c = nullptr;
   int rc = tail_ctx(&c);
   if (rc) return rc;
-  cudaError_t e = cudaEventRecord(c->ev_join, c->st);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaStreamWaitEvent((cudaStream_t)stream, c->ev_join, 0);
-  if (e != cudaSuccess) return (int)e;
+  for (int i = 0; i < TAIL_STREAMS; ++i) {
+    cudaError_t e = cudaEventRecord(c->ev_join[i], c->st[i]);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamWaitEvent((cudaStream_t)stream, c->ev_join[i], 0);
+    if (e != cudaSuccess) return (int)e;
+  }
   return 0;
 }

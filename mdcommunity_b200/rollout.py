@@ -330,6 +330,79 @@ class BatchRollout:
         return (ids - gi * S).cpu().numpy(), self.q[ids].cpu().numpy()
 
 
+class RolloutPipeline:
+    """Software pipeline over a QUEUE of rollout jobs: up to `depth` jobs are in flight, each on its own CUDA stream.
+
+    A single lock-step batch ends with a long under-occupied phase (the last few big graphs of the batch keep the
+    iteration going while most SMs idle); with the next batch already in flight on another stream its full-width
+    kernels fill those SMs.  Jobs never interact: results are identical to running them one after the other.
+
+    make_job(j) is called with the job's stream current and returns the BatchRollout to run (a persistent object that
+    the pipeline resets, or a freshly built one: GraphBatch upload + state allocation then happen on that stream);
+    finish_job(j, rollout) is called -- in job order, with the job's stream current -- when job j is terminal
+    (gather / download its results there)."""
+
+    def __init__(self, device, depth=2, chunk=8):
+        self.device = torch.device(device)
+        self.depth, self.chunk = depth, chunk
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(depth)]
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+        self._pins = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(depth)]
+
+    def run(self, n_jobs, make_job, finish_job=None, reset=True):
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+        slots = [None] * self.depth  # slot -> [job index, rollout, iterations enqueued, terminal?]
+        nxt, done_upto = 0, 0
+
+        def enqueue(i):
+            job = slots[i]
+            with torch.cuda.stream(self.streams[i]):
+                job[1]._enqueue_chunk(self.chunk, job[2] == 0)
+                self._pins[i].copy_(job[1].flags[8:9], non_blocking=True)
+                self.events[i].record(self.streams[i])
+            job[2] += self.chunk
+
+        while nxt < n_jobs or any(s is not None for s in slots):
+            for i in range(self.depth):
+                if slots[i] is None and nxt < n_jobs:
+                    with torch.cuda.stream(self.streams[i]), torch.cuda.device(self.device):
+                        ro = make_job(nxt)
+                        if reset:
+                            ro.reset()
+                        ro._begin_run()
+                    slots[i] = [nxt, ro, 0, False]
+                    nxt += 1
+                    enqueue(i)
+            # advance every slot whose chunk has completed; block on the OLDEST job if none has
+            order = sorted((i for i in range(self.depth) if slots[i] is not None), key=lambda i: slots[i][0])
+            ready = [i for i in order if not slots[i][3] and self.events[i].query()]
+            if not ready:
+                waiting = [i for i in order if not slots[i][3]]
+                if waiting:
+                    self.events[waiting[0]].synchronize()
+                    ready = [waiting[0]]
+            for i in ready:
+                job = slots[i]
+                if int(self._pins[i][0]) >= job[1].batch.B or job[2] > job[1].max_steps + self.chunk:
+                    job[3] = True
+                else:
+                    enqueue(i)
+            # finalize terminal jobs in job order (keeps every rank's collectives in the same order)
+            for i in order:
+                job = slots[i]
+                if job[3] and job[0] == done_upto:
+                    with torch.cuda.stream(self.streams[i]), torch.cuda.device(self.device):
+                        job[1]._finish_run()
+                        if finish_job is not None:
+                            finish_job(job[0], job[1])
+                    slots[i] = None
+                    done_upto += 1
+        for st in self.streams:
+            cur.wait_stream(st)
+
+
 class MultiStreamRollout:
     """The same lock-step rollout, with the batch cut into `parts` independent sub-batches that advance on their own CUDA
     streams.  Graphs never interact, so this changes nothing in the results; what it buys is overlap: the env step of

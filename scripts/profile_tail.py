@@ -26,3 +26,19 @@ for rep in range(3):
     b.record()
     torch.cuda.synchronize()
     print("rollout %.2f ms, %d graph-steps" % (a.elapsed_time(b), int(ro.n_steps.sum())))
+
+import ctypes as C
+buf = np.zeros((1024, 10), np.uint64)
+ro.lib.md_debug_read_tail(buf.ctypes.data_as(C.c_void_p))
+b = buf[:256].astype(np.int64)
+if b[:, 0].max() > 0:
+    st = np.maximum(b[:, 1], 1)
+    print("tail per graph: cycles min %d median %d max %d; steps min %d mean %.1f max %d; cycles/step median %d p90 %d" % (
+        b[:, 0].min(), np.median(b[:, 0]), b[:, 0].max(), b[:, 1].min(), b[:, 1].mean(), b[:, 1].max(),
+        np.median(b[:, 0] / st), np.percentile(b[:, 0] / st, 90)))
+    tot = b[:, 4:].sum(0)
+    print("phase share [setup, embed iters, graph rows, qhead+argmax, LMCC rounds, env rest]:", (tot / tot.sum()).round(3).tolist(),
+          " per step cycles:", (tot / b[:, 1].sum()).round(0).tolist())
+    sm, cnt = np.unique(b[:, 3], return_counts=True)
+    load = np.array([b[b[:, 3] == x, 0].sum() for x in sm])
+    print("SMs used %d, graphs per SM max %d, busiest SM %d cycles, mean %d" % (len(sm), cnt.max(), load.max(), load.mean()))

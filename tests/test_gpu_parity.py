@@ -634,3 +634,31 @@ def test_tail_kernel_matches_lock_step(variant):
     assert same_all >= len(graphs) // 2
     # final device state of a finished graph is the same in both modes: all remaining nodes singletons
     assert torch.equal(a.label, b.label) and torch.equal(a.rank, b.rank) and torch.equal(a.cov_edges, b.cov_edges) or same_all < len(graphs)
+
+
+def test_rollout_pipeline_matches_sequential():
+    """RolloutPipeline: several rollout jobs in flight on their own streams (persistent rollout objects that are reset, and
+    freshly uploaded batches) give, job by job, exactly the results of one rollout run alone."""
+    from mdcommunity_b200 import gmm
+    from mdcommunity_b200.rollout import RolloutPipeline
+    mdb = _mdb()
+    zs, graphs, _, _ = _load_batch("degree")
+    graphs = list(graphs) + [gmm.gmm_graph(n, 40 + n, cost="degree") for n in (300, 500, 640)]
+    batch = mdb.GraphBatch(graphs, cost="degree")
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_degree.npz"))), batch.device)
+    ref = mdb.BatchRollout(batch, w).run()
+    ros = [mdb.BatchRollout(batch, w) for _ in range(2)]
+    pipe = RolloutPipeline(batch.device, depth=2, chunk=4)
+    got, order = {}, []
+
+    def fin(j, r):
+        got[j] = r.results()
+        order.append(j)
+
+    pipe.run(5, lambda j: ros[j % 2], fin)
+    assert order == list(range(5))
+    pipe.run(3, lambda j: mdb.BatchRollout(mdb.GraphBatch(graphs, cost="degree"), w), lambda j, r: fin(10 + j, r), reset=False)
+    assert sorted(got) == [0, 1, 2, 3, 4, 10, 11, 12]
+    for j, r in got.items():
+        for k in ("score", "n_steps", "actions", "ranks", "maxcc"):
+            assert np.array_equal(r[k], ref[k]), (j, k)
