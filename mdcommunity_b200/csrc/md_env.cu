@@ -101,7 +101,8 @@ __device__ __forceinline__ long long block_sum_ll(long long v, BlockRed& r) {
 // one SM and a 256-graph batch runs in one wave instead of two), int32_t otherwise.
 template <typename IdxT>
 __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_t S, const int32_t* forced,
-                                                       int forced_stride, int forced_index, int init, int max_nnz) {
+                                                       int forced_stride, int forced_index, int init, int max_nnz,
+                                                       int dbg_flags) {
   extern __shared__ int smem[];
   const int g = blockIdx.x;
   const int tid = threadIdx.x;
@@ -115,11 +116,19 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int* tmp = smem + 2 * St;         // [St] scratch; later the compact list of active nodes
   int* arow = smem + 3 * St;        // [St] node (graph-local id) of input row p
   int* c_rp = smem + 4 * St;        // [L][St + 1] row offsets into c_cl / c_src
-  IdxT* c_cl = reinterpret_cast<IdxT*>(c_rp + L * (St + 1));  // [max_nnz] neighbour (graph-local id)
+  int* rowof = c_rp + L * (St + 1); // [St] node -> input row (-1: the node has no row)
+  int* vis = rowof + St;            // [St] incremental LMCC: visited list (its tail segment is the current frontier)
+  int* pend = vis + St;             // [St] pending-source bits, one per layer;  vis + pend = component-size table [2 St]
+  int* srcl = pend + St;            // [St] pending sources of the running round
+  int* gact = srcl + St;            // [St] per source group: has a frontier;     srcl + gact = smallest-member table [2 St]
+  int* grmin = gact + St;           // [St] per source group: smallest node
+  int* gnew = grmin + St;           // [St] per source group: fresh label (also scratch)
+  IdxT* c_cl = reinterpret_cast<IdxT*>(gnew + St);  // [max_nnz] neighbour (graph-local id)
   IdxT* c_src = c_cl + max_nnz;     // [max_nnz] row of the entry (static, staged); later the alive prefix
   __shared__ BlockRed red;
-  __shared__ int s_action;
+  __shared__ int s_action, s_lab_a;
   __shared__ int s_scan[ENV_W];
+  __shared__ int s_cnt[8];
 
   if (!init && S.done[g]) return;
   ENV_T0();
@@ -192,7 +201,10 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   if (!init) {
     // numCoveredEdges[l] += #neighbours still alive and not cut from a  (mvc_env.py:81-84) == deg_alive_l(a)
     if (tid < L) S.cov_edges[tid * G.n_graphs + g] += S.deg[tid][base + a];
-    if (tid == 0) lab[a] = -1;
+    if (tid == 0) {
+      s_lab_a = lab[a];
+      lab[a] = -1;
+    }
   }
   __syncthreads();
 
@@ -201,7 +213,173 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int stable = 0, l = 0;
   int rounds_dbg = 0;
   long long hook_dbg = 0, flat_dbg = 0, tq = 0;
-  while (stable < L) {
+  const bool incremental = init == 0 && !(dbg_flags & 16384);
+  if (incremental) {
+    // ---- incremental update (a step; s0 / set_state run the from-scratch rounds below) ---------------------------------
+    // Removing a can only change the block that contained a, and inside it only what hangs on the edges that just died.
+    // Invariant per layer l: every layer-l connected piece of a block contains a PENDING SOURCE of layer l, or the block is
+    // layer-l connected.  Initially the pending sources are a's alive neighbours.  One task = (block x, layer l) with >= 2
+    // pending sources: a multi-source search along the alive layer-l edges inside x, groups merging when they touch; it
+    // stops as soon as at most one group still has a frontier.  Groups that ran out of frontier are complete pieces: they
+    // leave x under fresh labels; the rest of x -- the group still searching plus everything never visited -- keeps x
+    // untouched.  Every edge of the OTHER layers between a piece and the rest dies, and its end points become pending
+    // sources there.  When nothing is pending every block is connected in every layer: the same fixpoint as the
+    // reference's alternating full recomputation (Mcc.py:30-38), reached in work proportional to what changed.
+    // (scripts/proto_incremental_lmcc.py checks the scheme against the from-scratch oracle.)
+    int* own = tmp;   // [St] 0 = unvisited, else 1 + index of the source whose group claimed the node
+    int* gpar = par;  // [St] union-find over the sources of the running task
+    const int x0 = s_lab_a;
+    for (int v = tid; v < St; v += ENV_T) {
+      own[v] = 0;
+      pend[v] = 0;
+      rowof[v] = -1;
+    }
+    if (tid == 0) s_cnt[4] = N;  // fresh labels N, N + 1, ... (canonical labels are node ids < N)
+    __syncthreads();
+    for (int p = tid; p < nprev; p += ENV_T) rowof[arow[p]] = p;
+    __syncthreads();
+    {
+      const int pa = rowof[a];
+      if (pa >= 0)
+        for (int ll = 0; ll < L; ++ll) {
+          const int* rp = c_rp + ll * (St + 1);
+          const int e1 = rp[pa + 1];
+          for (int e = rp[pa] + tid; e < e1; e += ENV_T) {
+            const int u = c_cl[e];
+            if (lab[u] == x0) atomicOr(&pend[u], 1 << ll);
+          }
+        }
+    }
+    __syncthreads();
+    int idle = 0;
+    while (idle < L) {
+      if (tid == 0) s_cnt[0] = 0;
+      __syncthreads();
+      for (int v = tid; v < N; v += ENV_T) {
+        const int pb = pend[v];
+        if (pb & (1 << l)) {
+          pend[v] = pb & ~(1 << l);
+          if (lab[v] >= 0) srcl[atomicAdd(&s_cnt[0], 1)] = v;
+        }
+      }
+      __syncthreads();
+      int rem = s_cnt[0];
+      __syncthreads();
+      if (rem == 0) {
+        ++idle;
+        l = (l + 1 == L) ? 0 : l + 1;
+        continue;
+      }
+      idle = 0;
+      const int* rp = c_rp + l * (St + 1);
+      while (rem > 0) {  // one block at a time: the block of the first remaining source
+        const int x = lab[srcl[0]];
+        if (tid == 0) s_cnt[1] = 0, s_cnt[6] = 0;
+        __syncthreads();
+        for (int i = tid; i < rem; i += ENV_T) {
+          const int v = srcl[i];
+          if (lab[v] == x) vis[atomicAdd(&s_cnt[1], 1)] = v;
+          else gnew[atomicAdd(&s_cnt[6], 1)] = v;
+        }
+        __syncthreads();
+        const int ns = s_cnt[1];
+        rem = s_cnt[6];
+        for (int i = tid; i < rem; i += ENV_T) srcl[i] = gnew[i];
+        __syncthreads();
+        if (ns < 2) continue;  // one source: by the invariant its block is connected in this layer
+        ++rounds_dbg;
+        for (int i = tid; i < ns; i += ENV_T) {
+          own[vis[i]] = i + 1;
+          gpar[i] = i;
+        }
+        __syncthreads();
+        int f0 = 0, f1 = ns, nroots = ns, nact = ns;
+        while (nroots > 1 && nact > 1) {
+          // expand the frontier vis[f0, f1): 8 lanes per node (hub rows do not serialise one thread)
+          for (int i = f0 + (tid >> 3); i < f1; i += ENV_T / 8) {
+            const int u = vis[i], gu = own[u] - 1, pu = rowof[u];
+            const int e1 = rp[pu + 1];
+            for (int e = rp[pu] + (tid & 7); e < e1; e += 8) {
+              const int v = c_cl[e];
+              if (lab[v] != x) continue;
+              const int o = atomicCAS(&own[v], 0, gu + 1);
+              if (o == 0) vis[atomicAdd(&s_cnt[1], 1)] = v;
+              else if (o - 1 != gu) uf_unite(gpar, o - 1, gu);
+            }
+          }
+          __syncthreads();
+          f0 = f1;
+          f1 = s_cnt[1];
+          for (int i = tid; i < ns; i += ENV_T) gact[i] = 0;
+          if (tid == 0) s_cnt[2] = 0, s_cnt[3] = 0;
+          __syncthreads();
+          for (int i = f0 + tid; i < f1; i += ENV_T) gact[uf_find(gpar, own[vis[i]] - 1)] = 1;
+          __syncthreads();
+          for (int i = tid; i < ns; i += ENV_T)
+            if (uf_find(gpar, i) == i) {
+              atomicAdd(&s_cnt[2], 1);
+              if (gact[i]) atomicAdd(&s_cnt[3], 1);
+            }
+          __syncthreads();
+          nroots = s_cnt[2];
+          nact = s_cnt[3];
+        }
+        const int nvis = f1;
+        if (nroots > 1) {
+          // the block splits: the group that is still searching (or, if all ran dry, the group with the smallest node)
+          // stays x, every other group is a complete piece and gets a fresh label
+          if (tid == 0) s_cnt[5] = -1, s_cnt[7] = 0x7fffffff;
+          for (int i = tid; i < ns; i += ENV_T) grmin[i] = 0x7fffffff;
+          __syncthreads();
+          if (nact == 1) {
+            for (int i = tid; i < ns; i += ENV_T)
+              if (gact[i] && uf_find(gpar, i) == i) s_cnt[5] = i;
+          } else {
+            for (int i = tid; i < nvis; i += ENV_T) atomicMin(&grmin[uf_find(gpar, own[vis[i]] - 1)], vis[i]);
+            __syncthreads();
+            for (int i = tid; i < ns; i += ENV_T)
+              if (uf_find(gpar, i) == i) atomicMin(&s_cnt[7], grmin[i]);
+            __syncthreads();
+            for (int i = tid; i < ns; i += ENV_T)
+              if (uf_find(gpar, i) == i && grmin[i] == s_cnt[7]) s_cnt[5] = i;
+          }
+          __syncthreads();
+          const int keep = s_cnt[5];
+          for (int i = tid; i < ns; i += ENV_T)
+            if (i != keep && uf_find(gpar, i) == i) gnew[i] = atomicAdd(&s_cnt[4], 1);
+          __syncthreads();
+          for (int i = tid; i < nvis; i += ENV_T) {
+            const int v = vis[i], r = uf_find(gpar, own[v] - 1);
+            if (r != keep) lab[v] = gnew[r];
+          }
+          __syncthreads();
+          // edges of the other layers that were alive inside x and cross labels now: both end points become pending
+          for (int i = tid >> 3; i < nvis; i += ENV_T / 8) {
+            const int v = vis[i], lv = lab[v];
+            if (lv == x) continue;  // only nodes that moved
+            const int pv = rowof[v];
+            for (int l2 = 0; l2 < L; ++l2) {
+              if (l2 == l) continue;
+              const int* rp2 = c_rp + l2 * (St + 1);
+              const int e1 = rp2[pv + 1];
+              for (int e = rp2[pv] + (tid & 7); e < e1; e += 8) {
+                const int u = c_cl[e], lu = lab[u];
+                if (lu >= 0 && lu != lv && (lu == x || own[u] != 0)) {
+                  atomicOr(&pend[v], 1 << l2);
+                  atomicOr(&pend[u], 1 << l2);
+                }
+              }
+            }
+          }
+          __syncthreads();
+        }
+        for (int i = tid; i < nvis; i += ENV_T) own[vis[i]] = 0;
+        __syncthreads();
+      }
+      l = (l + 1 == L) ? 0 : l + 1;
+    }
+  }
+  while (!incremental && stable < L) {
     for (int v = tid; v < N; v += ENV_T) par[v] = v;
     __syncthreads();
     tq = ENV_CLK();
@@ -237,14 +415,27 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   (void)hook_dbg, (void)flat_dbg, (void)tq, (void)rounds_dbg;
 
   // ---- component sizes -> LMCC rank (Mcc.find_max_set_length) ------------------------------------------
-  for (int v = tid; v < N; v += ENV_T) tmp[v] = 0;
+  // Labels are node ids < N (from-scratch rounds) or fresh ids in [N, 2N) (incremental splits): one table pass counts the
+  // members of every label and finds its smallest member, which becomes the canonical label again.
+  int* ccnt = vis;   // [2 St] (vis + pend)
+  int* cmin = srcl;  // [2 St] (srcl + gact)
+  for (int i = tid; i < 2 * St; i += ENV_T) {
+    ccnt[i] = 0;
+    cmin[i] = 0x7fffffff;
+  }
   __syncthreads();
   for (int v = tid; v < N; v += ENV_T)
-    if (lab[v] >= 0) atomicAdd(&tmp[lab[v]], 1);
+    if (lab[v] >= 0) {
+      atomicAdd(&ccnt[lab[v]], 1);
+      atomicMin(&cmin[lab[v]], v);
+    }
   __syncthreads();
   int mx = 0;
-  for (int v = tid; v < N; v += ENV_T) mx = max(mx, tmp[v]);
+  for (int i = tid; i < 2 * St; i += ENV_T) mx = max(mx, ccnt[i]);
   const int rank = block_max_i(mx, red);
+  for (int v = tid; v < N; v += ENV_T)
+    if (lab[v] >= 0) lab[v] = cmin[lab[v]];
+  __syncthreads();
 
   ENV_TICK();  // 3: component sizes
   // ---- per layer: alive CSR, alive degree, status counters (get_status_info) -------------------------------
@@ -437,13 +628,14 @@ extern "C" int md_debug_read_env_ctas(unsigned* host4096) {
 extern "C" int md_debug_read_env(long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, md::g_env_dbg, sizeof(long long) * n);
 }
+extern int g_md_debug_flags;  // bit 14 here: from-scratch prune rounds on every step (the A/B reference of the incremental update)
 static int g_force_large = 0;
 extern "C" int32_t md_env_small_max_stride(void) { return g_force_large ? 0 : md::ENV_SMALL_MAX; }
 // 1 if this batch takes the single-CTA (shared-memory) env kernel, 0 for the cooperative global-memory kernel
 static bool env_idx16(const md_graphs_t* g) { return g->max_graph_nnz < 65536 && g->stride < 65536; }
 static size_t env_small_smem(const md_graphs_t* g) {
   const size_t idx_bytes = env_idx16(g) ? 2 : 4;
-  return ((size_t)4 * g->stride + (size_t)g->n_layers * (g->stride + 1)) * sizeof(int) +
+  return ((size_t)11 * g->stride + (size_t)g->n_layers * (g->stride + 1)) * sizeof(int) +
          ((2 * (size_t)g->max_graph_nnz * idx_bytes + 15) & ~(size_t)15);
 }
 extern "C" int32_t md_env_uses_small_path(const md_graphs_t* g) {
@@ -477,9 +669,9 @@ static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* 
     }
   }
   if (i16)
-    md::env_step_small<uint16_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz);
+    md::env_step_small<uint16_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz, g_md_debug_flags);
   else
-    md::env_step_small<int32_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz);
+    md::env_step_small<int32_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz, g_md_debug_flags);
   MD_CHECK_LAUNCH();
   return 0;
 }
