@@ -535,7 +535,7 @@ def run_ours(args, cost, n, per_gpu, desc):
     host = mdb.GraphBatch.prepare_host(graphs, cost)
     batch = mdb.GraphBatch(graphs, dev, cost, host=host)
     depth = max(1, args.depth)
-    tail = None if not args.no_tail else False
+    tail = bool(args.tail)
     ros = [mdb.BatchRollout(batch, w, tail=tail) for _ in range(depth)]  # `depth` batches in flight (same graphs, own state)
     ro = ros[0]
     T = ro.max_steps
@@ -704,8 +704,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the N = 1M removal-steps/s leg (about 30 s)")
     ap.add_argument("--no-c3", action="store_true", help="skip the 1024-graph strong-scaling leg (C3)")
-    ap.add_argument("--depth", type=int, default=2, help="batches in flight (RolloutPipeline); 1 = strictly one after the other")
-    ap.add_argument("--no-tail", action="store_true", help="pure lock step: no hand-over of small graphs to md_rollout_tail")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight (RolloutPipeline); 1 = strictly one after the other")
+    ap.add_argument("--tail", action="store_true", help="hand graphs with <= 64 active nodes over to md_rollout_tail")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int stable = 0, l = 0;
   int rounds_dbg = 0;
   long long hook_dbg = 0, flat_dbg = 0, tq = 0;
-  const bool incremental = init == 0 && !(dbg_flags & 16384);
+  const bool incremental = init == 0 && (dbg_flags & 16384);  // opt-in: measured 2x SLOWER than the rounds at N = 1000 (below)
   if (incremental) {
     // ---- incremental update (a step; s0 / set_state run the from-scratch rounds below) ---------------------------------
     // Removing a can only change the block that contained a, and inside it only what hangs on the edges that just died.
@@ -225,7 +225,12 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
     // untouched.  Every edge of the OTHER layers between a piece and the rest dies, and its end points become pending
     // sources there.  When nothing is pending every block is connected in every layer: the same fixpoint as the
     // reference's alternating full recomputation (Mcc.py:30-38), reached in work proportional to what changed.
-    // (scripts/proto_incremental_lmcc.py checks the scheme against the from-scratch oracle.)
+    // (scripts/proto_incremental_lmcc.py checks the scheme against the from-scratch oracle; the GPU suite passes with it.)
+    // MEASURED (C2, 256 x N = 1000): bit-exact, but the rollout takes 38.7 instead of 21.8 ms.  A step needs 5-15 search tasks
+    // of ~4 levels each (cascades: every small piece that leaves the giant block re-opens the giant block in the other
+    // layer), i.e. some hundred block barriers, and together the searches visit 1.5-3 x n nodes -- no less than the 3-4 edge
+    // sweeps of the from-scratch rounds on graphs this small.  Kept behind md_debug_set_flags bit 14 as the reference
+    // implementation of the scheme for graphs where n >> what a removal touches.
     int* own = tmp;   // [St] 0 = unvisited, else 1 + index of the source whose group claimed the node
     int* gpar = par;  // [St] union-find over the sources of the running task
     const int x0 = s_lab_a;
@@ -628,7 +633,7 @@ extern "C" int md_debug_read_env_ctas(unsigned* host4096) {
 extern "C" int md_debug_read_env(long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, md::g_env_dbg, sizeof(long long) * n);
 }
-extern int g_md_debug_flags;  // bit 14 here: from-scratch prune rounds on every step (the A/B reference of the incremental update)
+extern int g_md_debug_flags;  // bit 14 here: incremental mutual-component update instead of the from-scratch prune rounds
 static int g_force_large = 0;
 extern "C" int32_t md_env_small_max_stride(void) { return g_force_large ? 0 : md::ENV_SMALL_MAX; }
 // 1 if this batch takes the single-CTA (shared-memory) env kernel, 0 for the cooperative global-memory kernel
