@@ -164,7 +164,7 @@ void md_debug_force_large_env(int32_t on);
  *   only when the embeddings exceed L2), bit 9 selects md_agg's register-load kernel instead of the cp.async ring,
  *   bit 12 disables iteration 0 from the alive degrees (unit cost) so that md_embed_init writes H0 again;
  * bit 13 keeps relu's argument e @ h1 of the two-layer tensor-core md_qhead on the FP32 pipes (A/B reference);
- * bit 14 (md_env_step, single-CTA path): incremental mutual-component update (multi-source search from the end points of
+ * bit 16 (md_env_step, single-CTA path): incremental mutual-component update (multi-source search from the end points of
  *   the edges that died) instead of the from-scratch prune rounds; same results, measured slower at N = 1000;
  * bits 14 / 15 (two-kernel md_embed_iter only): enqueue only the neighbour aggregation / only the transform, so that a
  *   caller can time the two kernels of an iteration separately (bit 14 call followed by bit 15 call == the normal sequence);

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int stable = 0, l = 0;
   int rounds_dbg = 0;
   long long hook_dbg = 0, flat_dbg = 0, tq = 0;
-  const bool incremental = init == 0 && (dbg_flags & 16384);  // opt-in: measured 2x SLOWER than the rounds at N = 1000 (below)
+  const bool incremental = init == 0 && (dbg_flags & 65536);  // opt-in: measured 2x SLOWER than the rounds at N = 1000 (below)
   if (incremental) {
     // ---- incremental update (a step; s0 / set_state run the from-scratch rounds below) ---------------------------------
     // Removing a can only change the block that contained a, and inside it only what hangs on the edges that just died.
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
     // MEASURED (C2, 256 x N = 1000): bit-exact, but the rollout takes 38.7 instead of 21.8 ms.  A step needs 5-15 search tasks
     // of ~4 levels each (cascades: every small piece that leaves the giant block re-opens the giant block in the other
     // layer), i.e. some hundred block barriers, and together the searches visit 1.5-3 x n nodes -- no less than the 3-4 edge
-    // sweeps of the from-scratch rounds on graphs this small.  Kept behind md_debug_set_flags bit 14 as the reference
+    // sweeps of the from-scratch rounds on graphs this small.  Kept behind md_debug_set_flags bit 16 as the reference
     // implementation of the scheme for graphs where n >> what a removal touches.
     int* own = tmp;   // [St] 0 = unvisited, else 1 + index of the source whose group claimed the node
     int* gpar = par;  // [St] union-find over the sources of the running task
@@ -633,7 +633,7 @@ extern "C" int md_debug_read_env_ctas(unsigned* host4096) {
 extern "C" int md_debug_read_env(long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, md::g_env_dbg, sizeof(long long) * n);
 }
-extern int g_md_debug_flags;  // bit 14 here: incremental mutual-component update instead of the from-scratch prune rounds
+extern int g_md_debug_flags;  // bit 16 here: incremental mutual-component update instead of the from-scratch prune rounds
 static int g_force_large = 0;
 extern "C" int32_t md_env_small_max_stride(void) { return g_force_large ? 0 : md::ENV_SMALL_MAX; }
 // 1 if this batch takes the single-CTA (shared-memory) env kernel, 0 for the cooperative global-memory kernel

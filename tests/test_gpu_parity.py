@@ -40,10 +40,10 @@ def _forced(zs, key, device):
 @pytest.fixture(params=["small", "large", "incremental"])
 def env_path(request):
     """small = one CTA per graph (shared memory), large = cooperative multi-CTA kernel (global memory), incremental = the
-    single-CTA kernel with the incremental mutual-component update (md_debug_set_flags bit 14) instead of the rounds."""
+    single-CTA kernel with the incremental mutual-component update (md_debug_set_flags bit 16) instead of the rounds."""
     from mdcommunity_b200 import _lib
     _lib.lib().md_debug_force_large_env(1 if request.param == "large" else 0)
-    _lib.lib().md_debug_set_flags(16384 if request.param == "incremental" else 0)
+    _lib.lib().md_debug_set_flags(65536 if request.param == "incremental" else 0)
     yield request.param
     _lib.lib().md_debug_force_large_env(0)
     _lib.lib().md_debug_set_flags(0)
