@@ -539,19 +539,28 @@ def run_ours(args, cost, n, per_gpu, desc):
     ros = [mdb.BatchRollout(batch, w, tail=tail) for _ in range(depth)]  # `depth` batches in flight (same graphs, own state)
     ro = ros[0]
     T = ro.max_steps
-    rec_w = 2 + 2 * T  # per-graph record: audc f64, n_steps, then actions / ranks
-    gather_buf = torch.empty(world * per_gpu, rec_w, dtype=torch.float64, device=dev) if world > 1 else None
     gather_ev = []
     pipe = RolloutPipeline(dev, depth=depth)
     timed = [False]
 
-    def gather(r):  # the only collective of the path: per-graph AUDC + removal sequences of one finished batch
+    gathered = [None]
+
+    def gather(r):
+        """The only collective of the path: per-graph AUDC (f64, bit-exact) + n_steps + removal sequence + LMCC trace of one
+        finished batch.  The traces are [B, N] buffers of which a rollout fills ~50-70 columns, so the ranks first agree on
+        the longest sequence (one 4-byte MAX all-reduce) and gather only that many columns."""
         if world > 1:
             if timed[0]:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-            rec = torch.cat([r.score[:, None], r.n_steps[:, None].double(), r.trace_action.double(), r.trace_rank.double()], 1)
-            dist.all_gather_into_tensor(gather_buf, rec)
+            mx = r.n_steps.max().reshape(1).clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            used = min(T, (int(mx.item()) + 15) // 16 * 16)
+            rec = torch.cat([r.score[:, None], r.n_steps[:, None].double(), r.trace_action[:, :used].double(),
+                             r.trace_rank[:, :used].double()], 1)
+            out = torch.empty(world * per_gpu, rec.shape[1], dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(out, rec)
+            gathered[0] = out
             if timed[0]:
                 b.record()
                 gather_ev.append((a, b))
@@ -665,7 +674,9 @@ def run_ours(args, cost, n, per_gpu, desc):
                     "d2h_bytes_per_step": int(d2h), "timing": "wall clock, max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "removal_steps_per_s": world * per_gpu * mean_steps * args.steps / (ms * 1e-3),
-            "per_rank_ms_per_step": per_rank_ms, "gather_ms_per_step": gather_ms,
+            "per_rank_ms_per_step": per_rank_ms, "gather_span_ms_per_step": gather_ms,
+            "gather_note": "CUDA-event span around (MAX all-reduce of n_steps, record packing, all_gather) on the finished batch's "
+                           "stream; other batches' kernels run inside the span, so it is an upper bound of the collective's cost",
             "single_batch_latency_ms": single_batch_ms,
         }
         if nccl_log:

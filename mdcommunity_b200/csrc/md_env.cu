@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int* gact = srcl + St;            // [St] per source group: has a frontier;     srcl + gact = smallest-member table [2 St]
   int* grmin = gact + St;           // [St] per source group: smallest node
   int* gnew = grmin + St;           // [St] per source group: fresh label (also scratch)
-  IdxT* c_cl = reinterpret_cast<IdxT*>(gnew + St);  // [max_nnz] neighbour (graph-local id)
+  // (the seven arrays above exist only when the incremental update is switched on: 28 KB at stride 1024 would cost the
+  // second resident CTA per SM)
+  const bool inc_layout = (dbg_flags & 65536) != 0;
+  IdxT* c_cl = reinterpret_cast<IdxT*>(inc_layout ? gnew + St : rowof);  // [max_nnz] neighbour (graph-local id)
   IdxT* c_src = c_cl + max_nnz;     // [max_nnz] row of the entry (static, staged); later the alive prefix
   __shared__ BlockRed red;
   __shared__ int s_action, s_lab_a;
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int stable = 0, l = 0;
   int rounds_dbg = 0;
   long long hook_dbg = 0, flat_dbg = 0, tq = 0;
-  const bool incremental = init == 0 && (dbg_flags & 65536);  // opt-in: measured 2x SLOWER than the rounds at N = 1000 (below)
+  const bool incremental = init == 0 && inc_layout;  // opt-in: measured 2x SLOWER than the rounds at N = 1000 (below)
   if (incremental) {
     // ---- incremental update (a step; s0 / set_state run the from-scratch rounds below) ---------------------------------
     // Removing a can only change the block that contained a, and inside it only what hangs on the edges that just died.
@@ -420,27 +423,39 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   (void)hook_dbg, (void)flat_dbg, (void)tq, (void)rounds_dbg;
 
   // ---- component sizes -> LMCC rank (Mcc.find_max_set_length) ------------------------------------------
-  // Labels are node ids < N (from-scratch rounds) or fresh ids in [N, 2N) (incremental splits): one table pass counts the
-  // members of every label and finds its smallest member, which becomes the canonical label again.
-  int* ccnt = vis;   // [2 St] (vis + pend)
-  int* cmin = srcl;  // [2 St] (srcl + gact)
-  for (int i = tid; i < 2 * St; i += ENV_T) {
-    ccnt[i] = 0;
-    cmin[i] = 0x7fffffff;
-  }
-  __syncthreads();
-  for (int v = tid; v < N; v += ENV_T)
-    if (lab[v] >= 0) {
-      atomicAdd(&ccnt[lab[v]], 1);
-      atomicMin(&cmin[lab[v]], v);
+  int rank;
+  if (inc_layout) {
+    // Labels are node ids < N (from-scratch rounds) or fresh ids in [N, 2N) (incremental splits): one table pass counts the
+    // members of every label and finds its smallest member, which becomes the canonical label again.
+    int* ccnt = vis;   // [2 St] (vis + pend)
+    int* cmin = srcl;  // [2 St] (srcl + gact)
+    for (int i = tid; i < 2 * St; i += ENV_T) {
+      ccnt[i] = 0;
+      cmin[i] = 0x7fffffff;
     }
-  __syncthreads();
-  int mx = 0;
-  for (int i = tid; i < 2 * St; i += ENV_T) mx = max(mx, ccnt[i]);
-  const int rank = block_max_i(mx, red);
-  for (int v = tid; v < N; v += ENV_T)
-    if (lab[v] >= 0) lab[v] = cmin[lab[v]];
-  __syncthreads();
+    __syncthreads();
+    for (int v = tid; v < N; v += ENV_T)
+      if (lab[v] >= 0) {
+        atomicAdd(&ccnt[lab[v]], 1);
+        atomicMin(&cmin[lab[v]], v);
+      }
+    __syncthreads();
+    int mx = 0;
+    for (int i = tid; i < 2 * St; i += ENV_T) mx = max(mx, ccnt[i]);
+    rank = block_max_i(mx, red);
+    for (int v = tid; v < N; v += ENV_T)
+      if (lab[v] >= 0) lab[v] = cmin[lab[v]];
+    __syncthreads();
+  } else {
+    for (int v = tid; v < N; v += ENV_T) tmp[v] = 0;
+    __syncthreads();
+    for (int v = tid; v < N; v += ENV_T)
+      if (lab[v] >= 0) atomicAdd(&tmp[lab[v]], 1);
+    __syncthreads();
+    int mx = 0;
+    for (int v = tid; v < N; v += ENV_T) mx = max(mx, tmp[v]);
+    rank = block_max_i(mx, red);
+  }
 
   ENV_TICK();  // 3: component sizes
   // ---- per layer: alive CSR, alive degree, status counters (get_status_info) -------------------------------
@@ -626,6 +641,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
 
 int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
                       int32_t forced_index, int init, md_stream_t stream);
+extern int g_md_debug_flags;  // bit 16 here: incremental mutual-component update instead of the from-scratch prune rounds
 
 extern "C" int md_debug_read_env_ctas(unsigned* host4096) {
   return (int)cudaMemcpyFromSymbol(host4096, md::g_env_cta, sizeof(unsigned) * 4096);
@@ -633,14 +649,14 @@ extern "C" int md_debug_read_env_ctas(unsigned* host4096) {
 extern "C" int md_debug_read_env(long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, md::g_env_dbg, sizeof(long long) * n);
 }
-extern int g_md_debug_flags;  // bit 16 here: incremental mutual-component update instead of the from-scratch prune rounds
 static int g_force_large = 0;
 extern "C" int32_t md_env_small_max_stride(void) { return g_force_large ? 0 : md::ENV_SMALL_MAX; }
 // 1 if this batch takes the single-CTA (shared-memory) env kernel, 0 for the cooperative global-memory kernel
 static bool env_idx16(const md_graphs_t* g) { return g->max_graph_nnz < 65536 && g->stride < 65536; }
 static size_t env_small_smem(const md_graphs_t* g) {
   const size_t idx_bytes = env_idx16(g) ? 2 : 4;
-  return ((size_t)11 * g->stride + (size_t)g->n_layers * (g->stride + 1)) * sizeof(int) +
+  const size_t arrays = (g_md_debug_flags & 65536) ? 11 : 4;  // + 7 arrays of the incremental update when it is switched on
+  return (arrays * g->stride + (size_t)g->n_layers * (g->stride + 1)) * sizeof(int) +
          ((2 * (size_t)g->max_graph_nnz * idx_bytes + 15) & ~(size_t)15);
 }
 extern "C" int32_t md_env_uses_small_path(const md_graphs_t* g) {
