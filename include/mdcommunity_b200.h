@@ -89,15 +89,18 @@ typedef struct md_state {
   int32_t cost_mode;     /* 0 = unit cost reward, 1 = degree cost reward */
   /* scratch for the large-graph (multi-CTA) LMCC path, may be NULL when stride <= md_env_small_max_stride() */
   int32_t* parent;       /* [n_total] */
-  int32_t* comp_size;    /* [n_total] */
-  int32_t* flags;        /* [16] scratch: [0..3] grid barrier / change flags of the multi-CTA env kernel, [4..5] tile queue of
+  int32_t* comp_size;    /* [n_total]; [3 * n_total] when lg_scratch is set */
+  int32_t* flags;        /* [32] scratch: [0..3] grid barrier / change flags of the multi-CTA env kernel, [4..5] tile queue of
                             md_qhead, [6..7] phase timers of the multi-CTA env kernel, [8] number of graphs that have LEFT the
-                            lock-step iteration (terminal, or handed over to md_rollout_tail) */
+                            lock-step iteration (terminal, or handed over to md_rollout_tail), [9..21] counters of the multi-CTA env kernel's
+                            incremental update ([16] = next fresh label, persists between launches) */
   int32_t* cur_action;   /* [B] action applied in the running step (-1 = graph untouched) */
   int32_t* tail_n;       /* [B] or NULL.  Non-NULL enables the hand-over to md_rollout_tail: when a step leaves a graph with
                             at most md_tail_max_nodes() active nodes (and md_tail_max_entries() alive entries per layer),
                             md_env_step stores that node count here and marks the graph finished FOR THE LOCK-STEP KERNELS
                             (n_act = 0, done = 1, n_done untouched); md_rollout_tail completes it.  Zero-initialised. */
+  int32_t* lg_scratch;   /* [9 * n_total] or NULL, ZERO-INITIALISED: scratch of the incremental mutual-component update of the
+                            multi-CTA env kernel (md_debug_set_flags bit 17); the kernel leaves its first 2 * n_total words zero */
 } md_state_t;
 
 /* The 14-tensor checkpoint (U/MultiDismantler_net_graphsage.py:42-89, U/MRGNN/mutil_layer_weight.py:252-264),
@@ -164,6 +167,7 @@ void md_debug_force_large_env(int32_t on);
  *   only when the embeddings exceed L2), bit 9 selects md_agg's register-load kernel instead of the cp.async ring,
  *   bit 12 disables iteration 0 from the alive degrees (unit cost) so that md_embed_init writes H0 again;
  * bit 13 keeps relu's argument e @ h1 of the two-layer tensor-core md_qhead on the FP32 pipes (A/B reference);
+ * bit 17 (md_env_step, multi-CTA path, needs s->lg_scratch): incremental mutual-component update, grid-wide;
  * bit 16 (md_env_step, single-CTA path): incremental mutual-component update (multi-source search from the end points of
  *   the edges that died) instead of the from-scratch prune rounds; same results, measured slower at N = 1000;
  * bits 14 / 15 (two-kernel md_embed_iter only): enqueue only the neighbour aggregation / only the transform, so that a

@@ -38,7 +38,7 @@ class MdState(C.Structure):
         ("done", _vp), ("n_steps", _vp), ("score", _vp), ("aux", _vp), ("best", _vp),
         ("trace_action", _vp), ("trace_rank", _vp), ("trace_maxcc", _vp), ("n_done", _vp),
         ("max_steps", C.c_int32), ("cost_mode", C.c_int32),
-        ("parent", _vp), ("comp_size", _vp), ("flags", _vp), ("cur_action", _vp), ("tail_n", _vp),
+        ("parent", _vp), ("comp_size", _vp), ("flags", _vp), ("cur_action", _vp), ("tail_n", _vp), ("lg_scratch", _vp),
     ]
 
 

@@ -56,9 +56,15 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
   __syncthreads();
 }
 
+// flags slots of the incremental update: counters [9..15] (sources / rest of the round (two parities), visited, roots,
+// active roots, kept root, smallest node), [16] next fresh label (persists from launch to launch), [17..20] pending
+// sources per layer
+constexpr int LF_SRC = 9, LF_VIS = 10, LF_ROOTS = 11, LF_ACT = 12, LF_KEEP = 13, LF_MIN = 14, LF_REST = 15, LF_NEXT = 16,
+              LF_PEND = 17, LF_SRC2 = 21;
+
 __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t S, const int32_t* forced,
                                                       int forced_stride, int forced_index, int init, int cpg,
-                                                      int chunk) {
+                                                      int chunk, int incremental) {
   const int tid = threadIdx.x;
   const int gtid = blockIdx.x * LG_T + tid;
   const int gsz = gridDim.x * LG_T;
@@ -100,11 +106,26 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
       if (a >= 0 && label[g * St + a] < 0) a = -1;
       if (a >= 0) {
         for (int l = 0; l < L; ++l) S.cov_edges[l * B + g] += S.deg[l][g * St + a];
+        if (incremental) {  // pending sources of the incremental update: a's alive neighbours, layer by layer
+          const int va = g * St + a, x0 = label[va];
+          int* pbits = S.lg_scratch + NT;
+          for (int l = 0; l < L; ++l) {
+            const int e1 = G.rowptr[l][va + 1];
+            for (int e = G.rowptr[l][va]; e < e1; ++e) {
+              const int u = G.col[l][e];
+              if (label[u] == x0 && !(atomicOr(&pbits[u], 1 << l) & (1 << l))) atomicAdd(&flags[LF_PEND + l], 1);
+            }
+          }
+        }
         label[g * St + a] = -1;
       }
     }
     S.cur_action[g] = a;
     S.best[g] = 0ull;
+    if (init && g == 0) {
+      flags[LF_NEXT] = NT;  // fresh labels of the incremental update start above the node ids
+      for (int l = 0; l < MD_MAX_LAYERS; ++l) flags[LF_PEND + l] = 0;
+    }
     S.rank[g] = (init || a >= 0) ? 0 : S.rank[g];
     if (init || a >= 0)
       for (int l = 0; l < L; ++l) {
@@ -127,6 +148,151 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
   unsigned long long t_ph = now_ns();
   // ---- Mcc.MCC --------------------------------------------------------------------------------------------
   int stable = 0, l = 0, round = 0;
+  if (incremental && !init) {
+    // ---- incremental update (same scheme as md_env.cu, grid-wide): only what hangs on the edges that just died is visited.
+    // At N = 1M a removal makes the searches visit some 10^4 nodes instead of the 3 x 4 sweeps over 10^6 nodes of the
+    // from-scratch rounds below.  Labels: node ids (< NT) from the from-scratch rounds, fresh ids (>= NT, one counter per
+    // rollout) for pieces that split off; the rest of a block keeps its label without being visited.
+    int* own = S.lg_scratch;  // [NT] 0 = unvisited, else 1 + index of the claiming source   (all zero between launches)
+    int* pbits = own + NT;    // [NT] pending-source bits, one per layer                      (all zero between launches)
+    int* vis = pbits + NT;    // [NT] visited list; its tail segment is the current frontier
+    int* srcl = vis + NT;     // [NT] pending sources of the running round
+    int* tmpl = srcl + NT;    // [NT] partition scratch
+    int* gpar = tmpl + NT;    // [NT] union-find over the sources of the running task
+    int* gact = gpar + NT;    // [NT] per source group: has a frontier
+    int* grmin = gact + NT;   // [NT] per source group: smallest node
+    int* gnew = grmin + NT;   // [NT] per source group: fresh label
+    int idle = 0, parity = 0;
+    while (idle < L) {
+      if (ld_volatile(&flags[LF_PEND + l]) == 0) {  // (last modified before a grid barrier: every CTA reads the same value)
+        ++idle;
+        l = (l + 1 == L) ? 0 : l + 1;
+        continue;
+      }
+      idle = 0;
+      const int* __restrict__ rp = G.rowptr[l];
+      const int* __restrict__ cl = G.col[l];
+      int* c_src = flags + (parity ? LF_SRC2 : LF_SRC);
+      parity ^= 1;
+      if (gtid == 0) *c_src = 0;
+      grid_barrier(bar, epoch);
+      if (gtid == 0) flags[LF_PEND + l] = 0;  // (every CTA has read it: nothing adds to this layer's count during its own round)
+      for (int v = gtid; v < NT; v += gsz) {
+        const int pb = pbits[v];
+        if (pb & (1 << l)) {
+          pbits[v] = pb & ~(1 << l);
+          if (label[v] >= 0) srcl[atomicAdd(c_src, 1)] = v;
+        }
+      }
+      grid_barrier(bar, epoch);
+      int rem = ld_volatile(c_src);
+      while (rem > 0) {  // one block at a time: the block of the first remaining source
+        const int x = label[srcl[0]];
+        if (gtid == 0) flags[LF_VIS] = 0, flags[LF_REST] = 0;
+        grid_barrier(bar, epoch);
+        for (int i = gtid; i < rem; i += gsz) {
+          const int v = srcl[i];
+          if (label[v] == x) vis[atomicAdd(&flags[LF_VIS], 1)] = v;
+          else tmpl[atomicAdd(&flags[LF_REST], 1)] = v;
+        }
+        grid_barrier(bar, epoch);
+        const int ns = ld_volatile(&flags[LF_VIS]);
+        rem = ld_volatile(&flags[LF_REST]);
+        for (int i = gtid; i < rem; i += gsz) srcl[i] = tmpl[i];
+        if (ns >= 2)
+          for (int i = gtid; i < ns; i += gsz) {
+            own[vis[i]] = i + 1;
+            gpar[i] = i;
+          }
+        grid_barrier(bar, epoch);
+        if (ns < 2) continue;  // one source: by the invariant its block is connected in this layer
+        ++round;
+        int f0 = 0, f1 = ns, nroots = ns, nact = ns;
+        while (nroots > 1 && nact > 1) {
+          for (int i = f0 + (gtid >> 3); i < f1; i += gsz / 8) {  // 8 lanes per frontier node
+            const int u = vis[i], gu = own[u] - 1;
+            const int e1 = rp[u + 1];
+            for (int e = rp[u] + (gtid & 7); e < e1; e += 8) {
+              const int v = cl[e];
+              if (label[v] != x) continue;
+              const int o = atomicCAS(&own[v], 0, gu + 1);
+              if (o == 0) vis[atomicAdd(&flags[LF_VIS], 1)] = v;
+              else if (o - 1 != gu) guf_unite(gpar, o - 1, gu);
+            }
+          }
+          grid_barrier(bar, epoch);
+          f0 = f1;
+          f1 = ld_volatile(&flags[LF_VIS]);
+          for (int i = gtid; i < ns; i += gsz) gact[i] = 0;
+          if (gtid == 0) flags[LF_ROOTS] = 0, flags[LF_ACT] = 0;
+          grid_barrier(bar, epoch);
+          for (int i = f0 + gtid; i < f1; i += gsz) gact[guf_find(gpar, own[vis[i]] - 1)] = 1;
+          grid_barrier(bar, epoch);
+          for (int i = gtid; i < ns; i += gsz)
+            if (guf_find(gpar, i) == i) {
+              atomicAdd(&flags[LF_ROOTS], 1);
+              if (gact[i]) atomicAdd(&flags[LF_ACT], 1);
+            }
+          grid_barrier(bar, epoch);
+          nroots = ld_volatile(&flags[LF_ROOTS]);
+          nact = ld_volatile(&flags[LF_ACT]);
+        }
+        const int nvis = f1;
+        if (nroots > 1) {
+          // split: the group that is still searching (or, if all ran dry, the one with the smallest node) stays x
+          if (gtid == 0) flags[LF_KEEP] = -1, flags[LF_MIN] = 0x7fffffff;
+          for (int i = gtid; i < ns; i += gsz) grmin[i] = 0x7fffffff;
+          grid_barrier(bar, epoch);
+          if (nact == 1) {
+            for (int i = gtid; i < ns; i += gsz)
+              if (gact[i] && guf_find(gpar, i) == i) flags[LF_KEEP] = i;
+          } else {
+            for (int i = gtid; i < nvis; i += gsz) atomicMin(&grmin[guf_find(gpar, own[vis[i]] - 1)], vis[i]);
+            grid_barrier(bar, epoch);
+            for (int i = gtid; i < ns; i += gsz)
+              if (guf_find(gpar, i) == i) atomicMin(&flags[LF_MIN], grmin[i]);
+            grid_barrier(bar, epoch);
+            const int mn = ld_volatile(&flags[LF_MIN]);
+            for (int i = gtid; i < ns; i += gsz)
+              if (guf_find(gpar, i) == i && grmin[i] == mn) flags[LF_KEEP] = i;
+          }
+          grid_barrier(bar, epoch);
+          const int keep = ld_volatile(&flags[LF_KEEP]);
+          for (int i = gtid; i < ns; i += gsz)
+            if (i != keep && guf_find(gpar, i) == i) gnew[i] = atomicAdd(&flags[LF_NEXT], 1);
+          grid_barrier(bar, epoch);
+          for (int i = gtid; i < nvis; i += gsz) {
+            const int v = vis[i], r = guf_find(gpar, own[v] - 1);
+            if (r != keep) label[v] = gnew[r];
+          }
+          grid_barrier(bar, epoch);
+          // edges of the other layers that were alive inside x and cross labels now: both end points become pending
+          for (int i = gtid >> 3; i < nvis; i += gsz / 8) {
+            const int v = vis[i], lv = label[v];
+            if (lv == x) continue;  // only nodes that moved
+            for (int l2 = 0; l2 < L; ++l2) {
+              if (l2 == l) continue;
+              const int* __restrict__ rp2 = G.rowptr[l2];
+              const int* __restrict__ cl2 = G.col[l2];
+              const int e1 = rp2[v + 1];
+              for (int e = rp2[v] + (gtid & 7); e < e1; e += 8) {
+                const int u = cl2[e], lu = label[u];
+                if (lu >= 0 && lu != lv && (lu == x || own[u] != 0)) {
+                  if (!(atomicOr(&pbits[v], 1 << l2) & (1 << l2))) atomicAdd(&flags[LF_PEND + l2], 1);
+                  if (!(atomicOr(&pbits[u], 1 << l2) & (1 << l2))) atomicAdd(&flags[LF_PEND + l2], 1);
+                }
+              }
+            }
+          }
+          grid_barrier(bar, epoch);
+        }
+        for (int i = gtid; i < nvis; i += gsz) own[vis[i]] = 0;
+        grid_barrier(bar, epoch);
+      }
+      l = (l + 1 == L) ? 0 : l + 1;
+    }
+    stable = L;  // skip the from-scratch rounds
+  }
   while (stable < L) {
     const int32_t* __restrict__ rp = G.rowptr[l];
     const int32_t* __restrict__ cl = G.col[l];
@@ -206,7 +372,8 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
   // ---- component sizes, alive degrees, per-graph counters -------------------------------------------------
   int* csz = S.comp_size;
   for (int g = gtid; g < B; g += gsz) S.best[g] = 0ull;  // (scratch of the MCC rounds; the arg-max key starts from 0)
-  for (int v = gtid; v < NT; v += gsz) csz[v] = 0;
+  const int n_labels = incremental ? 3 * NT : NT;  // incremental update: fresh labels in [NT, 3 NT)
+  for (int v = gtid; v < n_labels; v += gsz) csz[v] = 0;
   grid_barrier(bar, epoch);
   for (int v = gtid; v < NT; v += gsz) {
     const int lv = label[v];
@@ -246,7 +413,8 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
   for (int v = gtid; v < NT; v += gsz) {
     const int g = v / St;
     if (!init && S.cur_action[g] < 0) continue;
-    int c = csz[v];
+    const int lv2 = label[v];
+    int c = lv2 >= 0 ? csz[lv2] : 0;  // every node looks up the size of its own block (labels need not be node ids)
     const int g0 = __shfl_sync(0xffffffffu, g, 0);
     if (__all_sync(0xffffffffu, g == g0)) {
       c = warp_max_i(c);
@@ -437,6 +605,8 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
 
 }  // namespace md
 
+extern int g_md_debug_flags;  // bit 17 here: incremental mutual-component update (needs s->lg_scratch)
+
 int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
                       int32_t forced_index, int init, md_stream_t stream) {
   if (!s->parent || !s->comp_size || !s->flags || !s->cur_action) return MD_EINVAL;
@@ -469,7 +639,8 @@ int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* 
   cpg = (g->stride + chunk - 1) / chunk;
   md_graphs_t gg = *g;
   md_state_t ss = *s;
-  void* args[] = {&gg, &ss, (void*)&forced, &forced_stride, &forced_index, &init, &cpg, &chunk};
+  int incremental = (ss.lg_scratch != nullptr && (g_md_debug_flags & (1 << 17))) ? 1 : 0;
+  void* args[] = {&gg, &ss, (void*)&forced, &forced_stride, &forced_index, &init, &cpg, &chunk, &incremental};
   e = cudaLaunchCooperativeKernel((const void*)md::env_step_large, dim3(grid), dim3(md::LG_T), args, 0, st);
   if (e != cudaSuccess) return (int)e;
   return 0;

@@ -104,8 +104,9 @@ class BatchRollout:
         self.n_done = i32(1)
         self.large = not self.lib.md_env_uses_small_path(batch.ptr())
         self.parent = i32(nt) if self.large else None
-        self.comp_size = i32(nt) if self.large else None
-        self.flags = i32(16)
+        self.comp_size = i32(3 * nt) if self.large else None
+        self.lg_scratch = i32(9 * nt) if self.large else None  # incremental LMCC update of the multi-CTA env kernel
+        self.flags = i32(32)
         self.cur_action = i32(B)
         self.tail_n = i32(B)
         s = _lib.MdState()
@@ -121,6 +122,7 @@ class BatchRollout:
             setattr(s, name, getattr(self, name).data_ptr())
         s.parent = self.parent.data_ptr() if self.large else None
         s.comp_size = self.comp_size.data_ptr() if self.large else None
+        s.lg_scratch = self.lg_scratch.data_ptr() if self.large else None
         s.max_steps = self.max_steps
         s.cost_mode = 1 if batch.cost == "degree" else 0
         s.tail_n = None

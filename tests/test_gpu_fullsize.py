@@ -22,7 +22,18 @@ from conftest import GOLDEN, Q_ATOL, Q_RTOL
 pytestmark = pytest.mark.gpu
 
 
-def test_c4_million_node_three_layer_parity():
+@pytest.mark.parametrize("lmcc", ["rounds", "incremental"])
+def test_c4_million_node_three_layer_parity(lmcc):
+    """lmcc: from-scratch prune rounds, or the grid-wide incremental update (md_debug_set_flags bit 17) of md_env_step."""
+    from mdcommunity_b200 import _lib as _l
+    _l.lib().md_debug_set_flags((1 << 17) if lmcc == "incremental" else 0)
+    try:
+        _c4_parity()
+    finally:
+        _l.lib().md_debug_set_flags(0)
+
+
+def _c4_parity():
     import scipy.sparse as sp
     import mdcommunity_b200 as mdb
     from mdcommunity_b200 import _lib, gmm

@@ -37,13 +37,14 @@ def _forced(zs, key, device):
     return torch.from_numpy(a).to(device), T
 
 
-@pytest.fixture(params=["small", "large", "incremental"])
+@pytest.fixture(params=["small", "large", "incremental", "large-incremental"])
 def env_path(request):
-    """small = one CTA per graph (shared memory), large = cooperative multi-CTA kernel (global memory), incremental = the
-    single-CTA kernel with the incremental mutual-component update (md_debug_set_flags bit 16) instead of the rounds."""
+    """small = one CTA per graph (shared memory), large = cooperative multi-CTA kernel (global memory); incremental /
+    large-incremental = the same kernels with the incremental mutual-component update (md_debug_set_flags bits 16 / 17)
+    instead of the from-scratch prune rounds."""
     from mdcommunity_b200 import _lib
-    _lib.lib().md_debug_force_large_env(1 if request.param == "large" else 0)
-    _lib.lib().md_debug_set_flags(65536 if request.param == "incremental" else 0)
+    _lib.lib().md_debug_force_large_env(1 if request.param.startswith("large") else 0)
+    _lib.lib().md_debug_set_flags({"incremental": 1 << 16, "large-incremental": 1 << 17}.get(request.param, 0))
     yield request.param
     _lib.lib().md_debug_force_large_env(0)
     _lib.lib().md_debug_set_flags(0)
@@ -55,7 +56,7 @@ def test_env_random_actions_bit_exact(variant, env_path):
     mdb = _mdb()
     zs, graphs, batch, w = _load_batch(variant)
     ro = mdb.BatchRollout(batch, w)
-    assert ro.large == (env_path == "large")
+    assert ro.large == env_path.startswith("large")
     for z, g in zip(zs, graphs):
         assert g.max_rank == int(z["max_rank"])
     acts, T = _forced(zs, "random_actions", batch.device)
