@@ -391,16 +391,21 @@ def c4_leg(dev, steps=100):
     b_xf0 = L * (2 * 4 * D * n_act + 4 * n_act)                                 # iteration 0: H0 comes from the degrees
     b_qh = L * 4 * D * n_act + 4 * n_act + 4 * n_act                            # H_l rows, ids, q
     b_sweep = 4 * (n_act + 1) + 2 * 4 * nnz / L + 4 * n_act + n_act / 8         # one edge sweep of one layer
-    sweeps = R + 2 * L  # R prune rounds (one Afforest pass each, modelled as one sweep) + per layer: degrees / sizes, alive CSR
+    # env_step_large: the mutual-component update is INCREMENTAL (multi-source searches from the end points of the edges that
+    # died: R search tasks per step visiting ~1e4 of the 1e6 nodes; SURVEY 8(d): incremental variants count only the rows
+    # visited, which is negligible here), so the step's algorithmic bytes are the two remaining full passes per layer:
+    # alive degrees / component sizes, and the emission of the alive CSR in compact order.
+    sweeps = 2 * L
     kern = {
         "agg_deg (iteration 0: degree gather)": roof(med["agg0"], b_deg),
         "agg_ring (iterations 1, 2: 256-byte row gather)": roof((med["agg1"] + med["agg2"]) / 2, b_rows),
         "embed_iter_tc<PRE> (transform, iterations 1, 2)": roof((med["xform1"] + med["xform2"]) / 2, b_xf),
         "embed_iter_tc<PRE> (transform, iteration 0)": roof(med["xform0"], b_xf0),
         "qhead_tc<3>": roof(med["qhead"], b_qh),
-        "env_step_large": roof(med["env_step"], sweeps * b_sweep, R=R, L=L, S=1, sweeps=sweeps, B_sweep=b_sweep,
-                               model="(R + 2L) * B_sweep: R prune rounds x 1 sweep, + per layer one sweep for alive "
-                                     "degrees / component sizes and one for the alive-CSR emission"),
+        "env_step_large": roof(med["env_step"], sweeps * b_sweep, search_tasks=R, L=L, sweeps=sweeps, B_sweep=b_sweep,
+                               model="2L * B_sweep: per layer one sweep for alive degrees / component sizes and one for the "
+                                     "alive-CSR emission; the incremental mutual-component update (search_tasks multi-source "
+                                     "searches per step) visits ~1e4 nodes and is not counted"),
     }
     agg_ms = sum(med[k] for k in names[1:7])
     agg_bytes = b_deg + 2 * b_rows + b_xf0 + 2 * b_xf
@@ -715,7 +720,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the N = 1M removal-steps/s leg (about 30 s)")
     ap.add_argument("--no-c3", action="store_true", help="skip the 1024-graph strong-scaling leg (C3)")
-    ap.add_argument("--depth", type=int, default=3, help="batches in flight (RolloutPipeline); 1 = strictly one after the other")
+    ap.add_argument("--depth", type=int, default=4, help="batches in flight (RolloutPipeline); 1 = strictly one after the other")
     ap.add_argument("--tail", action="store_true", help="hand graphs with <= 64 active nodes over to md_rollout_tail")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -100,7 +100,7 @@ typedef struct md_state {
                             md_env_step stores that node count here and marks the graph finished FOR THE LOCK-STEP KERNELS
                             (n_act = 0, done = 1, n_done untouched); md_rollout_tail completes it.  Zero-initialised. */
   int32_t* lg_scratch;   /* [9 * n_total] or NULL, ZERO-INITIALISED: scratch of the incremental mutual-component update of the
-                            multi-CTA env kernel (md_debug_set_flags bit 17); the kernel leaves its first 2 * n_total words zero */
+                            multi-CTA env kernel (NULL = from-scratch prune rounds on every step); the kernel leaves its first 2 * n_total words zero */
 } md_state_t;
 
 /* The 14-tensor checkpoint (U/MultiDismantler_net_graphsage.py:42-89, U/MRGNN/mutil_layer_weight.py:252-264),
@@ -167,7 +167,8 @@ void md_debug_force_large_env(int32_t on);
  *   only when the embeddings exceed L2), bit 9 selects md_agg's register-load kernel instead of the cp.async ring,
  *   bit 12 disables iteration 0 from the alive degrees (unit cost) so that md_embed_init writes H0 again;
  * bit 13 keeps relu's argument e @ h1 of the two-layer tensor-core md_qhead on the FP32 pipes (A/B reference);
- * bit 17 (md_env_step, multi-CTA path, needs s->lg_scratch): incremental mutual-component update, grid-wide;
+ * bit 17 (md_env_step, multi-CTA path): from-scratch prune rounds on every step instead of the grid-wide incremental
+ *   mutual-component update that is the default when s->lg_scratch is set (A/B reference; same results);
  * bit 16 (md_env_step, single-CTA path): incremental mutual-component update (multi-source search from the end points of
  *   the edges that died) instead of the from-scratch prune rounds; same results, measured slower at N = 1000;
  * bits 14 / 15 (two-kernel md_embed_iter only): enqueue only the neighbour aggregation / only the transform, so that a

@@ -60,7 +60,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
 // active roots, kept root, smallest node), [16] next fresh label (persists from launch to launch), [17..20] pending
 // sources per layer
 constexpr int LF_SRC = 9, LF_VIS = 10, LF_ROOTS = 11, LF_ACT = 12, LF_KEEP = 13, LF_MIN = 14, LF_REST = 15, LF_NEXT = 16,
-              LF_PEND = 17, LF_SRC2 = 21;
+              LF_PEND = 17, LF_SRC2 = 21, LF_ROOTS2 = 22, LF_ACT2 = 23;
 
 __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t S, const int32_t* forced,
                                                       int forced_stride, int forced_index, int init, int cpg,
@@ -207,8 +207,15 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
         grid_barrier(bar, epoch);
         if (ns < 2) continue;  // one source: by the invariant its block is connected in this layer
         ++round;
-        int f0 = 0, f1 = ns, nroots = ns, nact = ns;
+        int f0 = 0, f1 = ns, nroots = ns, nact = ns, lvl = 0;
         while (nroots > 1 && nact > 1) {
+          // two grid barriers per level: (1) expand the frontier; (2) count the groups and those that still have a frontier.
+          // The counters of a level are cleared during the expansion of the NEXT level (two parities: a CTA that is late
+          // reading level k's counts cannot see level k + 1's reset of the same words).
+          int* c_roots = flags + ((lvl & 1) ? LF_ROOTS2 : LF_ROOTS);
+          int* c_act = flags + ((lvl & 1) ? LF_ACT2 : LF_ACT);
+          if (gtid == 0) *c_roots = 0, *c_act = 0;
+          for (int i = gtid; i < ns; i += gsz) gact[i] = 0;
           for (int i = f0 + (gtid >> 3); i < f1; i += gsz / 8) {  // 8 lanes per frontier node
             const int u = vis[i], gu = own[u] - 1;
             const int e1 = rp[u + 1];
@@ -223,19 +230,16 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
           grid_barrier(bar, epoch);
           f0 = f1;
           f1 = ld_volatile(&flags[LF_VIS]);
-          for (int i = gtid; i < ns; i += gsz) gact[i] = 0;
-          if (gtid == 0) flags[LF_ROOTS] = 0, flags[LF_ACT] = 0;
-          grid_barrier(bar, epoch);
-          for (int i = f0 + gtid; i < f1; i += gsz) gact[guf_find(gpar, own[vis[i]] - 1)] = 1;
-          grid_barrier(bar, epoch);
+          for (int i = f0 + gtid; i < f1; i += gsz) {  // (no unions in this phase: roots are stable)
+            const int r = guf_find(gpar, own[vis[i]] - 1);
+            if (atomicExch(&gact[r], 1) == 0) atomicAdd(c_act, 1);
+          }
           for (int i = gtid; i < ns; i += gsz)
-            if (guf_find(gpar, i) == i) {
-              atomicAdd(&flags[LF_ROOTS], 1);
-              if (gact[i]) atomicAdd(&flags[LF_ACT], 1);
-            }
+            if (guf_find(gpar, i) == i) atomicAdd(c_roots, 1);
           grid_barrier(bar, epoch);
-          nroots = ld_volatile(&flags[LF_ROOTS]);
-          nact = ld_volatile(&flags[LF_ACT]);
+          nroots = ld_volatile(c_roots);
+          nact = ld_volatile(c_act);
+          ++lvl;
         }
         const int nvis = f1;
         if (nroots > 1) {
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
 
 }  // namespace md
 
-extern int g_md_debug_flags;  // bit 17 here: incremental mutual-component update (needs s->lg_scratch)
+extern int g_md_debug_flags;  // bit 17 here: from-scratch prune rounds on every step (A/B reference of the incremental update)
 
 int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* forced, int32_t forced_stride,
                       int32_t forced_index, int init, md_stream_t stream) {
@@ -639,7 +643,7 @@ int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* 
   cpg = (g->stride + chunk - 1) / chunk;
   md_graphs_t gg = *g;
   md_state_t ss = *s;
-  int incremental = (ss.lg_scratch != nullptr && (g_md_debug_flags & (1 << 17))) ? 1 : 0;
+  int incremental = (ss.lg_scratch != nullptr && !(g_md_debug_flags & (1 << 17))) ? 1 : 0;
   void* args[] = {&gg, &ss, (void*)&forced, &forced_stride, &forced_index, &init, &cpg, &chunk, &incremental};
   e = cudaLaunchCooperativeKernel((const void*)md::env_step_large, dim3(grid), dim3(md::LG_T), args, 0, st);
   if (e != cudaSuccess) return (int)e;

@@ -22,11 +22,12 @@ from conftest import GOLDEN, Q_ATOL, Q_RTOL
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("lmcc", ["rounds", "incremental"])
+@pytest.mark.parametrize("lmcc", ["incremental", "rounds"])
 def test_c4_million_node_three_layer_parity(lmcc):
-    """lmcc: from-scratch prune rounds, or the grid-wide incremental update (md_debug_set_flags bit 17) of md_env_step."""
+    """lmcc: the grid-wide incremental update of md_env_step (default), or from-scratch prune rounds on every step
+    (md_debug_set_flags bit 17)."""
     from mdcommunity_b200 import _lib as _l
-    _l.lib().md_debug_set_flags((1 << 17) if lmcc == "incremental" else 0)
+    _l.lib().md_debug_set_flags((1 << 17) if lmcc == "rounds" else 0)
     try:
         _c4_parity()
     finally:

@@ -37,14 +37,14 @@ def _forced(zs, key, device):
     return torch.from_numpy(a).to(device), T
 
 
-@pytest.fixture(params=["small", "large", "incremental", "large-incremental"])
+@pytest.fixture(params=["small", "large", "incremental", "large-rounds"])
 def env_path(request):
-    """small = one CTA per graph (shared memory), large = cooperative multi-CTA kernel (global memory); incremental /
-    large-incremental = the same kernels with the incremental mutual-component update (md_debug_set_flags bits 16 / 17)
-    instead of the from-scratch prune rounds."""
+    """small = one CTA per graph (shared memory, from-scratch prune rounds), large = cooperative multi-CTA kernel (global
+    memory, incremental mutual-component update); incremental = the single-CTA kernel with the incremental update
+    (md_debug_set_flags bit 16), large-rounds = the multi-CTA kernel with from-scratch rounds on every step (bit 17)."""
     from mdcommunity_b200 import _lib
     _lib.lib().md_debug_force_large_env(1 if request.param.startswith("large") else 0)
-    _lib.lib().md_debug_set_flags({"incremental": 1 << 16, "large-incremental": 1 << 17}.get(request.param, 0))
+    _lib.lib().md_debug_set_flags({"incremental": 1 << 16, "large-rounds": 1 << 17}.get(request.param, 0))
     yield request.param
     _lib.lib().md_debug_force_large_env(0)
     _lib.lib().md_debug_set_flags(0)
