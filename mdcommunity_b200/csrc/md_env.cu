@@ -99,10 +99,10 @@ __device__ __forceinline__ long long block_sum_ll(long long v, BlockRed& r) {
 // message-passing iterations of the next forward stream it without re-checking labels.
 // IdxT: uint16_t when every graph of the batch has fewer than 65536 CSR entries (halves the staged CSR, so two CTAs fit
 // one SM and a 256-graph batch runs in one wave instead of two), int32_t otherwise.
-template <typename IdxT>
+// INC: the incremental mutual-component update is compiled in (md_debug_set_flags bit 16; + 7 shared arrays per CTA).
+template <typename IdxT, bool INC>
 __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_t S, const int32_t* forced,
-                                                       int forced_stride, int forced_index, int init, int max_nnz,
-                                                       int dbg_flags) {
+                                                       int forced_stride, int forced_index, int init, int max_nnz) {
   extern __shared__ int smem[];
   const int g = blockIdx.x;
   const int tid = threadIdx.x;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int* gnew = grmin + St;           // [St] per source group: fresh label (also scratch)
   // (the seven arrays above exist only when the incremental update is switched on: 28 KB at stride 1024 would cost the
   // second resident CTA per SM)
-  const bool inc_layout = (dbg_flags & 65536) != 0;
+  constexpr bool inc_layout = INC;
   IdxT* c_cl = reinterpret_cast<IdxT*>(inc_layout ? gnew + St : rowof);  // [max_nnz] neighbour (graph-local id)
   IdxT* c_src = c_cl + max_nnz;     // [max_nnz] row of the entry (static, staged); later the alive prefix
   __shared__ BlockRed red;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   int rounds_dbg = 0;
   long long hook_dbg = 0, flat_dbg = 0, tq = 0;
   const bool incremental = init == 0 && inc_layout;  // opt-in: measured 2x SLOWER than the rounds at N = 1000 (below)
-  if (incremental) {
+  if constexpr (INC) if (incremental) {
     // ---- incremental update (a step; s0 / set_state run the from-scratch rounds below) ---------------------------------
     // Removing a can only change the block that contained a, and inside it only what hangs on the edges that just died.
     // Invariant per layer l: every layer-l connected piece of a block contains a PENDING SOURCE of layer l, or the block is
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
 
   // ---- component sizes -> LMCC rank (Mcc.find_max_set_length) ------------------------------------------
   int rank;
-  if (inc_layout) {
+  if constexpr (INC) {
     // Labels are node ids < N (from-scratch rounds) or fresh ids in [N, 2N) (incremental splits): one table pass counts the
     // members of every label and finds its smallest member, which becomes the canonical label again.
     int* ccnt = vis;   // [2 St] (vis + pend)
@@ -672,11 +672,13 @@ static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* 
   const size_t smem = env_small_smem(g);
   if (!md_env_uses_small_path(g)) return md_env_step_large(g, s, forced, forced_stride, forced_index, init, stream);
   const bool i16 = env_idx16(g);
-  static md::PerDevice<size_t> configured_pd[2];
-  size_t& configured_smem = configured_pd[i16].get();
+  const bool inc = (g_md_debug_flags & 65536) != 0;
+  const void* fn = i16 ? (inc ? (const void*)md::env_step_small<uint16_t, true> : (const void*)md::env_step_small<uint16_t, false>)
+                       : (inc ? (const void*)md::env_step_small<int32_t, true> : (const void*)md::env_step_small<int32_t, false>);
+  static md::PerDevice<size_t> configured_pd[4];
+  size_t& configured_smem = configured_pd[2 * i16 + inc].get();
   if (smem > 48 * 1024 && smem > configured_smem) {
-    cudaError_t e = i16 ? cudaFuncSetAttribute(md::env_step_small<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                        : cudaFuncSetAttribute(md::env_step_small<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured_smem = smem;
   }
@@ -689,10 +691,12 @@ static int env_launch(const md_graphs_t* g, const md_state_t* s, const int32_t* 
       if (e != cudaSuccess) return (int)e;
     }
   }
-  if (i16)
-    md::env_step_small<uint16_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz, g_md_debug_flags);
-  else
-    md::env_step_small<int32_t><<<g->n_graphs, md::ENV_T, smem, st>>>(*g, *s, forced, forced_stride, forced_index, init, g->max_graph_nnz, g_md_debug_flags);
+  md_graphs_t gg = *g;
+  md_state_t ss = *s;
+  int max_nnz = g->max_graph_nnz;
+  void* args[] = {&gg, &ss, (void*)&forced, &forced_stride, &forced_index, &init, &max_nnz};
+  cudaError_t e = cudaLaunchKernel(fn, dim3(g->n_graphs), dim3(md::ENV_T), args, smem, st);
+  if (e != cudaSuccess) return (int)e;
   MD_CHECK_LAUNCH();
   return 0;
 }
