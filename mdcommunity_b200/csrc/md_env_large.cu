@@ -59,13 +59,12 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
 // flags slots of the incremental update: counters [9..15] (sources / rest of the round (two parities), visited, roots,
 // active roots, kept root, smallest node), [16] next fresh label (persists from launch to launch), [17..20] pending
 // sources per layer
-constexpr int LF_SUBBAR = 24;  // barrier counter of the CTAs that run the incremental update (cleared by the host per launch)
 constexpr int LF_SRC = 9, LF_VIS = 10, LF_ROOTS = 11, LF_ACT = 12, LF_KEEP = 13, LF_MIN = 14, LF_REST = 15, LF_NEXT = 16,
               LF_PEND = 17, LF_SRC2 = 21, LF_ROOTS2 = 22, LF_ACT2 = 23;
 
 __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t S, const int32_t* forced,
                                                       int forced_stride, int forced_index, int init, int cpg,
-                                                      int chunk, int incremental, int nsub) {
+                                                      int chunk, int incremental) {
   const int tid = threadIdx.x;
   const int gtid = blockIdx.x * LG_T + tid;
   const int gsz = gridDim.x * LG_T;
@@ -149,27 +148,7 @@ __global__ void __launch_bounds__(LG_T) env_step_large(md_graphs_t G, md_state_t
   unsigned long long t_ph = now_ns();
   // ---- Mcc.MCC --------------------------------------------------------------------------------------------
   int stable = 0, l = 0, round = 0;
-  if (incremental && !init && (int)blockIdx.x >= nsub) stable = L;  // (these CTAs wait at the next grid barrier)
-  if (incremental && !init && (int)blockIdx.x < nsub) {
-    // The searches touch ~1e4 nodes: they are barrier-bound, and a barrier over one CTA per SM is cheaper than one over
-    // the whole cooperative grid (4 CTAs per SM polling one word).  Only the first nsub CTAs take part, with their own
-    // barrier counter; the others go on to clear the component-size table and wait at the next grid-wide barrier.
-    const int gsz = nsub * LG_T;  // (shadows the grid-wide thread count inside this block)
-    unsigned* bar = reinterpret_cast<unsigned*>(S.flags) + LF_SUBBAR;
-    unsigned epoch = 0;
-    auto grid_barrier = [&](unsigned* counter, unsigned& ep) {
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        ep += 1;
-        const unsigned target = ep * (unsigned)nsub;
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
-        }
-        __threadfence();
-      }
-      __syncthreads();
-    };
+  if (incremental && !init) {
     // ---- incremental update (same scheme as md_env.cu, grid-wide): only what hangs on the edges that just died is visited.
     // At N = 1M a removal makes the searches visit some 10^4 nodes instead of the 3 x 4 sweeps over 10^6 nodes of the
     // from-scratch rounds below.  Labels: node ids (< NT) from the from-scratch rounds, fresh ids (>= NT, one counter per
@@ -665,12 +644,7 @@ int md_env_step_large(const md_graphs_t* g, const md_state_t* s, const int32_t* 
   md_graphs_t gg = *g;
   md_state_t ss = *s;
   int incremental = (ss.lg_scratch != nullptr && !(g_md_debug_flags & (1 << 17))) ? 1 : 0;
-  int nsub = grid / 4 > 0 ? grid / 4 : 1;  // ~ one CTA per SM (grid = SMs x resident CTAs, at most 4)
-  if (nsub > grid) nsub = grid;
-  if (g_md_debug_flags & (1 << 18)) nsub = grid;  // A/B: the whole grid takes part in the searches
-  e = cudaMemsetAsync(s->flags + 24, 0, 8 * sizeof(int32_t), st);
-  if (e != cudaSuccess) return (int)e;
-  void* args[] = {&gg, &ss, (void*)&forced, &forced_stride, &forced_index, &init, &cpg, &chunk, &incremental, &nsub};
+  void* args[] = {&gg, &ss, (void*)&forced, &forced_stride, &forced_index, &init, &cpg, &chunk, &incremental};
   e = cudaLaunchCooperativeKernel((const void*)md::env_step_large, dim3(grid), dim3(md::LG_T), args, 0, st);
   if (e != cudaSuccess) return (int)e;
   return 0;
