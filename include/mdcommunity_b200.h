@@ -285,6 +285,51 @@ int md_heuristic_select(const md_graphs_t* g, const md_state_t* s, int32_t kind,
 int md_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* val, const float* X, float* Y,
                     int32_t n_rows, int32_t D, md_stream_t stream);
 
+/* ---- dense primitives of the DQN training step, FP32, forward and backward -------------------
+ * Replace the torch ops of MultiDismantler_net.train_forward (U/MultiDismantler_net_graphsage.py:92-241), of
+ * BitwiseMultipyLogis (U/MRGNN/mutil_layer_weight.py:266-313), of calc_loss (U/MultiDismantler_torch.py:410-431), the
+ * backward torch autograd derives from them, and torch.optim.Adam (U/MultiDismantler_torch.py:136).  All matrices are
+ * dense row-major f32 device pointers; every reduction runs in a fixed order (no floating-point atomics). */
+
+/* C[M,N] = [C +] op(A) op(B); transA: A stored [K,M]; transB: B stored [N,K]; relu_a: A clamped at 0 on load.
+ * ws / ws_floats: optional workspace for a split over K (used when K >= 4096 and the output has < 64 tiles). */
+int md_gemm_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB,
+                int32_t accumulate, int32_t relu_a, float* ws, int64_t ws_floats, md_stream_t stream);
+/* H = x / max(|x|_2, 1e-12) per row, x = relu ? max(Z, 0) : Z  (F.normalize(torch.relu(.)), :113-116,:160-166); D <= 128 */
+int md_norm_fwd_f32(const float* Z, float* H, int32_t n, int32_t D, int32_t relu, md_stream_t stream);
+int md_norm_bwd_f32(const float* Z, const float* dH, float* dZ, int32_t n, int32_t D, int32_t relu, md_stream_t stream);
+/* T = tanh(Z + b) (mutil_layer_weight.py:270-276); dZ = dT (1 - T^2) */
+int md_tanh_bias_fwd_f32(const float* Z, const float* b, float* T, int32_t n, int32_t D, md_stream_t stream);
+int md_tanh_bwd_f32(const float* T, const float* dT, float* dZ, int32_t n, int32_t D, md_stream_t stream);
+/* out[c] = sum_r X[r, c] */
+int md_colsum_f32(const float* X, float* out, int32_t n, int32_t D, md_stream_t stream);
+/* two-layer fusion (mutil_layer_weight.py:278-301), width MD_EMBED: X_p = T_p + softmax_k(sigmoid(<T_k T_p, lw> + lb))[1-p] T_{1-p};
+ * saved [n, 8] keeps the gate scalars for the backward; Glw [n, 64] / Glb [n] are per-row contributions to d lw / d lb */
+int md_fuse2_fwd_f32(const float* T0, const float* T1, const float* lw, const float* lb, float* X0, float* X1, float* saved,
+                     int32_t n, md_stream_t stream);
+int md_fuse2_bwd_f32(const float* T0, const float* T1, const float* lw, const float* saved, const float* dX0, const float* dX1,
+                     float* dT0, float* dT1, float* Glw, float* Glb, int32_t n, md_stream_t stream);
+/* E[r,:] = H[r,:] * s[gid[r]]  ((hf yf^T) cross == hf * (yf . cross), net_graphsage.py:205-212) */
+int md_rowscale_f32(const float* H, const float* s, const int32_t* gid, float* E, int32_t n, int32_t D, md_stream_t stream);
+/* out[r] = A[r,:] . B[r,:] */
+int md_rowdot_f32(const float* A, const float* B, float* out, int32_t n, int32_t D, md_stream_t stream);
+/* out[g] = sum_{r in [off[g], off[g+1])} x[r] * (y ? y[r] : 1) */
+int md_seg_reduce_f32(const float* x, const float* y, const int64_t* off, float* out, int32_t B, md_stream_t stream);
+/* q[r] = sm0 (q0[r] + a0[g]) + sm1 (q1[r] + a1[g]), sm = softmax(gate0[g], gate1[g]), g = gid[r] (net_graphsage.py:214-241) */
+int md_head_mix_fwd_f32(const float* g0, const float* g1, const float* a0, const float* a1, const float* q0, const float* q1,
+                        const int32_t* gid, float* q, int32_t n, md_stream_t stream);
+/* dsum_q[g] = sum_r dq (q0 - q1), dqs[g] = sum_r dq (md_seg_reduce_f32) */
+int md_head_mix_bwd_f32(const float* g0, const float* g1, const float* a0, const float* a1, const float* dq, const float* dsum_q,
+                        const float* dqs, const int32_t* gid, float* dq0, float* dq1, float* dg0, float* dg1, float* da0,
+                        float* da1, int32_t n, int32_t B, md_stream_t stream);
+/* out = alpha a + beta b (b may be NULL); dX *= (X > 0); out[0] = a . b */
+int md_axpby_f32(const float* a, const float* b, float alpha, float beta, float* out, int64_t n, md_stream_t stream);
+int md_relu_mask_f32(const float* X, float* dX, int64_t n, md_stream_t stream);
+int md_dot_f32(const float* a, const float* b, float* out, int64_t n, md_stream_t stream);
+/* one Adam step (t = 1, 2, ...) on flat parameter / gradient / moment buffers */
+int md_adam_step_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                     int32_t t, md_stream_t stream);
+
 /* ---- sizing helpers (host) ------------------------------------------------------------------------------ */
 int64_t md_psum_floats(int32_t n_layers, int32_t n_total);
 /* sizeof(md_graphs_t), sizeof(md_state_t), sizeof(md_weights_t), sizeof(md_work_t) as compiled: lets a binding check

@@ -90,6 +90,23 @@ _SIGS = {
     "md_rollout_graph_destroy": ([_vp], C.c_int),
     "md_select_topk": ([C.POINTER(MdGraphs), C.POINTER(MdState), C.POINTER(MdWork), _vp, C.c_int32, _vp], C.c_int),
     "md_spmm_csr_f32": ([_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_gemm_f32": ([_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int64, _vp], C.c_int),
+    "md_norm_fwd_f32": ([_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_norm_bwd_f32": ([_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_tanh_bias_fwd_f32": ([_vp, _vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_tanh_bwd_f32": ([_vp, _vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_colsum_f32": ([_vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_fuse2_fwd_f32": ([_vp] * 7 + [C.c_int32, _vp], C.c_int),
+    "md_fuse2_bwd_f32": ([_vp] * 10 + [C.c_int32, _vp], C.c_int),
+    "md_rowscale_f32": ([_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_rowdot_f32": ([_vp, _vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_seg_reduce_f32": ([_vp, _vp, _vp, _vp, C.c_int32, _vp], C.c_int),
+    "md_head_mix_fwd_f32": ([_vp] * 8 + [C.c_int32, _vp], C.c_int),
+    "md_head_mix_bwd_f32": ([_vp] * 14 + [C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_axpby_f32": ([_vp, _vp, C.c_float, C.c_float, _vp, C.c_int64, _vp], C.c_int),
+    "md_relu_mask_f32": ([_vp, _vp, C.c_int64, _vp], C.c_int),
+    "md_dot_f32": ([_vp, _vp, _vp, C.c_int64, _vp], C.c_int),
+    "md_adam_step_f32": ([_vp, _vp, _vp, _vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _vp], C.c_int),
     "md_psum_floats": ([C.c_int32, C.c_int32], C.c_int64),
     "md_abi_sizes": ([_vp], None),
     "md_version": ([], C.c_char_p),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmdb200.so")
-SOURCES = ["md_env.cu", "md_env_large.cu", "md_embed.cu", "md_embed_iter.cu", "md_embed_iter_tc.cu", "md_agg.cu", "md_embed_fused.cu", "md_qhead.cu", "md_qhead_tc.cu", "md_tail.cu", "md_heuristic.cu", "md_spmm.cu", "md_api.cu"]
+SOURCES = ["md_env.cu", "md_env_large.cu", "md_embed.cu", "md_embed_iter.cu", "md_embed_iter_tc.cu", "md_agg.cu", "md_embed_fused.cu", "md_qhead.cu", "md_qhead_tc.cu", "md_tail.cu", "md_heuristic.cu", "md_spmm.cu", "md_train.cu", "md_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,

@@ -7,8 +7,9 @@ fusion module U/MRGNN/mutil_layer_weight.py:252-313 (BitwiseMultipyLogis / Logis
 For callers that keep the reference's own batch preparation (PrepareBatchGraph -> COO dicts) and only swap the network:
 the inputs are exactly what MultiDismantler.SetuppredAll / SetupTrain build (lists of two {"index","value","m","n"}
 dicts, aux_input [B,2,4], node_input None or [2,n,2], dense adj / v_adj accepted and ignored: the degree features they
-are used for are read off the sparse operands).  Neighbour aggregation runs in the CUDA SpMM kernel (`ops.spmm`,
-forward and backward); the 31 k-parameter dense algebra is torch on the same device.  `load_state_dict` of the
+are used for are read off the sparse operands).  Neighbour aggregation AND the dense algebra of the 31 k-parameter
+network run in the hand-written kernels of `dense.py` (csrc/md_train.cu, csrc/md_spmm.cu), forward and backward; torch
+only builds the CSR operands and carries the autograd edge.  `load_state_dict` of the
 reference's 14-key checkpoints works unchanged (`last_w` is the same Parameter as `h2_weight`, :69).
 The device-resident rollout (`MultiDismantler.GetSol`, `BatchRollout`) does not go through this class: it runs the
 hand-written forward kernels; this is the operator/model boundary of SURVEY 8(b).
@@ -16,7 +17,7 @@ hand-written forward kernels; this is the operator/model boundary of SURVEY 8(b)
 import torch
 import torch.nn.functional as F
 
-from . import ops
+from . import dense
 
 EMBEDDING_SIZE = 64   # U/MultiDismantler_torch.py:35
 REG_HIDDEN = 32       # :53
@@ -76,65 +77,44 @@ class MultiDismantler_net(torch.nn.Module):
             self.to(device)
 
     # ---- shared trunk ---------------------------------------------------------------------------------------------
-    def _embed(self, node_input, subgsum_param, n2nsum_param):
+    def _params(self):
+        law = self.layerNodeAttention_weight
+        return [self.w_n2l, self.p_node_conv, self.p_node_conv2, self.p_node_conv3, self.h1_weight, self.h2_weight, self.cross_product,
+                self.w_layer1, self.w_layer2, law.trans, law.bias, law.logis.parameter.weight, law.logis.parameter.bias]
+
+    def _network(self, node_input, subgsum_param, n2nsum_param, aux_input):
+        """(q of every node [n, 1], fused embeddings [2, n + B, 64], n) through the hand-written kernels (dense.py:
+        forward AND backward; torch only builds the CSR operands from the COO dicts)."""
         dev = self.w_n2l.device
-        nodes_cnt, B = n2nsum_param[0]["m"], subgsum_param[0]["m"]
-        gid = torch.zeros(nodes_cnt, dtype=torch.long, device=dev)
-        gid[subgsum_param[0]["index"][1].to(dev)] = subgsum_param[0]["index"][0].to(dev)  # node -> graph (subg_construct :308-340)
-        emb = []
-        for l in range(2):
-            index = n2nsum_param[l]["index"].to(dev)
-            value = n2nsum_param[l]["value"].to(dev).float()
-            if node_input is None:  # unit cost: degree / max degree of the graph (:100-112), read off the n2n operand
-                deg = torch.zeros(nodes_cnt, device=dev).index_add_(0, index[0], torch.ones_like(value))
+        n, B = n2nsum_param[0]["m"], subgsum_param[0]["m"]
+        if self.max_bp_iter != MAX_BP_ITER or self.embedding_size != EMBEDDING_SIZE:
+            raise ValueError("the kernels are built for embedding_size 64 and max_bp_iter 3 (U/MultiDismantler_torch.py:35,62)")
+        x = []
+        if node_input is None:  # unit cost: degree / max degree of the graph (:100-112), read off the n2n operand
+            gid = torch.zeros(n, dtype=torch.long, device=dev)
+            gid[subgsum_param[0]["index"][1].to(dev)] = subgsum_param[0]["index"][0].to(dev)  # node -> graph (subg_construct :308-340)
+            for l in range(2):
+                index = n2nsum_param[l]["index"].to(dev)
+                deg = torch.zeros(n, device=dev).index_add_(0, index[0], torch.ones(index.shape[1], device=dev))
                 dmax = torch.zeros(B, device=dev).scatter_reduce_(0, gid, deg, reduce="amax", include_self=True)
                 d = deg / dmax.clamp_min(1.0)[gid]
-                x = torch.stack([d, d], 1)
-            else:
-                x = torch.as_tensor(node_input[l], dtype=torch.float32, device=dev)
-            h = F.normalize(torch.relu(torch.matmul(x, self.w_n2l)), p=2, dim=1)
-            y = F.normalize(torch.relu(torch.matmul(torch.ones((B, 2), device=dev), self.w_n2l)), p=2, dim=1)
-            sindex, svalue = subgsum_param[l]["index"].to(dev), subgsum_param[l]["value"].to(dev).float()
-            for _ in range(self.max_bp_iter):
-                n2npool = ops.spmm(index, value, nodes_cnt, nodes_cnt, h)           # torch_sparse.spmm call site :139
-                y_n2npool = ops.spmm(sindex, svalue, B, nodes_cnt, h)               # :146
-                merged = torch.cat([torch.matmul(n2npool, self.p_node_conv), torch.matmul(h, self.p_node_conv2)], 1)
-                y_merged = torch.cat([torch.matmul(y_n2npool, self.p_node_conv), torch.matmul(y, self.p_node_conv2)], 1)
-                h = F.normalize(torch.relu(torch.matmul(merged, self.p_node_conv3)), p=2, dim=1)
-                y = F.normalize(torch.relu(torch.matmul(y_merged, self.p_node_conv3)), p=2, dim=1)
-            emb.append(torch.cat([h, y], 0))
-        fused = [F.normalize(self.layerNodeAttention_weight(emb, None, l), p=2, dim=1) for l in range(2)]
-        return fused, nodes_cnt, B, gid
-
-    def _heads(self, fused, nodes_cnt, gid, rows, aux_input):
-        """Q of the node rows `rows` (None = all nodes), graph of each row = gid[rows]."""
-        dev = self.w_n2l.device
-        aux = torch.as_tensor(aux_input, dtype=torch.float32, device=dev)
-        qs, gates = [], []
-        for l in range(2):
-            hf, yf = fused[l][:nodes_cnt], fused[l][nodes_cnt:]
-            g_of = gid if rows is None else gid[rows]
-            act = hf if rows is None else hf.index_select(0, rows)
-            rep_y = yf.index_select(0, g_of)
-            embed_s_a = act * torch.matmul(rep_y, self.cross_product)                # (act y^T) cross == act * (y . cross)
-            hidden = torch.relu(torch.matmul(embed_s_a, self.h1_weight))
-            qs.append(torch.matmul(torch.cat([hidden, aux[:, l, :].index_select(0, g_of)], 1), self.last_w))
-            gates.append(torch.matmul(torch.relu(torch.matmul(rep_y, self.w_layer1)), self.w_layer2))
-        sm = F.softmax(torch.cat(gates, 1), dim=1)
-        return sm[:, 0:1] * qs[0] + sm[:, 1:2] * qs[1]
+                x.append(torch.stack([d, d], 1))
+        else:
+            x = [torch.as_tensor(node_input[l], dtype=torch.float32, device=dev) for l in range(2)]
+        o = dense.Operands.from_coo(n, B, n2nsum_param, subgsum_param, x, aux_input)
+        q, fused = dense.network(self._params(), o)
+        return q, fused, n
 
     # ---- reference entry points -----------------------------------------------------------------------------------
     def train_forward(self, node_input, subgsum_param, n2nsum_param, action_select, aux_input, adj=None, v_adj=None):
         """-> (q_pred [B,1], cur_message_layer [2,n,64])  (:92-241)."""
-        fused, n, B, gid = self._embed(node_input, subgsum_param, n2nsum_param)
+        q, fused, n = self._network(node_input, subgsum_param, n2nsum_param, aux_input)
         dev = self.w_n2l.device
         a_index = action_select[0]["index"].to(dev)  # row = graph, col = node of the chosen action (:199-203)
-        rows = torch.zeros(B, dtype=torch.long, device=dev)
+        rows = torch.zeros(subgsum_param[0]["m"], dtype=torch.long, device=dev)
         rows[a_index[0]] = a_index[1]
-        q = self._heads(fused, n, gid, rows, aux_input)
-        return q, torch.stack([fused[0][:n], fused[1][:n]])
+        return dense.take_rows(q, rows), fused[:, :n]
 
     def test_forward(self, node_input, subgsum_param, n2nsum_param, rep_global, aux_input, adj=None, v_adj=None):
         """-> q_on_all [n,1]  (:243-394)."""
-        fused, n, B, gid = self._embed(node_input, subgsum_param, n2nsum_param)
-        return self._heads(fused, n, gid, None, aux_input)
+        return self._network(node_input, subgsum_param, n2nsum_param, aux_input)[0]

@@ -12,8 +12,11 @@ What runs where.  The environment (node removal, LMCC, alive CSR, status counter
 does in PrepareBatchGraph (compact re-indexing, COO of the alive edges, node / aux features) and the neighbour
 aggregation (torch_sparse.spmm -> `ops.spmm`, forward and backward through md_spmm_csr_f32) are CUDA: the batch is
 assembled from the env kernel's outputs with a handful of device-side index operations, no Python loop touches an edge.
-The small dense algebra of the 31 205-parameter network and its backward go through torch autograd on the same
-device.  Data parallelism: every rank takes the round-robin shard of the replay batch, the losses are normalised by
+The dense algebra of the 31 205-parameter network, the loss, their backward and the Adam update are hand-written too
+(`dense.py` over csrc/md_train.cu: FP32 tile GEMM with a deterministic split over K for the weight gradients, fused
+relu + L2-normalise, tanh, the two-layer fusion, the Q head and layer gate, forward AND backward; no cuBLAS, no torch
+autograd formula).  Both layers and both row kinds (nodes, graph rows) are stacked into one [2(n+B), 64] matrix, so an
+embedding iteration is 1 SpMM + 4 GEMMs + 1 normalise.  Data parallelism: every rank takes the round-robin shard of the replay batch, the losses are normalised by
 the GLOBAL batch size / edge counts (one tiny all-reduce), so the SUM all-reduce of one flat gradient buffer gives
 exactly the single-process gradient.
 
@@ -26,9 +29,8 @@ import random
 import numpy as np
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
-from . import ops
+from . import dense
 from .graph import GraphBatch
 from .rollout import BatchRollout, QWeights
 from .sharding import shard_indices
@@ -51,12 +53,19 @@ PARAM_SHAPES = {
 
 class QNet(torch.nn.Module):
     """The reference's parameter set under the reference's names (load_state_dict of its 14-key checkpoints works;
-    `last_w` is the same tensor as `h2_weight`, net_graphsage.py:69)."""
+    `last_w` is the same tensor as `h2_weight`, net_graphsage.py:69).  Every Parameter is a view into ONE flat buffer
+    (`flat`, offsets 16-byte aligned): the Adam kernel and the gradient all-reduce work on the flat buffers."""
 
     def __init__(self, device, seed=None):
         super().__init__()
         gen = torch.Generator().manual_seed(seed) if seed is not None else None
-        self._names = {}
+        self._names, self._slices, o = {}, {}, 0
+        for k, shp in PARAM_SHAPES.items():
+            k_el = int(np.prod(shp))
+            self._slices[k] = (o, k_el)
+            o += (k_el + 3) // 4 * 4
+        self.flat = torch.zeros(o, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros(o, dtype=torch.float32, device=device)
         for k, shp in PARAM_SHAPES.items():
             if k.endswith("trans"):
                 init = torch.eye(64)
@@ -66,10 +75,24 @@ class QNet(torch.nn.Module):
                 init = torch.fmod(torch.normal(0.0, 0.01, size=tuple(shp), generator=gen), 2)
             name = k.replace(".", "__")
             self._names[k] = name
-            self.register_parameter(name, torch.nn.Parameter(init.to(device)))
+            lo, k_el = self._slices[k]
+            view = self.flat[lo:lo + k_el].view(shp)
+            view.copy_(init)
+            self.register_parameter(name, torch.nn.Parameter(view))
 
     def p(self, key):
         return getattr(self, self._names[key])
+
+    def params_in_key_order(self):
+        return [self.p(k) for k in dense.PARAM_KEYS]
+
+    def tensors(self):
+        """reference key -> detached view of the parameter (what the dense kernels read)."""
+        return {k: self.p(k).detach() for k in PARAM_SHAPES}
+
+    def grad_tensors(self):
+        """reference key -> view into flat_grad (what dense.backward writes)."""
+        return {k: self.flat_grad[lo:lo + n_el].view(PARAM_SHAPES[k]) for k, (lo, n_el) in self._slices.items()}
 
     def state_dict_ref(self):
         sd = {k: self.p(k).detach().clone() for k in PARAM_SHAPES}
@@ -108,6 +131,7 @@ class TrainBatch:
         self.gidx = torch.full((b.n_total,), -1, dtype=torch.long, device=dev)
         self.gidx[v] = torch.arange(n, device=dev)
         self.index, self.node_input, self.edge_num = [], [], []
+        cnts, cols = [], []
         for l in range(L):
             a0, a1 = ro.aptr[l][slot].long(), ro.aptr[l][slot + 1].long()
             cnt = a1 - a0
@@ -116,6 +140,7 @@ class TrainBatch:
             e = torch.arange(int(cnt.sum()), device=dev) - start[row] + a0[row]
             col = self.gidx[ro.acol[l][e].long()]
             self.index.append(torch.stack([row, col]))
+            cnts.append(cnt), cols.append(col)
             self.edge_num.append(int(row.numel()))
             if b.cost == "degree":
                 wv = b.node_w[l][v].float()
@@ -125,6 +150,9 @@ class TrainBatch:
                 x = torch.stack([d, d], 1)
             self.node_input.append(x)
         self.aux = ro.aux.clone()                          # [B, L, 4]
+        self.N = n + B
+        # operands of the hand-written network: block CSR (aggregation + sub-graph sum), its transpose, the Laplacian
+        self.operands = dense.Operands.from_alive_csr(n, B, gid, off, n_act, cnts, cols, self.node_input, self.aux) if L == 2 else None
 
     def rows_of(self, local_ids, stride):
         """compact row of (graph i, local node id local_ids[i])."""
@@ -135,63 +163,20 @@ class TrainBatch:
         return rows
 
 
-def _fuse(net, e0, e1, p):
-    t = [torch.tanh(torch.matmul(e, net.p("layerNodeAttention_weight.trans")) + net.p("layerNodeAttention_weight.bias"))
-         for e in (e0, e1)]
-    sem = torch.stack([t[0] * t[p], t[1] * t[p]], dim=1)
-    a = torch.sigmoid(F.linear(sem, net.p("layerNodeAttention_weight.logis.parameter.weight"),
-                               net.p("layerNodeAttention_weight.logis.parameter.bias"))).reshape(-1, 2)
-    alpha = F.softmax(a, dim=1)
-    return t[p] + alpha[:, 1 - p].unsqueeze(1) * t[1 - p]
-
-
 def network(net: QNet, tb: TrainBatch):
-    """q for every compact row [n, 1] and the fused, normalised embeddings [L x [n + B, 64]] (train_forward :92-241 and
-    test_forward :243-394 share this arithmetic)."""
+    """q for every compact row [n, 1] and the fused, normalised embeddings [2, n + B, 64] (layer, node rows then graph
+    rows) -- train_forward :92-241 and test_forward :243-394 share this arithmetic.  Runs dense.forward (hand-written
+    kernels); differentiable through dense.backward."""
     assert tb.L == 2, "the reference network is hard-wired to two layers"
-    n, B, dev = tb.n, tb.B, tb.gid.device
-    emb = []
-    for l in range(tb.L):
-        ones = torch.ones(tb.index[l].shape[1], device=dev)
-        h = F.normalize(torch.relu(torch.matmul(tb.node_input[l], net.p("w_n2l"))), p=2, dim=1)
-        y = F.normalize(torch.relu(torch.matmul(torch.ones((B, 2), device=dev), net.p("w_n2l"))), p=2, dim=1)
-        for _ in range(MAX_BP_ITER):
-            pool = ops.spmm(tb.index[l], ones, n, n, h)                      # CUDA SpMM, autograd through A^T
-            y_pool = torch.zeros((B, h.shape[1]), device=dev).index_add_(0, tb.gid, h)
-            merged = torch.cat([torch.matmul(pool, net.p("p_node_conv")), torch.matmul(h, net.p("p_node_conv2"))], 1)
-            y_merged = torch.cat([torch.matmul(y_pool, net.p("p_node_conv")), torch.matmul(y, net.p("p_node_conv2"))], 1)
-            h = F.normalize(torch.relu(torch.matmul(merged, net.p("p_node_conv3"))), p=2, dim=1)
-            y = F.normalize(torch.relu(torch.matmul(y_merged, net.p("p_node_conv3"))), p=2, dim=1)
-        emb.append(torch.cat([h, y], 0))
-    fused = [F.normalize(_fuse(net, emb[0], emb[1], p), p=2, dim=1) for p in range(2)]
-    qs, gates = [], []
-    for l in range(2):
-        hf, yf = fused[l][:n], fused[l][n:]
-        rep_y = yf.index_select(0, tb.gid)
-        e_sa = hf * torch.matmul(rep_y, net.p("cross_product"))            # (hf yf^T) cross == hf * (yf . cross)
-        hidden = torch.relu(torch.matmul(e_sa, net.p("h1_weight")))
-        rep_aux = tb.aux[:, l, :].index_select(0, tb.gid)
-        qs.append(torch.matmul(torch.cat([hidden, rep_aux], 1), net.p("h2_weight")))
-        gates.append(torch.matmul(torch.relu(torch.matmul(rep_y, net.p("w_layer1"))), net.p("w_layer2")))
-    sm = F.softmax(torch.cat(gates, 1), dim=1)
-    return sm[:, 0:1] * qs[0] + sm[:, 1:2] * qs[1], fused
+    return dense.network(net.params_in_key_order(), tb.operands)
 
 
 def calc_loss(q_pred, fused, tb: TrainBatch, target, batch_global=None, edge_num_global=None, alpha=ALPHA):
     """MSE(target, q_pred) + alpha * sum_l 2 trace(H_l^T (D - A)_l H_l) / edge_num_l  (MultiDismantler_torch.py:410-431).
     batch_global / edge_num_global: normalisers of the whole (multi-rank) batch; default = this batch."""
-    n, dev = tb.n, q_pred.device
     bg = float(batch_global if batch_global is not None else q_pred.shape[0])
-    loss1 = ((target - q_pred) ** 2).sum() / bg
-    loss2 = torch.zeros((), device=dev)
-    for l in range(tb.L):
-        h = fused[l][:n]
-        row = tb.index[l][0]
-        deg = torch.bincount(row, minlength=n).to(h.dtype)
-        lap_h = deg.unsqueeze(1) * h - ops.spmm(tb.index[l], torch.ones(row.numel(), device=dev), n, n, h)
-        en = float(edge_num_global[l] if edge_num_global is not None else tb.edge_num[l])
-        loss2 = loss2 + 2 * (h * lap_h).sum() / max(en, 1.0)
-    return loss1 + alpha * loss2
+    en = [float(e) for e in (edge_num_global if edge_num_global is not None else tb.edge_num)]
+    return dense.loss(tb.operands, q_pred, fused, target.float().contiguous(), bg, en, alpha)
 
 
 def set_states(ro: BatchRollout, covered):
@@ -222,7 +207,8 @@ class DQNTrainer:
         self.net = QNet(self.device, seed)
         self.net_T = QNet(self.device, seed)
         self.TakeSnapShot()
-        self.optimizer = torch.optim.Adam(self.net.parameters(), lr=lr)
+        self.optimizer = dense.FlatAdam(self.net.flat, self.net.flat_grad, [self.net.p(k) for k in PARAM_SHAPES],
+                                        self.net._slices, PARAM_SHAPES, lr)
 
     def LoadModel(self, state_dict):
         self.net.load_state_dict_ref(state_dict)
@@ -231,33 +217,46 @@ class DQNTrainer:
     def TakeSnapShot(self):  # :312-313
         self.net_T.load_state_dict_ref(self.net.state_dict_ref())
 
-    def train_forward(self, g_list, covered, actions):
-        """(q_pred [B,1], cur_message_layer [2 x [n,64]], TrainBatch) for this process's graphs."""
+    def _train_batch(self, g_list, covered):
         batch = GraphBatch(g_list, self.device, self.cost)
         ro = BatchRollout(batch, None, fused=False)
         set_states(ro, covered)
-        tb = TrainBatch(ro)
+        return TrainBatch(ro), batch
+
+    def train_forward(self, g_list, covered, actions):
+        """(q_pred [B,1], cur_message_layer [2, n + B, 64], TrainBatch) for this process's graphs (autograd-enabled)."""
+        tb, batch = self._train_batch(g_list, covered)
         q, fused = network(self.net, tb)
         rows = tb.rows_of(actions, batch.S)
-        return q.index_select(0, rows), fused, tb
+        return dense.take_rows(q, rows), fused, tb
 
     def fit(self, g_list, covered, actions, list_target):
         """One optimizer step on the batch (MultiDismantler_torch.py:381-408).  Under torch.distributed every rank passes
-        the SAME full batch and works on its round-robin shard; returns the global loss."""
+        the SAME full batch and works on its round-robin shard; returns the global loss.  Forward, loss, backward and
+        Adam are direct calls of the hand-written kernels (no autograd graph is built)."""
         world = dist.get_world_size() if dist.is_initialized() else 1
         rank = dist.get_rank() if dist.is_initialized() else 0
         idx = shard_indices(len(g_list), rank, world)
-        self.optimizer.zero_grad()
         tgt = torch.as_tensor(np.asarray(list_target, dtype=np.float64).reshape(-1, 1)[idx]).float().to(self.device)
-        q_pred, fused, tb = self.train_forward([g_list[i] for i in idx], [covered[i] for i in idx], [actions[i] for i in idx])
+        tb, batch = self._train_batch([g_list[i] for i in idx], [covered[i] for i in idx])
+        o = tb.operands
+        rows = tb.rows_of([actions[i] for i in idx], batch.S)
         en = torch.tensor(tb.edge_num, dtype=torch.float64, device=self.device)
         if world > 1:
             dist.all_reduce(en)
-        loss = calc_loss(q_pred, fused, tb, tgt, batch_global=len(g_list), edge_num_global=en.tolist())
-        loss.backward()
+        params = self.net.tensors()
+        c = dense.forward(params, o)
+        q_pred = c["q"].index_select(0, rows)
+        loss, lc = dense.loss_forward(o, q_pred, c["F"], tgt.reshape(-1), len(g_list), en.tolist(), ALPHA)
+        dq_pred, dF = dense.loss_backward(o, lc)
+        dq = torch.zeros(tb.n, dtype=torch.float32, device=self.device)
+        dq.index_copy_(0, rows, dq_pred)
+        self.optimizer.zero_grad()
+        dense.backward(params, o, c, dq, dF, self.net.grad_tensors())
+        self.optimizer.adopt_flat_grads()
         lv = loss.detach().double().reshape(1)
         if world > 1:
-            allreduce_gradients(list(self.net.parameters()))
+            dist.all_reduce(self.net.flat_grad)              # SUM of the shard gradients == single-process gradient
             dist.all_reduce(lv)
         self.optimizer.step()
         return float(lv[0])
@@ -384,8 +383,7 @@ def fit_targets(trainer: DQNTrainer, sample: ReplaySample):
         set_states(ro, [sample.list_s_primes[i] for i in live])
         with torch.no_grad():
             tb = TrainBatch(ro)
-            q, _ = network(trainer.net_T, tb)
-            q = q[:, 0]
+            q = dense.forward(trainer.net_T.tensors(), tb.operands)["q"]
             for j, i in enumerate(live):
                 lo, hi = int(tb.off[j]), int(tb.off[j + 1])
                 target[i, 0] = GAMMA * (float(q[lo:hi].max()) if hi > lo else 0.0)

@@ -1,0 +1,199 @@
+"""Hand-written dense kernels of the training step (csrc/md_train.cu through mdcommunity_b200.dense) against a plain
+PyTorch fp32 restatement of the same ops: every primitive, then the whole network forward + loss + backward against
+torch autograd over the reference's formulas (MultiDismantler_net_graphsage.py:92-241, mutil_layer_weight.py:266-301,
+MultiDismantler_torch.py:410-431)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _close(a, b, tol=2e-5):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    scale = float(b.abs().max()) + 1e-12
+    assert float((a - b).abs().max()) <= tol * scale + 1e-9, (float((a - b).abs().max()), scale)
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb,relu", [(300, 64, 64, 0, 0, 0), (64, 64, 9000, 1, 0, 0), (2, 64, 5000, 1, 0, 0), (777, 1, 32, 0, 0, 1),
+                                              (32, 1, 4500, 1, 0, 1), (500, 128, 1, 0, 1, 0), (130, 64, 64, 0, 1, 0), (5, 64, 2, 0, 0, 0),
+                                              (128, 64, 70, 1, 1, 0)])
+def test_gemm(M, N, K, ta, tb, relu):
+    from mdcommunity_b200 import dense
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N + K)
+    a = torch.randn((K, M) if ta else (M, K), device=DEV, generator=g)
+    b = torch.randn((N, K) if tb else (K, N), device=DEV, generator=g)
+    ar = torch.relu(a) if relu else a
+    ref = ((ar.t() if ta else ar).double() @ (b.t() if tb else b).double())
+    out = dense.gemm(a, b, ta=bool(ta), tb=bool(tb), relu_a=bool(relu))
+    _close(out, ref, 1e-5)
+    c0 = torch.randn(M, N, device=DEV, generator=g)
+    out2 = dense.gemm(a, b, ta=bool(ta), tb=bool(tb), relu_a=bool(relu), out=c0.clone(), acc=True)
+    _close(out2, ref + c0.double(), 1e-5)
+    # deterministic: same bits on a second run (fixed-order split over K)
+    assert torch.equal(out, dense.gemm(a, b, ta=bool(ta), tb=bool(tb), relu_a=bool(relu)))
+
+
+@pytest.mark.parametrize("relu", [0, 1])
+def test_norm_fwd_bwd(relu):
+    from mdcommunity_b200 import dense
+    g = torch.Generator(device=DEV).manual_seed(3 + relu)
+    z = torch.randn(1001, 64, device=DEV, generator=g)
+    z[5] = 0.0        # clamped row: x / eps
+    z[6] = -1.0       # relu kills the row
+    zr = z.clone().requires_grad_(True)
+    h_ref = F.normalize(torch.relu(zr) if relu else zr, p=2, dim=1)
+    dh = torch.randn(1001, 64, device=DEV, generator=g)
+    h_ref.backward(dh)
+    _close(dense.norm_fwd(z, bool(relu)), h_ref, 1e-6)
+    _close(dense.norm_bwd(z, dh, bool(relu)), zr.grad, 1e-5)
+
+
+def test_tanh_colsum_rowops():
+    from mdcommunity_b200 import dense
+    g = torch.Generator(device=DEV).manual_seed(11)
+    z, b = torch.randn(513, 64, device=DEV, generator=g), torch.randn(64, device=DEV, generator=g)
+    t = dense.tanh_bias(z, b)
+    _close(t, torch.tanh(z + b), 1e-6)
+    dt = torch.randn(513, 64, device=DEV, generator=g)
+    _close(dense.tanh_bwd(t, dt), dt * (1 - torch.tanh(z + b) ** 2), 1e-5)
+    out = torch.empty(64, device=DEV)
+    _close(dense.colsum(z, out), z.double().sum(0), 1e-5)
+    n_act = torch.tensor([3, 0, 200, 310], device=DEV)
+    off = torch.zeros(5, dtype=torch.long, device=DEV)
+    off[1:] = torch.cumsum(n_act, 0)
+    gid = torch.repeat_interleave(torch.arange(4, device=DEV), n_act).to(torch.int32)
+    s = torch.randn(4, 1, device=DEV, generator=g)
+    _close(dense.rowscale(z, s, gid), z * s[gid.long()], 1e-6)
+    _close(dense.rowdot(z, dt), (z * dt).sum(1), 1e-5)
+    x, y = torch.randn(513, device=DEV, generator=g), torch.randn(513, device=DEV, generator=g)
+    ref = torch.zeros(4, device=DEV, dtype=torch.double).index_add_(0, gid.long(), (x * y).double())
+    _close(dense.seg_reduce(x, y, off), ref, 1e-5)
+    _close(dense.dot(x, y), (x.double() * y.double()).sum().reshape(1), 1e-5)
+    _close(dense.axpby(x, y, 0.5, -2.0), 0.5 * x - 2.0 * y, 1e-6)
+    dx = y.clone()
+    _close(dense.relu_mask(x, dx), y * (x > 0), 0)
+
+
+def test_adam_matches_torch():
+    from mdcommunity_b200 import dense
+    g = torch.Generator(device=DEV).manual_seed(5)
+    flat = torch.randn(1000, device=DEV, generator=g)
+    ref = torch.nn.Parameter(flat.clone())
+    opt_ref = torch.optim.Adam([ref], lr=1e-3)
+    fg = torch.zeros_like(flat)
+    p = torch.nn.Parameter(flat[:1000].view(1000))
+    opt = dense.FlatAdam(flat, fg, [p], {"p": (0, 1000)}, {"p": (1000,)}, 1e-3)
+    for it in range(5):
+        grad = torch.randn(1000, device=DEV, generator=g) * (10.0 ** (it - 2))
+        ref.grad = grad.clone()
+        opt_ref.step()
+        opt.zero_grad()
+        p.grad = grad.clone()
+        opt.step()
+        assert float((flat - ref.detach()).abs().max()) <= 2e-7 + 1e-6 * 1e-3
+
+
+# ---- whole network vs torch autograd over the reference's formulas ------------------------------------------------------
+def _fuse_ref(P, e0, e1, p):
+    t = [torch.tanh(torch.matmul(e, P["layerNodeAttention_weight.trans"]) + P["layerNodeAttention_weight.bias"]) for e in (e0, e1)]
+    sem = torch.stack([t[0] * t[p], t[1] * t[p]], dim=1)
+    a = torch.sigmoid(F.linear(sem, P["layerNodeAttention_weight.logis.parameter.weight"],
+                               P["layerNodeAttention_weight.logis.parameter.bias"])).reshape(-1, 2)
+    alpha = F.softmax(a, dim=1)
+    return t[p] + alpha[:, 1 - p].unsqueeze(1) * t[1 - p]
+
+
+def _network_ref(P, tb):
+    n, B, dev = tb.n, tb.B, tb.gid.device
+    emb = []
+    for l in range(2):
+        A = torch.sparse_coo_tensor(tb.index[l], torch.ones(tb.index[l].shape[1], device=dev), (n, n)).coalesce()
+        h = F.normalize(torch.relu(torch.matmul(tb.node_input[l], P["w_n2l"])), p=2, dim=1)
+        y = F.normalize(torch.relu(torch.matmul(torch.ones((B, 2), device=dev), P["w_n2l"])), p=2, dim=1)
+        for _ in range(3):
+            pool = torch.sparse.mm(A, h)
+            y_pool = torch.zeros((B, 64), device=dev).index_add(0, tb.gid, h)
+            merged = torch.cat([torch.matmul(pool, P["p_node_conv"]), torch.matmul(h, P["p_node_conv2"])], 1)
+            y_merged = torch.cat([torch.matmul(y_pool, P["p_node_conv"]), torch.matmul(y, P["p_node_conv2"])], 1)
+            h = F.normalize(torch.relu(torch.matmul(merged, P["p_node_conv3"])), p=2, dim=1)
+            y = F.normalize(torch.relu(torch.matmul(y_merged, P["p_node_conv3"])), p=2, dim=1)
+        emb.append(torch.cat([h, y], 0))
+    fused = [F.normalize(_fuse_ref(P, emb[0], emb[1], p), p=2, dim=1) for p in range(2)]
+    qs, gates = [], []
+    for l in range(2):
+        hf, yf = fused[l][:n], fused[l][n:]
+        rep_y = yf.index_select(0, tb.gid)
+        e_sa = hf * torch.matmul(rep_y, P["cross_product"])
+        hidden = torch.relu(torch.matmul(e_sa, P["h1_weight"]))
+        rep_aux = tb.aux[:, l, :].index_select(0, tb.gid)
+        qs.append(torch.matmul(torch.cat([hidden, rep_aux], 1), P["h2_weight"]))
+        gates.append(torch.matmul(torch.relu(torch.matmul(rep_y, P["w_layer1"])), P["w_layer2"]))
+    sm = F.softmax(torch.cat(gates, 1), dim=1)
+    return sm[:, 0:1] * qs[0] + sm[:, 1:2] * qs[1], fused
+
+
+def _loss_ref(q_pred, fused, tb, target, alpha):
+    n, dev = tb.n, q_pred.device
+    loss = ((target - q_pred) ** 2).sum() / q_pred.shape[0]
+    for l in range(2):
+        h = fused[l][:n]
+        row = tb.index[l][0]
+        A = torch.sparse_coo_tensor(tb.index[l], torch.ones(row.numel(), device=dev), (n, n)).coalesce()
+        deg = torch.bincount(row, minlength=n).to(h.dtype)
+        loss = loss + alpha * 2 * (h * (deg.unsqueeze(1) * h - torch.sparse.mm(A, h))).sum() / max(float(tb.edge_num[l]), 1.0)
+    return loss
+
+
+@pytest.mark.parametrize("cost", ["unit", "degree"])
+def test_network_loss_backward_vs_torch_autograd(cost):
+    from mdcommunity_b200 import gmm, train
+    from mdcommunity_b200.graph import GraphBatch
+    from mdcommunity_b200.rollout import BatchRollout
+    torch.manual_seed(7)
+    graphs = [gmm.gmm_graph(60 + 17 * i, 500 + i, cost=cost) for i in range(5)]
+    covered = [list(range(0, 3 * i, 3)) for i in range(5)]
+    tr = train.DQNTrainer(cost, seed=2)
+    with torch.no_grad():  # weights large enough for every path (relu masks, gates) to matter
+        for k, shp in train.PARAM_SHAPES.items():
+            if "trans" in k:
+                tr.net.p(k).add_(0.05 * torch.randn(shp, device=DEV))
+            else:
+                tr.net.p(k).copy_(0.3 * torch.randn(shp, device=DEV))
+    batch = GraphBatch(graphs, tr.device, cost)
+    ro = BatchRollout(batch, None, fused=False)
+    train.set_states(ro, covered)
+    tb = train.TrainBatch(ro)
+    actions = [int(ro.act_list[i * batch.S + 1]) - i * batch.S for i in range(5)]
+    rows = tb.rows_of(actions, batch.S)
+    target = torch.randn(5, 1, device=DEV)
+    alpha = 0.05  # larger than the reference's 0.001 so the reconstruction term is visible in the gradients
+    # torch autograd reference
+    P = {k: tr.net.p(k).detach().clone().requires_grad_(True) for k in train.PARAM_SHAPES}
+    q_ref, fused_ref = _network_ref(P, tb)
+    loss_ref = _loss_ref(q_ref.index_select(0, rows), fused_ref, tb, target, alpha)
+    loss_ref.backward()
+    # hand-written path through the autograd adapters
+    tr.optimizer.zero_grad()
+    q, fused = train.network(tr.net, tb)
+    _close(q, q_ref, 2e-5)
+    _close(fused[0], fused_ref[0], 2e-5)
+    _close(fused[1], fused_ref[1], 2e-5)
+    from mdcommunity_b200 import dense
+    loss = train.calc_loss(dense.take_rows(q, rows), fused, tb, target, alpha=alpha)
+    assert abs(float(loss) - float(loss_ref)) <= 2e-5 * abs(float(loss_ref)) + 1e-7
+    loss.backward()
+    for k in train.PARAM_SHAPES:
+        _close(tr.net.p(k).grad, P[k].grad, 2e-4)
+    # direct path (fit): same gradients in flat_grad
+    o = tb.operands
+    c = dense.forward(tr.net.tensors(), o)
+    l2, lc = dense.loss_forward(o, c["q"].index_select(0, rows), c["F"], target.reshape(-1), 5, tb.edge_num, alpha)
+    dq_pred, dF = dense.loss_backward(o, lc)
+    dq = torch.zeros(tb.n, device=DEV)
+    dq.index_copy_(0, rows, dq_pred)
+    dense.backward(tr.net.tensors(), o, c, dq, dF, tr.net.grad_tensors())
+    for k, gview in tr.net.grad_tensors().items():
+        _close(gview, P[k].grad, 2e-4)
