@@ -10,8 +10,13 @@
 //                         elected thread, accumulators double-buffered in tensor memory; the operand tile is released to
 //                         the loaders as soon as the MMAs have read it, so the next tile's gather overlaps the epilogue
 //   warps 0..7  epilogue: two threads per node row (column halves for the tanh, hidden-unit halves for h1): tcgen05.ld, tanh(. + bias), the pairwise (T_k . T_p . lw) gates,
-//                         softmax-of-sigmoid mix, normalise, scale by the per-graph s_p, relu(e_p @ h1) . h2 (FP32 FMA from
-//                         registers, h1 broadcast from shared memory), layer-gate mix, q[v], packed arg-max key.
+//                         softmax-of-sigmoid mix, normalise, scale by the per-graph s_p, relu(e_p @ h1) . h2, layer-gate mix,
+//                         q[v], packed arg-max key.
+//   HTC (default): the tanh outputs T are written back IN PLACE over the accumulators (tcgen05.st) and stay in tensor
+//   memory for the rest of the tile's epilogue -- every later pass re-reads its 16-column chunks with tcgen05.ld, shared
+//   memory carries no T at all (the FP32 variant's Ts[L][64][128] was 64 / 96 KB and 68 % of the LSU pipe) -- and
+//   relu's argument e_p @ h1 is a second tensor-core product (operand tiles written by the epilogue).  2 x 64 L accumulator
+//   columns + 128 for the hidden layer = 384 (L = 2) / 512 (L = 3) of the 512 TMEM columns.
 #include <cuda_fp16.h>
 #include "md_common.cuh"
 #include "md_umma.cuh"
@@ -23,7 +28,7 @@ constexpr int QT_T = 352;         // 8 epilogue + 2 loader + 1 MMA warps
 constexpr int QT_EPI = 256;
 constexpr uint32_t QT_KB = 16384;  // one 128-row x 128-byte operand tile
 
-// HTC: relu(e_p @ h1) on the tensor cores as well (two layers only: the extra operand tiles do not fit next to Ts[3])
+// HTC: T kept in tensor memory, relu(e_p @ h1) on the tensor cores
 template <int L, bool HTC>
 struct QTSmem {
   unsigned char A[2][QT_KB];     // raw fp32 rows of ONE layer's H_l (the layers of a tile pass through in turn), two K blocks
@@ -36,7 +41,8 @@ struct QTSmem {
   alignas(16) float bias[D];
   alignas(16) float lw[D];
   alignas(16) float h2[MD_HIDDEN];
-  float Ts[L][D][TILE_M];        // epilogue: tanh outputs, column-major so that a thread owns one conflict-free column
+  float Ts[HTC ? 1 : L][HTC ? 1 : D][TILE_M];  // FP32 variant: tanh outputs, column-major so that a thread owns one conflict-free column
+  float dpart[2][HTC ? L * (L + 1) / 2 : 1][TILE_M];  // HTC: [thread of the row] partial gate dot products over its 32 columns
   float hq[L][TILE_M];           // epilogue: partial hidden sums of the second thread of each row
   float ssq[2][2][HTC ? TILE_M : 1];  // HTC: [layer parity][thread of the row] half of |X_p|^2
   int vrow[2][TILE_M];           // [slot] global node id of the row, -1 = padding
@@ -58,6 +64,9 @@ __device__ __forceinline__ float tf32_rn(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
+// tanh(x) = 1 - 2 / (e^2x + 1) on the SFU (ex2.approx + rcp.approx): absolute error <= ~3e-7 over the whole range (the exact
+// tanhf costs ~25 instructions, 96 of them per thread and tile); saturates correctly (e -> inf: 1, e -> 0: -1)
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 __device__ __forceinline__ bool qt_elect() {
   uint32_t pred = 0;
   asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
@@ -257,50 +266,53 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
       const int g = sm.desc[slot][1];
       tc_fence_after();
       const int v = sm.vrow[slot][r];
-#pragma unroll 1
-      for (int lc = 0; lc < L * 2; ++lc) {
-        const int l = lc >> 1, c0 = 32 * half + (lc & 1) * 16;
-        float x[16];
-        tmem_ld16(tbase + ((uint32_t)(32 * quad) << 16) + slot * NCOL + 64 * l + c0, x);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) sm.Ts[l][c0 + j][r] = tanhf(x[j] + sm.bias[c0 + j]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.d_empty[slot]);  // accumulators consumed: release the stage early
-      asm volatile("bar.sync 2, 256;" ::: "memory");  // both column halves of T are in shared memory
       float part[L];
 #pragma unroll
       for (int p = 0; p < L; ++p) part[p] = 0.f;
       float gwp[L], aqp[L];
       if constexpr (HTC) {
-        // Same maths as the branch below up to e_p; relu's argument e_p @ h1 (64 x 32 per row: the 2 x 1024 FMAs per
-        // thread that made the epilogue the longest stage of the kernel) goes to the tensor cores as the usual 3-term
-        // product: thread `half` of a row writes columns [32 half, 32 half + 32) of e_p (= K block `half`) and their fp16
-        // remainders, one elected thread issues the 20 MMAs into 32 spare accumulator columns, both read 16 units back.
-        float am[L][L];
-        if (v >= 0) {
-          float dot[L][L];
+        // ---- T = tanh(acc + bias) written back over the accumulators; partial gate dot products from the registers ----
+        constexpr int NP = L * (L + 1) / 2;
+        const uint32_t trow = tbase + ((uint32_t)(32 * quad) << 16) + slot * NCOL + 32 * half;  // this thread's 32 columns of layer 0
+        float dp[NP];
 #pragma unroll
-          for (int p = 0; p < L; ++p)
+        for (int i = 0; i < NP; ++i) dp[i] = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+          float t[L][16];
 #pragma unroll
-            for (int k = 0; k < L; ++k) dot[p][k] = 0.f;
-#pragma unroll 4
-          for (int c = 0; c < D; ++c) {
-            float t[L];
+          for (int l = 0; l < L; ++l) tmem_ld16(trow + 64 * l + 16 * j, t[l]);
+          tmem_ld_wait();
 #pragma unroll
-            for (int l = 0; l < L; ++l) t[l] = sm.Ts[l][c][r];
-            const float w1 = sm.lw[c];
+          for (int i = 0; i < 16; ++i) {
+            const float b = sm.bias[32 * half + 16 * j + i];
+#pragma unroll
+            for (int l = 0; l < L; ++l) t[l][i] = tanh_fast(t[l][i] + b);
+          }
+#pragma unroll
+          for (int l = 0; l < L; ++l) tmem_st16(trow + 64 * l + 16 * j, t[l]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float w1 = sm.lw[32 * half + 16 * j + i];
+            int idx = 0;
 #pragma unroll
             for (int p = 0; p < L; ++p)
 #pragma unroll
-              for (int k = 0; k <= p; ++k) dot[p][k] = fmaf(t[k] * t[p], w1, dot[p][k]);
+              for (int k = 0; k <= p; ++k, ++idx) dp[idx] = fmaf(t[k][i] * t[p][i], w1, dp[idx]);
           }
+        }
+        tmem_st_wait();
+#pragma unroll
+        for (int i = 0; i < NP; ++i) sm.dpart[half][i][r] = dp[i];
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // both halves of the gate dot products are in shared memory
+        float am[L][L];
+        {
+          float dot[L][L];
+          int idx = 0;
 #pragma unroll
           for (int p = 0; p < L; ++p)
 #pragma unroll
-            for (int k = 0; k < p; ++k) dot[k][p] = dot[p][k];
+            for (int k = 0; k <= p; ++k, ++idx) dot[p][k] = dot[k][p] = sm.dpart[0][idx][r] + sm.dpart[1][idx][r];
 #pragma unroll
           for (int p = 0; p < L; ++p) {
             float mx = -1e30f, den = 0.f;
@@ -320,28 +332,43 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
         }
 #pragma unroll 1
         for (int p = 0; p < L; ++p) {
-          // one pass over this thread's 32 columns of X_p = T_p + sum_{k != p} a_k T_k: the UNSCALED rows go to the operand
-          // tiles and the scale 1/|X_p| * s_p is applied to the 32 products afterwards (the norm needs both threads' halves,
-          // exchanged through shared memory across the barrier that is there anyway)
+          // X_p = T_p + sum_{k != p} a_k T_k as sum_k cf[k] T_k (cf[p] = 1) over this thread's 32 columns, re-read from tensor
+          // memory: the UNSCALED rows go to the operand tiles and the scale 1/|X_p| * s_p is applied to the 32 products afterwards
+          // (the norm needs both threads' halves, exchanged through shared memory across the barrier that is there anyway)
+          float cf[L];
+#pragma unroll
+          for (int k = 0; k < L; ++k) {
+            cf[k] = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < L; ++pp)
+              if (pp == p) cf[k] = (k == pp) ? 1.f : am[pp][k];
+          }
           float ssh = 0.f, sg = 0.f;
+          gwp[p] = 0.f, aqp[p] = 0.f;
           if (v >= 0) {
             sg = K.gconst[(size_t)g * MD_GCONST + p];
             gwp[p] = K.gconst[(size_t)g * MD_GCONST + 4 + p];
             aqp[p] = K.gconst[(size_t)g * MD_GCONST + 8 + p];
-            unsigned char* erow = sm.E[half] + (uint32_t)r * 128u;
-            unsigned char* lrow = sm.ELO + (uint32_t)r * 128u;
-#pragma unroll 2
-            for (int ch = 0; ch < 8; ++ch) {  // 4 columns = one 16-byte chunk of the K block
+          }
+          unsigned char* erow = sm.E[half] + (uint32_t)r * 128u;
+          unsigned char* lrow = sm.ELO + (uint32_t)r * 128u;
+#pragma unroll 1
+          for (int j = 0; j < 2; ++j) {
+            float t[L][16];
+#pragma unroll
+            for (int l = 0; l < L; ++l) tmem_ld16(trow + 64 * l + 16 * j, t[l]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {  // 4 columns = one 16-byte chunk of the K block
+              const int ch = 4 * j + q4;
               float e[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int c = 32 * half + 4 * ch + j;
-                float x = sm.Ts[p][c][r];
+              for (int i = 0; i < 4; ++i) {
+                float x = cf[0] * t[0][4 * q4 + i];
 #pragma unroll
-                for (int k = 0; k < L; ++k)
-                  if (k != p) x = fmaf(am[p][k], sm.Ts[k][c][r], x);
+                for (int k = 1; k < L; ++k) x = fmaf(cf[k], t[k][4 * q4 + i], x);
                 ssh = fmaf(x, x, ssh);
-                e[j] = x;
+                e[i] = x;
               }
               const float4 eh = make_float4(tf32_rn(e[0]), tf32_rn(e[1]), tf32_rn(e[2]), tf32_rn(e[3]));
               *reinterpret_cast<float4*>(erow + ((ch ^ (r & 7)) << 4)) = eh;
@@ -403,7 +430,23 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
             hq = fmaf(fmaxf(((x[j] + xb[j]) + fmaf(xl[j], 1.f / 4096.f, xm[j])) * scale, 0.f), sm.h2[16 * half + j], hq);
           part[p] = hq;
         }
-      } else
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.d_empty[slot]);  // T (and the accumulators under it) consumed: release the stage
+      } else {
+#pragma unroll 1
+      for (int lc = 0; lc < L * 2; ++lc) {
+        const int l = lc >> 1, c0 = 32 * half + (lc & 1) * 16;
+        float x[16];
+        tmem_ld16(tbase + ((uint32_t)(32 * quad) << 16) + slot * NCOL + 64 * l + c0, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sm.Ts[l][c0 + j][r] = tanhf(x[j] + sm.bias[c0 + j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.d_empty[slot]);  // accumulators consumed: release the stage early
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // both column halves of T are in shared memory
       if (v >= 0) {
         float dot[L][L];
 #pragma unroll
@@ -478,6 +521,7 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
           for (int j = 0; j < MD_HIDDEN / 2; ++j) hq = fmaf(fmaxf(hid[j], 0.f), sm.h2[16 * half + j], hq);
           part[p] = hq;
         }
+      }
       }
       if (half == 1) {
 #pragma unroll
@@ -557,6 +601,16 @@ int md_qhead_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weigh
       configured = true;
     }
     md::qhead_tc_kernel<2, false><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
+  } else if (!(g_md_debug_flags & 8192)) {
+    static md::PerDevice<bool> configured_pd;
+    bool& configured = configured_pd.get();
+    const int smem = (int)sizeof(md::QTSmem<3, true>);
+    if (!configured) {
+      e = cudaFuncSetAttribute(md::qhead_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+    md::qhead_tc_kernel<3, true><<<grid, md::QT_T, smem, st>>>(*g, *s, *w, *k, counter);
   } else {
     static md::PerDevice<bool> configured_pd;
   bool& configured = configured_pd.get();
