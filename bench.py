@@ -397,10 +397,12 @@ def c4_leg(dev, steps=100):
     # alive degrees / component sizes, and the emission of the alive CSR in compact order.
     sweeps = 2 * L
     kern = {
-        "agg_deg (iteration 0: degree gather)": roof(med["agg0"], b_deg),
-        "agg_ring (iterations 1, 2: 256-byte row gather)": roof((med["agg1"] + med["agg2"]) / 2, b_rows),
-        "embed_iter_tc<PRE> (transform, iterations 1, 2)": roof((med["xform1"] + med["xform2"]) / 2, b_xf),
-        "embed_iter_tc<PRE> (transform, iteration 0)": roof(med["xform0"], b_xf0),
+        # unit cost: the embedding after iteration 0 is a function of the alive degree (md_agg.cu, agg_deg_kernel<1>), so
+        # iteration 0 launches nothing (agg0 / xform0 time an empty call) and iteration 1 gathers 4-byte degrees
+        "agg_deg<1> (iteration 1: degree gather, table H1(d))": roof(med["agg1"], b_deg),
+        "agg_ring (iteration 2: 256-byte row gather)": roof(med["agg2"], b_rows),
+        "embed_iter_tc<PRE> (transform, iteration 2)": roof(med["xform2"], b_xf),
+        "embed_iter_tc<PRE> (transform, iteration 1, own rows from the degrees)": roof(med["xform1"], b_xf0),
         "qhead_tc<3>": roof(med["qhead"], b_qh),
         "env_step_large": roof(med["env_step"], sweeps * b_sweep, search_tasks=R, L=L, sweeps=sweeps, B_sweep=b_sweep,
                                model="2L * B_sweep: per layer one sweep for alive degrees / component sizes and one for the "
@@ -408,17 +410,18 @@ def c4_leg(dev, steps=100):
                                      "searches per step) visits ~1e4 nodes and is not counted"),
     }
     agg_ms = sum(med[k] for k in names[1:7])
-    agg_bytes = b_deg + 2 * b_rows + b_xf0 + 2 * b_xf
+    agg_bytes = b_deg + b_rows + b_xf0 + b_xf
     step_bytes = agg_bytes + b_qh + sweeps * b_sweep
     out = {"workload": "C4: one synthetic 3-layer multiplex, N=1000000, 4000000 undirected edges per layer, unit cost, %d consecutive "
                        "greedy steps from the intact graph (score all nodes + arg-max + removal + LMCC recompute per step)" % len(r),
            "removal_steps_per_s": 1e3 / step_ms, "ms_per_step": step_ms, "steps_timed": len(r),
            "median_ms": {k: float(v) for k, v in med.items()},
-           "stage_ms": {"aggregation_9_layer_iterations": agg_ms, "graph_embed+qhead": med["graph_embed"] + med["qhead"],
+           "stage_ms": {"embedding_iterations": agg_ms, "graph_embed+qhead": med["graph_embed"] + med["qhead"],
                         "env_step_lmcc": med["env_step"]},
            "aggregation_roofline": dict(roof(agg_ms, agg_bytes), peak_source=src,
-                                        algorithmic_bytes_model="bytes actually required: iteration 0 = degree gather "
-                                        "(4 B per entry) + transform from degrees; iterations 1, 2 = 4(n+1) + 4 nnz + 256 nnz + 256 n "
+                                        algorithmic_bytes_model="bytes actually required: iteration 0 = nothing (H1 is a function "
+                                        "of the alive degree for unit-cost features); iteration 1 = degree gather (4 B per entry) + "
+                                        "transform with own rows from the degrees; iteration 2 = 4(n+1) + 4 nnz + 256 nnz + 256 n "
                                         "(SURVEY 8(d) no-reuse) + 3 x 256 n for the transform"),
            "kernels": kern, "step_roofline": roof(step_ms, step_bytes),
            "timing": "CUDA events around every launch, median over the steps, %d warm-up steps" % WARM, "setup_s": setup_s,

@@ -166,6 +166,8 @@ void md_debug_force_large_env(int32_t on);
  * bit 7 disables / bit 8 forces the two-kernel md_embed_iter (md_agg neighbour sums + tensor-core transform; default
  *   only when the embeddings exceed L2), bit 9 selects md_agg's register-load kernel instead of the cp.async ring,
  *   bit 12 disables iteration 0 from the alive degrees (unit cost) so that md_embed_init writes H0 again;
+ * bit 18 (two-kernel md_embed_iter, unit cost): materialise H1 -- by default iteration 0 launches nothing and iteration 1
+ *   takes both its neighbour sums and its own rows from the table H1(alive degree) (see md_embed_iter);
  * bit 13 keeps relu's argument e @ h1 of the two-layer tensor-core md_qhead on the FP32 pipes (A/B reference);
  * bit 17 (md_env_step, multi-CTA path): from-scratch prune rounds on every step instead of the grid-wide incremental
  *   mutual-component update that is the default when s->lg_scratch is set (A/B reference; same results);
@@ -204,7 +206,12 @@ int md_embed_init(const md_graphs_t* g, const md_state_t* s, const md_weights_t*
  * dense transforms (:294-309), relu + L2 normalise (:309-310), and the per-graph sum of the OLD embeddings
  * (spmm subgsum, :297-298) as per-tile partials.  iter = 0..2; reads h[iter&1], writes h[(iter+1)&1].
  * Embeddings beyond L2 (N = 1M): two launches, md_agg's neighbour sums into h[(iter+1)&1] and a tensor-core transform
- * that overwrites them in place.  md_graph_embed consumes the per-tile partials (call it once per forward). */
+ * that overwrites them in place.  md_graph_embed consumes the per-tile partials (call it once per forward).
+ * Unit-cost batches on that path: the features are [d/dmax, d/dmax], so relu(x @ w_n2l) normalised is the SAME vector c
+ * for every node with an alive neighbour, the first neighbour sum is deg(v) c, and the embedding after iteration 0 is
+ * H1(d) = normalise(relu(d (c @ w13) + c @ w23)), a function of the alive degree d only.  iter = 0 therefore enqueues
+ * nothing and leaves h[1] untouched; iter = 1 gathers 4-byte degrees instead of 256-byte rows and also writes iteration
+ * 0's per-tile partials; from iter = 2 on everything is as described above (md_debug_set_flags bit 18 materialises H1). */
 int md_embed_iter(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                   int32_t iter, md_stream_t stream);
 

@@ -318,13 +318,20 @@ __global__ void __launch_bounds__(RG_T, 1) agg_ring_kernel(md_graphs_t G, md_sta
 }
 
 
-// ---- iteration 0, unit cost: no embedding gather at all ------------------------------------------------------------------
+// ---- iterations 0 and 1, unit cost: no embedding gather at all ------------------------------------------------------------
 // The first embedding of a node is a function of its alive degree only: relu([d/dmax, d/dmax] @ w_n2l), normalised
 // (MultiDismantler_net_graphsage.py:248-287 with the unit-cost features of PrepareBatchGraph.py).  So the first neighbour
 // sum needs no 256-byte row per neighbour: a table of the <= DG_CAP + 1 distinct rows of the (layer, graph) lives in shared
 // memory (built with exactly embed_init_kernel's arithmetic) and the gather reads 4 bytes (the neighbour's alive degree,
 // L2-resident) per entry.  The rows are still added one by one in CSR order.  md_embed_init is skipped altogether on this
 // path; the transform kernel forms its own-row operand from the degrees as well (md_embed_iter_tc.cu).
+//
+// LEVEL 1 goes one step further.  relu([x, x] @ w_n2l) = x relu(w_n2l[0] + w_n2l[1]) for x > 0, so after the normalise
+// EVERY node with an alive neighbour has the same first embedding c = relu(w0 + w1) / |relu(w0 + w1)| (to the last bit
+// or two of the rounding of x), the first neighbour sum is deg(v) c, and the embedding after iteration 0 is again a function
+// of the alive degree only:  H1(d) = normalise(relu(d (c @ W13) + c @ W23)).  Iteration 0 therefore needs no kernel at all,
+// and iteration 1's neighbour sum is this kernel with the table H1(d) (one table for all layers and graphs) instead of a
+// 256-byte gather per neighbour.  Deviation from adding the rows one by one: a few 1e-7 relative (parity bar 2e-5 / 1e-4).
 constexpr int DG_T = 512;
 constexpr int DG_W = DG_T / 32;
 constexpr int DG_CAP = 63;
@@ -336,10 +343,36 @@ __device__ __forceinline__ float2 h0_pair(float x0, float w0a, float w0b, float 
   const float den = fmaxf(sqrtf(warp_sum(a * a + b * b)), 1e-12f);
   return make_float2(a / den, b / den);
 }
+// columns (2 lane, 2 lane + 1) of H1(d) = normalise(relu(d a + b)); a = c @ W13, b = c @ W23 (this lane's two columns each)
+__device__ __forceinline__ float2 h1_pair(float d, float2 a, float2 b) {
+  const float x = d > 0.f ? fmaxf(fmaf(d, a.x, b.x), 0.f) : 0.f;  // (d = 0: isolated node, first embedding 0, no neighbours)
+  const float y = d > 0.f ? fmaxf(fmaf(d, a.y, b.y), 0.f) : 0.f;
+  const float den = fmaxf(sqrtf(warp_sum(x * x + y * y)), 1e-12f);
+  return make_float2(x / den, y / den);
+}
+// c (shared, 64 floats) and this lane's columns of a = c @ W13, b = c @ W23; all threads of the CTA call it
+__device__ __forceinline__ void h1_coeffs(const md_weights_t& W, float* c_sm, float2& a, float2& b) {
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    const float2 c = h0_pair(1.f, W.w_n2l[2 * lane], W.w_n2l[2 * lane + 1], W.w_n2l[D + 2 * lane], W.w_n2l[D + 2 * lane + 1]);
+    c_sm[2 * lane] = c.x, c_sm[2 * lane + 1] = c.y;
+  }
+  __syncthreads();
+  a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+  for (int k = 0; k < D; ++k) {
+    const float ck = c_sm[k];
+    const float2 w13 = *reinterpret_cast<const float2*>(W.w13 + k * D + 2 * lane);
+    const float2 w23 = *reinterpret_cast<const float2*>(W.w23 + k * D + 2 * lane);
+    a.x = fmaf(ck, w13.x, a.x), a.y = fmaf(ck, w13.y, a.y);
+    b.x = fmaf(ck, w23.x, b.x), b.y = fmaf(ck, w23.y, b.y);
+  }
+}
 
+template <int LEVEL>
 __global__ void __launch_bounds__(DG_T, 2) agg_deg_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K) {
   __shared__ float2 tab[DG_CAP + 1][32];
   __shared__ int du[DG_W][DG_IDS];
+  __shared__ float c_sm[D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int B = G.n_graphs, St = G.stride;
   const int l = blockIdx.y / B, g = blockIdx.y - l * B;
@@ -348,11 +381,18 @@ __global__ void __launch_bounds__(DG_T, 2) agg_deg_kernel(md_graphs_t G, md_stat
   const float w0a = W.w_n2l[2 * lane], w0b = W.w_n2l[2 * lane + 1];
   const float w1a = W.w_n2l[D + 2 * lane], w1b = W.w_n2l[D + 2 * lane + 1];
   const float dmax = (float)S.max_deg[l * B + g];
-  for (int d = warp; d <= DG_CAP; d += DG_W) tab[d][lane] = h0_pair((float)d / dmax, w0a, w0b, w1a, w1b);
+  float2 ca, cb;
+  if constexpr (LEVEL == 1) h1_coeffs(W, c_sm, ca, cb);
+  auto row_of = [&](int d) -> float2 {  // this lane's two columns of the table row of alive degree d (whole warp calls it)
+    if constexpr (LEVEL == 1) return h1_pair((float)d, ca, cb);
+    else return h0_pair((float)d / dmax, w0a, w0b, w1a, w1b);
+  };
+  for (int d = warp; d <= DG_CAP; d += DG_W) tab[d][lane] = row_of(d);
   __syncthreads();
   const int32_t* __restrict__ deg = S.deg[l];
   const int32_t* __restrict__ acol_l = S.acol[l];
-  float2* __restrict__ Pout = reinterpret_cast<float2*>(K.h[1][l]) + lane;  // iteration 0 writes buffer 1
+  // iteration 0 writes its neighbour sums into buffer 1, iteration 1 into buffer 0 (where the transform expects them)
+  float2* __restrict__ Pout = reinterpret_cast<float2*>(K.h[1 - LEVEL][l]) + lane;
   const int n_chunks = (n + 31) / 32;
   for (int c = blockIdx.x * DG_W + warp; c < n_chunks; c += gridDim.x * DG_W) {
     const int p0 = 32 * c, rows = min(32, n - p0);
@@ -377,7 +417,7 @@ __global__ void __launch_bounds__(DG_T, 2) agg_deg_kernel(md_graphs_t G, md_stat
       // lane j8 owns columns [4 j8, 4 j8 + 4) and [32 + 4 j8, 36 + 4 j8): every 8-lane phase of an LDS.128 / STG.128 then
       // covers 128 contiguous bytes (no bank conflicts, full sectors)
       const float4* tab4 = reinterpret_cast<const float4*>(&tab[0][0]) + j8;  // row d: tab4[16 * d], tab4[16 * d + 8]
-      float4* __restrict__ Pout4 = reinterpret_cast<float4*>(K.h[1][l]) + j8;
+      float4* __restrict__ Pout4 = reinterpret_cast<float4*>(K.h[1 - LEVEL][l]) + j8;
       for (int pass = 0; pass < 4 && 8 * pass < rows; ++pass) {
         const int rA = 8 * pass + q, rB = rA + 4;
         const int e0A = __shfl_sync(0xffffffffu, ap, rA) - e_begin, e0B = __shfl_sync(0xffffffffu, ap, rB) - e_begin;
@@ -412,7 +452,7 @@ __global__ void __launch_bounds__(DG_T, 2) agg_deg_kernel(md_graphs_t G, md_stat
         float2 acc = make_float2(0.f, 0.f);
         for (int e = e0; e < e1; ++e) {
           const int d = e < DG_IDS ? du[warp][e] : deg[acol[e]];  // (warp-uniform)
-          const float2 x = d <= DG_CAP ? tab[d][lane] : h0_pair((float)d / dmax, w0a, w0b, w1a, w1b);
+          const float2 x = d <= DG_CAP ? tab[d][lane] : row_of(d);
           acc.x += x.x;
           acc.y += x.y;
         }
@@ -459,8 +499,8 @@ int md_agg_rows_launch(const md_graphs_t* g, const md_state_t* s, const md_work_
   return 0;
 }
 
-// iteration 0 of the unit-cost variant on the two-kernel path (see agg_deg_kernel)
-int md_agg_deg_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, cudaStream_t st) {
+// iteration 0 (level 0) / iteration 1 (level 1) of the unit-cost variant on the two-kernel path (see agg_deg_kernel)
+int md_agg_deg_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, int level, cudaStream_t st) {
   static md::PerDevice<int> nsm_pd;
   int& nsm = nsm_pd.get();
   if (nsm <= 0) {
@@ -474,7 +514,8 @@ int md_agg_deg_launch(const md_graphs_t* g, const md_state_t* s, const md_weight
   const int max_per = (g->stride / 32 + md::DG_W - 1) / md::DG_W;
   if (per > max_per) per = max_per;
   if (per < 1) per = 1;
-  md::agg_deg_kernel<<<dim3(per, units), md::DG_T, 0, st>>>(*g, *s, *w, *k);
+  if (level == 1) md::agg_deg_kernel<1><<<dim3(per, units), md::DG_T, 0, st>>>(*g, *s, *w, *k);
+  else md::agg_deg_kernel<0><<<dim3(per, units), md::DG_T, 0, st>>>(*g, *s, *w, *k);
   MD_CHECK_LAUNCH();
   return 0;
 }

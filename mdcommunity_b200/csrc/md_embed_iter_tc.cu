@@ -46,8 +46,11 @@ struct IterTcSmem {
   int nlong, nxtra;
   uint64_t a_full, a_empty, d_full[2], d_empty[2];
   uint32_t tmem;
-  float h0_x[64], h0_inv[64];  // PRE, iteration 0 from the degrees: x = d / dmax and 1 / |relu([x, x] @ w_n2l)| per alive degree d
+  alignas(16) float h0_x[64], h0_inv[64];  // PRE, iteration 0 from the degrees: x = d / dmax and 1 / |relu([x, x] @ w_n2l)| per alive degree d
+                               // PRE, iteration 1 from the degrees (H1 mode): a = c @ W13 and b = c @ W23
   int h0_key;                  // (layer, graph, dmax) the two tables were built for
+  float c0[64];                // H1 mode: the common first embedding c = relu(w0 + w1) / |relu(w0 + w1)|
+  int cnt[2][NGW];             // H1 mode: [tile parity] rows of the tile with an alive neighbour, per gather warp
 };
 static_assert(sizeof(IterTcSmem) <= 232448, "IterTcSmem exceeds the shared memory of one CTA");
 
@@ -124,6 +127,40 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
       }
     }
   }
+  if (PRE && (dbg & (1 << 21))) {
+    // H1 mode (unit cost, iteration 1; see agg_deg_kernel<1> in md_agg.cu): the embedding after iteration 0 is a function of
+    // the alive degree only, H1(d) = normalise(relu(d a + b)), a = c @ W13, b = c @ W23; table of d <= 63 in sm.extra
+    // (unused in PRE mode), a / b kept for the hub rows beyond it
+    if (warp == 0) {
+      const float w0a = W.w_n2l[2 * lane], w0b = W.w_n2l[2 * lane + 1], w1a = W.w_n2l[D + 2 * lane], w1b = W.w_n2l[D + 2 * lane + 1];
+      const float ca = fmaxf(fmaf(1.f, w1a, w0a), 0.f), cb = fmaxf(fmaf(1.f, w1b, w0b), 0.f);
+      float ss = ca * ca + cb * cb;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float den = fmaxf(sqrtf(ss), 1e-12f);
+      sm.c0[2 * lane] = ca / den, sm.c0[2 * lane + 1] = cb / den;
+    }
+    __syncthreads();
+    if (tid < D) {
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < D; ++k) {
+        a = fmaf(sm.c0[k], W.w13[k * D + tid], a);
+        b = fmaf(sm.c0[k], W.w23[k * D + tid], b);
+      }
+      sm.h0_x[tid] = a, sm.h0_inv[tid] = b;
+    }
+    __syncthreads();
+    for (int d = warp; d < 64; d += TC_T / 32) {
+      const float fd = (float)d;
+      const float x = d > 0 ? fmaxf(fmaf(fd, sm.h0_x[lane], sm.h0_inv[lane]), 0.f) : 0.f;
+      const float y = d > 0 ? fmaxf(fmaf(fd, sm.h0_x[lane + 32], sm.h0_inv[lane + 32]), 0.f) : 0.f;
+      float ss = x * x + y * y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      sm.extra[d * D + lane] = x * inv, sm.extra[d * D + lane + 32] = y * inv;
+    }
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -170,7 +207,7 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
         // 2 lines); the demand loads follow one tile period later and find the lines in L2
         if (!(dbg & 2048)) {
           const int vv = __shfl_sync(0xffffffffu, v, lane >> 2);
-          if (vv >= 0 && !((lane & 2) && (dbg & (1 << 20)))) {  // (no H rows to fetch when they come from the degrees)
+          if (vv >= 0 && !((lane & 2) && (dbg & (3 << 20)))) {  // (no H rows to fetch when they come from the degrees)
             const float* base = (lane & 2) ? K.h[iter & 1][tt.l] : K.h[(iter + 1) & 1][tt.l];
             asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)vv * D + 32 * (lane & 1)));
           }
@@ -231,6 +268,7 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
         float4 pv[4], own[4];
         int vr[4];
         const bool h0_from_deg = (dbg & (1 << 20)) != 0;  // iteration 0, unit cost: H0 was never written (see md_agg.cu)
+        const bool h1_from_deg = (dbg & (1 << 21)) != 0;  // iteration 1, unit cost: neither was H1
         int dg[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {  // all 8 row loads of this lane are in flight before anything is waited for
@@ -240,7 +278,7 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
           dg[i] = 0;
           if (vr[i] >= 0) {
             pv[i] = __ldcg(P4 + (size_t)vr[i] * (D / 4) + l16);  // other rows of this buffer are being overwritten: no .nc
-            if (h0_from_deg) dg[i] = S.deg[l][vr[i]];
+            if (h0_from_deg || h1_from_deg) dg[i] = S.deg[l][vr[i]];
             else own[i] = __ldcg(H4 + (size_t)vr[i] * (D / 4) + l16);  // .cg: with 216 KB of shared memory the L1 is ~30 KB
           }
         }
@@ -292,6 +330,35 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
             }
             own[i] = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
           }
+        }
+        if (h1_from_deg) {
+          bool big = false;
+          int c0n = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) big |= dg[i] > 63, c0n += (l16 == 0 && dg[i] >= 1) ? 1 : 0;
+          big = __any_sync(0xffffffffu, big);  // hub rows beyond the table: the whole warp takes the direct formula
+          const float4 a4 = *reinterpret_cast<const float4*>(&sm.h0_x[4 * l16]), b4 = *reinterpret_cast<const float4*>(&sm.h0_inv[4 * l16]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (!big) {
+              own[i] = *reinterpret_cast<const float4*>(&sm.extra[dg[i] * D + 4 * l16]);
+            } else {
+              const float fd = (float)dg[i];
+              float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (dg[i] > 0) z = make_float4(fmaxf(fmaf(fd, a4.x, b4.x), 0.f), fmaxf(fmaf(fd, a4.y, b4.y), 0.f),
+                                             fmaxf(fmaf(fd, a4.z, b4.z), 0.f), fmaxf(fmaf(fd, a4.w, b4.w), 0.f));
+              float ss = (z.x * z.x + z.y * z.y) + (z.z * z.z + z.w * z.w);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+              const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+              own[i] = make_float4(z.x * inv, z.y * inv, z.z * inv, z.w * inv);
+            }
+          }
+          // iteration 0's column sums (the graph row's input) were never formed either: sum_v H0[v] = (rows with an alive neighbour) c
+          c0n = warp_sum_i(c0n);
+          if (lane == 0) sm.cnt[buf][warp] = c0n;
         }
         if (have) prefetch(ti, buf ^ 1);  // node ids of the next tile: behind the row loads, off the critical path
         if (it >= 2) mbar_wait(&sm.d_empty[buf], ((it >> 1) - 1) & 1);  // epilogue of tile it-2 is done with v[buf]
@@ -472,6 +539,12 @@ __global__ void __launch_bounds__(TC_T, 1) embed_iter_tc_kernel(md_graphs_t G, m
 #pragma unroll
         for (int w2 = 0; w2 < NGW; ++w2) s += sm.cs[buf][w2][tid];
         K.psum[(((size_t)iter * G.n_layers + l) * cur.tiles_per_layer + cur.gt) * D + tid] = s;
+        if (PRE && (dbg & (1 << 21))) {
+          int n0 = 0;
+#pragma unroll
+          for (int w2 = 0; w2 < NGW; ++w2) n0 += sm.cnt[buf][w2];
+          K.psum[(((size_t)0 * G.n_layers + l) * cur.tiles_per_layer + cur.gt) * D + tid] = (float)n0 * sm.c0[tid];
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -584,7 +657,7 @@ extern int g_md_debug_flags;
 //    vs 417 us per launch, C4 9.2 vs 9.0 ms per step): with the gather inside, the iteration is bound by the 16 gather
 //    warps' row loads, which the FMA consumers overlapped for free; kept as the A/B reference of that finding.
 int md_agg_rows_launch(const md_graphs_t* g, const md_state_t* s, const md_work_t* k, int iter, cudaStream_t st);
-int md_agg_deg_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, cudaStream_t st);
+int md_agg_deg_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, int level, cudaStream_t st);
 
 static bool tc_pre_path(const md_graphs_t* g) {
   const int f = g_md_debug_flags;
@@ -595,6 +668,10 @@ static bool tc_pre_path(const md_graphs_t* g) {
 // true when the first embedding is never materialised: two-kernel path, unit cost (features = alive degree / max alive
 // degree), not switched off by md_debug_set_flags bit 12.  md_embed_init asks this to become a no-op.
 bool md_h0_on_the_fly(const md_graphs_t* g) { return tc_pre_path(g) && g->node_w[0] == nullptr && !(g_md_debug_flags & 4096); }
+// true when the embedding after iteration 0 is not materialised either (md_agg.cu, agg_deg_kernel<1>): iteration 0 launches
+// nothing, iteration 1 works from the alive degrees.  md_debug_set_flags bit 18 switches it off (iteration 0 then runs as
+// agg_deg_kernel<0> + transform and leaves H1 in buffer 1: the A/B reference and what tests that look at H1 use).
+static bool h1_on_the_fly(const md_graphs_t* g) { return md_h0_on_the_fly(g) && !(g_md_debug_flags & (1 << 18)); }
 
 int md_embed_iter_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k, int iter,
                             cudaStream_t st, int* launched) {
@@ -622,15 +699,21 @@ int md_embed_iter_tc_launch(const md_graphs_t* g, const md_state_t* s, const md_
   const int n_tiles = g->n_graphs * (g->stride / MD_TILE_M) * g->n_layers;
   const int grid = nsm < n_tiles ? nsm : n_tiles;
   if (pre) {
+    const bool h1 = h1_on_the_fly(g);
+    if (h1 && iter == 0) {  // nothing to do: H1 is a function of the alive degrees
+      *launched = 1;
+      return 0;
+    }
     const bool h0 = iter == 0 && md_h0_on_the_fly(g);
+    const bool h1it = h1 && iter == 1;
     // bits 14 / 15: enqueue only the aggregation / only the transform (bench.py times the two kernels of an iteration
     // separately by calling md_embed_iter twice; together the two calls are exactly the normal launch sequence)
     if (!(f & 32768)) {
-      const int rc = h0 ? md_agg_deg_launch(g, s, w, k, st) : md_agg_rows_launch(g, s, k, iter, st);
+      const int rc = (h0 || h1it) ? md_agg_deg_launch(g, s, w, k, h1it ? 1 : 0, st) : md_agg_rows_launch(g, s, k, iter, st);
       if (rc) return rc;
     }
     if (!(f & 16384))
-      md::embed_iter_tc_kernel<true><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter, (f & 0x3fff) | (h0 ? (1 << 20) : 0));
+      md::embed_iter_tc_kernel<true><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter, (f & 0x3fff) | (h0 ? (1 << 20) : 0) | (h1it ? (1 << 21) : 0));
   } else {
     md::embed_iter_tc_kernel<false><<<grid, md::TC_T, smem, st>>>(*g, *s, *w, *k, iter, f);
   }

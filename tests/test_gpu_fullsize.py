@@ -116,10 +116,27 @@ def _c4_parity():
     ids = np.nonzero(active)[0]
     n = len(ids)
     gp, sp_, wp, kp, st = ro._g(), C.byref(ro.s), ro.w.ptr(), C.byref(ro.k), ro._stream()
-    _lib.check(lib.md_embed_init(gp, sp_, wp, kp, st), "init")
-    _lib.check(lib.md_embed_iter(gp, sp_, wp, kp, 0, st), "iter0")  # h[1] = H1
-    lib.md_debug_set_flags(1024)
+    # bit 18: materialise H1 (by default iteration 0 launches nothing on this path: H1 is a function of the alive degree)
+    H1_OFF = 1 << 18
+    lib.md_debug_set_flags(H1_OFF)
     try:
+        _lib.check(lib.md_embed_init(gp, sp_, wp, kp, st), "init")
+        _lib.check(lib.md_embed_iter(gp, sp_, wp, kp, 0, st), "iter0")  # h[1] = H1
+        lib.md_debug_set_flags(1024 | H1_OFF)
+        _lib.check(lib.md_embed_iter(gp, sp_, wp, kp, 1, st), "iter1")
+        torch.cuda.synchronize()
+        p_rows = [ro.h[0][l][torch.from_numpy(ids).to(batch.device)].cpu().numpy() for l in range(L)]
+        # the default path: iteration 1's neighbour sums from the degree table H1(d) (agg_deg_kernel<1>), no H1 in memory
+        lib.md_debug_set_flags(1024)
+        _lib.check(lib.md_embed_iter(gp, sp_, wp, kp, 0, st), "iter0 (no-op)")
+        _lib.check(lib.md_embed_iter(gp, sp_, wp, kp, 1, st), "iter1 from degrees")
+        torch.cuda.synchronize()
+        for l in range(L):
+            p_tab = ro.h[0][l][torch.from_numpy(ids).to(batch.device)].cpu().numpy()
+            tol = 5e-6 * np.maximum(1.0, degs[l][ids])[:, None]  # H1 from the tensor-core transform vs H1(d) in FP32
+            assert np.all(np.abs(p_tab - p_rows[l]) <= tol), (l, float(np.abs(p_tab - p_rows[l]).max()))
+        # restore P from the row gather for the scipy comparison below
+        lib.md_debug_set_flags(1024 | H1_OFF)
         _lib.check(lib.md_embed_iter(gp, sp_, wp, kp, 1, st), "iter1")
     finally:
         lib.md_debug_set_flags(0)
