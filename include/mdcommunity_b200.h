@@ -299,7 +299,7 @@ int md_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* val,
  * dense row-major f32 device pointers; every reduction runs in a fixed order (no floating-point atomics). */
 
 /* C[M,N] = [C +] op(A) op(B); transA: A stored [K,M]; transB: B stored [N,K]; relu_a: A clamped at 0 on load.
- * ws / ws_floats: optional workspace for a split over K (used when K >= 4096 and the output has < 64 tiles). */
+ * ws / ws_floats: optional workspace for a split over K (used when K >= 1024 and the output has < 64 tiles). */
 int md_gemm_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB,
                 int32_t accumulate, int32_t relu_a, float* ws, int64_t ws_floats, md_stream_t stream);
 /* H = x / max(|x|_2, 1e-12) per row, x = relu ? max(Z, 0) : Z  (F.normalize(torch.relu(.)), :113-116,:160-166); D <= 128 */
@@ -308,8 +308,8 @@ int md_norm_bwd_f32(const float* Z, const float* dH, float* dZ, int32_t n, int32
 /* T = tanh(Z + b) (mutil_layer_weight.py:270-276); dZ = dT (1 - T^2) */
 int md_tanh_bias_fwd_f32(const float* Z, const float* b, float* T, int32_t n, int32_t D, md_stream_t stream);
 int md_tanh_bwd_f32(const float* T, const float* dT, float* dZ, int32_t n, int32_t D, md_stream_t stream);
-/* out[c] = sum_r X[r, c] */
-int md_colsum_f32(const float* X, float* out, int32_t n, int32_t D, md_stream_t stream);
+/* out[c] = sum_r X[r, c]; ws / ws_floats: optional workspace (row chunks summed in parallel, folded in chunk order) */
+int md_colsum_f32(const float* X, float* out, int32_t n, int32_t D, float* ws, int64_t ws_floats, md_stream_t stream);
 /* two-layer fusion (mutil_layer_weight.py:278-301), width MD_EMBED: X_p = T_p + softmax_k(sigmoid(<T_k T_p, lw> + lb))[1-p] T_{1-p};
  * saved [n, 8] keeps the gate scalars for the backward; Glw [n, 64] / Glb [n] are per-row contributions to d lw / d lb */
 int md_fuse2_fwd_f32(const float* T0, const float* T1, const float* lw, const float* lb, float* X0, float* X1, float* saved,

@@ -95,7 +95,7 @@ _SIGS = {
     "md_norm_bwd_f32": ([_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp], C.c_int),
     "md_tanh_bias_fwd_f32": ([_vp, _vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
     "md_tanh_bwd_f32": ([_vp, _vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
-    "md_colsum_f32": ([_vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),
+    "md_colsum_f32": ([_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, _vp], C.c_int),
     "md_fuse2_fwd_f32": ([_vp] * 7 + [C.c_int32, _vp], C.c_int),
     "md_fuse2_bwd_f32": ([_vp] * 10 + [C.c_int32, _vp], C.c_int),
     "md_rowscale_f32": ([_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp], C.c_int),

@@ -64,7 +64,9 @@ struct FusedSmem {
   uint32_t rbe[FZ_ROWS];            // row -> first | (one-past-last << 16) entry of its neighbour list
   uint16_t rowv[FZ_ROWS];           // row -> graph-local node id
   float red[FZ_GW][32];
-  alignas(16) float wn2l[2 * D];
+  alignas(16) float wn2l[2 * D];     // first-embedding coefficients: relu(x1 * wn2l[64 + c] + x0 * wn2l[c]) (see H1 mode below)
+  float c0[D];                      // H1 mode: the common first embedding c
+  int cnt0;                         // H1 mode: rows of the unit with an alive neighbour
   alignas(128) float zrow[32];      // one all-zero 128-byte row: where a finished row's lane group points its loads
   uint16_t bbase[32];
   uint64_t bar_full, bar_empty, bar_w, bar_h, bar_res;
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(256) fused_prep_kernel(md_graphs_t G, md_state
 
 __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K,
                                                              unsigned char* ws, const int* __restrict__ order,
-                                                             int n_units) {
+                                                             int n_units, int dbg) {
   // NOTE: no pointer arithmetic on the base -- the compiler must keep seeing the shared state space, otherwise every
   // access below turns into a generic LD/ST (measured: 4x slower gather).  Alignment is asserted instead.
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -198,7 +200,29 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     mbar_fence_init();
   }
   if (warp == FZ_GW) tmem_alloc(&sm.tmem, 512);
-  if (tid < 2 * D) sm.wn2l[tid] = W.w_n2l[tid];
+  // H1 mode (unit cost; same identity as md_agg.cu's agg_deg_kernel<1>): the features are [x, x], x = alive degree / max,
+  // so the first embedding is the SAME vector c = relu(w0 + w1) / |relu(w0 + w1)| for every node with an alive neighbour,
+  // the first neighbour sum is deg(v) c and the embedding after iteration 0 is H1(d) = normalise(relu(d a + b)) with
+  // a = c @ W13, b = c @ W23: iteration 0 (a third of the gather / MMA / epilogue work) is skipped and iteration 1 starts
+  // from rows filled with that formula.  md_debug_set_flags bit 18 switches it off.
+  const bool h1_mode = G.node_w[0] == nullptr && !(dbg & (1 << 18));
+  const int it0 = h1_mode ? 1 : 0;
+  if (h1_mode) {
+    if (warp == 0) {
+      const float ca = fmaxf(W.w_n2l[lane] + W.w_n2l[D + lane], 0.f), cb = fmaxf(W.w_n2l[32 + lane] + W.w_n2l[D + 32 + lane], 0.f);
+      const float den = fmaxf(sqrtf(warp_sum(ca * ca + cb * cb)), 1e-12f);
+      sm.c0[lane] = ca / den, sm.c0[32 + lane] = cb / den;
+    }
+    __syncthreads();
+    if (tid < D) {
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < D; ++k) {
+        a = fmaf(sm.c0[k], W.w13[k * D + tid], a);
+        b = fmaf(sm.c0[k], W.w23[k * D + tid], b);
+      }
+      sm.wn2l[tid] = a, sm.wn2l[D + tid] = b;
+    }
+  } else if (tid < 2 * D) sm.wn2l[tid] = W.w_n2l[tid];
   for (int i = tid; i < FZ_IDX_CAP + 64; i += FZ_T) sm.idx[i] = 0;
   if (tid < 32) sm.zrow[tid] = 0.f;  // every entry is always a valid J (< 8192)
   tc_fence_before();
@@ -248,7 +272,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
       const uint64_t b13h = desc_k_sw128(smem_u32(sm.Wt), 0), b13l = desc_k_sw128(smem_u32(sm.Wt) + 8192, 0);
       const uint64_t b23h = desc_k_sw128(smem_u32(sm.Wt) + 16384, 0), b23l = desc_k_sw128(smem_u32(sm.Wt) + 24576, 0);
       const uint64_t bbf = desc_k_sw128(smem_u32(sm.Wt) + 32768, 0);
-      for (int it = 0; it < MD_BP_ITERS; ++it) {
+      for (int it = it0; it < MD_BP_ITERS; ++it) {
         for (int pass = 0; pass < 2; ++pass) {
           FZ_CLK(c3);
           mbar_wait(&sm.bar_w, wloads & 1);
@@ -313,6 +337,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     const int32_t* __restrict__ aptr_g = S.aptr[l] + base;
     const int32_t* __restrict__ acol_g = S.acol[l] + e0;
 
+    if (gtid == 0) sm.cnt0 = 0;  // (ordered before the fill's atomics by the barriers of the sort below)
     // ---- row order: descending alive degree (buckets 31+, 30, ..., 1), stable inside a bucket => deterministic ----
     {
       uint16_t* cnt = sm.idx;  // [32 chunks of 32 rows][32 buckets], reused by the neighbour cache afterwards
@@ -386,10 +411,10 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     auto ld_J = [&](uint32_t J) -> F4P { return lds128p(hs_a + ((J ^ (uint32_t)q) << 4)); };
 
     FZ_CLK(c0);
-    for (int it = 0; it < MD_BP_ITERS; ++it) {
+    for (int it = it0; it < MD_BP_ITERS; ++it) {
       for (int pass = 0; pass < 2; ++pass) {
         // ---------------- resident column half ----------------
-        if (it == 0) {
+        if (it == it0) {
           if (uses > 0) mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // every earlier MMA (they read Hs) has completed
           const float dmax = (float)S.max_deg[l * B + g];
           float xf[4];  // the thread's (up to) 4 rows: fetch the features first, the loads are independent
@@ -402,6 +427,13 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
               xf[k] = degree_cost ? G.node_w[l][v] : (float)S.deg[l][v];
             }
           }
+          if (h1_mode && pass == 0) {  // iteration 0's column sums are (rows with an alive neighbour) x c: count them
+            int c1n = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c1n += xf[k] > 0.f ? 1 : 0;
+            c1n = warp_sum_i(c1n);
+            if (lane == 0 && c1n) atomicAdd(&sm.cnt0, c1n);
+          }
 #pragma unroll 1
           for (int k = 0; k < 4; ++k) {
             const int r = gtid + FZ_GT * k;
@@ -411,6 +443,9 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
               if (degree_cost) {
                 x0 = xf[k];
                 x1 = 1.0f;
+              } else if (h1_mode) {  // H1(d) = normalise(relu(d a + b)); d = 0: no neighbour, first embedding 0, H1 = 0
+                x0 = xf[k];
+                x1 = xf[k] > 0.f ? 1.0f : 0.f;
               } else {
                 x0 = xf[k] / dmax;  // degree / degree_max, both exact small integers in f32
                 x1 = x0;
@@ -603,6 +638,11 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           float* ps = K.psum + (((size_t)it * L + l) * tiles_per_layer + (size_t)g * tpg) * D + 32 * pass + lane;
           ps[0] = s;
           for (int t = 1; t < ntile; ++t) ps[(size_t)t * D] = 0.f;
+          if (h1_mode && it == it0) {  // the skipped iteration's column sums
+            float* ps0 = K.psum + (((size_t)0 * L + l) * tiles_per_layer + (size_t)g * tpg) * D + 32 * pass + lane;
+            ps0[0] = (float)sm.cnt0 * sm.c0[32 * pass + lane];
+            for (int t = 1; t < ntile; ++t) ps0[(size_t)t * D] = 0.f;
+          }
         }
         FZ_CLK(c5);
       }
@@ -769,7 +809,7 @@ extern "C" int md_embed_fused(const md_graphs_t* g, const md_state_t* s, const m
   int* order = reinterpret_cast<int*>(ws + fused_order_off());
   md::fused_prep_kernel<<<(n_units + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*g, *s, *w, ws, order, n_units);
   MD_CHECK_LAUNCH();
-  md::embed_fused_kernel<<<grid, md::FZ_T, smem, (cudaStream_t)stream>>>(*g, *s, *w, *k, ws, order, n_units);
+  md::embed_fused_kernel<<<grid, md::FZ_T, smem, (cudaStream_t)stream>>>(*g, *s, *w, *k, ws, order, n_units, g_md_debug_flags);
   MD_CHECK_LAUNCH();
   return 0;
 }

@@ -170,12 +170,15 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ T, const float* __rest
 }
 
 // ---- column sums: out[c] = sum_r X[r, c]   (fixed order: 8 row groups per block column, then a tree over the groups) ------
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int n, int D) {
+// gridDim.y > 1: block y sums the rows [y * rchunk, min(n, (y + 1) * rchunk)) into out + y * D (folded by splitk_reduce_kernel)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int n, int D, int rchunk) {
   __shared__ float part[8][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), q = threadIdx.x >> 5;
+  const int rbeg = blockIdx.y * rchunk, rend = min(n, rbeg + rchunk);
+  out += (size_t)blockIdx.y * D;
   float s = 0.f;
   if (c < D)
-    for (int r = q; r < n; r += 8) s += X[(size_t)r * D + c];
+    for (int r = rbeg + q; r < rend; r += 8) s += X[(size_t)r * D + c];
   part[q][threadIdx.x & 31] = s;
   __syncthreads();
   if (q == 0 && c < D) {
@@ -378,8 +381,8 @@ extern "C" int md_gemm_f32(const float* A, const float* B, float* C, int32_t M, 
   dim3 grid((N + GM_BN - 1) / GM_BN, (M + GM_BM - 1) / GM_BM);
   // long reductions into a small output (the weight gradients: K = rows of the batch): split K over up to 64 slices
   int S = 1;
-  if (ws && K >= 4096 && (long long)grid.x * grid.y < 64) {
-    S = (K + 2047) / 2048;
+  if (ws && K >= 1024 && (long long)grid.x * grid.y < 64) {
+    S = (K + 255) / 256;
     if (S > 64) S = 64;
     while (S > 1 && (long long)S * M * N > ws_floats) --S;
   }
@@ -424,9 +427,23 @@ extern "C" int md_tanh_bwd_f32(const float* T, const float* dT, float* dZ, int32
   MD_CHECK_LAUNCH();
   return 0;
 }
-extern "C" int md_colsum_f32(const float* X, float* out, int32_t n, int32_t D, md_stream_t stream) {
+extern "C" int md_colsum_f32(const float* X, float* out, int32_t n, int32_t D, float* ws, int64_t ws_floats, md_stream_t stream) {
   if (!X || !out || D < 1) return MD_EINVAL;
-  colsum_kernel<<<(D + 31) / 32, 256, 0, (cudaStream_t)stream>>>(X, out, n, D);
+  cudaStream_t st = (cudaStream_t)stream;
+  int S = 1;
+  if (ws && n >= 1024) {  // many rows: row chunks in parallel, folded in chunk order
+    S = (n + 255) / 256;
+    if (S > 128) S = 128;
+    while (S > 1 && (long long)S * D > ws_floats) --S;
+  }
+  if (S > 1) {
+    const int rchunk = (n + S - 1) / S;
+    S = (n + rchunk - 1) / rchunk;
+    colsum_kernel<<<dim3((D + 31) / 32, S), 256, 0, st>>>(X, ws, n, D, rchunk);
+    splitk_reduce_kernel<<<blocks_for(D, 256), 256, 0, st>>>(ws, out, S, D, 0);
+  } else {
+    colsum_kernel<<<(D + 31) / 32, 256, 0, st>>>(X, out, n, D, n > 0 ? n : 1);
+  }
   MD_CHECK_LAUNCH();
   return 0;
 }

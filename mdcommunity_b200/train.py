@@ -252,7 +252,7 @@ class DQNTrainer:
         dq = torch.zeros(tb.n, dtype=torch.float32, device=self.device)
         dq.index_copy_(0, rows, dq_pred)
         self.optimizer.zero_grad()
-        dense.backward(params, o, c, dq, dF, self.net.grad_tensors())
+        dense.backward(params, o, c, dq, dF, self.net.grad_tensors(), zeroed=True)
         self.optimizer.adopt_flat_grads()
         lv = loss.detach().double().reshape(1)
         if world > 1:

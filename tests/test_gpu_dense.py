@@ -61,6 +61,9 @@ def test_tanh_colsum_rowops():
     _close(dense.tanh_bwd(t, dt), dt * (1 - torch.tanh(z + b) ** 2), 1e-5)
     out = torch.empty(64, device=DEV)
     _close(dense.colsum(z, out), z.double().sum(0), 1e-5)
+    zl = torch.randn(9001, 64, device=DEV, generator=g)  # many rows: row chunks in parallel, folded in a fixed order
+    _close(dense.colsum(zl, out), zl.double().sum(0), 1e-5)
+    assert torch.equal(dense.colsum(zl, out).clone(), dense.colsum(zl, torch.empty_like(out)))
     n_act = torch.tensor([3, 0, 200, 310], device=DEV)
     off = torch.zeros(5, dtype=torch.long, device=DEV)
     off[1:] = torch.cumsum(n_act, 0)

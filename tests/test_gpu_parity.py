@@ -666,3 +666,44 @@ def test_rollout_pipeline_matches_sequential():
     for j, r in got.items():
         for k in ("score", "n_steps", "actions", "ranks", "maxcc"):
             assert np.array_equal(r[k], ref[k]), (j, k)
+
+
+@pytest.mark.parametrize("path", ["fused", "two_kernel"])
+def test_unit_cost_h1_from_degrees_matches_materialised_iteration(path):
+    """Unit-cost features are [x, x]: the embedding after iteration 0 is a function of the alive degree, so the default
+    kernels skip iteration 0 (md_embed_fused) / launch nothing for it (two-kernel md_embed_iter) and start from the
+    table H1(d).  A/B against md_debug_set_flags bit 18, which runs iteration 0 as the reference writes it: final
+    embeddings within 2e-5, the per-tile column sums of EVERY iteration (iteration 0's come from a node count) within
+    1e-4, Q within tolerance, on states along the golden greedy trajectories."""
+    from mdcommunity_b200 import _lib
+    mdb = _mdb()
+    zs, graphs, batch, w = _load_batch("unit")
+    fused = path == "fused"
+    a = mdb.BatchRollout(batch, w, fused=fused)
+    b = mdb.BatchRollout(batch, w, fused=fused)
+    acts, T = _forced(zs, "greedy_actions", batch.device)
+    lib = _lib.lib()
+    base = 0 if fused else 256  # bit 8: the two-kernel md_embed_iter on graphs this small
+    S = batch.S
+    try:
+        for t in range(6):
+            lib.md_debug_set_flags(base)
+            a.forward()
+            lib.md_debug_set_flags(base | (1 << 18))
+            b.forward()
+            for i in range(batch.B):
+                n = int(a.n_act[i])
+                if n == 0:
+                    continue
+                ids = a.act_list[i * S:i * S + n].long()
+                for l in range(batch.L):
+                    assert float((a.h[1][l][ids] - b.h[1][l][ids]).abs().max()) <= 2e-5, (i, t, l)
+                qa, qb = a.q[ids], b.q[ids]
+                assert float(((qa - qb).abs() - (Q_RTOL * qb.abs() + Q_ATOL)).max()) <= 0, (i, t)
+            if fused:  # same tile layout of the partial sums on both sides
+                torch.testing.assert_close(a.psum, b.psum, rtol=1e-4, atol=1e-5)
+            a.step(acts)
+            b.step(acts)
+        assert torch.equal(a.label, b.label)
+    finally:
+        lib.md_debug_set_flags(0)
