@@ -31,7 +31,9 @@ def _stamp():
         if os.path.isfile(p):
             h.update(f.encode())
             h.update(open(p, "rb").read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # (the -I paths are absolute and differ between checkouts of the same tree, e.g. the GPU box's scratch copy: a stamp
+    # that included them made every box rebuild the library -- and N ranks of one job race on the output file)
+    h.update(" ".join(f for f in NVCC_FLAGS if not f.startswith("-I")).encode())
     return h.hexdigest()
 
 
@@ -47,6 +49,16 @@ def build(force=False, verbose=False):
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return LIB
+    # one builder at a time (several ranks of one job may get here together); the others wait and re-check the stamp
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+            return LIB
+        return _build_locked(stamp, stamp_file, verbose)
+
+
+def _build_locked(stamp, stamp_file, verbose):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -63,8 +75,10 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [_nvcc(), "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB)  # atomic: a concurrent dlopen sees the old or the new file, never a partial one
     with open(stamp_file, "w") as f:
         f.write(stamp)
     return LIB

@@ -117,6 +117,17 @@ def build_csr(num_nodes, edges):
     return rowptr, src[order]
 
 
+def _graph_csr(g, l):
+    """build_csr of layer l of graph g, kept on the graph object (a replay batch draws the same few graphs over and over:
+    the reference re-inserts every edge into a fresh graph_struct per batch, PrepareBatchGraph.py:142-161)."""
+    cache = g.__dict__.setdefault("_mdb_csr", {})
+    hit = cache.get(l)
+    if hit is None or hit[0] is not g.edge_list[l]:
+        hit = (g.edge_list[l],) + build_csr(g.num_nodes, g.edge_list[l])
+        cache[l] = hit
+    return hit[1], hit[2]
+
+
 class GraphBatch:
     """B graphs resident in HBM as one block-diagonal multi-layer CSR (md_graphs_t).
 
@@ -145,7 +156,7 @@ class GraphBatch:
             cols = []
             pos = 0
             for gi, g in enumerate(graphs):
-                r, c = build_csr(g.num_nodes, g.edge_list[l])
+                r, c = _graph_csr(g, l)
                 rp[gi * S:gi * S + g.num_nodes + 1] = r + pos
                 rp[gi * S + g.num_nodes + 1:(gi + 1) * S + 1] = r[-1] + pos
                 cols.append(c + gi * S)
