@@ -552,18 +552,26 @@ def run_ours(args, cost, n, per_gpu, desc):
     timed = [False]
 
     gathered = [None]
+    width = [None]                                        # columns of the trace buffers that are gathered
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def gather(r):
         """The only collective of the path: per-graph AUDC (f64, bit-exact) + n_steps + removal sequence + LMCC trace of one
-        finished batch.  The traces are [B, N] buffers of which a rollout fills ~50-70 columns, so the ranks first agree on
-        the longest sequence (one 4-byte MAX all-reduce) and gather only that many columns."""
+        finished batch.  The traces are [B, N] buffers of which a rollout fills ~50-70 columns: the ranks agree ONCE (first
+        call, during warm-up: one 4-byte MAX all-reduce read back by the host) on a record width = the longest sequence + 25 %
+        head room; afterwards a batch is handed to the collective without any host round trip (a host read of a collective's
+        result per batch stalls the other batches in flight until the slowest rank gets there: 8 GPUs lost 17 % to it).  A
+        sequence longer than the width sets a device-side flag that is checked after the timed region."""
         if world > 1:
             if timed[0]:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
             mx = r.n_steps.max().reshape(1).clone()
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            used = min(T, (int(mx.item()) + 15) // 16 * 16)
+            if width[0] is None:
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                width[0] = min(T, (int(1.25 * int(mx.item())) + 16) // 16 * 16)
+            used = width[0]
+            overflow.add_((mx > used).to(torch.int32))
             rec = torch.cat([r.score[:, None], r.n_steps[:, None].double(), r.trace_action[:, :used].double(),
                              r.trace_rank[:, :used].double()], 1)
             out = torch.empty(world * per_gpu, rec.shape[1], dtype=torch.float64, device=dev)
@@ -599,6 +607,8 @@ def run_ours(args, cost, n, per_gpu, desc):
     per_rank_ms = [my_ms / args.steps]
     gather_ms = None
     if world > 1:
+        if int(overflow.item()):
+            raise RuntimeError("a removal sequence was longer than the gathered record width %d" % width[0])
         allms = torch.zeros(world, device=dev)
         dist.all_gather_into_tensor(allms, ms.clone())
         per_rank_ms = [float(x) / args.steps for x in allms.cpu()]
@@ -683,7 +693,7 @@ def run_ours(args, cost, n, per_gpu, desc):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "removal_steps_per_s": world * per_gpu * mean_steps * args.steps / (ms * 1e-3),
             "per_rank_ms_per_step": per_rank_ms, "gather_span_ms_per_step": gather_ms,
-            "gather_note": "CUDA-event span around (MAX all-reduce of n_steps, record packing, all_gather) on the finished batch's "
+            "gather_note": "CUDA-event span around (record packing, all_gather; width agreed once during warm-up) on the finished batch's "
                            "stream; other batches' kernels run inside the span, so it is an upper bound of the collective's cost",
             "single_batch_latency_ms": single_batch_ms,
         }
