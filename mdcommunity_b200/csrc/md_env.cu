@@ -36,7 +36,7 @@ __device__ __forceinline__ int uf_find(volatile int* par, int x) {
   int p = par[x];
   while (p != x) {  // path halving; parents only ever move towards smaller ids, racy writes stay valid
     int gp = par[p];
-    par[x] = gp;
+    if (gp != p) par[x] = gp;  // (p is a root: x already points at it, no store)
     x = gp;
     p = par[x];
   }
@@ -111,9 +111,9 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
   const int base = g * St;
   const int N = G.n_nodes[g];
   const int L = G.n_layers;
-  int* lab = smem;                  // [St] graph-local label, -1 = removed / padding
-  int* par = smem + St;             // [St] union-find parent; later the alive degree of the current layer
-  int* tmp = smem + 2 * St;         // [St] scratch; later the compact list of active nodes
+  int* lab = smem;                  // [St] graph-local label, -1 = removed / padding   (lab and tmp swap roles after every
+  int* par = smem + St;             // [St] union-find parent; later the alive degree     prune round: the flattened labels
+  int* tmp = smem + 2 * St;         // [St] scratch; later the compact list of active nodes   are written into the other one)
   int* arow = smem + 3 * St;        // [St] node (graph-local id) of input row p
   int* c_rp = smem + 4 * St;        // [L][St + 1] row offsets into c_cl / c_src
   int* rowof = c_rp + L * (St + 1); // [St] node -> input row (-1: the node has no row)
@@ -395,7 +395,9 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       const int v = c_src[e], u = c_cl[e];
       if (u < v) {
         const int lv = lab[v];
-        if (lv >= 0 && lab[u] == lv) uf_unite(par, u, v);
+        // equal parents = same tree already: most entries of a sweep once the giant block has formed (two loads instead of
+        // two root walks with their path-halving stores)
+        if (lv >= 0 && lab[u] == lv && par[u] != par[v]) uf_unite(par, u, v);
       }
     }
     __syncthreads();
@@ -410,9 +412,12 @@ __global__ void __launch_bounds__(ENV_T) env_step_small(md_graphs_t G, md_state_
       }
       tmp[v] = r;
     }
-    changed = __syncthreads_or(changed);
-    for (int v = tid; v < N; v += ENV_T) lab[v] = tmp[v];
-    __syncthreads();
+    changed = __syncthreads_or(changed);  // (also orders this round's label reads before the next round's writes)
+    {
+      int* t = lab;  // the new labels become `lab` without a copy pass (entries >= N of both arrays hold -1 / are never read)
+      lab = tmp;
+      tmp = t;
+    }
     flat_dbg += ENV_CLK() - tq;
     stable = changed ? 1 : stable + 1;
     l = (l + 1 == L) ? 0 : l + 1;

@@ -4,7 +4,8 @@
 // rollout (ncu: 36 % FMA-pipe utilisation, static tile -> CTA map idle for most of the rollout).
 //
 //   persistent CTA per SM, 11 warps, dynamic tile queue (live (graph, 128-row) tiles only):
-//   warps 8..9  loaders : gather the tile's H_l rows from HBM/L2 (16 row fetches per warp in flight), store them as raw
+//   warps 8..9  loaders : gather the tile's H_l rows from HBM/L2 (32 row fetches per lane in flight, issued before the wait for
+//                         the operand tiles; the next layer's rows are prefetched into L2), store them as raw
 //                         fp32 into SWIZZLE_128B K-major operand tiles + the fp16 remainders (x - tf32(x))
 //   warp  10    MMA     : T_pre_l = H_l @ trans as the 3-term product (tf32 hi x hi, hi x lo, fp16 remainder pass), one
 //                         elected thread, accumulators double-buffered in tensor memory; the operand tile is released to
@@ -34,8 +35,9 @@ struct QTSmem {
   unsigned char A[2][QT_KB];     // raw fp32 rows of ONE layer's H_l (the layers of a tile pass through in turn), two K blocks
   unsigned char ALO[QT_KB];      // fp16 remainders of the same rows, 64 columns per row
   unsigned char Bt[40960];       // trans^T: tf32 hi (2 K blocks), tf32 lo (2 K blocks), fp16 (64 columns)
-  unsigned char E[HTC ? 2 : 1][HTC ? QT_KB : 16];   // HTC: e_p = fused, normalised, scaled rows of one layer (raw fp32, two K blocks)
-  unsigned char ELO[HTC ? QT_KB : 16];              // HTC: their fp16 remainders
+  unsigned char E[HTC ? 2 : 1][HTC ? 2 : 1][HTC ? QT_KB : 16];  // HTC: [buffer][K block] X_p = fused rows of one layer (raw fp32);
+                                                                // two buffers: layer p + 1 is written while layer p's MMAs run
+  unsigned char ELO[HTC ? 2 : 1][HTC ? QT_KB : 16];             // HTC: [buffer] their fp16 remainders
   unsigned char Bh[HTC ? 20480 : 16];               // HTC: h1^T (32 hidden units x 64): tf32 hi (2 x 4 KB), tf32 lo (2 x 4 KB), fp16 (4 KB)
   alignas(16) float h1[HTC ? 4 : D * MD_HIDDEN];
   alignas(16) float bias[D];
@@ -45,8 +47,8 @@ struct QTSmem {
   float dpart[2][HTC ? L * (L + 1) / 2 : 1][TILE_M];  // HTC: [thread of the row] partial gate dot products over its 32 columns
   float hq[L][TILE_M];           // epilogue: partial hidden sums of the second thread of each row
   float ssq[2][2][HTC ? TILE_M : 1];  // HTC: [layer parity][thread of the row] half of |X_p|^2
-  int vrow[2][TILE_M];           // [slot] global node id of the row, -1 = padding
-  int desc[2][4];                // [slot] tile, graph
+  int vrow[4][TILE_M];           // [tile number & 3] global node id of the row, -1 = padding
+  int desc[4][4];                // [tile number & 3] tile, graph
   int next_tile;
   uint64_t a_full, a_empty, d_full[2], d_empty[2], h_full;
   uint32_t tmem;
@@ -162,14 +164,21 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
       }
       asm volatile("bar.sync 1, 64;" ::: "memory");
       const int tile = sm.next_tile;
-      if (use >= 1) mbar_wait(&sm.d_empty[slot], (use - 1) & 1);  // epilogue of tile i-2 is done with vrow / desc [slot]
+      // Row ids / descriptor of tile i live in slot i & 3 and need no wait: the loaders got here by storing the last layer of
+      // tile i - 1, for which the MMAs of that tile's first layer had to be issued, which waited for the accumulator stage of
+      // tile i - 3 to be released -- and the epilogue reads its row id and descriptor before it releases a stage.  So the
+      // gather of tile i can start while the epilogues of tiles i - 2 and i - 1 are still running (with two slots it had to
+      // wait for the END of epilogue i - 2 once T stayed in tensor memory: 18 % of the epilogue's time was spent waiting for
+      // the next tile).
+      const uint32_t ms = i & 3;
+      (void)slot, (void)use;
       const int g = tile >= 0 ? tile / tpg : 0, tt = tile >= 0 ? tile - g * tpg : 0;
       if (tile >= 0) {
         const int rows = min(TILE_M, S.n_act[g] - tt * TILE_M);
-        sm.vrow[slot][ltid] = ltid < rows ? S.act_list[g * G.stride + tt * TILE_M + ltid] : -1;
-        sm.vrow[slot][ltid + 64] = ltid + 64 < rows ? S.act_list[g * G.stride + tt * TILE_M + ltid + 64] : -1;
+        sm.vrow[ms][ltid] = ltid < rows ? S.act_list[g * G.stride + tt * TILE_M + ltid] : -1;
+        sm.vrow[ms][ltid + 64] = ltid + 64 < rows ? S.act_list[g * G.stride + tt * TILE_M + ltid + 64] : -1;
       }
-      if (ltid == 0) sm.desc[slot][0] = tile, sm.desc[slot][1] = g;
+      if (ltid == 0) sm.desc[ms][0] = tile, sm.desc[ms][1] = g;
       asm volatile("bar.sync 1, 64;" ::: "memory");  // vrow visible to all loaders; next_tile may be overwritten
       if (tile < 0) {
         if (lane == 0) mbar_arrive(&sm.a_full);
@@ -179,25 +188,41 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
 #pragma unroll 1
       for (int l = 0; l < L; ++l) {
         const uint32_t ld = i * L + l;                       // operand-tile hand-off number
-        if (ld >= 1) mbar_wait(&sm.a_empty, (ld - 1) & 1);   // the MMAs of the previous layer / tile have read the tiles
         const float* __restrict__ H = K.h[hsel][l];
+        // all 32 row fetches of this lane (the warp's 64 rows) are in flight BEFORE the wait for the operand tiles: the load
+        // latency overlaps the MMAs of the previous layer instead of following them
+        float4 val[2][16];
 #pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {                     // the warp's 64 rows in two batches of 16 fetches per lane
-          const int r0 = 64 * lw_ + 32 * hb;
-          float4 val[16];
+        for (int hb = 0; hb < 2; ++hb) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int r = r0 + 2 * j + half;
-            const int v = sm.vrow[slot][r];
-            val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (v >= 0) val[j] = __ldg(reinterpret_cast<const float4*>(H + (size_t)v * D) + c);
+            const int r = 64 * lw_ + 32 * hb + 2 * j + half;
+            const int v = sm.vrow[ms][r];
+            val[hb][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v >= 0) val[hb][j] = __ldg(reinterpret_cast<const float4*>(H + (size_t)v * D) + c);
           }
+        }
+        if (l + 1 < L) {  // next layer's rows of this tile: DRAM -> L2 now (two 128-byte lines per row, one row pair per lane)
+          const float* __restrict__ Hn = K.h[hsel][l + 1];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int v = sm.vrow[ms][64 * lw_ + 2 * lane + j];
+            if (v >= 0) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(Hn + (size_t)v * D));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(Hn + (size_t)v * D + 32));
+            }
+          }
+        }
+        if (ld >= 1) mbar_wait(&sm.a_empty, (ld - 1) & 1);   // the MMAs of the previous layer / tile have read the tiles
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const uint32_t r = r0 + 2 * j + half;
-            *reinterpret_cast<float4*>(sm.A[c >> 3] + r * 128u + (((c & 7) ^ (r & 7)) << 4)) = val[j];
-            const __half2 p0 = __floats2half2_rn(val[j].x - tf32_hi(val[j].x), val[j].y - tf32_hi(val[j].y));
-            const __half2 p1 = __floats2half2_rn(val[j].z - tf32_hi(val[j].z), val[j].w - tf32_hi(val[j].w));
+            const uint32_t r = 64 * lw_ + 32 * hb + 2 * j + half;
+            const float4 x = val[hb][j];
+            *reinterpret_cast<float4*>(sm.A[c >> 3] + r * 128u + (((c & 7) ^ (r & 7)) << 4)) = x;
+            const __half2 p0 = __floats2half2_rn(x.x - tf32_hi(x.x), x.y - tf32_hi(x.y));
+            const __half2 p1 = __floats2half2_rn(x.z - tf32_hi(x.z), x.w - tf32_hi(x.w));
             *reinterpret_cast<uint2*>(sm.ALO + r * 128u + (((c >> 1) ^ (r & 7)) << 4) + 8 * (c & 1)) =
                 make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
           }
@@ -219,7 +244,7 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
     for (uint32_t i = 0;; ++i) {
       const uint32_t slot = i & 1, use = i >> 1;
       mbar_wait(&sm.a_full, (i * L) & 1);  // first layer of the tile (or the end marker) is in place
-      const int tile = sm.desc[slot][0];
+      const int tile = sm.desc[i & 3][0];
       if (tile < 0) {
         if (lane == 0) mbar_arrive(&sm.d_full[slot]);
         break;
@@ -261,11 +286,11 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
     for (uint32_t i = 0;; ++i) {
       const uint32_t slot = i & 1, use = i >> 1;
       mbar_wait(&sm.d_full[slot], use & 1);
-      const int tile = sm.desc[slot][0];
+      const int tile = sm.desc[i & 3][0];
       if (tile < 0) break;
-      const int g = sm.desc[slot][1];
+      const int g = sm.desc[i & 3][1];
       tc_fence_after();
-      const int v = sm.vrow[slot][r];
+      const int v = sm.vrow[i & 3][r];
       float part[L];
 #pragma unroll
       for (int p = 0; p < L; ++p) part[p] = 0.f;
@@ -330,11 +355,14 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
             for (int k = 0; k < L; ++k) am[p][k] = am[p][k] / den;
           }
         }
-#pragma unroll 1
-        for (int p = 0; p < L; ++p) {
-          // X_p = T_p + sum_{k != p} a_k T_k as sum_k cf[k] T_k (cf[p] = 1) over this thread's 32 columns, re-read from tensor
-          // memory: the UNSCALED rows go to the operand tiles and the scale 1/|X_p| * s_p is applied to the 32 products afterwards
-          // (the norm needs both threads' halves, exchanged through shared memory across the barrier that is there anyway)
+        // X_p = T_p + sum_{k != p} a_k T_k as sum_k cf[k] T_k (cf[p] = 1) over this thread's 32 columns, re-read from tensor
+        // memory: the UNSCALED rows go to the operand tiles and the scale 1/|X_p| * s_p is applied to the 32 products afterwards
+        // (the norm needs both threads' halves, exchanged through shared memory across the barrier that is there anyway).
+        // Two operand buffers: X_{p+1} is written while the tensor core works on X_p (the wait for those ~20 small MMAs was
+        // 14 % of the epilogue's time when it was exposed once per layer).
+        float sgv[L];
+        auto write_x = [&](int p) {
+          const int buf = p & 1;
           float cf[L];
 #pragma unroll
           for (int k = 0; k < L; ++k) {
@@ -343,15 +371,15 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
             for (int pp = 0; pp < L; ++pp)
               if (pp == p) cf[k] = (k == pp) ? 1.f : am[pp][k];
           }
-          float ssh = 0.f, sg = 0.f;
-          gwp[p] = 0.f, aqp[p] = 0.f;
+          float ssh = 0.f;
+          sgv[p] = 0.f, gwp[p] = 0.f, aqp[p] = 0.f;
           if (v >= 0) {
-            sg = K.gconst[(size_t)g * MD_GCONST + p];
+            sgv[p] = K.gconst[(size_t)g * MD_GCONST + p];
             gwp[p] = K.gconst[(size_t)g * MD_GCONST + 4 + p];
             aqp[p] = K.gconst[(size_t)g * MD_GCONST + 8 + p];
           }
-          unsigned char* erow = sm.E[half] + (uint32_t)r * 128u;
-          unsigned char* lrow = sm.ELO + (uint32_t)r * 128u;
+          unsigned char* erow = sm.E[buf][half] + (uint32_t)r * 128u;
+          unsigned char* lrow = sm.ELO[buf] + (uint32_t)r * 128u;
 #pragma unroll 1
           for (int j = 0; j < 2; ++j) {
             float t[L][16];
@@ -381,10 +409,14 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
                   make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
             }
           }
-          sm.ssq[p & 1][half][r] = ssh;
+          sm.ssq[buf][half][r] = ssh;
+        };
+        write_x(0);
+#pragma unroll 1
+        for (int p = 0; p < L; ++p) {
           fence_proxy_async_smem();
           tc_fence_before();
-          asm volatile("bar.sync 3, 256;" ::: "memory");  // e_p complete; the previous layer's accumulator reads are done
+          asm volatile("bar.sync 3, 256;" ::: "memory");  // X_p complete; the previous layer's accumulator reads are done
           if (warp == 0) {
             tc_fence_after();
             if (qt_elect()) {
@@ -393,7 +425,7 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
               const uint32_t d = tbase + HCOL;
 #pragma unroll
               for (int kb = 0; kb < 2; ++kb) {
-                const uint64_t ae = desc_k_sw128(smem_u32(sm.E[kb]), 0);
+                const uint64_t ae = desc_k_sw128(smem_u32(sm.E[p & 1][kb]), 0);
                 const uint64_t bhi = desc_k_sw128(bh + kb * 4096, 0), blo = desc_k_sw128(bh + 8192 + kb * 4096, 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -405,13 +437,16 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
                   mma_tf32(d + 64, ae + 2 * k, blo + 2 * k, idt, (kb | k) != 0);
                 }
               }
-              const uint64_t al = desc_k_sw128(smem_u32(sm.ELO), 0), bf = desc_k_sw128(bh + 16384, 0);
+              const uint64_t al = desc_k_sw128(smem_u32(sm.ELO[p & 1]), 0), bf = desc_k_sw128(bh + 16384, 0);
 #pragma unroll
               for (int k = 0; k < 4; ++k) mma_f16(d + 96, al + 2 * k, bf + 2 * k, idb, k != 0);
               mma_commit(&sm.h_full);
             }
             __syncwarp();
           }
+          // the other buffer is free: its MMAs (layer p - 1) completed before that layer's products were read, and every
+          // thread read its ssq[.] entries before the barrier above
+          if (p + 1 < L) write_x(p + 1);
           mbar_wait(&sm.h_full, hph & 1);
           ++hph;
           tc_fence_after();
@@ -423,7 +458,7 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
           tmem_ld16(hta + 96, xl);
           tmem_ld_wait();
           const float ss = sm.ssq[p & 1][0][r] + sm.ssq[p & 1][1][r];
-          const float scale = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f)) * sg;  // e_p = X_p / |X_p| * s_p
+          const float scale = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f)) * sgv[p];  // e_p = X_p / |X_p| * s_p
           float hq = 0.f;
 #pragma unroll
           for (int j = 0; j < MD_HIDDEN / 2; ++j)

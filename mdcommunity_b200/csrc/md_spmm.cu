@@ -1,48 +1,53 @@
 // CSR SpMM, the operator-level boundary: drop-in for torch_sparse.spmm (torch-sparse 0.6.18) as the reference
 // calls it at MultiDismantler_net_graphsage.py:139,146,199,290,297,350,377 and MultiDismantler_torch.py:420.
 //   Y[r, :] = sum_{e in row r} val[e] * X[col[e], :]        (val == NULL: all ones, aggregatorID = 0)
-// One warp per row; each lane owns D/4 <= ... float4 column chunks; neighbours are taken in CSR order so the
-// f32 sum is deterministic and matches a sequential scatter-add in COO order.
+// One warp per row (a half-warp per row for D <= 64, so that no lane idles at the embedding width); each lane owns float4
+// column chunks; neighbours are taken in CSR order so the f32 sum is deterministic and matches a sequential scatter-add in
+// COO order.
 #include "md_common.cuh"
 
 namespace md {
 
-template <int VEC>  // number of float4 chunks per lane (D = 128 * VEC max)
+template <int VEC, int LPR>  // VEC float4 chunks per lane; LPR lanes per row (16: two rows per warp when D <= 64, else 32)
 __global__ void __launch_bounds__(256) spmm_csr_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                       const float* __restrict__ val, const float* __restrict__ X,
                                                       float* __restrict__ Y, int n_rows, int D4) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;
   const int wpb = blockDim.x >> 5;
-  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * wpb) {
-    const int b = rowptr[row], e = rowptr[row + 1];
+  for (int row0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * RPW; row0 < n_rows; row0 += gridDim.x * wpb * RPW) {
+    const int row = row0 + sub;
+    const bool live = row < n_rows;
+    const int b = live ? rowptr[row] : 0, e = live ? rowptr[row + 1] : 0;
     float4 acc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c0 = b; c0 < e; c0 += 32) {
+    for (int c0 = b; __any_sync(0xffffffffu, c0 < e); c0 += LPR) {  // (the rows of a warp may differ in length)
       int u = 0;
       float w = 1.f;
-      if (c0 + lane < e) {
-        u = col[c0 + lane];
-        if (val) w = val[c0 + lane];
+      if (c0 + sl < e) {
+        u = col[c0 + sl];
+        if (val) w = val[c0 + sl];
       }
-      const int cnt = min(32, e - c0);
-      for (int j0 = 0; j0 < cnt; j0 += 4) {
+      const int cnt = max(0, min(LPR, e - c0));
+      for (int j0 = 0; __any_sync(0xffffffffu, j0 < cnt); j0 += 4) {
         float4 x[4][VEC];
         float ws[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          const int uu = __shfl_sync(0xffffffffu, u, (j0 + jj) & 31);
-          ws[jj] = __shfl_sync(0xffffffffu, w, (j0 + jj) & 31);
+          const int srcl = sub * LPR + ((j0 + jj) % LPR);
+          const int uu = __shfl_sync(0xffffffffu, u, srcl);
+          ws[jj] = __shfl_sync(0xffffffffu, w, srcl);
           const bool ok = j0 + jj < cnt;
 #pragma unroll
           for (int j = 0; j < VEC; ++j) {
             x[jj][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok && lane + 32 * j < D4) x[jj][j] = __ldg(reinterpret_cast<const float4*>(X) + (size_t)uu * D4 + lane + 32 * j);
+            if (ok && sl + LPR * j < D4) x[jj][j] = __ldg(reinterpret_cast<const float4*>(X) + (size_t)uu * D4 + sl + LPR * j);
           }
         }
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
-          if (j0 + jj < cnt) {
+          if (j0 + jj < cnt) {  // neighbours in CSR order: the f32 sum is deterministic
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
               acc[j].x = fmaf(ws[jj], x[jj][j].x, acc[j].x);
@@ -53,9 +58,11 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const int32_t* __restrict
           }
       }
     }
+    if (live) {
 #pragma unroll
-    for (int j = 0; j < VEC; ++j)
-      if (lane + 32 * j < D4) reinterpret_cast<float4*>(Y)[(size_t)row * D4 + lane + 32 * j] = acc[j];
+      for (int j = 0; j < VEC; ++j)
+        if (sl + LPR * j < D4) reinterpret_cast<float4*>(Y)[(size_t)row * D4 + sl + LPR * j] = acc[j];
+    }
   }
 }
 
@@ -71,12 +78,14 @@ extern "C" int md_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   const int wpb = 8;
-  long long want = ((long long)n_rows + wpb - 1) / wpb;
+  const int rpb = D4 <= 16 ? 2 * wpb : wpb;  // rows per block
+  long long want = ((long long)n_rows + rpb - 1) / rpb;
   int grid = (int)(want < (long long)nsm * 8 ? want : (long long)nsm * 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (D4 <= 32) md::spmm_csr_kernel<1><<<grid, 256, 0, st>>>(rowptr, col, val, X, Y, n_rows, D4);
-  else if (D4 <= 64) md::spmm_csr_kernel<2><<<grid, 256, 0, st>>>(rowptr, col, val, X, Y, n_rows, D4);
-  else md::spmm_csr_kernel<4><<<grid, 256, 0, st>>>(rowptr, col, val, X, Y, n_rows, D4);
+  if (D4 <= 16) md::spmm_csr_kernel<1, 16><<<grid, 256, 0, st>>>(rowptr, col, val, X, Y, n_rows, D4);
+  else if (D4 <= 32) md::spmm_csr_kernel<1, 32><<<grid, 256, 0, st>>>(rowptr, col, val, X, Y, n_rows, D4);
+  else if (D4 <= 64) md::spmm_csr_kernel<2, 32><<<grid, 256, 0, st>>>(rowptr, col, val, X, Y, n_rows, D4);
+  else md::spmm_csr_kernel<4, 32><<<grid, 256, 0, st>>>(rowptr, col, val, X, Y, n_rows, D4);
   MD_CHECK_LAUNCH();
   return 0;
 }
