@@ -172,7 +172,7 @@ class GraphBatch:
         gnnz = np.zeros(B, np.int64)
         for l in range(L):
             gnnz += 2 * np.array([g.num_edges[l] for g in graphs], np.int64)
-        out = dict(B=B, L=L, S=S, rowptr=rowptr, col=col, src=src, nnz=nnz, cost=cost, max_graph_nnz=int(gnnz.max()),
+        out = dict(B=B, L=L, S=S, rowptr=rowptr, col=col, src=src, nnz=nnz, cost=cost, max_graph_nnz=int(gnnz.max()), graphs=graphs,
                    n_nodes=_pin(torch.tensor([g.num_nodes for g in graphs], dtype=torch.int32)),
                    n_edges=_pin(torch.tensor([[g.num_edges[l] for g in graphs] for l in range(L)], dtype=torch.int32)))
         if cost == "degree":
@@ -218,6 +218,7 @@ class GraphBatch:
         self.src = [up(t) for t in host["src"]]
         self.n_nodes, self.n_edges = up(host["n_nodes"]), up(host["n_edges"])
         self.max_rank = torch.ones(B, dtype=torch.int32, device=dev)
+        self._upload_max_rank()
         self.node_w, self.node_cost = [], None
         if self.cost == "degree":
             self.node_w = [up(t) for t in host["node_w"]]
@@ -239,6 +240,40 @@ class GraphBatch:
         st.max_rank = self.max_rank.data_ptr()
         st.node_cost = self.node_cost.data_ptr() if self.node_cost is not None else None
         self.c = st
+
+    def _upload_max_rank(self):
+        """The LMCC of the intact graphs, when already known (an earlier batch computed it; the reference computes it when it
+        builds the Graph object, U/graph.py:30-37), is uploaded instead of being read back after s0 -- that read-back is a
+        host synchronize per batch, which stalls every other batch in flight.  Unknown: BatchRollout.reset() fills it in."""
+        known = [int(g.max_rank) for g in self.graphs]
+        self._max_rank_set = all(r > 0 for r in known)
+        if self._max_rank_set:
+            self.max_rank.copy_(torch.tensor(known, dtype=torch.int32), non_blocking=True)
+
+    def upload(self, host):
+        """Refresh the resident CSR (and degree-cost node weights) from another prepared host batch of EXACTLY the same shape
+        (B, stride, entries per layer): asynchronous copies from the pinned host tensors on the current stream, no
+        allocation -- the device buffers, every BatchRollout bound to this batch and their captured CUDA graphs stay valid.
+        The serving pattern: a pool of resident batches that new inputs are streamed into."""
+        if (host["B"], host["L"], host["S"], host["cost"]) != (self.B, self.L, self.S, self.cost) or list(host["nnz"]) != self.nnz:
+            raise ValueError("upload needs a host batch of the same shape (B, L, stride, cost, entries per layer)")
+        with torch.cuda.device(self.device):
+            for l in range(self.L):
+                self.rowptr[l].copy_(host["rowptr"][l], non_blocking=True)
+                self.col[l].copy_(host["col"][l], non_blocking=True)
+                self.src[l].copy_(host["src"][l], non_blocking=True)
+                if self.cost == "degree":
+                    self.node_w[l].copy_(host["node_w"][l], non_blocking=True)
+            self.n_nodes.copy_(host["n_nodes"], non_blocking=True)
+            self.n_edges.copy_(host["n_edges"], non_blocking=True)
+            if self.cost == "degree":
+                self.node_cost.copy_(host["node_cost"], non_blocking=True)
+            if int(host["max_graph_nnz"]) > int(self.c.max_graph_nnz) or \
+                    max(g.num_nodes for g in host["graphs"]) > max(g.num_nodes for g in self.graphs):
+                raise ValueError("a graph of the new batch is larger (nodes or CSR entries) than the resident batch was sized for")
+            self.graphs = list(host["graphs"])
+            self._upload_max_rank()
+        return self
 
     def ptr(self):
         return C.byref(self.c)

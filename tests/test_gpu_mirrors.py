@@ -243,3 +243,34 @@ def test_sharded_getsolbatch_two_gpus(tmp_path):
         T = min(z["actions"].shape[1], res["actions"].shape[1])
         assert np.array_equal(z["actions"][:, :T], res["actions"][:, :T])
         assert np.array_equal(z["max_rank"], [g.max_rank for g in graphs])
+
+
+def test_graphbatch_upload_streams_a_new_batch_into_resident_buffers():
+    """GraphBatch.upload: another batch of the same shape is copied into the resident device buffers (no allocation; the
+    rollout object and its captured CUDA graph stay bound).  The same graphs in reversed order have the same shape and a
+    different content: the rollout after the upload must equal the reversed results bit for bit, twice (eager, then the
+    CUDA-graph replay), and a batch of another shape is refused."""
+    import mdcommunity_b200 as mdb
+    from mdcommunity_b200 import gmm
+    cost = "degree"
+    graphs = [gmm.gmm_graph(90 + 7 * i, 300 + i, cost=cost) for i in range(6)]
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_%s.npz" % cost))), torch.device("cuda:0"))
+    batch = mdb.GraphBatch(graphs, cost=cost)
+    ro = mdb.BatchRollout(batch, w)
+    r1 = ro.run()
+    fresh = [mdb.Graph_test(g.edge_list[0], g.edge_list[1], num_nodes=g.num_nodes, cost=cost) for g in graphs[::-1]]
+    host2 = mdb.GraphBatch.prepare_host(fresh, cost)  # LMCC of the intact graphs not known yet: reset() fills it in
+    for rep in range(3):
+        batch.upload(host2)
+        ro.reset()
+        r2 = ro.run()
+        for k in ("score", "n_steps", "actions"):
+            assert np.array_equal(r2[k], r1[k][::-1]), (rep, k)
+        for i in range(len(graphs)):  # (trace columns beyond n_steps keep whatever an earlier rollout left there)
+            n = int(r2["n_steps"][i])
+            j = len(graphs) - 1 - i
+            assert np.array_equal(r2["ranks"][i, :n], r1["ranks"][j, :n]) and np.array_equal(r2["maxcc"][i, :n], r1["maxcc"][j, :n]), (rep, i)
+        assert [g.max_rank for g in fresh] == [g.max_rank for g in graphs[::-1]]
+    other = mdb.GraphBatch.prepare_host([gmm.gmm_graph(90, 1, cost=cost) for _ in range(6)], cost)
+    with pytest.raises(ValueError):
+        batch.upload(other)
