@@ -745,7 +745,14 @@ def main():
     ap.add_argument("--depth", type=int, default=6, help="batches in flight (RolloutPipeline); 1 = strictly one after the other "
                     "(measured at 20 steps: depth 4 / 6 / 8 = 19.6 / 20.1 / 20.1 k graphs/s)")
     ap.add_argument("--tail", action="store_true", help="hand graphs with <= 64 active nodes over to md_rollout_tail")
+    ap.add_argument("--fused-pack", type=int, default=0, help="md_debug_set_fused_pack (A/B): 0 = default bin budget, > 0 fixed, < 0 every unit alone")
+    ap.add_argument("--fused-legacy", action="store_true", help="md_embed_fused without packing of small units (debug bit 19; A/B)")
     args = ap.parse_args()
+    if args.impl == "ours" and (args.fused_pack or args.fused_legacy):
+        from mdcommunity_b200 import _lib
+        _lib.lib().md_debug_set_fused_pack(args.fused_pack)
+        if args.fused_legacy:
+            _lib.lib().md_debug_set_flags(1 << 19)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     cost, n, per_gpu, desc = WORKLOADS[args.workload]

@@ -176,8 +176,14 @@ void md_debug_force_large_env(int32_t on);
  * bits 14 / 15 (two-kernel md_embed_iter only): enqueue only the neighbour aggregation / only the transform, so that a
  *   caller can time the two kernels of an iteration separately (bit 14 call followed by bit 15 call == the normal sequence);
  * bits 10 / 11 (timing experiments, results become wrong / unchanged): transform kernel without its global stores /
- *   without its L2 prefetch of the next tile */
+ *   without its L2 prefetch of the next tile;
+ * bit 19 (md_embed_fused): every (graph, layer) unit alone and on the single-unit code path, i.e. the kernel as it was
+ *   before small units were packed (A/B reference: embeddings within rounding of the column sums' order) */
 void md_debug_set_flags(int32_t flags);
+/* md_embed_fused packs (graph, layer) units of few active rows into bins that one persistent CTA processes together.
+ * rows = 0: weight budget of a bin chosen per launch (the small units' total spread over the SMs, whole tiles, 256..768);
+ * rows > 0: that budget (clamped to 256..768); rows < 0: every unit alone.  Results do not depend on the setting. */
+void md_debug_set_fused_pack(int32_t rows);
 /* profiling hook: clock64 phase times of CTA 0 of the last md_env_step (labels in, CSR staged, prune rounds,
  * component sizes, alive CSR + degrees) and, at index 16, the number of prune rounds */
 int md_debug_read_env(long long* host, int n);

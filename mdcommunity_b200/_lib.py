@@ -61,6 +61,7 @@ _SIGS = {
     "md_env_small_max_stride": ([], C.c_int32),
     "md_debug_force_large_env": ([C.c_int32], None),
     "md_debug_set_flags": ([C.c_int32], None),
+    "md_debug_set_fused_pack": ([C.c_int32], None),
     "md_debug_read_env": ([_vp, C.c_int32], C.c_int),
     "md_debug_read_env_ctas": ([_vp], C.c_int),
     "md_debug_read_fused": ([_vp, C.c_int32], C.c_int),

@@ -53,6 +53,21 @@ constexpr uint32_t FZ_WPASS_B = 40960; // B operands of one pass: W13 hi, W13 lo
 constexpr size_t FZ_WS_CTR = 2 * FZ_WPASS_B;
 constexpr size_t FZ_WS_SPILL = FZ_WS_CTR + 1024;
 constexpr size_t FZ_SPILL_B = 8 * FZ_TILE_B;
+// ---- packing of small units (see fused_prep_kernel) ----
+constexpr int FZ_MAXM = 32;          // most (graph, layer) units one CTA takes together (a "bin")
+constexpr int FZ_SMALL = 256;        // a unit is packable when it has at most this many active rows ...
+constexpr int FZ_SMALL_E = 2048;     // ... and at most this many alive entries (8 per row of FZ_SMALL)
+constexpr int FZ_PACK_GRAPHS = 1024; // batches beyond this many graphs (or FZ_PACK_UNITS units) are not packed
+constexpr int FZ_PACK_UNITS = 2048;
+constexpr int FZ_CAP_MIN = 256, FZ_CAP_MAX = 768;  // bounds of a bin's weight budget (rows < budget + FZ_SMALL <= FZ_ROWS)
+
+struct FusedBins {     // written by fused_prep_kernel, read by embed_fused_kernel
+  int* hdr;            // [0] bin counter of the persistent CTAs, [1] number of bins
+  int* order;          // [n_units] bins in the order the CTAs take them (heavy first)
+  int* bin_start;      // [n_units + 1] bin b = member[bin_start[b] .. bin_start[b + 1])
+  int* member;         // [n_units] unit ids (g * L + l); all members of a bin share the layer
+  uint16_t* wpos;      // [L][n_total] packed bins: node slot -> J code of its row inside the bin (see nbrJ)
+};
 
 struct FusedSmem {
   unsigned char Hs[8 * FZ_TILE_B];  // resident column half of the unit's embeddings (SWIZZLE_128B tiles)
@@ -60,10 +75,16 @@ struct FusedSmem {
   unsigned char LO[FZ_TILE_B];      // staging: fp16 remainders, row = [P_lo (32) | H_lo (32)]
   unsigned char Wt[FZ_WPASS_B];     // B operands of the running pass
   uint16_t idx[FZ_IDX_CAP + 64];    // neighbour entries of the unit's alive CSR (see nbrJ); setup: sort counters
-  uint16_t pos[FZ_ROWS];            // graph-local node id -> row (degree-sorted compact order)
+  uint16_t pos[FZ_ROWS];            // single big unit: graph-local node id -> row (degree-sorted compact order);
+                                    // packed bin: compact index (member row offset + p) -> J code of the row
   uint32_t rbe[FZ_ROWS];            // row -> first | (one-past-last << 16) entry of its neighbour list
-  uint16_t rowv[FZ_ROWS];           // row -> graph-local node id
-  float red[FZ_GW][32];
+  uint16_t rowv[FZ_ROWS];           // row -> graph-local node id | member index << 10
+  uint16_t mg[FZ_MAXM];             // member -> graph
+  uint16_t mrow[FZ_MAXM + 1];       // member -> first compact index (prefix sum of the members' active rows)
+  uint32_t meo[FZ_MAXM + 1];        // member -> first entry inside the bin's concatenated neighbour lists
+  int32_t me0[FZ_MAXM];             // member -> first entry of its alive CSR in S.acol
+  int nm, nrows, nent, layer, packed;
+  alignas(16) float red[FZ_GW][32];
   alignas(16) float wn2l[2 * D];     // first-embedding coefficients: relu(x1 * wn2l[64 + c] + x0 * wn2l[c]) (see H1 mode below)
   float c0[D];                      // H1 mode: the common first embedding c
   int cnt0;                         // H1 mode: rows of the unit with an alive neighbour
@@ -139,50 +160,182 @@ __device__ __forceinline__ uint32_t lds16(uint32_t addr) {
   return v;
 }
 
-constexpr int FZ_ORDER_MAX = 8192;  // units ranked by work (O(U^2) ranking); larger batches run in index order
-
-// Per launch: weight images (both passes) in the exact shared-memory layout, reset of the unit counter, and the order in
-// which the persistent CTAs take the (graph, layer) units: heaviest first (alive entries + 4 per active node), so the
-// tail of the launch is made of the cheap units.  One warp ranks one unit (block b: units [8 b, 8 b + 8)).
-__global__ void __launch_bounds__(256) fused_prep_kernel(md_graphs_t G, md_state_t S, md_weights_t W, unsigned char* ws,
-                                                         int* order, int n_units) {
-  __shared__ int key[FZ_ORDER_MAX];
-  const int L = G.n_layers;
-  const int lane = threadIdx.x & 31, u = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (n_units <= FZ_ORDER_MAX) {
-    for (int v = threadIdx.x; v < n_units; v += 256) {
-      const int g = v / L, l = v - g * L, n = S.n_act[g], base = g * G.stride;
-      key[v] = n > 0 ? (S.aptr[l][base + n] - S.aptr[l][base]) + 4 * n : 0;
+// Per launch, two blocks.  Block 1: the weight images (both passes) in the exact shared-memory layout.  Block 0: the BINS.
+//
+// Towards the end of a rollout most graphs of a batch have a few dozen active nodes left, and a (graph, layer) unit of 30
+// rows costs a persistent CTA nearly as much as one of 300 (sort, fill, six passes with their barriers and MMA round trips,
+// three epilogues: ~38 k cycles, measured).  So units of <= FZ_SMALL rows and <= FZ_SMALL_E alive entries are PACKED: a bin
+// is a run of consecutive (in graph order) small units of one layer whose rows are concatenated into one resident buffer
+// and go through the kernel like a single unit.  Nothing in a unit's arithmetic depends on its bin mates (neighbour sums
+// run in CSR order, the tensor core and the epilogue work row by row, column sums run per member in the member's own
+// order), so a graph's embeddings are bit-identical packed, alone, or in another batch.
+//
+// Packing is a prefix sum, not a search: unit weight w = max(rows, entries / 8, budget / FZ_MAXM); a unit whose exclusive
+// prefix W falls into [k * budget, (k + 1) * budget) belongs to bin k of its layer.  Hence rows < budget + FZ_SMALL <=
+// FZ_ROWS, entries < 8 (budget + FZ_SMALL) <= FZ_IDX_CAP, members <= FZ_MAXM.  budget = the small units' total weight
+// spread over the SMs, rounded up to whole tiles, within [FZ_CAP_MIN, FZ_CAP_MAX] (md_debug_set_fused_pack overrides it;
+// < 0: every unit alone).  Larger units get a bin each.  Bins are handed out heavy first (64 weight classes, counting
+// sort; the order inside a class is whatever the atomics give -- it decides which CTA takes a bin, not any result).
+__global__ void __launch_bounds__(1024) fused_prep_kernel(md_graphs_t G, md_state_t S, md_weights_t W, unsigned char* ws,
+                                                          FusedBins bn, int n_units, int nsm, int pack) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (blockIdx.x == 1) {
+    for (int i = tid; i < 2 * 64 * 32; i += 1024) {
+      const int p = i >> 11, n = (i >> 5) & 63, k = i & 31;
+      const float w13 = W.w13[(32 * p + k) * D + n], w23 = W.w23[(32 * p + k) * D + n];
+      unsigned char* img = ws + (size_t)p * FZ_WPASS_B;
+      const uint32_t off = sw128_off(n, k >> 2) + 4 * (k & 3);
+      *reinterpret_cast<float*>(img + off) = tf32_hi(w13);
+      *reinterpret_cast<float*>(img + 8192 + off) = w13 - tf32_hi(w13);
+      *reinterpret_cast<float*>(img + 16384 + off) = tf32_hi(w23);
+      *reinterpret_cast<float*>(img + 24576 + off) = w23 - tf32_hi(w23);
+      *reinterpret_cast<__half*>(img + 32768 + sw128_off(n, k >> 3) + 2 * (k & 7)) = __float2half_rn(w13);
+      *reinterpret_cast<__half*>(img + 32768 + sw128_off(n, 4 + (k >> 3)) + 2 * (k & 7)) = __float2half_rn(w23);
     }
-    __syncthreads();
-    if (u < n_units) {
-      const int k = key[u];
-      int rank = 0;
-      for (int v = lane; v < n_units; v += 32) rank += (key[v] > k) || (key[v] == k && v < u);
-      rank = warp_sum_i(rank);
-      if (lane == 0) order[rank] = u;
+    return;
+  }
+  const int L = G.n_layers, B = G.n_graphs, St = G.stride;
+  if (B > FZ_PACK_GRAPHS || n_units > FZ_PACK_UNITS) {  // very large batches: one bin per unit, index order
+    for (int u = tid; u < n_units; u += 1024) bn.bin_start[u] = u, bn.member[u] = u, bn.order[u] = u;
+    if (tid == 0) bn.bin_start[n_units] = n_units, bn.hdr[0] = 0, bn.hdr[1] = n_units;
+    return;
+  }
+  __shared__ int key[FZ_PACK_UNITS];                      // weight of a bin (hand-out order)
+  __shared__ int lbst[MD_MAX_LAYERS][FZ_PACK_GRAPHS + 1];  // layer, local bin -> rank of its first member among the layer's small units
+  __shared__ int wsum[3][32];
+  __shared__ int tot[MD_MAX_LAYERS][3];                    // per layer: total weight, small units, big units
+  __shared__ int snb[MD_MAX_LAYERS];                       // per layer: bins of small units
+  __shared__ int hist[64], cursor[64];
+  __shared__ int t_small;
+  for (int i = tid; i < FZ_PACK_UNITS; i += 1024) key[i] = 0;
+  for (int i = tid; i < MD_MAX_LAYERS * (FZ_PACK_GRAPHS + 1); i += 1024) (&lbst[0][0])[i] = 0x7fffffff;
+  if (tid < 64) hist[tid] = 0;
+  if (tid < MD_MAX_LAYERS) snb[tid] = 0;
+  if (tid == 0) t_small = 0;
+  __syncthreads();
+  // ---- the thread's graph: rows, entries and class of its unit in every layer ----
+  const int n = tid < B ? S.n_act[tid] : 0;
+  int e_[MD_MAX_LAYERS], cls_[MD_MAX_LAYERS], w_[MD_MAX_LAYERS];  // class: 0 = nothing to do, 1 = small (packable), 2 = big
+  int tsm = 0;
+#pragma unroll
+  for (int l = 0; l < MD_MAX_LAYERS; ++l) {
+    e_[l] = 0, cls_[l] = 0, w_[l] = 0;
+    if (l < L && n > 0) {
+      e_[l] = S.aptr[l][tid * St + n] - S.aptr[l][tid * St];
+      cls_[l] = (n <= FZ_SMALL && e_[l] <= FZ_SMALL_E) ? 1 : 2;
+      w_[l] = max(n, (e_[l] + 7) >> 3);
+      if (cls_[l] == 1) tsm += w_[l];
     }
-  } else if (u < n_units && lane == 0) {
-    order[u] = u;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int*>(ws + FZ_WS_CTR) = 0;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < 2 * 64 * 32; i += gridDim.x * 256) {  // spread over the blocks
-    const int p = i >> 11, n = (i >> 5) & 63, k = i & 31;
-    const float w13 = W.w13[(32 * p + k) * D + n], w23 = W.w23[(32 * p + k) * D + n];
-    unsigned char* img = ws + (size_t)p * FZ_WPASS_B;
-    const uint32_t off = sw128_off(n, k >> 2) + 4 * (k & 3);
-    *reinterpret_cast<float*>(img + off) = tf32_hi(w13);
-    *reinterpret_cast<float*>(img + 8192 + off) = w13 - tf32_hi(w13);
-    *reinterpret_cast<float*>(img + 16384 + off) = tf32_hi(w23);
-    *reinterpret_cast<float*>(img + 24576 + off) = w23 - tf32_hi(w23);
-    *reinterpret_cast<__half*>(img + 32768 + sw128_off(n, k >> 3) + 2 * (k & 7)) = __float2half_rn(w13);
-    *reinterpret_cast<__half*>(img + 32768 + sw128_off(n, 4 + (k >> 3)) + 2 * (k & 7)) = __float2half_rn(w23);
+  tsm = warp_sum_i(tsm);
+  if (lane == 0 && tsm) atomicAdd(&t_small, tsm);
+  __syncthreads();
+  int cap = 0;
+  if (pack > 0) cap = min(max(pack, FZ_CAP_MIN), FZ_CAP_MAX);
+  else if (pack == 0) cap = min(max(((t_small + nsm - 1) / nsm + TILE_M - 1) / TILE_M * TILE_M, FZ_CAP_MIN), FZ_CAP_MAX);
+  const int wmin = (cap + FZ_MAXM - 1) / FZ_MAXM;
+  // ---- exclusive prefixes over the graphs, per layer: weight, small units, big units ----
+  int wex_[MD_MAX_LAYERS], srk_[MD_MAX_LAYERS], brk_[MD_MAX_LAYERS];
+#pragma unroll
+  for (int l = 0; l < MD_MAX_LAYERS; ++l) {
+    wex_[l] = srk_[l] = brk_[l] = 0;
+    if (l < L) {  // (L is uniform: the barriers below are reached by every thread)
+      int v[3] = {cls_[l] == 1 ? max(w_[l], wmin) : 0, cls_[l] == 1 ? 1 : 0, cls_[l] == 2 ? 1 : 0};
+      int inc[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        int x = v[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, x, o);
+          if (lane >= o) x += y;
+        }
+        inc[j] = x;
+        if (lane == 31) wsum[j][warp] = x;
+      }
+      __syncthreads();
+      if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int t = wsum[j][lane];
+          int x = t;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+          }
+          wsum[j][lane] = x - t;
+          if (lane == 31) tot[l][j] = x;
+        }
+      }
+      __syncthreads();
+      wex_[l] = inc[0] - v[0] + wsum[0][warp];
+      srk_[l] = inc[1] - v[1] + wsum[1][warp];
+      brk_[l] = inc[2] - v[2] + wsum[2][warp];
+      __syncthreads();  // wsum is reused by the next layer
+    }
   }
+  // ---- local bin of every small unit; first member and number of bins per layer ----
+  int k_[MD_MAX_LAYERS];
+#pragma unroll
+  for (int l = 0; l < MD_MAX_LAYERS; ++l) {
+    k_[l] = 0;
+    if (l < L && cls_[l] == 1) {
+      k_[l] = cap ? wex_[l] / cap : srk_[l];
+      atomicMin(&lbst[l][k_[l]], srk_[l]);
+      atomicMax(&snb[l], k_[l] + 1);
+    }
+  }
+  __syncthreads();
+  int n_big = 0, n_bins = 0, n_mem = 0;
+#pragma unroll
+  for (int l = 0; l < MD_MAX_LAYERS; ++l)
+    if (l < L) n_big += tot[l][2];
+  n_bins = n_mem = n_big;
+  {
+    int bigoff = 0;
+#pragma unroll
+    for (int l = 0; l < MD_MAX_LAYERS; ++l) {
+      if (l < L) {
+        const int boff = n_bins, moff = n_mem;  // first bin / first member slot of this layer's small units
+        if (cls_[l] == 2) {
+          const int b = bigoff + brk_[l];
+          bn.member[b] = tid * L + l;
+          bn.bin_start[b] = b;
+          key[b] = e_[l] + 4 * n;
+        } else if (cls_[l] == 1) {
+          bn.member[moff + srk_[l]] = tid * L + l;
+          atomicAdd(&key[boff + k_[l]], e_[l] + 4 * n);
+        }
+        for (int k = tid; k < snb[l]; k += 1024) bn.bin_start[boff + k] = moff + lbst[l][k];
+        bigoff += tot[l][2];
+        n_bins += snb[l];
+        n_mem += tot[l][1];
+      }
+    }
+  }
+  if (tid == 0) bn.bin_start[n_bins] = n_mem, bn.hdr[0] = 0, bn.hdr[1] = n_bins;
+  __syncthreads();
+  // ---- hand-out order: heavy bins first ----
+  for (int b = tid; b < n_bins; b += 1024) atomicAdd(&hist[63 - min(63, key[b] >> 8)], 1);
+  __syncthreads();
+  if (warp == 0) {
+    const int t0 = hist[2 * lane], t1 = hist[2 * lane + 1];
+    int x = t0 + t1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    cursor[2 * lane] = x - t0 - t1;
+    cursor[2 * lane + 1] = x - t1;
+  }
+  __syncthreads();
+  for (int b = tid; b < n_bins; b += 1024) bn.order[atomicAdd(&cursor[63 - min(63, key[b] >> 8)], 1)] = b;
 }
 
 __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_state_t S, md_weights_t W, md_work_t K,
-                                                             unsigned char* ws, const int* __restrict__ order,
-                                                             int n_units, int dbg) {
+                                                             unsigned char* ws, FusedBins bn, int dbg) {
   // NOTE: no pointer arithmetic on the base -- the compiler must keep seeing the shared state space, otherwise every
   // access below turns into a generic LD/ST (measured: 4x slower gather).  Alignment is asserted instead.
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -231,8 +384,9 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
   const uint32_t tbase = sm.tmem;
   unsigned char* const spill = ws + FZ_WS_SPILL + (size_t)blockIdx.x * FZ_SPILL_B;
   const unsigned char* const wimg = ws;
-  int* const counter = reinterpret_cast<int*>(ws + FZ_WS_CTR);
+  int* const counter = bn.hdr;
   const bool degree_cost = G.node_w[0] != nullptr;
+  const bool legacy = (dbg & (1 << 19)) != 0;  // every unit alone and on the single-unit code path (A/B reference)
 
 #ifdef MD_PROFILE
   const long long t_start = clock64();
@@ -252,17 +406,48 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
   for (;;) {
     if (tid == 0) {
       const int slot = atomicAdd(counter, 1);
-      sm.unit = slot < n_units ? order[slot] : -1;
+      sm.unit = slot < bn.hdr[1] ? bn.order[slot] : -1;
     }
     __syncthreads();
-    const int unit = sm.unit;
+    const int bin = sm.unit;
+    if (bin < 0) break;
+    if (warp == 0) {  // the bin's members: graph, rows, entries; prefix sums over the members
+      const int m0 = bn.bin_start[bin], nm = min(bn.bin_start[bin + 1] - m0, FZ_MAXM);
+      const int lay = bn.member[m0] % L;
+      int g_i = 0, n_i = 0, e_i = 0, e0_i = 0;
+      if (lane < nm) {
+        g_i = bn.member[m0 + lane] / L;
+        n_i = max(S.n_act[g_i], 0);
+        e0_i = S.aptr[lay][g_i * St];
+        e_i = S.aptr[lay][g_i * St + n_i] - e0_i;
+      }
+      int rs = n_i, es = e_i;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, rs, o), z = __shfl_up_sync(0xffffffffu, es, o);
+        if (lane >= o) rs += y, es += z;
+      }
+      if (lane < nm) {
+        sm.mg[lane] = (uint16_t)g_i;
+        sm.mrow[lane] = (uint16_t)(rs - n_i);
+        sm.meo[lane] = (uint32_t)(es - e_i);
+        sm.me0[lane] = e0_i;
+      }
+      if (lane == nm - 1) {
+        sm.mrow[nm] = (uint16_t)rs;
+        sm.meo[nm] = (uint32_t)es;
+        sm.nm = nm, sm.nrows = rs, sm.nent = es, sm.layer = lay;
+        // a unit beyond the packable size runs alone on the single-unit path (column sums from the gather's own rows,
+        // node ids translated through shared memory); everything else takes the member-wise path, alone or not
+        sm.packed = (legacy || (nm == 1 && (n_i > FZ_SMALL || e_i > FZ_SMALL_E))) ? 0 : 1;
+      }
+    }
     __syncthreads();
-    if (unit < 0) break;
-    const int g = unit / L, l = unit - g * L;
-    const int n = S.n_act[g];
-    if (n <= 0) continue;
+    const int l = sm.layer, n = sm.nrows, nm = sm.nm;
+    const bool packed = sm.packed != 0;
+    if (n <= 0 || n > FZ_ROWS) continue;
     const int ntile = (n + TILE_M - 1) / TILE_M;
-    const int base = g * St;
+    const int g = sm.mg[0], base = g * St;  // (single-unit path; the packed path reads the member tables)
 
     if (warp == FZ_GW) {
       // ============================== MMA / bulk-copy warp (warp-uniform control flow) ==============================
@@ -332,10 +517,29 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     ++n_units_done;
     const int gtid = tid;  // 0..FZ_GT-1
     const int gi = lane >> 3, q = lane & 7;
-    const int e0 = S.aptr[l][base];
-    const int nnz = S.aptr[l][base + n] - e0;
-    const int32_t* __restrict__ aptr_g = S.aptr[l] + base;
-    const int32_t* __restrict__ acol_g = S.acol[l] + e0;
+    const int e0 = sm.me0[0];
+    const int nnz = sm.nent;
+    const int32_t* __restrict__ aptr_l = S.aptr[l];
+    const int32_t* __restrict__ acol_l = S.acol[l];
+    const int32_t* __restrict__ acol_g = acol_l + e0;  // single-unit path
+    uint16_t* const wpos_l = bn.wpos + (size_t)l * G.n_total;
+    // member of a compact index / of an entry of the bin (binary search over the prefix tables; <= 5 steps)
+    auto member_of_row = [&](int p) -> int {
+      int lo = 0, hi = nm;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)sm.mrow[mid] <= p) lo = mid; else hi = mid;
+      }
+      return lo;
+    };
+    auto member_of_entry = [&](int e) -> int {
+      int lo = 0, hi = nm;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)sm.meo[mid] <= e) lo = mid; else hi = mid;
+      }
+      return lo;
+    };
 
     if (gtid == 0) sm.cnt0 = 0;  // (ordered before the fill's atomics by the barriers of the sort below)
     // ---- row order: descending alive degree (buckets 31+, 30, ..., 1), stable inside a bucket => deterministic ----
@@ -350,9 +554,12 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
         const bool valid = p < n;
         int a0 = 0, a1 = 0;
         if (valid) {
-          a0 = aptr_g[p] - e0;
-          a1 = aptr_g[p + 1] - e0;
-          v_[k] = S.act_list[base + p] - base;
+          const int mi = nm > 1 ? member_of_row(p) : 0;
+          const int bs = (int)sm.mg[mi] * St, pl = p - (int)sm.mrow[mi];
+          const int eo = (int)sm.meo[mi] - sm.me0[mi];
+          a0 = aptr_l[bs + pl] + eo;
+          a1 = aptr_l[bs + pl + 1] + eo;
+          v_[k] = (S.act_list[bs + pl] - bs) | (mi << 10);
         }
         d_[k] = a1 - a0;
         beg_[k] = a0;
@@ -383,7 +590,13 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
         const int c = warp + FZ_GW * k;
         if (b_[k] < 32) {
           const int r = sm.bbase[b_[k]] + cnt[c * 32 + b_[k]] + rank_[k];
-          sm.pos[v_[k]] = (uint16_t)r;
+          if (packed) {
+            const uint16_t Jr = (uint16_t)((r << 3) | (r & 7));
+            sm.pos[32 * c + lane] = Jr;
+            wpos_l[(int)sm.mg[v_[k] >> 10] * St + (v_[k] & 1023)] = Jr;
+          } else {
+            sm.pos[v_[k]] = (uint16_t)r;
+          }
           sm.rowv[r] = (uint16_t)v_[k];
           sm.rbe[r] = (uint32_t)beg_[k] | ((uint32_t)(beg_[k] + d_[k]) << 16);
         }
@@ -394,9 +607,17 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     // sits at byte ((J ^ q) << 4) of the resident buffer (SWIZZLE_128B: chunk ^= row & 7)
     {
       const int ncache = min(nnz, FZ_IDX_CAP);
-      for (int e = gtid; e < ncache; e += FZ_GT) {
-        const uint32_t j = sm.pos[acol_g[e] - base];
-        sm.idx[e] = (uint16_t)((j << 3) | (j & 7));
+      if (!packed) {
+        for (int e = gtid; e < ncache; e += FZ_GT) {
+          const uint32_t j = sm.pos[acol_g[e] - base];
+          sm.idx[e] = (uint16_t)((j << 3) | (j & 7));
+        }
+      } else {  // node slot -> row code through the global map this CTA has just written (ordered by the barrier above)
+        for (int e = gtid; e < ncache; e += FZ_GT) {
+          const int mi = nm > 1 ? member_of_entry(e) : 0;
+          const int src = acol_l[sm.me0[mi] + (e - (int)sm.meo[mi])];
+          sm.idx[e] = __ldcg(wpos_l + src);
+        }
       }
     }
     // (visibility of idx: the barrier after the first resident-half fill below)
@@ -416,18 +637,19 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
         // ---------------- resident column half ----------------
         if (it == it0) {
           if (uses > 0) mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // every earlier MMA (they read Hs) has completed
-          const float dmax = (float)S.max_deg[l * B + g];
-          float xf[4];  // the thread's (up to) 4 rows: fetch the features first, the loads are independent
+          float xf[4], dmx[4];  // the thread's (up to) 4 rows: fetch the features first, the loads are independent
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int r = gtid + FZ_GT * k;
-            xf[k] = 0.f;
+            xf[k] = 0.f, dmx[k] = 1.f;
             if (r < n) {
-              const int v = base + sm.rowv[r];
+              const int rv = sm.rowv[r], gg = sm.mg[rv >> 10];
+              const int v = gg * St + (rv & 1023);
               xf[k] = degree_cost ? G.node_w[l][v] : (float)S.deg[l][v];
+              if (!degree_cost && !h1_mode) dmx[k] = (float)S.max_deg[l * B + gg];
             }
           }
-          if (h1_mode && pass == 0) {  // iteration 0's column sums are (rows with an alive neighbour) x c: count them
+          if (h1_mode && pass == 0 && !packed) {  // iteration 0's column sums are (rows with an alive neighbour) x c: count them
             int c1n = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) c1n += xf[k] > 0.f ? 1 : 0;
@@ -447,7 +669,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
                 x0 = xf[k];
                 x1 = xf[k] > 0.f ? 1.0f : 0.f;
               } else {
-                x0 = xf[k] / dmax;  // degree / degree_max, both exact small integers in f32
+                x0 = xf[k] / dmx[k];  // degree / degree_max, both exact small integers in f32
                 x1 = x0;
               }
             }
@@ -551,8 +773,10 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             own4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < n && rt >= nl_t) own4[k] = unpack4(ld_J((uint32_t)((r << 3) | (r & 7))));
           }
+          if (!packed) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) add4(csum, own4[k]);
+            for (int k = 0; k < 4; ++k) add4(csum, own4[k]);
+          }
           FZ_CLK(d2);
           if (uses > 0) {
             mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // staging tile free again (MMAs of the previous tile complete)
@@ -603,7 +827,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             a.w += __shfl_xor_sync(0xffffffffu, a.w, 16);
             if (gi == 0) {
               const float4 own = unpack4(ld_J((uint32_t)((r << 3) | (r & 7))));
-              add4(csum, own);
+              if (!packed) add4(csum, own);
               const uint32_t ro = (uint32_t)rt * 128u;
               *reinterpret_cast<float4*>(sm.P + ro + ((q ^ (rt & 7)) << 4)) = a;
               *reinterpret_cast<uint2*>(sm.LO + ro + (((q >> 1) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_f16x4(a);
@@ -619,29 +843,77 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
         }
         // ---------------- end of pass ----------------
         FZ_CLK(c3);
+        // column sums of this half of the iteration's input embeddings (spmm subgsum)
+        if (packed) {
+          // member-wise, straight from the resident half, in the member's own (ascending node) order: one warp per
+          // (member, 128 rows) piece, lane = column; independent of the bin's composition.  Runs while the last MMAs of the
+          // pass drain (it only reads the resident half).
+          const uint32_t pos_a = smem_u32(sm.pos), rbe_a = smem_u32(sm.rbe);
+          const uint32_t laneoff = (uint32_t)(((lane >> 2) << 4) | ((lane & 3) << 2));
+          int item = 0;
+          for (int mi = 0; mi < nm; ++mi) {
+            const int p0 = sm.mrow[mi], p1 = sm.mrow[mi + 1];
+            for (int c0p = p0, ch = 0; c0p < p1; c0p += TILE_M, ++ch, ++item) {
+              if ((item & (FZ_GW - 1)) != warp) continue;
+              const int pe = min(c0p + TILE_M, p1);
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+              int p = c0p;
+              for (; p + 3 < pe; p += 4) {
+                const uint32_t J0 = lds16(pos_a + 2 * p), J1 = lds16(pos_a + 2 * p + 2), J2 = lds16(pos_a + 2 * p + 4),
+                               J3 = lds16(pos_a + 2 * p + 6);
+                float v0, v1, v2, v3;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(hs_a + ((J0 << 4) ^ laneoff)));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(hs_a + ((J1 << 4) ^ laneoff)));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v2) : "r"(hs_a + ((J2 << 4) ^ laneoff)));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v3) : "r"(hs_a + ((J3 << 4) ^ laneoff)));
+                s0 += v0, s1 += v1, s2 += v2, s3 += v3;
+              }
+              for (; p < pe; ++p) {
+                float v0;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(hs_a + ((lds16(pos_a + 2 * p) << 4) ^ laneoff)));
+                s0 += v0;
+              }
+              const size_t slot = (size_t)sm.mg[mi] * tpg + ch;
+              K.psum[(((size_t)it * L + l) * tiles_per_layer + slot) * D + 32 * pass + lane] = (s0 + s1) + (s2 + s3);
+              if (h1_mode && it == it0) {  // the skipped iteration's column sums: (rows with an alive neighbour) x c
+                int c1n = 0;
+                for (int pp = c0p + lane; pp < pe; pp += 32) {
+                  const uint32_t J = lds16(pos_a + 2 * pp);
+                  uint32_t be;
+                  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(be) : "r"(rbe_a + 4 * (J >> 3)));
+                  c1n += (be >> 16) > (be & 0xffffu) ? 1 : 0;
+                }
+                c1n = warp_sum_i(c1n);
+                K.psum[(((size_t)0 * L + l) * tiles_per_layer + slot) * D + 32 * pass + lane] = (float)c1n * sm.c0[32 * pass + lane];
+              }
+            }
+          }
+        }
         mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // all MMAs of the pass (hence all gathers) are complete
-        // column sums of this half of the iteration's input embeddings (spmm subgsum): groups, then warps, fixed order
-        csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 8);
-        csum.y += __shfl_xor_sync(0xffffffffu, csum.y, 8);
-        csum.z += __shfl_xor_sync(0xffffffffu, csum.z, 8);
-        csum.w += __shfl_xor_sync(0xffffffffu, csum.w, 8);
-        csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 16);
-        csum.y += __shfl_xor_sync(0xffffffffu, csum.y, 16);
-        csum.z += __shfl_xor_sync(0xffffffffu, csum.z, 16);
-        csum.w += __shfl_xor_sync(0xffffffffu, csum.w, 16);
-        if (lane < 8) *reinterpret_cast<float4*>(&sm.red[warp][4 * q]) = csum;
-        gw_sync();
-        if (warp == 0) {
-          float s = 0.f;
+        if (packed) gw_sync();  // ... and every warp's column sums: the resident half may be overwritten from here on
+        if (!packed) {  // single unit: the sums of the rows every thread has walked; groups, then warps, fixed order
+          csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 8);
+          csum.y += __shfl_xor_sync(0xffffffffu, csum.y, 8);
+          csum.z += __shfl_xor_sync(0xffffffffu, csum.z, 8);
+          csum.w += __shfl_xor_sync(0xffffffffu, csum.w, 8);
+          csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 16);
+          csum.y += __shfl_xor_sync(0xffffffffu, csum.y, 16);
+          csum.z += __shfl_xor_sync(0xffffffffu, csum.z, 16);
+          csum.w += __shfl_xor_sync(0xffffffffu, csum.w, 16);
+          if (lane < 8) *reinterpret_cast<float4*>(&sm.red[warp][4 * q]) = csum;
+          gw_sync();
+          if (warp == 0) {
+            float s = 0.f;
 #pragma unroll
-          for (int w2 = 0; w2 < FZ_GW; ++w2) s += sm.red[w2][lane];
-          float* ps = K.psum + (((size_t)it * L + l) * tiles_per_layer + (size_t)g * tpg) * D + 32 * pass + lane;
-          ps[0] = s;
-          for (int t = 1; t < ntile; ++t) ps[(size_t)t * D] = 0.f;
-          if (h1_mode && it == it0) {  // the skipped iteration's column sums
-            float* ps0 = K.psum + (((size_t)0 * L + l) * tiles_per_layer + (size_t)g * tpg) * D + 32 * pass + lane;
-            ps0[0] = (float)sm.cnt0 * sm.c0[32 * pass + lane];
-            for (int t = 1; t < ntile; ++t) ps0[(size_t)t * D] = 0.f;
+            for (int w2 = 0; w2 < FZ_GW; ++w2) s += sm.red[w2][lane];
+            float* ps = K.psum + (((size_t)it * L + l) * tiles_per_layer + (size_t)g * tpg) * D + 32 * pass + lane;
+            ps[0] = s;
+            for (int t = 1; t < ntile; ++t) ps[(size_t)t * D] = 0.f;
+            if (h1_mode && it == it0) {  // the skipped iteration's column sums
+              float* ps0 = K.psum + (((size_t)0 * L + l) * tiles_per_layer + (size_t)g * tpg) * D + 32 * pass + lane;
+              ps0[0] = (float)sm.cnt0 * sm.c0[32 * pass + lane];
+              for (int t = 1; t < ntile; ++t) ps0[(size_t)t * D] = 0.f;
+            }
           }
         }
         FZ_CLK(c5);
@@ -709,7 +981,8 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
                 const int rr = 32 * lg + 4 * i + gi, rg = TILE_M * t + rr;
                 if (rg < n) {
                   const float4 v = lds128(stg_a + (uint32_t)rr * 128u + (uint32_t)((q ^ (rr & 7)) << 4));
-                  *reinterpret_cast<float4*>(outb + (size_t)(base + sm.rowv[rg]) * D + 32 * h + 4 * q) = v;
+                  const int rv = sm.rowv[rg];
+                  *reinterpret_cast<float4*>(outb + (size_t)((int)sm.mg[rv >> 10] * St + (rv & 1023)) * D + 32 * h + 4 * q) = v;
                 }
               }
               quad_sync(quad);
@@ -783,10 +1056,27 @@ static int fused_sm_count() {
 
 static size_t fused_order_off() { return md::FZ_WS_SPILL + (size_t)fused_sm_count() * md::FZ_SPILL_B; }
 
+// scratch behind the spill images: bin header, hand-out order, bin starts, members, node slot -> row code map
+static md::FusedBins fused_bins(unsigned char* ws, const md_graphs_t* g) {
+  const size_t nu = (size_t)g->n_graphs * (size_t)g->n_layers;
+  md::FusedBins b;
+  int* p = reinterpret_cast<int*>(ws + fused_order_off());
+  b.hdr = p;
+  b.order = p + 4;
+  b.bin_start = b.order + nu;
+  b.member = b.bin_start + nu + 1;
+  b.wpos = reinterpret_cast<uint16_t*>(b.member + nu + 1);
+  return b;
+}
+
 extern "C" int64_t md_fused_ws_bytes(const md_graphs_t* g) {
   if (!g) return 0;
-  return (int64_t)(fused_order_off() + sizeof(int) * (size_t)g->n_graphs * (size_t)g->n_layers);
+  const size_t nu = (size_t)g->n_graphs * (size_t)g->n_layers;
+  return (int64_t)(fused_order_off() + sizeof(int) * (3 * nu + 8) + sizeof(uint16_t) * (size_t)g->n_layers * (size_t)g->n_total + 64);
 }
+
+static int g_md_fused_pack = 0;
+extern "C" void md_debug_set_fused_pack(int32_t rows) { g_md_fused_pack = rows; }
 
 extern "C" int md_embed_fused(const md_graphs_t* g, const md_state_t* s, const md_weights_t* w, const md_work_t* k,
                               md_stream_t stream) {
@@ -806,10 +1096,11 @@ extern "C" int md_embed_fused(const md_graphs_t* g, const md_state_t* s, const m
   const int n_units = g->n_graphs * g->n_layers;
   const int nsm = fused_sm_count();
   const int grid = nsm < n_units ? nsm : n_units;
-  int* order = reinterpret_cast<int*>(ws + fused_order_off());
-  md::fused_prep_kernel<<<(n_units + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*g, *s, *w, ws, order, n_units);
+  const md::FusedBins bn = fused_bins(ws, g);
+  const int pack = (g_md_debug_flags & (1 << 19)) ? -1 : g_md_fused_pack;
+  md::fused_prep_kernel<<<2, 1024, 0, (cudaStream_t)stream>>>(*g, *s, *w, ws, bn, n_units, nsm, pack);
   MD_CHECK_LAUNCH();
-  md::embed_fused_kernel<<<grid, md::FZ_T, smem, (cudaStream_t)stream>>>(*g, *s, *w, *k, ws, order, n_units, g_md_debug_flags);
+  md::embed_fused_kernel<<<grid, md::FZ_T, smem, (cudaStream_t)stream>>>(*g, *s, *w, *k, ws, bn, g_md_debug_flags);
   MD_CHECK_LAUNCH();
   return 0;
 }

@@ -19,7 +19,12 @@ ap.add_argument("--cost", default="degree")
 ap.add_argument("--n", type=int, default=1000)
 ap.add_argument("--graphs", type=int, default=256)
 ap.add_argument("--every", type=int, default=8)
+ap.add_argument("--pack", type=int, default=0, help="md_debug_set_fused_pack: 0 = default budget, > 0 fixed, < 0 no packing")
+ap.add_argument("--legacy", action="store_true", help="md_embed_fused as it was before small units were packed (debug bit 19)")
 args = ap.parse_args()
+_lib.lib().md_debug_set_fused_pack(args.pack)
+if args.legacy:
+    _lib.lib().md_debug_set_flags(1 << 19)
 
 graphs = [gmm.gmm_graph(args.n, i, cost=args.cost) for i in range(args.graphs)]
 batch = mdb.GraphBatch(graphs, "cuda:0", args.cost)

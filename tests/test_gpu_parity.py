@@ -707,3 +707,69 @@ def test_unit_cost_h1_from_degrees_matches_materialised_iteration(path):
         assert torch.equal(a.label, b.label)
     finally:
         lib.md_debug_set_flags(0)
+
+
+@pytest.mark.parametrize("variant", ["unit", "degree"])
+def test_fused_packed_bins_bit_identical_to_units_alone(variant):
+    """md_embed_fused packs (graph, layer) units of few active rows into bins that one CTA processes together.  A unit's
+    arithmetic must not depend on its bin mates: embeddings, per-graph sums, Q and whole rollouts are BIT-identical for
+    every bin budget and with every unit alone (md_debug_set_fused_pack < 0); against the kernel as it was before packing
+    (md_debug_set_flags bit 19: single-unit path for everything) they agree within the embedding tolerance."""
+    from mdcommunity_b200 import gmm, _lib
+    mdb = _mdb()
+    lib = _lib.lib()
+    sizes = [1000, 40, 60, 300, 25, 1000, 90, 130, 200, 33, 500, 256, 257, 128, 64, 45, 31, 30, 29, 700, 26, 27, 50, 55]
+    graphs = [gmm.gmm_graph(n, 700 + i, cost=variant) for i, n in enumerate(sizes)]
+    batch = mdb.GraphBatch(graphs, cost=variant)
+    w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_%s.npz" % variant))), batch.device)
+
+    def trajectory(pack, flags=0, force=None):
+        lib.md_debug_set_fused_pack(pack)
+        lib.md_debug_set_flags(flags)
+        try:
+            ro = mdb.BatchRollout(batch, w, fused=True)
+            snaps = []
+            for t in range(48):
+                ro.forward()
+                if t % 6 == 0:
+                    snaps.append([x.clone() for x in (ro.h[1][0], ro.h[1][1], ro.psum, ro.q, ro.best, ro.n_act, ro.act_list)])
+                if force is not None:
+                    ro.best.copy_(force[t])
+                    snaps.append(None)
+                else:
+                    snaps.append(ro.best.clone())
+                ro.step()
+            res = ro.run()
+            torch.cuda.synchronize()
+            return snaps, res
+        finally:
+            lib.md_debug_set_fused_pack(0)
+            lib.md_debug_set_flags(0)
+
+    ref_snaps, ref_res = trajectory(-1)
+    for pack in (0, 256, 768):
+        snaps, res = trajectory(pack)
+        for a, b in zip(snaps, ref_snaps):
+            if isinstance(a, list):
+                for x, y in zip(a, b):
+                    assert torch.equal(x, y), pack
+            else:
+                assert torch.equal(a, b), pack
+        for k in ("score", "n_steps", "actions", "ranks"):
+            assert np.array_equal(res[k], ref_res[k]), (pack, k)
+    # the pre-packing kernel on the same action sequence: embeddings 2e-5, Q within the tolerance
+    forced = [s for s in ref_snaps if not isinstance(s, list)]
+    old_snaps, _ = trajectory(0, flags=1 << 19, force=forced)
+    S = batch.S
+    for a, b in zip([s for s in old_snaps if isinstance(s, list)], [s for s in ref_snaps if isinstance(s, list)]):
+        assert torch.equal(a[5], b[5]) and torch.equal(a[6], b[6])
+        n_act = a[5].cpu().numpy()
+        for i in range(batch.B):
+            n = int(n_act[i])
+            if n == 0:
+                continue
+            ids = a[6][i * S:i * S + n].long()
+            for l in range(2):
+                assert float((a[l][ids] - b[l][ids]).abs().max()) <= 2e-5, (i, l)
+            qa, qb = a[3][ids], b[3][ids]
+            assert float(((qa - qb).abs() - (Q_RTOL * qb.abs() + Q_ATOL)).max()) <= 0, i
