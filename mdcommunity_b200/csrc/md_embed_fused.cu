@@ -45,11 +45,12 @@ using namespace umma;
 constexpr int FZ_ROWS = 1024;          // largest stride (node slots per graph) the resident path handles
 constexpr int FZ_GW = 8;               // gather / epilogue warps
 constexpr int FZ_GT = FZ_GW * 32;
-constexpr int FZ_T = FZ_GT + 32;       // + the MMA / bulk-copy warp
+constexpr int FZ_T = FZ_GT;            // no separate MMA warp: a ninth warp would cap every thread at 168 registers (three warps on
+                                       // one of the SM's four register files), and at 168 ptxas serialises the gather's four load chains
 constexpr int FZ_IDX_CAP = 8192;       // alive directed edges of one unit cached in shared memory
 constexpr int FZ_LONG = 24;            // rows with more alive neighbours are summed by the whole warp (< 31: exact sort buckets)
 constexpr uint32_t FZ_TILE_B = 16384;  // one 128-row x 128-byte tile
-constexpr uint32_t FZ_WPASS_B = 40960; // B operands of one pass: W13 hi, W13 lo, W23 hi, W23 lo (tf32), [W13|W23] fp16
+constexpr uint32_t FZ_WPASS_B = 16384; // B operands of one pass: [W13 hi | W13 lo] and [W23 hi | W23 lo], fp16, 64 rows x 128 B each
 constexpr size_t FZ_WS_CTR = 2 * FZ_WPASS_B;
 constexpr size_t FZ_WS_SPILL = FZ_WS_CTR + 1024;
 constexpr size_t FZ_SPILL_B = 8 * FZ_TILE_B;
@@ -71,9 +72,9 @@ struct FusedBins {     // written by fused_prep_kernel, read by embed_fused_kern
 
 struct FusedSmem {
   unsigned char Hs[8 * FZ_TILE_B];  // resident column half of the unit's embeddings (SWIZZLE_128B tiles)
-  unsigned char P[FZ_TILE_B];       // staging: neighbour sums of one tile, raw fp32
-  unsigned char LO[FZ_TILE_B];      // staging: fp16 remainders, row = [P_lo (32) | H_lo (32)]
-  unsigned char Wt[FZ_WPASS_B];     // B operands of the running pass
+  unsigned char P[FZ_TILE_B];       // staging: neighbour sums of one tile as fp16 pairs, row = [P_hi (32) | P_lo (32)]
+  unsigned char LO[FZ_TILE_B];      // staging: the rows' own embeddings the same way, row = [H_hi (32) | H_lo (32)]
+  unsigned char Wt[2 * FZ_WPASS_B]; // B operands of both passes (loaded once per CTA)
   uint16_t idx[FZ_IDX_CAP + 64];    // neighbour entries of the unit's alive CSR (see nbrJ); setup: sort counters
   uint16_t pos[FZ_ROWS];            // single big unit: graph-local node id -> row (degree-sorted compact order);
                                     // packed bin: compact index (member row offset + p) -> J code of the row
@@ -90,7 +91,9 @@ struct FusedSmem {
   int cnt0;                         // H1 mode: rows of the unit with an alive neighbour
   alignas(128) float zrow[32];      // one all-zero 128-byte row: where a finished row's lane group points its loads
   uint16_t bbase[32];
-  uint64_t bar_full, bar_empty, bar_w, bar_h, bar_res;
+  uint64_t bar_empty, bar_w, bar_h;
+  int arrive_cnt;                   // warps that have staged their rows (8 per tile; the last one issues the tile's MMAs)
+  int long_ctr;                     // tickets for the long rows of a pass's first tile
   uint32_t tmem;
   int unit;
 };
@@ -121,10 +124,21 @@ __device__ __forceinline__ void add4(float4& a, const float4& b) {
   a.z += b.z;
   a.w += b.w;
 }
-__device__ __forceinline__ uint2 lo_f16x4(const float4& v) {
-  const __half2 a = __floats2half2_rn(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y));
-  const __half2 b = __floats2half2_rn(v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
-  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits (|x| >= 2^-14; below that 2^-25 absolute)
+__device__ __forceinline__ void split_f16x4(const float4& v, uint2& hi, uint2& lo) {
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+// staging row `rt` of a [hi (32) | lo (32)] fp16 tile: lane q of the row's group owns columns 4q .. 4q + 3
+__device__ __forceinline__ void stage_f16(unsigned char* tile, int rt, int q, const float4& v) {
+  uint2 hi, lo;
+  split_f16x4(v, hi, lo);
+  const uint32_t ro = (uint32_t)rt * 128u + 8 * (q & 1);
+  *reinterpret_cast<uint2*>(tile + ro + (((q >> 1) ^ (rt & 7)) << 4)) = hi;
+  *reinterpret_cast<uint2*>(tile + ro + (((4 + (q >> 1)) ^ (rt & 7)) << 4)) = lo;
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -181,16 +195,15 @@ __global__ void __launch_bounds__(1024) fused_prep_kernel(md_graphs_t G, md_stat
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (blockIdx.x == 1) {
     for (int i = tid; i < 2 * 64 * 32; i += 1024) {
-      const int p = i >> 11, n = (i >> 5) & 63, k = i & 31;
+      const int p = i >> 11, n = (i >> 5) & 63, k = i & 31;  // pass, output column (B operand row), input column of the half
       const float w13 = W.w13[(32 * p + k) * D + n], w23 = W.w23[(32 * p + k) * D + n];
       unsigned char* img = ws + (size_t)p * FZ_WPASS_B;
-      const uint32_t off = sw128_off(n, k >> 2) + 4 * (k & 3);
-      *reinterpret_cast<float*>(img + off) = tf32_hi(w13);
-      *reinterpret_cast<float*>(img + 8192 + off) = w13 - tf32_hi(w13);
-      *reinterpret_cast<float*>(img + 16384 + off) = tf32_hi(w23);
-      *reinterpret_cast<float*>(img + 24576 + off) = w23 - tf32_hi(w23);
-      *reinterpret_cast<__half*>(img + 32768 + sw128_off(n, k >> 3) + 2 * (k & 7)) = __float2half_rn(w13);
-      *reinterpret_cast<__half*>(img + 32768 + sw128_off(n, 4 + (k >> 3)) + 2 * (k & 7)) = __float2half_rn(w23);
+      const __half h13 = __float2half_rn(w13), h23 = __float2half_rn(w23);
+      const uint32_t ohi = sw128_off(n, k >> 3) + 2 * (k & 7), olo = sw128_off(n, 4 + (k >> 3)) + 2 * (k & 7);
+      *reinterpret_cast<__half*>(img + ohi) = h13;
+      *reinterpret_cast<__half*>(img + olo) = __float2half_rn(w13 - __half2float(h13));
+      *reinterpret_cast<__half*>(img + 8192 + ohi) = h23;
+      *reinterpret_cast<__half*>(img + 8192 + olo) = __float2half_rn(w23 - __half2float(h23));
     }
     return;
   }
@@ -345,14 +358,14 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
   const int L = G.n_layers, St = G.stride, B = G.n_graphs;
   const int tpg = St / TILE_M, tiles_per_layer = B * tpg;
   if (tid == 0) {
-    mbar_init(&sm.bar_full, FZ_GW);
+    sm.arrive_cnt = 0;
+    sm.long_ctr = 0;
     mbar_init(&sm.bar_empty, 1);
     mbar_init(&sm.bar_w, 1);
     mbar_init(&sm.bar_h, 1);
-    mbar_init(&sm.bar_res, 1);
     mbar_fence_init();
   }
-  if (warp == FZ_GW) tmem_alloc(&sm.tmem, 512);
+  if (warp == 0) tmem_alloc(&sm.tmem, 512);
   // H1 mode (unit cost; same identity as md_agg.cu's agg_deg_kernel<1>): the features are [x, x], x = alive degree / max,
   // so the first embedding is the SAME vector c = relu(w0 + w1) / |relu(w0 + w1)| for every node with an alive neighbour,
   // the first neighbour sum is deg(v) c and the embedding after iteration 0 is H1(d) = normalise(relu(d a + b)) with
@@ -395,12 +408,12 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
   uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0;  // gather sub-phases
   int n_units_done = 0;
   uint32_t uses = 0;    // staging-tile hand-offs so far (same sequence in the gather warps and the MMA warp)
-  uint32_t wloads = 0;  // weight images consumed (MMA warp)
+  bool w_ready = false; // this warp has seen the weight images arrive
+  int long_base = 0;    // first long-row ticket of the next first tile (the same in every thread)
   uint32_t hloads = 0;  // resident-half reloads consumed (gather warps)
-  uint32_t passes = 0;  // passes started (MMA warp: phases of bar_res)
-  if (warp == FZ_GW && elect_one()) {
-    mbar_arrive_expect_tx(&sm.bar_w, FZ_WPASS_B);
-    bulk_g2s(sm.Wt, wimg, FZ_WPASS_B, &sm.bar_w);
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&sm.bar_w, 2 * FZ_WPASS_B);
+    bulk_g2s(sm.Wt, wimg, 2 * FZ_WPASS_B, &sm.bar_w);
   }
 
   for (;;) {
@@ -449,74 +462,15 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     const int ntile = (n + TILE_M - 1) / TILE_M;
     const int g = sm.mg[0], base = g * St;  // (single-unit path; the packed path reads the member tables)
 
-    if (warp == FZ_GW) {
-      // ============================== MMA / bulk-copy warp (warp-uniform control flow) ==============================
-      const uint32_t idt = idesc(FMT_TF32, 128, 64), idb = idesc(FMT_F16, 128, 64);
-      const uint64_t dP = desc_k_sw128(smem_u32(sm.P), 0), dLO = desc_k_sw128(smem_u32(sm.LO), 0);
-      const uint64_t dH0 = desc_k_sw128(smem_u32(sm.Hs), 0);
-      const uint64_t b13h = desc_k_sw128(smem_u32(sm.Wt), 0), b13l = desc_k_sw128(smem_u32(sm.Wt) + 8192, 0);
-      const uint64_t b23h = desc_k_sw128(smem_u32(sm.Wt) + 16384, 0), b23l = desc_k_sw128(smem_u32(sm.Wt) + 24576, 0);
-      const uint64_t bbf = desc_k_sw128(smem_u32(sm.Wt) + 32768, 0);
-      for (int it = it0; it < MD_BP_ITERS; ++it) {
-        for (int pass = 0; pass < 2; ++pass) {
-          FZ_CLK(c3);
-          mbar_wait(&sm.bar_w, wloads & 1);
-          ++wloads;
-          mbar_wait(&sm.bar_res, passes & 1);  // resident half in place, accumulators of the previous iteration drained
-          ++passes;
-          FZ_CLK(c0);
-          tc_fence_after();
-          // own-embedding term first: it needs nothing from the gather
-          if (elect_one()) {
-            for (int t = 0; t < ntile; ++t) {
-              const uint32_t d = tbase + 64 * t;
-              const uint64_t dH = dH0 + (uint64_t)((t * FZ_TILE_B) >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ko = 2 * k;  // 32 bytes per K step, in 16-byte units
-                mma_tf32(d, dH + ko, b23h + ko, idt, (pass | k) != 0);
-                mma_tf32(d, dH + ko, b23l + ko, idt, 1);
-              }
-            }
-          }
-          __syncwarp();
-          for (int t = 0; t < ntile; ++t) {
-            FZ_CLK(c1);
-            mbar_wait(&sm.bar_full, uses & 1);
-            FZ_CLK(c2);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t d = tbase + 64 * t;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ko = 2 * k;
-                mma_tf32(d, dP + ko, b13h + ko, idt, 1);
-                mma_tf32(d, dP + ko, b13l + ko, idt, 1);
-                mma_f16(d, dLO + ko, bbf + ko, idb, 1);
-              }
-              mma_commit(&sm.bar_empty);
-            }
-            __syncwarp();
-            ++uses;
-          }
-          FZ_CLK(c1);
-          // pass complete -> the weight tile is free: fetch the other pass's image
-          mbar_wait(&sm.bar_empty, (uses - 1) & 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&sm.bar_w, FZ_WPASS_B);
-            bulk_g2s(sm.Wt, wimg + (size_t)(pass ^ 1) * FZ_WPASS_B, FZ_WPASS_B, &sm.bar_w);
-          }
-          __syncwarp();
-        }
-      }
-      continue;
-    }
-
     // ================================== gather / epilogue warps ==================================
     FZ_CLK(c7);
     ++n_units_done;
     const int gtid = tid;  // 0..FZ_GT-1
     const int gi = lane >> 3, q = lane & 7;
+    // tile row of lane group gi in sweep k (k = 0..3): the warp's four rows are neighbours in the degree order (equal length)
+    // with swizzle phases {b, b + 1, b + 4, b + 5}: their 8-byte staging stores then cover all 32 banks (two of the rows use
+    // chunks 0..3, two use chunks 4..7) instead of piling four rows onto the same 16
+    const int rt_w = 8 * (warp >> 1) + 2 * (warp & 1) + (gi & 1) + 4 * (gi >> 1);
     const int e0 = sm.me0[0];
     const int nnz = sm.nent;
     const int32_t* __restrict__ aptr_l = S.aptr[l];
@@ -632,12 +586,14 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     auto ld_J = [&](uint32_t J) -> F4P { return lds128p(hs_a + ((J ^ (uint32_t)q) << 4)); };
 
     FZ_CLK(c0);
+    float inv0[4] = {0.f, 0.f, 0.f, 0.f};
     for (int it = it0; it < MD_BP_ITERS; ++it) {
       for (int pass = 0; pass < 2; ++pass) {
         // ---------------- resident column half ----------------
         if (it == it0) {
           if (uses > 0) mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // every earlier MMA (they read Hs) has completed
           float xf[4], dmx[4];  // the thread's (up to) 4 rows: fetch the features first, the loads are independent
+          // (inv0[]: the rows' inverse norms, formed in pass 0 and reused in pass 1 -- declared outside the pass loop)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int r = gtid + FZ_GT * k;
@@ -656,7 +612,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             c1n = warp_sum_i(c1n);
             if (lane == 0 && c1n) atomicAdd(&sm.cnt0, c1n);
           }
-#pragma unroll 1
+#pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int r = gtid + FZ_GT * k;
             if (r >= ntile * TILE_M) break;
@@ -675,18 +631,21 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             }
             const float4* w0v = reinterpret_cast<const float4*>(sm.wn2l);
             const float4* w1v = reinterpret_cast<const float4*>(sm.wn2l + D);
-            float ss = 0.f;
+            if (pass == 0) {
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains
 #pragma unroll
-            for (int c4 = 0; c4 < D / 4; ++c4) {
-              const float4 w0 = w0v[c4], w1 = w1v[c4];
-              const float a0 = fmaxf(fmaf(x1, w1.x, x0 * w0.x), 0.f), a1 = fmaxf(fmaf(x1, w1.y, x0 * w0.y), 0.f);
-              const float a2 = fmaxf(fmaf(x1, w1.z, x0 * w0.z), 0.f), a3 = fmaxf(fmaf(x1, w1.w, x0 * w0.w), 0.f);
-              ss = fmaf(a0, a0, ss);
-              ss = fmaf(a1, a1, ss);
-              ss = fmaf(a2, a2, ss);
-              ss = fmaf(a3, a3, ss);
+              for (int c4 = 0; c4 < D / 4; ++c4) {
+                const float4 w0 = w0v[c4], w1 = w1v[c4];
+                const float a0 = fmaxf(fmaf(x1, w1.x, x0 * w0.x), 0.f), a1 = fmaxf(fmaf(x1, w1.y, x0 * w0.y), 0.f);
+                const float a2 = fmaxf(fmaf(x1, w1.z, x0 * w0.z), 0.f), a3 = fmaxf(fmaf(x1, w1.w, x0 * w0.w), 0.f);
+                s0 = fmaf(a0, a0, s0);
+                s1 = fmaf(a1, a1, s1);
+                s2 = fmaf(a2, a2, s2);
+                s3 = fmaf(a3, a3, s3);
+              }
+              inv0[k] = __frcp_rn(fmaxf(sqrtf((s0 + s1) + (s2 + s3)), 1e-12f));
             }
-            const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
+            const float inv = inv0[k];
             unsigned char* rowp = sm.Hs + (uint32_t)r * 128u;
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
@@ -712,7 +671,6 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           ++hloads;
           FZ_CLK(c2);
         }  // it > 0, pass 0: written by the epilogue below
-        if (gtid == 0) mbar_arrive(&sm.bar_res);
 
         // ---------------- tiles: gather -> staging -> MMA ----------------
         // Tile row 32*k + 4*warp + gi (k = 0..3): a lane group walks FOUR rows at once, one neighbour of each per step
@@ -730,7 +688,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           bool all_cached = true;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int rt = 32 * k + 4 * warp + gi, r = TILE_M * t + rt;
+            const int rt = 32 * k + rt_w, r = TILE_M * t + rt;
             uint32_t be = 0;
             if (r < n && rt >= nl_t) be = sm.rbe[r];
             ia[k] = idx_a + 2 * (be & 0xffffu);
@@ -769,7 +727,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           float4 own4[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int rt = 32 * k + 4 * warp + gi, r = TILE_M * t + rt;
+            const int rt = 32 * k + rt_w, r = TILE_M * t + rt;
             own4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < n && rt >= nl_t) own4[k] = unpack4(ld_J((uint32_t)((r << 3) | (r & 7))));
           }
@@ -784,18 +742,19 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int rt = 32 * k + 4 * warp + gi;
+            const int rt = 32 * k + rt_w;
             if (rt >= nl_t) {
-              const float4 accf = unpack4(a4[k]);
-              const uint32_t ro = (uint32_t)rt * 128u;
-              *reinterpret_cast<float4*>(sm.P + ro + ((q ^ (rt & 7)) << 4)) = accf;
-              *reinterpret_cast<uint2*>(sm.LO + ro + (((q >> 1) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_f16x4(accf);
-              *reinterpret_cast<uint2*>(sm.LO + ro + (((4 + (q >> 1)) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_f16x4(own4[k]);
+              stage_f16(sm.P, rt, q, unpack4(a4[k]));
+              stage_f16(sm.LO, rt, q, own4[k]);
             }
           }
           FZ_CLK(d3);
-          // long rows of this tile: one warp per row, lane group gi takes every 4th neighbour
-          for (int rt = warp; rt < nl_t; rt += FZ_GW) {
+          // long rows of this tile: one warp per row, lane group gi takes every 4th neighbour.  In the first tile (where all
+          // of them are unless more than 128 rows are long) the warps TAKE rows from a counter as they become free -- a static
+          // deal left the warp with the largest hubs behind at every tile -- which changes who sums a row, not how: tickets
+          // count on from long_base (every warp ends a tile with one ticket beyond its rows; two uses are always separated
+          // by the barrier at the end of a pass).
+          auto long_row = [&](int rt) {
             const int r = TILE_M * t + rt;
             const uint32_t be = sm.rbe[r];
             const int en = (int)(be >> 16);
@@ -827,17 +786,72 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             a.w += __shfl_xor_sync(0xffffffffu, a.w, 16);
             if (gi == 0) {
               const float4 own = unpack4(ld_J((uint32_t)((r << 3) | (r & 7))));
-              if (!packed) add4(csum, own);
-              const uint32_t ro = (uint32_t)rt * 128u;
-              *reinterpret_cast<float4*>(sm.P + ro + ((q ^ (rt & 7)) << 4)) = a;
-              *reinterpret_cast<uint2*>(sm.LO + ro + (((q >> 1) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_f16x4(a);
-              *reinterpret_cast<uint2*>(sm.LO + ro + (((4 + (q >> 1)) ^ (rt & 7)) << 4) + 8 * (q & 1)) = lo_f16x4(own);
+              stage_f16(sm.P, rt, q, a);
+              stage_f16(sm.LO, rt, q, own);
+            }
+          };
+          if (nl_t > 0) {
+            if (t == 0 && !(dbg & (1 << 20))) {
+              for (;;) {
+                int tk = 0;
+                if (lane == 0) tk = atomicAdd(&sm.long_ctr, 1);
+                tk = __shfl_sync(0xffffffffu, tk, 0) - long_base;
+                if (tk >= nl_t) break;
+                long_row(tk);
+              }
+              long_base += nl_t + FZ_GW;
+            } else {
+              for (int rt = warp; rt < nl_t; rt += FZ_GW) long_row(rt);
+            }
+            // single-unit path: the long rows' part of the column sums, by a FIXED deal (the sums must not depend on who
+            // happened to take a row)
+            if (!packed && gi == 0) {
+              for (int rt = warp; rt < nl_t; rt += FZ_GW) {
+                const int r = TILE_M * t + rt;
+                add4(csum, unpack4(ld_J((uint32_t)((r << 3) | (r & 7)))));
+              }
             }
           }
           FZ_CLK(d4);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.bar_full);
+          // the LAST warp to get here issues the tile's MMAs (8 arrivals per tile; a warp can only arrive for tile t + 1 after
+          // the MMAs of tile t have completed, so the groups of 8 never mix)
+          int last = 0;
+          if (lane == 0) {
+            __threadfence_block();
+            last = (atomicAdd(&sm.arrive_cnt, 1) & (FZ_GW - 1)) == FZ_GW - 1;
+            __threadfence_block();
+          }
+          if (__ballot_sync(0xffffffffu, last != 0) != 0u) {  // (a vote: the compiler keeps the MMA issue on the uniform path)
+            // a.w = a_hi.w_hi + a_hi.w_lo + a_lo.w_hi with every factor in fp16 (products exact in the fp32 accumulator, the
+            // dropped a_lo.w_lo is 2^-22 of the term): 12 kind::f16 MMAs (K = 16) over the two staging tiles
+            // [P_hi | P_lo], [H_hi | H_lo] and the pass's weight tiles [W13_hi | W13_lo], [W23_hi | W23_lo]
+            if (!w_ready) {
+              mbar_wait(&sm.bar_w, 0);
+              w_ready = true;
+            }
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t idb = idesc(FMT_F16, 128, 64);
+              const uint64_t dP = desc_k_sw128(smem_u32(sm.P), 0), dH = desc_k_sw128(smem_u32(sm.LO), 0);
+              const uint64_t b13 = desc_k_sw128(smem_u32(sm.Wt) + pass * FZ_WPASS_B, 0);
+              const uint64_t b23 = desc_k_sw128(smem_u32(sm.Wt) + pass * FZ_WPASS_B + 8192, 0);
+              const uint32_t d = tbase + 64 * t;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {  // 32 bytes (16 halves) per K step; hi halves at bytes 0..63, lo at 64..127
+                const uint64_t ko = 2 * k;
+                mma_f16(d, dP + ko, b13 + ko, idb, (pass | k) != 0);
+                mma_f16(d, dP + ko, b13 + 4 + ko, idb, 1);
+                mma_f16(d, dP + 4 + ko, b13 + ko, idb, 1);
+                mma_f16(d, dH + ko, b23 + ko, idb, 1);
+                mma_f16(d, dH + ko, b23 + 4 + ko, idb, 1);
+                mma_f16(d, dH + 4 + ko, b23 + ko, idb, 1);
+              }
+              mma_commit(&sm.bar_empty);
+            }
+            __syncwarp();
+          }
           ++uses;
           FZ_CLK(d5);
         }
@@ -923,27 +937,30 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
       // One thread per row holds the 64 outputs.  Columns 0..31 go straight into the resident buffer.  Everything bound for
       // global memory is first laid out in the (now idle) staging tiles -- P for warps 0..3, LO for warps 4..7 -- because
       // 16-byte stores scattered at a 128-byte stride cost ~1 cycle each on the SM (measured: 10 k cycles per epilogue):
-      // the scratch image leaves as ONE bulk copy per tile, the final embeddings as fully coalesced 128-byte row pieces.
+      // the scratch image leaves as one 4 KB bulk copy per warp and tile (a warp's 32 rows are contiguous in the tile, so
+      // the warps of a tile need no barrier among themselves), the final embeddings as fully coalesced 128-byte row pieces.
       tc_fence_after();
       {
         const int quad = warp >> 2, lg = warp & 3;
         unsigned char* const stg = quad ? sm.LO : sm.P;
         const uint32_t stg_a = smem_u32(stg);
         const bool last = it + 1 == MD_BP_ITERS;
-        const bool issuer = lg == 0 && lane == 0;
         for (int t = quad; t < ntile; t += FZ_GW / 4) {
           const uint32_t taddr = tbase + ((uint32_t)(32 * lg) << 16) + 64 * t;
           float x[64];
 #pragma unroll
           for (int c0 = 0; c0 < 64; c0 += 16) tmem_ld16(taddr + c0, *reinterpret_cast<float(*)[16]>(&x[c0]));
           tmem_ld_wait();
-          float ss = 0.f;
+          float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;  // four chains
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            x[c] = fmaxf(x[c], 0.f);
-            ss = fmaf(x[c], x[c], ss);
+          for (int c = 0; c < 64; c += 4) {
+            x[c] = fmaxf(x[c], 0.f), x[c + 1] = fmaxf(x[c + 1], 0.f), x[c + 2] = fmaxf(x[c + 2], 0.f), x[c + 3] = fmaxf(x[c + 3], 0.f);
+            ss0 = fmaf(x[c], x[c], ss0);
+            ss1 = fmaf(x[c + 1], x[c + 1], ss1);
+            ss2 = fmaf(x[c + 2], x[c + 2], ss2);
+            ss3 = fmaf(x[c + 3], x[c + 3], ss3);
           }
-          const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
+          const float inv = __frcp_rn(fmaxf(sqrtf((ss0 + ss1) + (ss2 + ss3)), 1e-12f));
           const int rt = 32 * lg + lane, r = TILE_M * t + rt;
           FZ_CLK(c6);
           if (!last) {
@@ -952,18 +969,18 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             for (int ch = 0; ch < 8; ++ch)
               *reinterpret_cast<float4*>(hp + ((ch ^ (rt & 7)) << 4)) =
                   make_float4(x[4 * ch] * inv, x[4 * ch + 1] * inv, x[4 * ch + 2] * inv, x[4 * ch + 3] * inv);
-            if (t != quad) {  // the previous tile's bulk copy must have read the staging tile
-              if (issuer) bulk_wait_read0();
-              quad_sync(quad);
+            if (t != quad) {  // this warp's previous bulk copy must have read its rows of the staging tile
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
             }
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch)
               *reinterpret_cast<float4*>(stg + (uint32_t)rt * 128u + ((ch ^ (rt & 7)) << 4)) =
                   make_float4(x[32 + 4 * ch] * inv, x[33 + 4 * ch] * inv, x[34 + 4 * ch] * inv, x[35 + 4 * ch] * inv);
             fence_proxy_async_smem();
-            quad_sync(quad);
-            if (issuer) {
-              bulk_s2g(spill + (size_t)t * FZ_TILE_B, stg, FZ_TILE_B);
+            __syncwarp();
+            if (lane == 0) {
+              bulk_s2g(spill + (size_t)t * FZ_TILE_B + (uint32_t)lg * 4096u, stg + (uint32_t)lg * 4096u, 4096u);
               bulk_commit();
             }
           } else {
@@ -974,7 +991,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
               for (int ch = 0; ch < 8; ++ch)
                 *reinterpret_cast<float4*>(stg + (uint32_t)rt * 128u + ((ch ^ (rt & 7)) << 4)) = make_float4(
                     x[32 * h + 4 * ch] * inv, x[32 * h + 4 * ch + 1] * inv, x[32 * h + 4 * ch + 2] * inv, x[32 * h + 4 * ch + 3] * inv);
-              quad_sync(quad);
+              __syncwarp();  // (the warp reads back only the 32 rows it has written itself)
               // copy-out: 8 lanes per row, 4 rows per instruction, 128 contiguous bytes per row
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -985,12 +1002,12 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
                   *reinterpret_cast<float4*>(outb + (size_t)((int)sm.mg[rv >> 10] * St + (rv & 1023)) * D + 32 * h + 4 * q) = v;
                 }
               }
-              quad_sync(quad);
+              __syncwarp();
             }
           }
           FZ_CLK(c8);
         }
-        if (!last && issuer) bulk_wait0();  // scratch image complete before it is fetched back for pass 1
+        if (!last && lane == 0) bulk_wait0();  // this warp's pieces of the scratch image are complete (fetched back for pass 1)
       }
       fence_proxy_async_smem();  // the resident half is read by the tensor core (async proxy) next
       tc_fence_before();
@@ -1015,10 +1032,10 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
 #endif
 
   // teardown: the MMA warp still has one weight-image copy in flight
-  if (warp == FZ_GW) mbar_wait(&sm.bar_w, wloads & 1);
+  if (tid == 0) mbar_wait(&sm.bar_w, 0);  // (a CTA that got no bin: its weight copy is still in flight)
   tc_fence_before();
   __syncthreads();
-  if (warp == FZ_GW) tmem_dealloc(tbase, 512);
+  if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
 }  // namespace md

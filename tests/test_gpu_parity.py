@@ -725,7 +725,7 @@ def test_fused_packed_bins_bit_identical_to_units_alone(variant):
 
     def trajectory(pack, flags=0, force=None):
         lib.md_debug_set_fused_pack(pack)
-        lib.md_debug_set_flags(flags)
+        lib.md_debug_set_flags(flags | int(os.environ.get("MDB200_TEST_FLAGS", "0")))
         try:
             ro = mdb.BatchRollout(batch, w, fused=True)
             snaps = []
@@ -749,12 +749,16 @@ def test_fused_packed_bins_bit_identical_to_units_alone(variant):
     ref_snaps, ref_res = trajectory(-1)
     for pack in (0, 256, 768):
         snaps, res = trajectory(pack)
-        for a, b in zip(snaps, ref_snaps):
+        for si, (a, b) in enumerate(zip(snaps, ref_snaps)):
             if isinstance(a, list):
-                for x, y in zip(a, b):
-                    assert torch.equal(x, y), pack
+                for xi, (x, y) in enumerate(zip(a, b)):
+                    if not torch.equal(x, y):
+                        bad = (x != y).nonzero().flatten()
+                        raise AssertionError("pack %d snapshot %d tensor %d (h0 h1 psum q best n_act act_list): %d entries differ, "
+                                             "first at %d, max |d| %.3e" % (pack, si, xi, bad.numel(), int(bad[0]),
+                                                                           float((x.double() - y.double()).abs().max())))
             else:
-                assert torch.equal(a, b), pack
+                assert torch.equal(a, b), (pack, si)
         for k in ("score", "n_steps", "actions", "ranks"):
             assert np.array_equal(res[k], ref_res[k]), (pack, k)
     # the pre-packing kernel on the same action sequence: embeddings 2e-5, Q within the tolerance
