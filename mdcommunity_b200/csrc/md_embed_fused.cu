@@ -43,7 +43,13 @@ namespace md {
 using namespace umma;
 
 constexpr int FZ_ROWS = 1024;          // largest stride (node slots per graph) the resident path handles
-constexpr int FZ_GW = 8;               // gather / epilogue warps
+#ifndef FZ_WARPS
+#define FZ_WARPS 16
+#endif
+constexpr int FZ_GW = FZ_WARPS;        // warps of the CTA (8 or 16); all of them gather, warps 0..7 run the epilogue
+constexpr int FZ_RPT = 1024 / (FZ_GW * 32);   // rows of a unit per thread (sort, first-embedding fill)
+constexpr int FZ_RPG = 128 / (4 * FZ_GW);     // rows of a tile per lane group (gather)
+static_assert(FZ_GW == 8 || FZ_GW == 16, "8 or 16 warps");
 constexpr int FZ_GT = FZ_GW * 32;
 constexpr int FZ_T = FZ_GT;            // no separate MMA warp: a ninth warp would cap every thread at 168 registers (three warps on
                                        // one of the SM's four register files), and at 168 ptxas serialises the gather's four load chains
@@ -470,7 +476,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     // tile row of lane group gi in sweep k (k = 0..3): the warp's four rows are neighbours in the degree order (equal length)
     // with swizzle phases {b, b + 1, b + 4, b + 5}: their 8-byte staging stores then cover all 32 banks (two of the rows use
     // chunks 0..3, two use chunks 4..7) instead of piling four rows onto the same 16
-    const int rt_w = 8 * (warp >> 1) + 2 * (warp & 1) + (gi & 1) + 4 * (gi >> 1);
+    const int rt_w = 8 * (warp >> 1) + 2 * (warp & 1) + 4 * (gi & 1) + (gi >> 1);
     const int e0 = sm.me0[0];
     const int nnz = sm.nent;
     const int32_t* __restrict__ aptr_l = S.aptr[l];
@@ -501,9 +507,9 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
       uint16_t* cnt = sm.idx;  // [32 chunks of 32 rows][32 buckets], reused by the neighbour cache afterwards
       for (int i = gtid; i < 1024; i += FZ_GT) cnt[i] = 0;
       gw_sync();
-      int b_[4], rank_[4], beg_[4], d_[4], v_[4];
+      int b_[FZ_RPT], rank_[FZ_RPT], beg_[FZ_RPT], d_[FZ_RPT], v_[FZ_RPT];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < FZ_RPT; ++k) {
         const int c = warp + FZ_GW * k, p = 32 * c + lane;
         const bool valid = p < n;
         int a0 = 0, a1 = 0;
@@ -540,7 +546,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
       }
       gw_sync();
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < FZ_RPT; ++k) {
         const int c = warp + FZ_GW * k;
         if (b_[k] < 32) {
           const int r = sm.bbase[b_[k]] + cnt[c * 32 + b_[k]] + rank_[k];
@@ -586,16 +592,16 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     auto ld_J = [&](uint32_t J) -> F4P { return lds128p(hs_a + ((J ^ (uint32_t)q) << 4)); };
 
     FZ_CLK(c0);
-    float inv0[4] = {0.f, 0.f, 0.f, 0.f};
+    float inv0[FZ_RPT] = {};
     for (int it = it0; it < MD_BP_ITERS; ++it) {
       for (int pass = 0; pass < 2; ++pass) {
         // ---------------- resident column half ----------------
         if (it == it0) {
           if (uses > 0) mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // every earlier MMA (they read Hs) has completed
-          float xf[4], dmx[4];  // the thread's (up to) 4 rows: fetch the features first, the loads are independent
+          float xf[FZ_RPT], dmx[FZ_RPT];  // the thread's (up to) FZ_RPT rows: fetch the features first, the loads are independent
           // (inv0[]: the rows' inverse norms, formed in pass 0 and reused in pass 1 -- declared outside the pass loop)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < FZ_RPT; ++k) {
             const int r = gtid + FZ_GT * k;
             xf[k] = 0.f, dmx[k] = 1.f;
             if (r < n) {
@@ -608,12 +614,12 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           if (h1_mode && pass == 0 && !packed) {  // iteration 0's column sums are (rows with an alive neighbour) x c: count them
             int c1n = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) c1n += xf[k] > 0.f ? 1 : 0;
+            for (int k = 0; k < FZ_RPT; ++k) c1n += xf[k] > 0.f ? 1 : 0;
             c1n = warp_sum_i(c1n);
             if (lane == 0 && c1n) atomicAdd(&sm.cnt0, c1n);
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < FZ_RPT; ++k) {
             const int r = gtid + FZ_GT * k;
             if (r >= ntile * TILE_M) break;
             float x0 = 0.f, x1 = 0.f;
@@ -681,14 +687,14 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = 0; t < ntile; ++t) {
           const int nl_t = min(max(n_long - TILE_M * t, 0), TILE_M);
-          uint32_t ia[4];
-          int m[4];
-          F4P a4[4];
+          uint32_t ia[FZ_RPG];
+          int m[FZ_RPG];
+          F4P a4[FZ_RPG];
           int cnt = 0;
           bool all_cached = true;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int rt = 32 * k + rt_w, r = TILE_M * t + rt;
+          for (int k = 0; k < FZ_RPG; ++k) {
+            const int rt = 4 * FZ_GW * k + rt_w, r = TILE_M * t + rt;
             uint32_t be = 0;
             if (r < n && rt >= nl_t) be = sm.rbe[r];
             ia[k] = idx_a + 2 * (be & 0xffffu);
@@ -702,38 +708,38 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             // branch-free: every step loads one entry of each of the four rows (a finished row re-reads entries just past
             // its end -- always inside the cache array) and a finished row is pointed at the all-zero row, so the four
             // load chains overlap and the adds need no predicate
-#pragma unroll 2
+#pragma unroll 8 / FZ_RPG
             for (int i = 0; i < cnt; ++i) {
-              uint32_t J[4];
-              F4P v[4];
+              uint32_t J[FZ_RPG];
+              F4P v[FZ_RPG];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < FZ_RPG; ++k) {
                 const uint32_t Jl = lds16(ia[k] + 2 * i);
                 J[k] = i < m[k] ? Jl : Jz;
               }
 #pragma unroll
-              for (int k = 0; k < 4; ++k) v[k] = ld_J(J[k]);
+              for (int k = 0; k < FZ_RPG; ++k) v[k] = ld_J(J[k]);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) add4p(a4[k], v[k]);
+              for (int k = 0; k < FZ_RPG; ++k) add4p(a4[k], v[k]);
             }
           } else {  // units with more alive entries than the cache holds
             for (int i = 0; i < cnt; ++i) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
+              for (int k = 0; k < FZ_RPG; ++k)
                 if (i < m[k]) add4p(a4[k], ld_J(nbrJ((int)((ia[k] - idx_a) >> 1) + i)));
             }
           }
           FZ_CLK(d1);
-          float4 own4[4];
+          float4 own4[FZ_RPG];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int rt = 32 * k + rt_w, r = TILE_M * t + rt;
+          for (int k = 0; k < FZ_RPG; ++k) {
+            const int rt = 4 * FZ_GW * k + rt_w, r = TILE_M * t + rt;
             own4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < n && rt >= nl_t) own4[k] = unpack4(ld_J((uint32_t)((r << 3) | (r & 7))));
           }
           if (!packed) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) add4(csum, own4[k]);
+            for (int k = 0; k < FZ_RPG; ++k) add4(csum, own4[k]);
           }
           FZ_CLK(d2);
           if (uses > 0) {
@@ -741,8 +747,8 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             FZ_CLK(c4);
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int rt = 32 * k + rt_w;
+          for (int k = 0; k < FZ_RPG; ++k) {
+            const int rt = 4 * FZ_GW * k + rt_w;
             if (rt >= nl_t) {
               stage_f16(sm.P, rt, q, unpack4(a4[k]));
               stage_f16(sm.LO, rt, q, own4[k]);
@@ -940,12 +946,12 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
       // the scratch image leaves as one 4 KB bulk copy per warp and tile (a warp's 32 rows are contiguous in the tile, so
       // the warps of a tile need no barrier among themselves), the final embeddings as fully coalesced 128-byte row pieces.
       tc_fence_after();
-      {
+      if (warp < 8) {
         const int quad = warp >> 2, lg = warp & 3;
         unsigned char* const stg = quad ? sm.LO : sm.P;
         const uint32_t stg_a = smem_u32(stg);
         const bool last = it + 1 == MD_BP_ITERS;
-        for (int t = quad; t < ntile; t += FZ_GW / 4) {
+        for (int t = quad; t < ntile; t += 2) {
           const uint32_t taddr = tbase + ((uint32_t)(32 * lg) << 16) + 64 * t;
           float x[64];
 #pragma unroll
