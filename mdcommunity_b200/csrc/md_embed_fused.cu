@@ -97,8 +97,8 @@ struct FusedSmem {
   int cnt0;                         // H1 mode: rows of the unit with an alive neighbour
   alignas(128) float zrow[32];      // one all-zero 128-byte row: where a finished row's lane group points its loads
   uint16_t bbase[32];
-  uint64_t bar_empty, bar_w, bar_h;
-  int arrive_cnt;                   // warps that have staged their rows (8 per tile; the last one issues the tile's MMAs)
+  // per staging tile: "full" = every warp has staged its rows (FZ_GW arrivals), "empty" = the MMAs that read it have completed
+  uint64_t bar_fullH, bar_fullP, bar_emptyH, bar_emptyP, bar_w, bar_h;
   int long_ctr;                     // tickets for the long rows of a pass's first tile
   uint32_t tmem;
   int unit;
@@ -364,9 +364,11 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
   const int L = G.n_layers, St = G.stride, B = G.n_graphs;
   const int tpg = St / TILE_M, tiles_per_layer = B * tpg;
   if (tid == 0) {
-    sm.arrive_cnt = 0;
+    mbar_init(&sm.bar_fullH, FZ_GW);
+    mbar_init(&sm.bar_fullP, FZ_GW);
+    mbar_init(&sm.bar_emptyH, 1);
     sm.long_ctr = 0;
-    mbar_init(&sm.bar_empty, 1);
+    mbar_init(&sm.bar_emptyP, 1);
     mbar_init(&sm.bar_w, 1);
     mbar_init(&sm.bar_h, 1);
     mbar_fence_init();
@@ -590,6 +592,38 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
       return (j << 3) | (j & 7);
     };
     auto ld_J = [&](uint32_t J) -> F4P { return lds128p(hs_a + ((J ^ (uint32_t)q) << 4)); };
+    // every MMA issued so far has completed (both groups of the last tile; `uses` tiles handed over so far)
+    auto mma_drain = [&]() {
+      if (uses > 0) {
+        mbar_wait(&sm.bar_emptyH, (uses - 1) & 1);
+        mbar_wait(&sm.bar_emptyP, (uses - 1) & 1);
+      }
+    };
+    // MMA group g (0: own rows x W23, 1: neighbour sums x W13) of tile t: a.w = a_hi.w_hi + a_hi.w_lo + a_lo.w_hi with every
+    // factor in fp16 (products exact in the fp32 accumulator, the dropped a_lo.w_lo is 2^-22 of the term): 6 kind::f16 MMAs
+    // (K = 16) over the staging tile [hi (32) | lo (32)] and the pass's weight tile [W_hi | W_lo]
+    auto issue_group = [&](int grp, int t, int pass) {
+      if (!w_ready) {
+        mbar_wait(&sm.bar_w, 0);
+        w_ready = true;
+      }
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t idb = idesc(FMT_F16, 128, 64);
+        const uint64_t da = desc_k_sw128(smem_u32(grp ? sm.P : sm.LO), 0);
+        const uint64_t db = desc_k_sw128(smem_u32(sm.Wt) + pass * FZ_WPASS_B + (grp ? 0u : 8192u), 0);
+        const uint32_t d = tbase + 64 * t;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {  // 32 bytes (16 halves) per K step; hi halves at bytes 0..63, lo at 64..127
+          const uint64_t ko = 2 * k;
+          mma_f16(d, da + ko, db + ko, idb, (grp | pass | k) != 0);  // the own-row group comes first: it opens the accumulator
+          mma_f16(d, da + ko, db + 4 + ko, idb, 1);
+          mma_f16(d, da + 4 + ko, db + ko, idb, 1);
+        }
+        mma_commit(grp ? &sm.bar_emptyP : &sm.bar_emptyH);
+      }
+      __syncwarp();
+    };
 
     FZ_CLK(c0);
     float inv0[FZ_RPT] = {};
@@ -597,7 +631,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
       for (int pass = 0; pass < 2; ++pass) {
         // ---------------- resident column half ----------------
         if (it == it0) {
-          if (uses > 0) mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // every earlier MMA (they read Hs) has completed
+          mma_drain();  // (every earlier MMA has completed)
           float xf[FZ_RPT], dmx[FZ_RPT];  // the thread's (up to) FZ_RPT rows: fetch the features first, the loads are independent
           // (inv0[]: the rows' inverse norms, formed in pass 0 and reused in pass 1 -- declared outside the pass loop)
 #pragma unroll
@@ -668,7 +702,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
           gw_sync();
           FZ_CLK(c1);
         } else if (pass == 1) {
-          mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // pass 0 of this iteration: all gathers and MMAs done
+          mma_drain();  // pass 0 of this iteration: all gathers and MMAs done
           if (gtid == 0) {
             mbar_arrive_expect_tx(&sm.bar_h, ntile * FZ_TILE_B);
             bulk_g2s(sm.Hs, spill, ntile * FZ_TILE_B, &sm.bar_h);
@@ -703,6 +737,31 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             cnt = max(cnt, m[k]);
             a4[k].lo = 0ull, a4[k].hi = 0ull;
           }
+          // ---- the rows' own embeddings first (every row of the tile, long or not): they need no gathering, and their half
+          // of the tile's MMAs then runs under the gather
+          {
+            float4 own4[FZ_RPG];
+#pragma unroll
+            for (int k = 0; k < FZ_RPG; ++k) {
+              const int r = TILE_M * t + 4 * FZ_GW * k + rt_w;
+              own4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r < n) own4[k] = unpack4(ld_J((uint32_t)((r << 3) | (r & 7))));
+            }
+            if (!packed) {
+#pragma unroll
+              for (int k = 0; k < FZ_RPG; ++k) add4(csum, own4[k]);
+            }
+            if (uses > 0) mbar_wait(&sm.bar_emptyH, (uses - 1) & 1);  // own-row staging free (previous tile's own-row MMAs complete)
+#pragma unroll
+            for (int k = 0; k < FZ_RPG; ++k) stage_f16(sm.LO, 4 * FZ_GW * k + rt_w, q, own4[k]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.bar_fullH);
+            if (warp == (int)(uses & (FZ_GW - 1))) {  // this tile's issuer of the own-row group (the warps take turns)
+              mbar_wait(&sm.bar_fullH, uses & 1);
+              issue_group(0, t, pass);
+            }
+          }
           FZ_CLK(d0);
           if (all_cached) {
             // branch-free: every step loads one entry of each of the four rows (a finished row re-reads entries just past
@@ -730,29 +789,14 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             }
           }
           FZ_CLK(d1);
-          float4 own4[FZ_RPG];
-#pragma unroll
-          for (int k = 0; k < FZ_RPG; ++k) {
-            const int rt = 4 * FZ_GW * k + rt_w, r = TILE_M * t + rt;
-            own4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < n && rt >= nl_t) own4[k] = unpack4(ld_J((uint32_t)((r << 3) | (r & 7))));
-          }
-          if (!packed) {
-#pragma unroll
-            for (int k = 0; k < FZ_RPG; ++k) add4(csum, own4[k]);
-          }
-          FZ_CLK(d2);
           if (uses > 0) {
-            mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // staging tile free again (MMAs of the previous tile complete)
+            mbar_wait(&sm.bar_emptyP, (uses - 1) & 1);  // P staging free again (the neighbour-sum MMAs of the previous tile complete)
             FZ_CLK(c4);
           }
 #pragma unroll
           for (int k = 0; k < FZ_RPG; ++k) {
             const int rt = 4 * FZ_GW * k + rt_w;
-            if (rt >= nl_t) {
-              stage_f16(sm.P, rt, q, unpack4(a4[k]));
-              stage_f16(sm.LO, rt, q, own4[k]);
-            }
+            if (rt >= nl_t) stage_f16(sm.P, rt, q, unpack4(a4[k]));
           }
           FZ_CLK(d3);
           // long rows of this tile: one warp per row, lane group gi takes every 4th neighbour.  In the first tile (where all
@@ -790,11 +834,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             a.y += __shfl_xor_sync(0xffffffffu, a.y, 16);
             a.z += __shfl_xor_sync(0xffffffffu, a.z, 16);
             a.w += __shfl_xor_sync(0xffffffffu, a.w, 16);
-            if (gi == 0) {
-              const float4 own = unpack4(ld_J((uint32_t)((r << 3) | (r & 7))));
-              stage_f16(sm.P, rt, q, a);
-              stage_f16(sm.LO, rt, q, own);
-            }
+            if (gi == 0) stage_f16(sm.P, rt, q, a);
           };
           if (nl_t > 0) {
             if (t == 0 && !(dbg & (1 << 20))) {
@@ -809,54 +849,14 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             } else {
               for (int rt = warp; rt < nl_t; rt += FZ_GW) long_row(rt);
             }
-            // single-unit path: the long rows' part of the column sums, by a FIXED deal (the sums must not depend on who
-            // happened to take a row)
-            if (!packed && gi == 0) {
-              for (int rt = warp; rt < nl_t; rt += FZ_GW) {
-                const int r = TILE_M * t + rt;
-                add4(csum, unpack4(ld_J((uint32_t)((r << 3) | (r & 7)))));
-              }
-            }
           }
           FZ_CLK(d4);
           fence_proxy_async_smem();
           __syncwarp();
-          // the LAST warp to get here issues the tile's MMAs (8 arrivals per tile; a warp can only arrive for tile t + 1 after
-          // the MMAs of tile t have completed, so the groups of 8 never mix)
-          int last = 0;
-          if (lane == 0) {
-            __threadfence_block();
-            last = (atomicAdd(&sm.arrive_cnt, 1) & (FZ_GW - 1)) == FZ_GW - 1;
-            __threadfence_block();
-          }
-          if (__ballot_sync(0xffffffffu, last != 0) != 0u) {  // (a vote: the compiler keeps the MMA issue on the uniform path)
-            // a.w = a_hi.w_hi + a_hi.w_lo + a_lo.w_hi with every factor in fp16 (products exact in the fp32 accumulator, the
-            // dropped a_lo.w_lo is 2^-22 of the term): 12 kind::f16 MMAs (K = 16) over the two staging tiles
-            // [P_hi | P_lo], [H_hi | H_lo] and the pass's weight tiles [W13_hi | W13_lo], [W23_hi | W23_lo]
-            if (!w_ready) {
-              mbar_wait(&sm.bar_w, 0);
-              w_ready = true;
-            }
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t idb = idesc(FMT_F16, 128, 64);
-              const uint64_t dP = desc_k_sw128(smem_u32(sm.P), 0), dH = desc_k_sw128(smem_u32(sm.LO), 0);
-              const uint64_t b13 = desc_k_sw128(smem_u32(sm.Wt) + pass * FZ_WPASS_B, 0);
-              const uint64_t b23 = desc_k_sw128(smem_u32(sm.Wt) + pass * FZ_WPASS_B + 8192, 0);
-              const uint32_t d = tbase + 64 * t;
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {  // 32 bytes (16 halves) per K step; hi halves at bytes 0..63, lo at 64..127
-                const uint64_t ko = 2 * k;
-                mma_f16(d, dP + ko, b13 + ko, idb, (pass | k) != 0);
-                mma_f16(d, dP + ko, b13 + 4 + ko, idb, 1);
-                mma_f16(d, dP + 4 + ko, b13 + ko, idb, 1);
-                mma_f16(d, dH + ko, b23 + ko, idb, 1);
-                mma_f16(d, dH + ko, b23 + 4 + ko, idb, 1);
-                mma_f16(d, dH + 4 + ko, b23 + ko, idb, 1);
-              }
-              mma_commit(&sm.bar_empty);
-            }
-            __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.bar_fullP);
+          if (warp == (int)((uses + FZ_GW / 2) & (FZ_GW - 1))) {  // this tile's issuer of the neighbour-sum group
+            mbar_wait(&sm.bar_fullP, uses & 1);
+            issue_group(1, t, pass);
           }
           ++uses;
           FZ_CLK(d5);
@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
             }
           }
         }
-        mbar_wait(&sm.bar_empty, (uses - 1) & 1);  // all MMAs of the pass (hence all gathers) are complete
+        mma_drain();  // all MMAs of the pass (hence all gathers) are complete
         if (packed) gw_sync();  // ... and every warp's column sums: the resident half may be overwritten from here on
         if (!packed) {  // single unit: the sums of the rows every thread has walked; groups, then warps, fixed order
           csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 8);
