@@ -28,6 +28,7 @@ using namespace umma;
 constexpr int QT_T = 352;         // 8 epilogue + 2 loader + 1 MMA warps
 constexpr int QT_EPI = 256;
 constexpr uint32_t QT_KB = 16384;  // one 128-row x 128-byte operand tile
+constexpr int QT_PMAX = 2048;      // batches of up to this many graphs: tiles are cut from the CONCATENATED active lists
 
 // HTC: T kept in tensor memory, relu(e_p @ h1) on the tensor cores
 template <int L, bool HTC>
@@ -48,6 +49,8 @@ struct QTSmem {
   float hq[L][TILE_M];           // epilogue: partial hidden sums of the second thread of each row
   float ssq[2][2][HTC ? TILE_M : 1];  // HTC: [layer parity][thread of the row] half of |X_p|^2
   int vrow[4][TILE_M];           // [tile number & 3] global node id of the row, -1 = padding
+  int pfx[QT_PMAX + 1];          // compact tiles: exclusive prefix sums of the graphs' active-node counts
+  int wtot[12];
   int desc[4][4];                // [tile number & 3] tile, graph
   int next_tile;
   uint64_t a_full, a_empty, d_full[2], d_empty[2], h_full;
@@ -87,6 +90,50 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
   constexpr uint32_t HCOL = 2 * NCOL;                  // HTC: 4 x 32 accumulator columns of relu's argument e_p @ h1
   const int tpg = G.stride / TILE_M;
   const int n_tiles = G.n_graphs * tpg;
+  // Compact tiles: a tile is 128 consecutive rows of the concatenation of all graphs' active lists, whatever graphs they
+  // belong to (every per-graph quantity of the epilogue is looked up per row).  Towards the end of a rollout, when most
+  // graphs are down to a few dozen active nodes, this is a quarter of the (graph, 128-row) tiles -- and the CTAs beyond
+  // the number of tiles leave before the set-up below (operand images of the weights, tensor memory).
+  const bool compact = G.n_graphs <= QT_PMAX;
+  int n_work = n_tiles;
+  if (compact) {
+    const int B = G.n_graphs;
+    int carry = 0;
+    for (int base = 0; base < B; base += QT_T) {
+      const int gq = base + tid;
+      const int v = gq < B ? max(S.n_act[gq], 0) : 0;
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) sm.wtot[warp] = x;
+      __syncthreads();
+      int woff = 0, tot = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < QT_T / 32; ++w2) {
+        const int tw = sm.wtot[w2];
+        woff += w2 < warp ? tw : 0;
+        tot += tw;
+      }
+      if (gq < B) sm.pfx[gq] = carry + woff + x - v;
+      carry += tot;
+      __syncthreads();
+    }
+    if (tid == 0) sm.pfx[B] = carry;
+    n_work = (carry + TILE_M - 1) / TILE_M;
+    if ((int)blockIdx.x >= n_work) {  // nothing for this CTA (tiles are handed out dynamically: n_work CTAs suffice)
+      if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(counter + 1, 1) == (int)gridDim.x - 1) {
+          counter[0] = 0;
+          counter[1] = 0;
+        }
+      }
+      return;
+    }
+  }
 
   if (tid == 0) {
     mbar_init(&sm.a_full, 2);
@@ -151,14 +198,19 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
       const uint32_t slot = i & 1, use = i >> 1;
       if (ltid == 0) {  // next live tile
         int t;
-        for (;;) {
+        if (compact) {
           t = atomicAdd(counter, 1);
-          if (t >= n_tiles) {
-            t = -1;
-            break;
+          if (t >= n_work) t = -1;
+        } else {
+          for (;;) {
+            t = atomicAdd(counter, 1);
+            if (t >= n_tiles) {
+              t = -1;
+              break;
+            }
+            const int g = t / tpg;
+            if ((t - g * tpg) * TILE_M < S.n_act[g]) break;
           }
-          const int g = t / tpg;
-          if ((t - g * tpg) * TILE_M < S.n_act[g]) break;
         }
         sm.next_tile = t;
       }
@@ -172,8 +224,24 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
       // the next tile).
       const uint32_t ms = i & 3;
       (void)slot, (void)use;
-      const int g = tile >= 0 ? tile / tpg : 0, tt = tile >= 0 ? tile - g * tpg : 0;
-      if (tile >= 0) {
+      const int g = tile >= 0 && !compact ? tile / tpg : 0, tt = tile >= 0 && !compact ? tile - g * tpg : 0;
+      if (tile >= 0 && compact) {
+        const int B = G.n_graphs, total = sm.pfx[B];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int j = tile * TILE_M + ltid + 64 * hh;
+          int v = -1;
+          if (j < total) {
+            int lo = 0, hi = B;  // pfx[lo] <= j < pfx[hi]
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              if (sm.pfx[mid] <= j) lo = mid; else hi = mid;
+            }
+            v = S.act_list[lo * G.stride + (j - sm.pfx[lo])];
+          }
+          sm.vrow[ms][ltid + 64 * hh] = v;
+        }
+      } else if (tile >= 0) {
         const int rows = min(TILE_M, S.n_act[g] - tt * TILE_M);
         sm.vrow[ms][ltid] = ltid < rows ? S.act_list[g * G.stride + tt * TILE_M + ltid] : -1;
         sm.vrow[ms][ltid + 64] = ltid + 64 < rows ? S.act_list[g * G.stride + tt * TILE_M + ltid + 64] : -1;
@@ -288,9 +356,9 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
       mbar_wait(&sm.d_full[slot], use & 1);
       const int tile = sm.desc[i & 3][0];
       if (tile < 0) break;
-      const int g = sm.desc[i & 3][1];
       tc_fence_after();
       const int v = sm.vrow[i & 3][r];
+      const int g = v >= 0 ? v / G.stride : -1;  // the row's graph (rows of several graphs share a compact tile)
       float part[L];
 #pragma unroll
       for (int p = 0; p < L; ++p) part[p] = 0.f;
@@ -573,12 +641,16 @@ __global__ void __launch_bounds__(QT_T, 1) qhead_tc_kernel(md_graphs_t G, md_sta
         key = ((unsigned long long)orderable(q) << 32) | (0xffffffffu - local);
       }
       if (half == 0) {
+        // arg-max per graph: a graph's rows are consecutive lanes, so a segmented suffix maximum leaves every graph's
+        // best key in the first of its lanes
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-          key = other > key ? other : key;
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long other = __shfl_down_sync(0xffffffffu, key, o);
+          const int og = __shfl_down_sync(0xffffffffu, g, o);
+          if (lane + o < 32 && og == g && other > key) key = other;
         }
-        if (lane == 0 && key != 0ull) atomicMax(&S.best[g], key);
+        const int gprev = __shfl_up_sync(0xffffffffu, g, 1);
+        if (g >= 0 && (lane == 0 || gprev != g) && key != 0ull) atomicMax(&S.best[g], key);
       }
     }
   }
