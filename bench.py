@@ -195,7 +195,7 @@ def roofline_pass(mdb, batch, w):
     from mdcommunity_b200 import _lib
     ro = mdb.BatchRollout(batch, w)
     lib = ro.lib
-    evs, byts, smem_b = [], [], []
+    evs, byts, smem_b, smem_min = [], [], [], []
     env_evs, env_byts = [], []
     D = 64
     N_nodes = torch.as_tensor([g.num_nodes for g in batch.graphs], dtype=torch.float64)
@@ -213,7 +213,9 @@ def roofline_pass(mdb, batch, w):
             e1.record()
             evs.append((e0, e1))
             byts.append(3 * floor)
-            smem_b.append(smem_model_bytes(n, [int(z) for z in nnz]))
+            fb, mb = smem_model_bytes(n, [int(z) for z in nnz], iters=2 if batch.cost == "unit" else 3)
+            smem_b.append(fb)
+            smem_min.append(mb)
         else:
             _lib.check(lib.md_embed_init(g, s, wp, k, st), "init")
             for it in range(3):
@@ -265,13 +267,19 @@ def roofline_pass(mdb, batch, w):
             mhz = 1965
         speak = 128.0 * props.multi_processor_count * mhz * 1e6 / 1e9  # 128 B / clk / SM
         sach = float(sum(smem_b)) / (tot_ms * 1e-3) / 1e9
+        smin = float(sum(smem_min)) / (tot_ms * 1e-3) / 1e9
         smem = {"bound": "shared memory bandwidth (the embeddings of a (graph, layer) unit stay resident in one SM's shared "
-                         "memory: DRAM traffic is 6.5x below the HBM model, so HBM is not what limits this kernel)",
+                         "memory: DRAM traffic is ~7x below the HBM model, so HBM is not what limits this kernel)",
                 "achieved": sach, "peak": speak, "unit": "GB/s", "frac": sach / speak,
                 "first_launch_gbs": smem_b[0] / (ms[0] * 1e-3) / 1e9, "first_launch_frac": smem_b[0] / (ms[0] * 1e-3) / 1e9 / speak,
+                "min_model_gbs": smin, "min_model_frac": smin / speak,
                 "peak_source": "128 B/clk/SM x %d SMs x %d MHz (max SM clock)" % (props.multi_processor_count, mhz),
-                "model": "per launch 3 x sum_l (256 nnz_l [neighbour rows gathered] + 4 x 256 n [own row, two MMA operand "
-                         "rows, new embedding written])"}
+                "model": "traffic of the formulation, per launch and layer-iteration: 260 nnz_l (half rows gathered in both "
+                         "passes + 2-byte neighbour codes) + 2432 n (own rows 256, fp16 operand rows staged 512, MMA operand "
+                         "fetches 1152, epilogue 512); min_model = 256 nnz_l + 1024 n, what any shared-memory-resident "
+                         "formulation moves (the round-1 figure)",
+                "ncu": "profiles/r2z_ncu_embed_fused_16warps_summary.txt: 46.5 M LSU wavefronts (5.96 GB) + ~1.8 GB of MMA "
+                       "operand fetches in 402 us = 19 TB/s at the intact state, 5.8 M wavefronts are bank conflicts"}
     return {"bound": "hbm", "kernel": name, "lmcc": lmcc, "smem": smem,
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "traffic_unit": "bytes per launch (first, intact-state launch; compare with first_launch_algorithmic_bytes)",
@@ -463,11 +471,21 @@ def _nccl_log_summary(path):
     return out
 
 
-def smem_model_bytes(n, nnz_per_layer, D=64):
-    """Shared-memory traffic md_embed_fused cannot avoid, per launch (3 iterations, all layers): per layer-iteration the
-    gather reads one 256-byte row per alive entry (256 nnz) and each row's own embedding (256 n), the tensor core reads
-    the two operand rows P and H (2 x 256 n), the epilogue writes the new embedding (256 n)."""
-    return 3 * sum(4 * D * z + 4 * 4 * D * n for z in nnz_per_layer)
+def smem_model_bytes(n, nnz_per_layer, D=64, iters=3):
+    """Shared-memory traffic of md_embed_fused's formulation, per launch (`iters` iterations, all layers, two column-half
+    passes per iteration), in bytes; n = active rows of the batch, nnz = alive directed entries per layer.  Per layer-iteration:
+      gather            256 nnz   one 128-byte half row per entry and pass
+      neighbour ids       4 nnz   2-byte row codes, read in both passes
+      own rows          256 n     read for the own-embedding operand and the column sums
+      staging writes    512 n     [P_hi | P_lo] and [H_hi | H_lo] fp16 operand rows, 2 x 128 B per row and pass
+      MMA operand reads 1152 n    12 MMAs per 128-row tile and pass, each fetching a 4 KB A slice and a 2 KB B slice
+      epilogue          512 n     new embedding: 128 B into the resident half, 128 B into the staging tile, read by the bulk
+                                  copy to the scratch image and written back by the reload for pass 1
+    -> (260 nnz + 2432 n) per layer-iteration.  `min` is the part no shared-memory-resident formulation avoids (gather, own
+    rows, operand rows read once, new embedding written once: 256 nnz + 1024 n), the figure round 1 reported."""
+    full = iters * sum(260 * z + 2432 * n for z in nnz_per_layer)
+    mn = iters * sum(4 * D * z + 4 * 4 * D * n for z in nnz_per_layer)
+    return full, mn
 
 
 def c3_strong_leg(mdb, dist, dev, world, rank, graphs, idx, w, steps=3, warmup=1):

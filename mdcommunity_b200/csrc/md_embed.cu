@@ -117,26 +117,48 @@ __global__ void __launch_bounds__(MD_MAX_LAYERS* D) graph_embed_kernel(md_graphs
     yv = yv / fmaxf(nrm, 1e-12f);
   }
   y[l][c] = yv;
-  for (int it = 0; it < MD_BP_ITERS; ++it) {
-    float s = 0.f;
-    const float* ps = K.psum + (((size_t)it * L + l) * tiles_per_layer + (size_t)g * tpg) * D + c;
+  // The kernel is a chain of small dependent steps: everything that does not depend on the chain is fetched up front, with
+  // all loads in flight at once -- this thread's columns of W13 / W23 (reused by the three iterations) and of trans, and the
+  // per-tile column sums of all three iterations (before: ~9 exposed L2 round-trip chains, 16 us per launch).
+  float w13c[D], w23c[D], trc[D], sv[MD_BP_ITERS];
+#pragma unroll
+  for (int k = 0; k < D; ++k) w13c[k] = W.w13[k * D + c], w23c[k] = W.w23[k * D + c];
+#pragma unroll
+  for (int k = 0; k < D; ++k) trc[k] = W.trans[k * D + c];
+  {
     const int nsum = ntile > PSUM_REDUCE_MIN_TILES ? 1 : ntile;  // many tiles: psum_reduce_kernel left the total in tile 0
-    for (int t = 0; t < nsum; ++t) s += ps[(size_t)t * D];
-    sbuf[l][c] = s;
+#pragma unroll
+    for (int it = 0; it < MD_BP_ITERS; ++it) {
+      const float* ps = K.psum + (((size_t)it * L + l) * tiles_per_layer + (size_t)g * tpg) * D + c;
+      float s = 0.f;
+      for (int t = 0; t < nsum; ++t) s += ps[(size_t)t * D];
+      sv[it] = s;
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < MD_BP_ITERS; ++it) {
+    sbuf[l][c] = sv[it];
     __syncthreads();
     float o = 0.f;
-    for (int k = 0; k < D; ++k) o = fmaf(sbuf[l][k], W.w13[k * D + c], o);
-    for (int k = 0; k < D; ++k) o = fmaf(y[l][k], W.w23[k * D + c], o);
+#pragma unroll
+    for (int k = 0; k < D; ++k) o = fmaf(sbuf[l][k], w13c[k], o);
+#pragma unroll
+    for (int k = 0; k < D; ++k) o = fmaf(y[l][k], w23c[k], o);
     o = fmaxf(o, 0.f);
     const float nrm = sqrtf(group_sum64(o * o, scratch, l, c));  // contains __syncthreads: y reads are done
     y[l][c] = o / fmaxf(nrm, 1e-12f);
     __syncthreads();
   }
 
+  // (the two columns of w_layer1 this thread needs at the very end: in flight under the fusion phase)
+  float wg0[D], wg1[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) wg0[k] = W.wl1[k * MD_GATE + c], wg1[k] = W.wl1[k * MD_GATE + c + D];
   // ---- fusion of the graph rows (BitwiseMultipyLogis) ------------------------------------------------
   {
     float o = 0.f;
-    for (int k = 0; k < D; ++k) o = fmaf(y[l][k], W.trans[k * D + c], o);
+#pragma unroll
+    for (int k = 0; k < D; ++k) o = fmaf(y[l][k], trc[k], o);
     T[l][c] = tanhf(o + W.bias[c]);
   }
   __syncthreads();
@@ -172,10 +194,16 @@ __global__ void __launch_bounds__(MD_MAX_LAYERS* D) graph_embed_kernel(md_graphs
     const float s = group_sum64(x * W.cross[c], scratch, l, c);
     if (c == 0) sval[l] = s;
   }
-  for (int j = c; j < MD_GATE; j += D) {
-    float o = 0.f;
-    for (int k = 0; k < D; ++k) o = fmaf(y[l][k], W.wl1[k * MD_GATE + j], o);
-    hid[l][j] = fmaxf(o, 0.f) * W.wl2[j];
+  static_assert(MD_GATE == 2 * D, "the gate's hidden layer is two columns per thread");
+  {
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      o0 = fmaf(y[l][k], wg0[k], o0);
+      o1 = fmaf(y[l][k], wg1[k], o1);
+    }
+    hid[l][c] = fmaxf(o0, 0.f) * W.wl2[c];
+    hid[l][c + D] = fmaxf(o1, 0.f) * W.wl2[c + D];
   }
   __syncthreads();
   {

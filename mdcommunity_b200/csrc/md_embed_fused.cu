@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
       sm.wn2l[tid] = a, sm.wn2l[D + tid] = b;
     }
   } else if (tid < 2 * D) sm.wn2l[tid] = W.w_n2l[tid];
-  for (int i = tid; i < FZ_IDX_CAP + 64; i += FZ_T) sm.idx[i] = 0;
+  for (int i = tid; i < (FZ_IDX_CAP + 64) / 8; i += FZ_T) reinterpret_cast<uint4*>(sm.idx)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 32) sm.zrow[tid] = 0.f;  // every entry is always a valid J (< 8192)
   tc_fence_before();
   __syncthreads();

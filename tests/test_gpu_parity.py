@@ -777,3 +777,29 @@ def test_fused_packed_bins_bit_identical_to_units_alone(variant):
                 assert float((a[l][ids] - b[l][ids]).abs().max()) <= 2e-5, (i, l)
             qa, qb = a[3][ids], b[3][ids]
             assert float(((qa - qb).abs() - (Q_RTOL * qb.abs() + Q_ATOL)).max()) <= 0, i
+
+
+def test_very_large_batches_of_small_graphs_match_smaller_batches():
+    """Beyond 1024 graphs md_embed_fused stops packing (one bin per unit, index order) and beyond 2048 md_qhead goes back to
+    (graph, 128-row) tiles: a 2100-graph batch must reproduce, bit for bit, the rollouts of the same graphs in batches of
+    700 (packed bins, compact Q-head tiles) -- a graph's result never depends on its batch."""
+    from mdcommunity_b200 import gmm
+    mdb = _mdb()
+    graphs = [gmm.gmm_graph(30 + (i % 11), 4000 + i, cost="unit") for i in range(2100)]
+    w = None
+    parts = []
+    for lo in range(0, 2100, 700):
+        batch = mdb.GraphBatch(graphs[lo:lo + 700], cost="unit")
+        if w is None:
+            w = mdb.QWeights(dict(np.load(os.path.join(GOLDEN, "weights_unit.npz"))), batch.device)
+        parts.append(mdb.BatchRollout(batch, w).run())
+    big = mdb.BatchRollout(mdb.GraphBatch(graphs, cost="unit"), w).run()
+    T = big["actions"].shape[1]
+    for k in ("score", "n_steps"):
+        assert np.array_equal(big[k], np.concatenate([p[k] for p in parts])), k
+    for k in ("actions", "ranks"):
+        cat = np.concatenate([np.pad(p[k], ((0, 0), (0, T - p[k].shape[1])), constant_values=(-1 if k == "actions" else 0))
+                              for p in parts])
+        n = big["n_steps"]
+        for i in range(2100):
+            assert np.array_equal(big[k][i, :n[i]], cat[i, :n[i]]), (k, i)
