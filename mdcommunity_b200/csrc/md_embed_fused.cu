@@ -7,32 +7,30 @@
 // Why a second formulation: ncu on md_embed_iter showed the neighbour gather pinned at the L2 -> SM path (one 256-byte
 // row per alive edge, ~37 B/cycle/SM at best) with the FP32-FMA transform fighting it for issue slots.  For graphs of
 // <= 1024 active nodes one graph-layer's embeddings are 256 KB: too large for one SM's shared memory in full, but one
-// COLUMN HALF (32 of 64 columns, 128 B per row) is 128 KB.  So a persistent CTA owns one (graph, layer) unit at a time:
+// COLUMN HALF (32 of 64 columns, 128 B per row) is 128 KB.  So a persistent CTA owns one BIN at a time -- one (graph, layer)
+// unit, or several small units of one layer packed together (fused_prep_kernel below):
 //
 //   per iteration, two passes p = 0,1 over the column halves:
-//     resident  Hs = H[:, 32p:32p+32] in shared memory, compact row order, stored directly in the tcgen05
-//               SWIZZLE_128B K-major tile layout (a 128-byte row is exactly one swizzle span), so the very same bytes
-//               serve the gather (8 lanes x LDS.128 per neighbour row, conflict-free) and, as MMA operand A, the
-//               "own embedding" term of the transform.
-//     gather    8 warps; 8 lanes per row (4 rows per warp instruction); neighbour lists come from a shared-memory copy of
-//               the unit's alive CSR (uint16 entries, translated once per unit).  Rows are re-ordered per unit by
-//               descending alive degree (deterministic counting sort) and dealt to the lane groups so that the four
-//               rows a warp walks together have (nearly) equal length: without this the power-law degree spread made
-//               every step wait for its longest row.  Sums stay in CSR order; rows longer than FZ_LONG are spread over
-//               the warp's four lane groups.  Per 128-row tile the warps write P = A_adj.H (raw fp32) and the fp16
-//               remainders [P - tf32(P) | H - tf32(H)] into a staging tile.
-//     transform one elected thread issues tcgen05.mma: D_tile += P.W13[32p:32p+32] + H.W23[32p:32p+32] as
-//               kind::tf32 (operands are truncated to tf32 by the tensor core -- measured, scripts/microbench/umma_probe.cu)
-//               with hi and lo planes of the weights, plus one kind::f16 (fp16) pass for the operand remainders:
-//               a.w ~= a_hi.w_hi + a_hi.w_lo + a_lo.w.  The remainders are kept in fp16, not bf16: a_lo <= 2^-10 |a| is far
-//               from fp16's range limits and keeps 11 bits there (error ~2^-21 relative instead of 2^-19, which showed
-//               as 1.6e-4 relative Q differences on dense graphs; the bf16 probe measured 1.3e-6 of max |D|).
-//               Accumulators for ALL tiles of the unit (<= 8 x 64 columns = the whole 512-column TMEM) stay in tensor
-//               memory across the two passes, which is what makes the column split free: no partial sums are exchanged.
-//   epilogue    tcgen05.ld (one thread per row holds the 64 outputs): relu, L2 normalise; columns 0..31 go straight into
-//               the resident buffer for the next iteration's pass 0, columns 32..63 into a per-CTA scratch image
-//               (L2-resident) that one cp.async.bulk brings back for pass 1.  The last iteration writes H to HBM for
-//               md_qhead.  Per-graph column sums of every iteration's input (the subgsum spmm) fall out of the gather.
+//     resident  Hs = H[:, 32p:32p+32] in shared memory, compact row order, in the SWIZZLE_128B tile geometry (a 128-byte
+//               row is one swizzle span: 8 lanes x LDS.128 per neighbour row, conflict-free).
+//     gather    all 16 warps; 8 lanes per row (4 rows per warp instruction); neighbour lists come from a shared-memory copy of
+//               the bin's alive CSR (uint16 codes, translated once per bin).  Rows are re-ordered per bin by descending
+//               alive degree (deterministic counting sort) and dealt to the lane groups so that the rows a warp walks
+//               together have (nearly) equal length.  Sums stay in CSR order; rows longer than FZ_LONG are spread over the
+//               warp's four lane groups (first tile of a pass: taken from a counter as warps become free).
+//     staging   per 128-row tile two tiles of fp16 pairs: [H_hi | H_lo] (the rows' own embeddings, staged first) and
+//               [P_hi | P_lo] (P = A_adj.H), x = hi + lo, hi = fp16(x), lo = fp16(x - hi).
+//     transform D_tile += P.W13[32p:32p+32] + H.W23[32p:32p+32] as a.w ~= a_hi.w_hi + a_hi.w_lo + a_lo.w_hi, all kind::f16 with
+//               fp32 accumulation (12 MMAs of K = 16 per tile and pass; the weight images [W_hi | W_lo] of both passes stay
+//               resident).  No MMA warp: the warps take turns waiting for a staging tile to be complete and issuing its MMAs
+//               (a 17th warp would cost every thread registers: see FZ_T).  Accumulators for ALL tiles of the bin
+//               (<= 8 x 64 columns = the whole 512-column TMEM) stay in tensor memory across the two passes, which is what
+//               makes the column split free: no partial sums are exchanged.
+//   epilogue    warps 0..7, tcgen05.ld (one thread per row holds the 64 outputs): relu, L2 normalise; columns 0..31 go
+//               straight into the resident buffer for the next iteration's pass 0, columns 32..63 into a per-CTA scratch image
+//               (L2-resident; one 4 KB bulk copy per warp and tile) that one cp.async.bulk brings back for pass 1.  The last
+//               iteration writes H to HBM for md_qhead.  Per-graph column sums of every iteration's input (the subgsum spmm)
+//               fall out of the gather (single units) or are formed member by member from the resident half (bins).
 //
 // HBM traffic per unit and forward: alive CSR once + final H once (+ features); everything else stays on chip / in L2.
 #include <cuda_fp16.h>
