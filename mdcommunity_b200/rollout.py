@@ -419,10 +419,31 @@ class MultiStreamRollout:
     """The same lock-step rollout, with the batch cut into `parts` independent sub-batches that advance on their own CUDA
     streams.  Graphs never interact, so this changes nothing in the results; what it buys is overlap: the env step of
     a sub-batch waits for its slowest graph and the tail of every kernel leaves SMs idle -- the other
-    sub-batches' kernels fill them.  Sub-batch p holds graphs [p * ceil(B / parts), ...) in order."""
+    sub-batches' kernels fill them.  Sub-batch p holds graphs [p * ceil(B / parts), ...) in order.
 
-    def __init__(self, graphs, weights, device=None, cost=None, parts=2, chunk=8):
+    order="size": the graphs are first sorted by their number of edges (descending), so that graphs of similar size -- and
+    hence rollouts of similar length -- share a sub-batch.  A lock-step batch runs as long as its longest rollout (C3: 390
+    removals for a mean of 68): mixed with short ones the long rollouts keep a wide, mostly finished batch iterating,
+    sorted they form a narrow sub-batch of their own whose iterations are cheap and whose tail the other sub-batches fill.
+    results() always returns the graphs in their ORIGINAL order.  parts=None: one sub-batch per 128 graphs, 2..8.
+    MEASURED on C3 (1024 unit-cost graphs, one GPU): 1 / 2 / 4 / 8 size-sorted sub-batches = 98 / 100 / 121 / 129 ms per pass --
+    the pass is bound by its longest rollout's chain of ~2000 dependent launches, and every other sub-batch's kernels
+    (persistent CTAs that own an SM for ~100 us) delay that chain more than they fill its idle SMs.  Sub-batches pay when
+    there are many batches of similar length (RolloutPipeline: +70 % on C2), not inside one batch: bench.py and GetSolBatch
+    keep a single lock-step batch per rank."""
+
+    def __init__(self, graphs, weights, device=None, cost=None, parts=2, chunk=8, order=None):
         graphs = list(graphs)
+        if parts is None:
+            parts = max(2, min(8, len(graphs) // 128))
+        parts = max(1, min(parts, len(graphs)))
+        self.perm = np.arange(len(graphs))
+        if order == "size":
+            self.perm = np.argsort([-sum(int(e) for e in g.num_edges) for g in graphs], kind="stable")
+        elif order is not None:
+            raise ValueError("order: None or 'size'")
+        graphs = [graphs[i] for i in self.perm]
+        self.inv = np.argsort(self.perm, kind="stable")
         per = (len(graphs) + parts - 1) // parts
         self.slices = [graphs[i:i + per] for i in range(0, len(graphs), per)]
         self.batches = [GraphBatch(s, device, cost) for s in self.slices]
@@ -444,22 +465,33 @@ class MultiStreamRollout:
             with torch.cuda.stream(st):
                 ro.reset()
                 ro._begin_run()
+        # every sub-batch advances on its own: a chunk is enqueued as soon as the previous one of the SAME sub-batch has
+        # completed and left graphs alive (no round structure: a narrow sub-batch of long rollouts must not wait for the
+        # chunks of the wide ones)
+        its = [0] * len(self.rollouts)
+
+        def enqueue(i):
+            ro = self.rollouts[i]
+            with torch.cuda.stream(self.streams[i]):
+                ro._enqueue_chunk(self.chunk, its[i] == 0)
+                self._pins[i].copy_(ro.flags[8:9], non_blocking=True)
+                self.events[i].record(self.streams[i])
+            its[i] += self.chunk
+
         live = list(range(len(self.rollouts)))
-        it = 0
+        for i in live:
+            enqueue(i)
         while live:
-            for i in live:
+            ready = [i for i in live if self.events[i].query()]
+            if not ready:
+                self.events[live[0]].synchronize()
+                ready = [live[0]]
+            for i in ready:
                 ro = self.rollouts[i]
-                with torch.cuda.stream(self.streams[i]):
-                    ro._enqueue_chunk(self.chunk, it == 0)
-                    self._pins[i].copy_(ro.flags[8:9], non_blocking=True)
-                    self.events[i].record(self.streams[i])
-            nxt = []
-            for i in live:
-                self.events[i].synchronize()
-                if int(self._pins[i][0]) < self.rollouts[i].batch.B and it <= self.rollouts[i].max_steps + self.chunk:
-                    nxt.append(i)
-            live = nxt
-            it += self.chunk
+                if int(self._pins[i][0]) >= ro.batch.B or its[i] > ro.max_steps + self.chunk:
+                    live.remove(i)
+                else:
+                    enqueue(i)
         for ro, st in zip(self.rollouts, self.streams):
             with torch.cuda.stream(st):
                 ro._finish_run()
@@ -470,6 +502,8 @@ class MultiStreamRollout:
         rs = [r.results() for r in self.rollouts]
         T = max(r["actions"].shape[1] for r in rs)
         pad = lambda a, fill: np.concatenate([a, np.full((a.shape[0], T - a.shape[1]), fill, a.dtype)], 1)
-        return dict(score=np.concatenate([r["score"] for r in rs]), n_steps=np.concatenate([r["n_steps"] for r in rs]),
-                    actions=np.concatenate([pad(r["actions"], -1) for r in rs]), ranks=np.concatenate([pad(r["ranks"], 0) for r in rs]),
-                    maxcc=np.concatenate([pad(r["maxcc"], 0) for r in rs]))
+        inv = self.inv
+        return dict(score=np.concatenate([r["score"] for r in rs])[inv], n_steps=np.concatenate([r["n_steps"] for r in rs])[inv],
+                    actions=np.concatenate([pad(r["actions"], -1) for r in rs])[inv],
+                    ranks=np.concatenate([pad(r["ranks"], 0) for r in rs])[inv],
+                    maxcc=np.concatenate([pad(r["maxcc"], 0) for r in rs])[inv])

@@ -361,9 +361,9 @@ def test_multi_stream_rollout_matches_single_stream():
     mdb = _mdb()
     zs, graphs, batch, w = _load_batch("degree")
     ref = mdb.BatchRollout(batch, w).run()
-    for parts in (2, 3):
-        mr = MultiStreamRollout(graphs, w, batch.device, "degree", parts=parts)
-        for _ in range(2):  # the second run replays captured chunks
+    for parts, order in ((2, None), (3, None), (3, "size"), (None, "size")):
+        mr = MultiStreamRollout(graphs, w, batch.device, "degree", parts=parts, order=order)  # "size": sorted by edge count,
+        for _ in range(2):  # results back in the original order; the second run replays captured chunks
             r = mr.run()
             T = min(r["actions"].shape[1], ref["actions"].shape[1])
             assert np.array_equal(r["score"], ref["score"]) and np.array_equal(r["n_steps"], ref["n_steps"])
