@@ -573,17 +573,33 @@ def run_ours(args, cost, n, per_gpu, desc):
     width = [None]                                        # columns of the trace buffers that are gathered
     overflow = torch.zeros(1, dtype=torch.int32, device=dev)
 
+    pending = []  # packed records of the finished batches of the running call, waiting for the collective
+
+    def flush():
+        """ONE all_gather for all the batches a run_steps / e2e_steps call has finished (inside the timed region).  A
+        collective per batch couples the ranks at every batch: a rank whose rollouts happen to be short waits -- with NCCL's
+        CTAs resident and spinning, on SMs where no embed_fused CTA (the whole register file) can start -- for the rank with
+        the longest one, 8 to 10 % of the step at 2 to 8 GPUs; the records of a 20-step job are 16 MB per rank."""
+        if world > 1 and pending:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rec = torch.stack(pending)
+            out = torch.empty((world,) + tuple(rec.shape), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(out, rec)
+            gathered[0] = out
+            if timed[0]:
+                b.record()
+                gather_ev.append((a, b))
+        pending.clear()
+
     def gather(r):
-        """The only collective of the path: per-graph AUDC (f64, bit-exact) + n_steps + removal sequence + LMCC trace of one
-        finished batch.  The traces are [B, N] buffers of which a rollout fills ~50-70 columns: the ranks agree ONCE (first
+        """The only collective of the path: per-graph AUDC (f64, bit-exact) + n_steps + removal sequence + LMCC trace of the
+        finished batches: packed here per batch, gathered by flush().  The traces are [B, N] buffers of which a rollout fills ~50-70 columns: the ranks agree ONCE (first
         call, during warm-up: one 4-byte MAX all-reduce read back by the host) on a record width = the longest sequence + 25 %
         head room; afterwards a batch is handed to the collective without any host round trip (a host read of a collective's
         result per batch stalls the other batches in flight until the slowest rank gets there: 8 GPUs lost 17 % to it).  A
         sequence longer than the width sets a device-side flag that is checked after the timed region."""
         if world > 1:
-            if timed[0]:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
             mx = r.n_steps.max().reshape(1).clone()
             if width[0] is None:
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -592,17 +608,19 @@ def run_ours(args, cost, n, per_gpu, desc):
             overflow.add_((mx > used).to(torch.int32))
             rec = torch.cat([r.score[:, None], r.n_steps[:, None].double(), r.trace_action[:, :used].double(),
                              r.trace_rank[:, :used].double()], 1)
-            out = torch.empty(world * per_gpu, rec.shape[1], dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(out, rec)
-            gathered[0] = out
-            if timed[0]:
-                b.record()
-                gather_ev.append((a, b))
+            pending.append(rec)
 
     def run_steps(k):
         """k steps = k complete rollouts of the batch, `depth` of them in flight at a time (RolloutPipeline): a step's
         under-occupied straggler phase overlaps the next step's full-width kernels."""
+        t0 = time.perf_counter()
         pipe.run(k, lambda j: ros[j % depth], lambda j, r: gather(r))
+        t1 = time.perf_counter()
+        flush()
+        if os.environ.get("MDB200_BENCH_TRACE"):
+            torch.cuda.synchronize()
+            sys.stderr.write("rank %d: run_steps(%d): pipeline host time %.2f ms, flush (to sync) %.2f ms\n"
+                             % (rank, k, 1e3 * (t1 - t0), 1e3 * (time.perf_counter() - t1)))
 
     run_steps(max(args.warmup, 2 * depth))  # every rollout object has run twice: its CUDA graph exists
     torch.cuda.synchronize()
@@ -631,7 +649,7 @@ def run_ours(args, cost, n, per_gpu, desc):
         dist.all_gather_into_tensor(allms, ms.clone())
         per_rank_ms = [float(x) / args.steps for x in allms.cpu()]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        gather_ms = float(np.mean([a.elapsed_time(b) for a, b in gather_ev]))
+        gather_ms = float(np.sum([a.elapsed_time(b) for a, b in gather_ev])) / args.steps
     ms = float(ms[0])
     launches = sum(r.kernel_launches for r in ros) - launches0
     res = ro.results()
@@ -668,6 +686,7 @@ def run_ours(args, cost, n, per_gpu, desc):
 
     def e2e_steps(k):
         pipe.run(k, e2e_make, e2e_finish, reset=True)
+        flush()
 
     e2e_steps(max(args.warmup, 2 * depth))  # every pooled rollout has run twice: its CUDA graph exists
     torch.cuda.synchronize()
@@ -708,7 +727,7 @@ def run_ours(args, cost, n, per_gpu, desc):
                        "l2": "no flush: per-step working set (4 embedding buffers, %.0f MB) exceeds the 126 MB L2"
                              % (4 * batch.n_total * 256 / 1e6),
                        "mean_removals_per_graph": mean_steps, "mean_audc": mean_audc,
-                       "sharding": "independent graphs per rank, NCCL all_gather of per-graph records",
+                       "sharding": "independent graphs per rank; ONE NCCL all_gather of the per-graph records of all timed steps, inside the timed region",
                        "batches_in_flight": depth, "tail_kernel": bool(ro.tail),
                        "step": "one complete rollout (s0 -> all terminal) of the batch; %d steps are in flight at a time on "
                                "their own streams (RolloutPipeline), all of them inside the timed region" % depth},
@@ -720,8 +739,8 @@ def run_ours(args, cost, n, per_gpu, desc):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "removal_steps_per_s": world * per_gpu * mean_steps * args.steps / (ms * 1e-3),
             "per_rank_ms_per_step": per_rank_ms, "gather_span_ms_per_step": gather_ms,
-            "gather_note": "CUDA-event span around (record packing, all_gather; width agreed once during warm-up) on the finished batch's "
-                           "stream; other batches' kernels run inside the span, so it is an upper bound of the collective's cost",
+            "gather_note": "ONE all_gather of the records of all timed steps at the end of the timed region (records packed per batch on the batch's stream; width agreed once during warm-up); span of that collective divided by the steps (a collective per finished batch, as in the previous "
+                           "builds, coupled the ranks at every batch: 8-10 % of the step at 2-8 GPUs)",
             "single_batch_latency_ms": single_batch_ms,
         }
         if nccl_log:
