@@ -779,8 +779,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the N = 1M removal-steps/s leg (about 30 s)")
     ap.add_argument("--no-c3", action="store_true", help="skip the 1024-graph strong-scaling leg (C3)")
-    ap.add_argument("--depth", type=int, default=6, help="batches in flight (RolloutPipeline); 1 = strictly one after the other "
-                    "(measured at 20 steps: depth 4 / 6 / 8 = 19.6 / 20.1 / 20.1 k graphs/s)")
+    ap.add_argument("--depth", type=int, default=10, help="batches in flight (RolloutPipeline); 1 = strictly one after the other "
+                    "(measured at 20 steps, final round-2 build: depth 6 / 8 / 10 / 12 / 16 = 22.6 / 23.0 / 23.5 / 23.6 / 23.6 k graphs/s)")
     ap.add_argument("--tail", action="store_true", help="hand graphs with <= 64 active nodes over to md_rollout_tail")
     ap.add_argument("--fused-pack", type=int, default=0, help="md_debug_set_fused_pack (A/B): 0 = default bin budget, > 0 fixed, < 0 every unit alone")
     ap.add_argument("--fused-legacy", action="store_true", help="md_embed_fused without packing of small units (debug bit 19; A/B)")

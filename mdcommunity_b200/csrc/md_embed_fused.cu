@@ -119,8 +119,6 @@ __device__ unsigned g_fz_cta[160][2];  // per CTA: cycles from start to end of t
 #endif
 
 __device__ __forceinline__ void gw_sync() { asm volatile("bar.sync 1, %0;" ::"n"(FZ_GT) : "memory"); }
-// the four warps that share one TMEM lane quadrant set / staging tile in the epilogue (quad = warp / 4)
-__device__ __forceinline__ void quad_sync(int quad) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quad) : "memory"); }
 
 __device__ __forceinline__ void add4(float4& a, const float4& b) {
   a.x += b.x;
@@ -1029,7 +1027,6 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
     g_fz_dbg[5] = c5, g_fz_dbg[6] = c6, g_fz_dbg[7] = c7, g_fz_dbg[12] = c8, g_fz_dbg[13] = c9, g_fz_dbg[15] = n_units_done;
     g_fz_gath[0] = d0, g_fz_gath[1] = d1, g_fz_gath[2] = d2, g_fz_gath[3] = d3, g_fz_gath[4] = d4, g_fz_gath[5] = d5;
   }
-  if (blockIdx.x == 0 && tid == FZ_GT) g_fz_dbg[8] = c0, g_fz_dbg[9] = c1, g_fz_dbg[10] = c2, g_fz_dbg[11] = c3;
 #else
   (void)t_dbg, (void)c0, (void)c1, (void)c2, (void)c3, (void)c4, (void)c5, (void)c6, (void)c7, (void)c8, (void)c9;
   (void)d0, (void)d1, (void)d2, (void)d3, (void)d4, (void)d5, (void)n_units_done;
