@@ -709,11 +709,12 @@ __global__ void __launch_bounds__(FZ_T, 1) embed_fused_kernel(md_graphs_t G, md_
         }  // it > 0, pass 0: written by the epilogue below
 
         // ---------------- tiles: gather -> staging -> MMA ----------------
-        // Tile row 32*k + 4*warp + gi (k = 0..3): a lane group walks FOUR rows at once, one neighbour of each per step
-        // (four independent load chains; the rows are 32 apart in the degree-sorted order, so they end together); the four
-        // groups of a warp take adjacent rows (equal degree, and four different swizzle phases: no bank conflicts when
-        // they store their staging rows).  Rows longer than FZ_LONG (the first n_long rows of the unit) are summed
-        // afterwards by whole warps.
+        // Tile row 4 FZ_GW k + rt_w (k < FZ_RPG): a lane group walks FZ_RPG rows at once, one neighbour of each per step, several
+        // steps unrolled (8 independent row loads in flight per lane; the rows are 4 FZ_GW apart in the degree-sorted order, so
+        // they end together); the four groups of a warp take neighbouring rows (equal degree; rt_w: swizzle phases chosen so
+        // that the half-warps of an 8-byte staging store fall into different bank halves).  Per tile: own rows staged and their
+        // MMA group issued first, then the gather, then the neighbour sums staged and the second MMA group.  Rows longer than
+        // FZ_LONG (the first n_long rows of the bin) are summed afterwards by whole warps.
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = 0; t < ntile; ++t) {
           const int nl_t = min(max(n_long - TILE_M * t, 0), TILE_M);
